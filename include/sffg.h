@@ -1,0 +1,137 @@
+/*
+ * sffg.h -- C ABI of the B200 collision-and-neighbour engine for the Space-Filling Forest* planner.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, never throws.  Every entry
+ * point names the reference interface it replaces (paths relative to the reference repository root).
+ * The library (libsffg.so) is CUDA-only: there is NO CPU fallback; every compute call returns
+ * SFFG_ERR_NO_DEVICE when no sm_100 device is usable.
+ *
+ * Conventions
+ *   - all functions return an int status (SFFG_OK == 0) unless stated; sffg_last_error() gives the text
+ *   - triangle soups are double [n][9] = p1.xyz p2.xyz p3.xyz, already offset+scaled the way
+ *     Obstacle<T>::addPoint does it (src/environment.h:198-211)
+ *   - poses are [n][6] = x y z yaw pitch roll (Point<T>, src/primitives.h:86-102), angles in radians
+ *   - "host" calls take caller-owned host pointers and block until results are in the output arrays
+ *   - "_device" calls take device pointers + a cudaStream_t (as void*), enqueue, and return immediately
+ *   - one host thread per handle at a time
+ */
+#ifndef SFFG_H_
+#define SFFG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SFFG_API __attribute__((visibility("default")))
+#else
+#define SFFG_API
+#endif
+
+#define SFFG_OK 0
+#define SFFG_ERR_NO_DEVICE 1    /* no CUDA device / wrong architecture: the engine refuses to run            */
+#define SFFG_ERR_CUDA 2         /* a CUDA runtime call failed (text in sffg_last_error)                        */
+#define SFFG_ERR_ARG 3          /* bad argument (null pointer, negative size, dim not 2 or 6, k out of range)  */
+#define SFFG_ERR_IO 4           /* mesh file unreadable / malformed                                            */
+#define SFFG_ERR_CAPACITY 5     /* caller-provided result buffer too small (needed size is reported)           */
+#define SFFG_ERR_DOMAIN 6       /* angle outside the range for which the float metric is bit-exact (|a|<=7)    */
+#define SFFG_ERR_INTERNAL 7     /* traversal stack overflow or similar -- a bug, never a silent wrong answer   */
+
+#define SFFG_ROT_REFERENCE 0    /* interior edge samples carry identity rotation (src/problemStruct.h:157-163) */
+#define SFFG_ROT_INTERPOLATE 1  /* opt-in: angles interpolated along the wrapped difference                    */
+
+#define SFFG_MAX_K 128
+
+typedef struct sffg_env sffg_env;       /* obstacle BVH + robot mesh resident on one GPU  (Environment<T>)     */
+typedef struct sffg_index sffg_index;   /* append-only node set resident on one GPU        (flann::Index)      */
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+SFFG_API int sffg_version(void);
+SFFG_API const char *sffg_last_error(void);              /* thread-local, valid until the next call on this thread      */
+SFFG_API int sffg_init(int device);                      /* bind this process/thread to a GPU; checks sm_100            */
+SFFG_API int sffg_device_count(void);
+
+/* ---- meshes: Obstacle<T>::ParseOBJFile / ParseMapFile / addPoint / addFacet, src/environment.h:125-223 -- */
+/* is_obj != 0: OBJ (every token starting with 'v' is a vertex, only the first 3 indices of an 'f' line are
+ * used, 'o' never changes the index offset); is_obj == 0: 2-D ".tri" map (x1 y1 x2 y2 x3 y3, z = 0).
+ * vertex = (file value + position[i]) * scale.  *tris_out is malloc'ed by the library: free with sffg_free.
+ * bbox_out (optional) = minX maxX minY maxY minZ maxZ over all parsed vertices (Obstacle::localRange).       */
+SFFG_API int sffg_mesh_load(const char *path, int is_obj, const double position[3], double scale,
+                   double **tris_out, int64_t *n_tris_out, double bbox_out[6]);
+SFFG_API void sffg_free(void *p);
+
+/* ---- environment: RAPID_model::{BeginModel,AddTri,EndModel} (call sites src/environment.h:102-114,:222) -- */
+/* The obstacle soup is the union of all Obstacles (the reference ORs over them, src/environment.h:312-314;
+ * all sit at identity).  n_obst == 0 reproduces HasMap == false: nothing ever collides (:307-309).           */
+SFFG_API int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot_tris, int64_t n_robot,
+                    sffg_env **out);
+SFFG_API int sffg_env_destroy(sffg_env *env);
+
+typedef struct {
+  int64_t n_obst_tris, n_robot_tris;
+  int64_t n_nodes;          /* 8-wide BVH nodes                                                               */
+  int32_t depth;            /* levels of the wide BVH                                                         */
+  int64_t device_bytes;     /* HBM held by this environment                                                   */
+  double build_ms;          /* host BVH build + upload                                                        */
+} sffg_env_info_t;
+SFFG_API int sffg_env_info(const sffg_env *env, sffg_env_info_t *out);
+
+/* ---- pose verdicts: Environment<T>::Collide(Point<T>), src/environment.h:306-316
+ *      = RAPID_Collide(I, 0, obstacle, R(pose), T(pose), robot) != 0 contacts, :269-276 ---------------------- */
+SFFG_API int sffg_collide_poses_f32(sffg_env *env, const float *poses, int64_t n, uint8_t *verdict_out);
+SFFG_API int sffg_collide_poses_f64(sffg_env *env, const double *poses, int64_t n, uint8_t *verdict_out);
+SFFG_API int sffg_collide_poses_device(sffg_env *env, const void *d_poses, int poses_are_f64, int64_t n,
+                              uint8_t *d_verdict_out, void *stream);
+
+/* ---- edge verdicts: Solver<T,R>::isPathFree(start, finish), src/problemStruct.h:154-168 -------------------
+ * parts = distance6(start, finish) / sample_dist; samples index = 1 .. (index < parts); position =
+ * start + index * dir / parts; stops at the first colliding sample.  free_out[i] = 1 if no sample collides;
+ * first_hit_out (optional) = index of the first colliding sample, 0 if free.
+ * The reference hard-codes sample_dist = 0.1 (collisionSampleSize, :121).                                     */
+SFFG_API int sffg_check_edges(sffg_env *env, const double *starts, const double *ends, int64_t m, double sample_dist,
+                     int rot_mode, uint8_t *free_out, int32_t *first_hit_out);
+SFFG_API int sffg_check_edges_device(sffg_env *env, const double *d_starts, const double *d_ends, int64_t m,
+                            double sample_dist, int rot_mode, uint8_t *d_free_out, int32_t *d_first_hit_out,
+                            void *stream);
+
+/* work counters of the last call on this env (debug/roofline): poses past the root cull, BVH child-box tests,
+ * triangle-pair FP32 SAT tests, FP64 exact re-tests                                                          */
+typedef struct { int64_t poses, poses_past_root, box_tests, pair_tests, exact_tests; } sffg_counters_t;
+SFFG_API int sffg_env_enable_counters(sffg_env *env, int on);
+/* after *_device calls: waits for the device and reports a traversal failure (SFFG_ERR_INTERNAL) if one was flagged */
+SFFG_API int sffg_env_sync_check(sffg_env *env);
+SFFG_API int sffg_env_read_counters(sffg_env *env, sffg_counters_t *out);
+
+/* ---- synthetic pose stream: Philox4x32-10(seed, index); distribution of
+ *      RandGen<T>::randomPointInSpace, src/randGen.h:123-146.  range = minX maxX minY maxY minZ maxZ --------- */
+SFFG_API int sffg_gen_poses_device(uint64_t seed, uint64_t first_index, int64_t n, const float range[6], float *d_poses_out,
+                          void *stream);
+
+/* ---- neighbour index: flann::Index<D6Distance<float>> as used by the planner
+ *      ctor+buildIndex src/forest.h:72-73; addPoints :367; knnSearch :317; radiusSearch :266-267
+ *      (API lib/flann/src/cpp/flann/flann.hpp:101-115,:149-152,:289-296,:361-368).
+ * Exact search with the INTENDED metric (src/primitives.h:404-438 with += ; == squared Point::distance
+ * in float); ids are 0-based insertion order; distances are squared; ties resolve to the lower id. ---------- */
+SFFG_API int sffg_index_create(int dim /* 2 or 6 */, sffg_index **out);
+SFFG_API int sffg_index_destroy(sffg_index *idx);
+SFFG_API int sffg_index_add(sffg_index *idx, const float *pts /* [n][dim] */, int64_t n);   /* copies; ids continue */
+SFFG_API int sffg_index_add_device(sffg_index *idx, const float *d_pts, int64_t n, void *stream);
+SFFG_API int64_t sffg_index_size(const sffg_index *idx);
+
+/* k nearest, ascending (d2,id); rows shorter than k (index smaller than k) are padded with id -1, d2 +inf */
+SFFG_API int sffg_knn(sffg_index *idx, const float *queries, int64_t nq, int k, int32_t *ids_out, float *d2_out);
+SFFG_API int sffg_knn_device(sffg_index *idx, const float *d_queries, int64_t nq, int k, int32_t *d_ids_out, float *d2_out,
+                    void *stream);
+
+/* all points with d2 < r2 (strict), each row sorted by (d2,id); rows packed in query order.
+ * counts_out[nq] is always written; *total_out = sum(counts).  Pass ids_out == NULL to size the buffers
+ * (two-call protocol); otherwise capacity must be >= total or SFFG_ERR_CAPACITY is returned.                */
+SFFG_API int sffg_radius(sffg_index *idx, const float *queries, int64_t nq, float r2, int32_t *counts_out,
+                int32_t *ids_out, float *d2_out, int64_t capacity, int64_t *total_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFFG_H_ */

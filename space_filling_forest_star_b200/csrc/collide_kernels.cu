@@ -1,0 +1,713 @@
+// collide_kernels.cu -- sm_100a kernels for pose and edge collision verdicts.
+//
+// Replaces the inside of Environment<T>::Collide -> Obstacle<T>::Collide -> RAPID_Collide
+// (reference src/environment.h:306-316, :269-276) and of Solver<T,R>::isPathFree (src/problemStruct.h:154-168).
+//
+// Execution model (one warp = one pose at a time):
+//   phase A  lane-per-pose: load 32 poses, cull the robot's bounding sphere against the obstacle AABB, build R
+//   phase B  warp-per-pose for the survivors:
+//            - 8-wide AABB BVH, warp-shared DFS stack in shared memory; each step pops up to 4 nodes and the 32
+//              lanes test the 4x8 child boxes against the robot's oriented box (6-axis conservative SAT)
+//            - surviving leaf triangles are transformed into the robot frame (as RAPID does) lane-per-triangle,
+//              then lane-per-(obstacle triangle, robot triangle) pair runs the 17-axis separating-axis test in FP32
+//              as a *certificate* test: an axis only counts when its gap exceeds a rigorous rounding bound
+//            - pairs without an FP32 certificate are decided by the exact stage: the same 17 axes in FP64 with the
+//              operation order of the CPU oracle, one axis per lane; __all_sync gives the pair verdict
+//            - __ballot/__any early-out on the first confirmed contact (verdict-equivalent to RAPID's ALL_CONTACTS
+//              because the caller only looks at num_contacts != 0)
+// The result equals "OR over all triangle pairs of the double-precision SAT" -- the oracle's ground truth.
+#include <cstdint>
+
+#include "collide_kernels.cuh"
+
+namespace sffg {
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kStackCap = 384;   // node ids pending for one pose
+constexpr int kTriCap = 64;      // candidate triangles pending for one pose
+constexpr int kTriFlush = 12;    // run the triangle stage once this many candidates are pending
+constexpr unsigned kFull = 0xffffffffu;
+constexpr float kEpsBox = 1.52587890625e-05f;   // 2^-16, relative slack of the box culls   (>= 140 ulp)
+constexpr float kEpsSat = 1.52587890625e-05f;   // 2^-16, relative position error of the FP32 SAT stage
+
+struct XTri {        // obstacle triangle in the robot frame (FP32), 48 B
+  float v[9];
+  float err;         // absolute position error bound of these 9 values
+  float mabs;        // max |v|
+  int tri;           // triangle index (leaf order) for the exact stage
+};
+
+struct WarpScratch {
+  int stack[kStackCap];
+  int tri[kTriCap];
+  XTri xt[32];
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// FP32 certificate SAT
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float min3f(float a, float b, float c) { return fminf(a, fminf(b, c)); }
+__device__ __forceinline__ float max3f(float a, float b, float c) { return fmaxf(a, fmaxf(b, c)); }
+
+// true when axis (ax,ay,az) separates the two triangles by more than the rounding bound
+__device__ __forceinline__ bool axis_certifies(float ax, float ay, float az, const float *p, const float (*q)[3],
+                                               float errpos) {
+  float P1 = ax * p[0] + ay * p[1] + az * p[2];
+  float P2 = ax * p[3] + ay * p[4] + az * p[5];
+  float P3 = ax * p[6] + ay * p[7] + az * p[8];
+  float Q1 = ax * q[0][0] + ay * q[0][1] + az * q[0][2];
+  float Q2 = ax * q[1][0] + ay * q[1][1] + az * q[1][2];
+  float Q3 = ax * q[2][0] + ay * q[2][1] + az * q[2][2];
+  float gap = fmaxf(min3f(P1, P2, P3) - max3f(Q1, Q2, Q3), min3f(Q1, Q2, Q3) - max3f(P1, P2, P3));
+  float bound = (fabsf(ax) + fabsf(ay) + fabsf(az)) * errpos;
+  return gap > bound;
+}
+
+// axis with a host-precomputed (outward rounded) projection interval of the robot triangle
+__device__ __forceinline__ bool axis_certifies_pre(const float *a, const float *p, float qlo, float qhi, float errpos) {
+  float P1 = a[0] * p[0] + a[1] * p[1] + a[2] * p[2];
+  float P2 = a[0] * p[3] + a[1] * p[4] + a[2] * p[5];
+  float P3 = a[0] * p[6] + a[1] * p[7] + a[2] * p[8];
+  float gap = fmaxf(min3f(P1, P2, P3) - qhi, qlo - max3f(P1, P2, P3));
+  float bound = (fabsf(a[0]) + fabsf(a[1]) + fabsf(a[2])) * errpos;
+  return gap > bound;
+}
+
+// returns true when the pair is PROVEN disjoint in FP32; false = undecided (exact stage must look at it)
+__device__ bool pair_certified_disjoint(const XTri &x, const RobotTri &rt) {
+  const float *p = x.v;
+  const float errpos = 2.0f * x.err + kEpsSat * fmaxf(x.mabs, rt.qmax);
+  // AABB prefilter in the robot frame
+  {
+    float lo0 = min3f(p[0], p[3], p[6]) - errpos, hi0 = max3f(p[0], p[3], p[6]) + errpos;
+    float lo1 = min3f(p[1], p[4], p[7]) - errpos, hi1 = max3f(p[1], p[4], p[7]) + errpos;
+    float lo2 = min3f(p[2], p[5], p[8]) - errpos, hi2 = max3f(p[2], p[5], p[8]) + errpos;
+    if (lo0 > rt.hi[0] || hi0 < rt.lo[0] || lo1 > rt.hi[1] || hi1 < rt.lo[1] || lo2 > rt.hi[2] || hi2 < rt.lo[2])
+      return true;
+  }
+  // robot face normal, then obstacle face normal: these two reject most pairs
+  if (axis_certifies_pre(rt.m, p, rt.m_lo, rt.m_hi, errpos)) return true;
+  float e[3][3];
+  e[0][0] = p[3] - p[0]; e[0][1] = p[4] - p[1]; e[0][2] = p[5] - p[2];
+  e[1][0] = p[6] - p[3]; e[1][1] = p[7] - p[4]; e[1][2] = p[8] - p[5];
+  e[2][0] = p[0] - p[6]; e[2][1] = p[1] - p[7]; e[2][2] = p[2] - p[8];
+  float n[3];
+  n[0] = e[0][1] * e[1][2] - e[0][2] * e[1][1];
+  n[1] = e[0][2] * e[1][0] - e[0][0] * e[1][2];
+  n[2] = e[0][0] * e[1][1] - e[0][1] * e[1][0];
+  if (axis_certifies(n[0], n[1], n[2], p, rt.q, errpos)) return true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (axis_certifies_pre(rt.h[k], p, rt.h_lo[k], rt.h_hi[k], errpos)) return true;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float gx = e[i][1] * n[2] - e[i][2] * n[1];
+    float gy = e[i][2] * n[0] - e[i][0] * n[2];
+    float gz = e[i][0] * n[1] - e[i][1] * n[0];
+    if (axis_certifies(gx, gy, gz, p, rt.q, errpos)) return true;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float cx = e[i][1] * rt.f[j][2] - e[i][2] * rt.f[j][1];
+      float cy = e[i][2] * rt.f[j][0] - e[i][0] * rt.f[j][2];
+      float cz = e[i][0] * rt.f[j][1] - e[i][1] * rt.f[j][0];
+      if (axis_certifies(cx, cy, cz, p, rt.q, errpos)) return true;
+    }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FP64 exact stage -- operation order of oracle/sff_oracle.c (make_xform, xform_point, orc_tri_contact).
+// Explicit *_rn intrinsics keep ptxas from contracting a*b+c into an FMA, which the CPU oracle does not do.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double ddot(const double *a, const double *b) {
+  return dadd(dadd(dmul(a[0], b[0]), dmul(a[1], b[1])), dmul(a[2], b[2]));
+}
+__device__ __forceinline__ void dcross(double *r, const double *a, const double *b) {
+  r[0] = dsub(dmul(a[1], b[2]), dmul(a[2], b[1]));
+  r[1] = dsub(dmul(a[2], b[0]), dmul(a[0], b[2]));
+  r[2] = dsub(dmul(a[0], b[1]), dmul(a[1], b[0]));
+}
+
+// Point<T>::FillRotationMatrix (reference src/primitives.h:252-262), double
+__device__ void rotation_f64(double yaw, double pitch, double roll, double *m) {
+  double sy, cy, sp, cp, sr, cr;
+  sincos(yaw, &sy, &cy);
+  sincos(pitch, &sp, &cp);
+  sincos(roll, &sr, &cr);
+  m[0] = dmul(cy, cp);
+  m[1] = dsub(dmul(dmul(cy, sp), sr), dmul(sy, cr));
+  m[2] = dadd(dmul(dmul(cy, sp), cr), dmul(sy, sr));
+  m[3] = dmul(sy, cp);
+  m[4] = dadd(dmul(dmul(sy, sp), sr), dmul(cy, cr));
+  m[5] = dsub(dmul(dmul(sy, sp), cr), dmul(cy, sr));
+  m[6] = -sp;
+  m[7] = dmul(cp, sr);
+  m[8] = dmul(cp, cr);
+}
+
+// all 32 lanes call this with identical arguments; lane k < 17 evaluates axis k.  Returns the pair verdict.
+__device__ __noinline__ bool exact_pair_contact(const double *R2, const double *T2, const double *ot, const double *rq,
+                                                int lane) {
+  // mT = R2^T * (0 - T2); vertex = (R2^T row . p) * 1.0 + mT
+  double u[3] = {dsub(0.0, T2[0]), dsub(0.0, T2[1]), dsub(0.0, T2[2])};
+  double mT[3], P[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) mT[i] = dadd(dadd(dmul(R2[0 + i], u[0]), dmul(R2[3 + i], u[1])), dmul(R2[6 + i], u[2]));
+#pragma unroll
+  for (int v = 0; v < 3; ++v)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double s = dadd(dadd(dmul(R2[0 + i], ot[3 * v]), dmul(R2[3 + i], ot[3 * v + 1])), dmul(R2[6 + i], ot[3 * v + 2]));
+      P[v][i] = dadd(dmul(1.0, s), mT[i]);
+    }
+  // everything relative to P[0]
+  double p[3][3], q[3][3], vec[8][3];   // vec: e1 e2 e3 f1 f2 f3 n1 m1
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    p[0][k] = dsub(P[0][k], P[0][k]);
+    p[1][k] = dsub(P[1][k], P[0][k]);
+    p[2][k] = dsub(P[2][k], P[0][k]);
+    q[0][k] = dsub(rq[k], P[0][k]);
+    q[1][k] = dsub(rq[3 + k], P[0][k]);
+    q[2][k] = dsub(rq[6 + k], P[0][k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    vec[0][k] = dsub(p[1][k], p[0][k]);
+    vec[1][k] = dsub(p[2][k], p[1][k]);
+    vec[2][k] = dsub(p[0][k], p[2][k]);
+    vec[3][k] = dsub(q[1][k], q[0][k]);
+    vec[4][k] = dsub(q[2][k], q[1][k]);
+    vec[5][k] = dsub(q[0][k], q[2][k]);
+  }
+  dcross(vec[6], vec[0], vec[1]);
+  dcross(vec[7], vec[3], vec[4]);
+  // axis table: 0: n1, 1: m1, 2..10: e_i x f_j, 11..13: e_i x n1, 14..16: f_j x m1
+  bool overlaps = true;
+  if (lane < 17) {
+    double ax[3];
+    if (lane == 0) { ax[0] = vec[6][0]; ax[1] = vec[6][1]; ax[2] = vec[6][2]; }
+    else if (lane == 1) { ax[0] = vec[7][0]; ax[1] = vec[7][1]; ax[2] = vec[7][2]; }
+    else {
+      int a, b;
+      if (lane < 11) { a = (lane - 2) / 3; b = 3 + (lane - 2) % 3; }
+      else if (lane < 14) { a = lane - 11; b = 6; }
+      else { a = 3 + (lane - 14); b = 7; }
+      dcross(ax, vec[a], vec[b]);
+    }
+    double P1 = ddot(ax, p[0]), P2 = ddot(ax, p[1]), P3 = ddot(ax, p[2]);
+    double Q1 = ddot(ax, q[0]), Q2 = ddot(ax, q[1]), Q3 = ddot(ax, q[2]);
+    double mx1 = fmax(P1, fmax(P2, P3)), mn1 = fmin(P1, fmin(P2, P3));
+    double mx2 = fmax(Q1, fmax(Q2, Q3)), mn2 = fmin(Q1, fmin(Q2, Q3));
+    if (mn1 > mx2) overlaps = false;
+    if (mn2 > mx1) overlaps = false;
+  }
+  return __all_sync(kFull, overlaps);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-pose warp traversal
+// ---------------------------------------------------------------------------------------------------------
+struct PoseU {          // warp-uniform copy of one pose
+  float R[9];           // row-major, world <- robot
+  float Thi[3], Tlo[3]; // T = Thi + Tlo (+ negligible)
+};
+
+struct Tally { unsigned long long past_root, box, pair, exact; };
+
+template <bool COUNT>
+__device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *srob, const PoseU &P,
+                              double Tdx, double Tdy, double Tdz, double yaw, double pitch, double roll, int src,
+                              int lane, Tally &tally) {
+  // ---- per-pose constants of the oriented-box test
+  float o[3], ra[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    o[k] = P.R[3 * k] * E.rob_c[0] + P.R[3 * k + 1] * E.rob_c[1] + P.R[3 * k + 2] * E.rob_c[2] + P.Tlo[k];
+    ra[k] = fabsf(P.R[3 * k]) * E.rob_h[0] + fabsf(P.R[3 * k + 1]) * E.rob_h[1] + fabsf(P.R[3 * k + 2]) * E.rob_h[2];
+  }
+  const float rob_sz = 2.0f * E.rob_radius + fabsf(P.Tlo[0]) + fabsf(P.Tlo[1]) + fabsf(P.Tlo[2]);
+  const unsigned lt = (1u << lane) - 1u;
+
+  int sp = 1, ntri = 0;
+  if (lane == 0) ws.stack[0] = 0;
+  __syncwarp();
+  bool hit = false;
+  bool have_R2 = false;
+  double R2[9], T2[3];
+  if (COUNT) tally.past_root += 1;
+
+  while (true) {
+    if (sp > 0 && ntri <= kTriCap - 32) {
+      const int take = sp < 4 ? sp : 4;
+      const int grp = lane >> 3;
+      const bool active = grp < take;
+      const int node = active ? ws.stack[sp - 1 - grp] : 0;
+      __syncwarp();
+      sp -= take;
+      bool ov = false;
+      int child = kEmptyChild;
+      if (active) {
+        const float4 *s = E.slots + ((size_t)node * kWide + (lane & 7)) * 2;
+        const float4 a = __ldg(s), b = __ldg(s + 1);
+        child = __float_as_int(a.w);
+        if (child != kEmptyChild) {
+          const float tx = (a.x - P.Thi[0]) - o[0], ty = (a.y - P.Thi[1]) - o[1], tz = (a.z - P.Thi[2]) - o[2];
+          const float pad = kEpsBox * (fabsf(tx) + fabsf(ty) + fabsf(tz) + b.x + b.y + b.z + rob_sz);
+          ov = !(fabsf(tx) > b.x + ra[0] + pad) && !(fabsf(ty) > b.y + ra[1] + pad) && !(fabsf(tz) > b.z + ra[2] + pad);
+          if (ov) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const float s_j = P.R[j] * tx + P.R[3 + j] * ty + P.R[6 + j] * tz;
+              const float rb = fabsf(P.R[j]) * b.x + fabsf(P.R[3 + j]) * b.y + fabsf(P.R[6 + j]) * b.z;
+              const float hj = j == 0 ? E.rob_h[0] : (j == 1 ? E.rob_h[1] : E.rob_h[2]);
+              if (fabsf(s_j) > hj + rb + pad) ov = false;
+            }
+          }
+        }
+      }
+      const unsigned m_tested = COUNT ? __ballot_sync(kFull, active && child != kEmptyChild) : 0u;
+      const unsigned m_int = __ballot_sync(kFull, ov && child >= 0);
+      const unsigned m_leaf = __ballot_sync(kFull, ov && child < 0);
+      if (COUNT) tally.box += __popc(m_tested);
+      if (ov && child >= 0) {
+        const int pos = sp + __popc(m_int & lt);
+        if (pos < kStackCap) ws.stack[pos] = child;
+      }
+      if (ov && child < 0) ws.tri[ntri + __popc(m_leaf & lt)] = ~child;
+      sp += __popc(m_int);
+      ntri += __popc(m_leaf);
+      if (sp > kStackCap) {     // never silently drop work: flag the launch as failed
+        if (lane == 0) atomicExch(E.status, 1);
+        sp = kStackCap;
+      }
+      __syncwarp();
+      if (sp > 0 && ntri < kTriFlush) continue;
+    }
+    if (ntri == 0) {
+      if (sp == 0) break;
+      continue;
+    }
+    // ---------------- triangle stage ----------------
+    for (int base = 0; base < ntri && !hit; base += 32) {
+      const int cnt = (ntri - base) < 32 ? (ntri - base) : 32;
+      bool keep = false;
+      XTri x;
+      if (lane < cnt) {
+        const int t = ws.tri[base + lane];
+        const float4 v0 = __ldg(E.tris32 + 3 * (size_t)t), v1 = __ldg(E.tris32 + 3 * (size_t)t + 1),
+                     v2 = __ldg(E.tris32 + 3 * (size_t)t + 2);
+        const float w[9] = {(v0.x - P.Thi[0]) - P.Tlo[0], (v0.y - P.Thi[1]) - P.Tlo[1], (v0.z - P.Thi[2]) - P.Tlo[2],
+                            (v1.x - P.Thi[0]) - P.Tlo[0], (v1.y - P.Thi[1]) - P.Tlo[1], (v1.z - P.Thi[2]) - P.Tlo[2],
+                            (v2.x - P.Thi[0]) - P.Tlo[0], (v2.y - P.Thi[1]) - P.Tlo[1], (v2.z - P.Thi[2]) - P.Tlo[2]};
+        float mabs = 0.f;
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float val = P.R[c] * w[3 * v] + P.R[3 + c] * w[3 * v + 1] + P.R[6 + c] * w[3 * v + 2];
+            x.v[3 * v + c] = val;
+            mabs = fmaxf(mabs, fabsf(val));
+          }
+        x.err = v0.w;
+        x.mabs = mabs;
+        x.tri = t;
+        const float padT = 2.0f * x.err + kEpsSat * fmaxf(mabs, E.rob_radius);
+        keep = true;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float lo = min3f(x.v[c], x.v[3 + c], x.v[6 + c]) - padT, hi = max3f(x.v[c], x.v[3 + c], x.v[6 + c]) + padT;
+          const float rc = c == 0 ? E.rob_c[0] : (c == 1 ? E.rob_c[1] : E.rob_c[2]);
+          const float rh = c == 0 ? E.rob_h[0] : (c == 1 ? E.rob_h[1] : E.rob_h[2]);
+          if (lo > rc + rh || hi < rc - rh) keep = false;
+        }
+      }
+      const unsigned km = __ballot_sync(kFull, keep);
+      const int nx = __popc(km);
+      if (keep) ws.xt[__popc(km & lt)] = x;
+      __syncwarp();
+      const int npairs = nx * E.n_robot;
+      for (int pb = 0; pb < npairs && !hit; pb += 32) {
+        const int pidx = pb + lane;
+        bool undecided = false;
+        if (pidx < npairs) {
+          const int xi = pidx / E.n_robot, r = pidx - xi * E.n_robot;
+          undecided = !pair_certified_disjoint(ws.xt[xi], srob[r]);
+        }
+        unsigned um = __ballot_sync(kFull, undecided);
+        if (COUNT) {
+          const int np = (npairs - pb) < 32 ? (npairs - pb) : 32;
+          tally.pair += np;
+          tally.exact += __popc(um);
+        }
+        while (um) {
+          const int l = __ffs(um) - 1;
+          um &= um - 1;
+          if (!have_R2) {
+            const double ty_ = __shfl_sync(kFull, yaw, src), tp_ = __shfl_sync(kFull, pitch, src),
+                         tr_ = __shfl_sync(kFull, roll, src);
+            T2[0] = __shfl_sync(kFull, Tdx, src);
+            T2[1] = __shfl_sync(kFull, Tdy, src);
+            T2[2] = __shfl_sync(kFull, Tdz, src);
+            rotation_f64(ty_, tp_, tr_, R2);
+            have_R2 = true;
+          }
+          const int pp = pb + l;
+          const int xi = pp / E.n_robot, r = pp - xi * E.n_robot;
+          const int t = ws.xt[xi].tri;
+          if (exact_pair_contact(R2, T2, E.tris64 + 9 * (size_t)t, E.robot64 + 9 * (size_t)r, lane)) {
+            hit = true;
+            break;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (hit) break;
+    ntri = 0;
+    if (sp == 0) break;
+  }
+  return hit;
+}
+
+// lane-per-pose cull: robot bounding sphere (about the robot origin) against the obstacle AABB
+__device__ __forceinline__ bool sphere_hits_root(const EnvDev &E, float tx, float ty, float tz, float tlo_mag) {
+  const float dx = fmaxf(fabsf(tx - E.root_c[0]) - E.root_h[0], 0.f);
+  const float dy = fmaxf(fabsf(ty - E.root_c[1]) - E.root_h[1], 0.f);
+  const float dz = fmaxf(fabsf(tz - E.root_c[2]) - E.root_h[2], 0.f);
+  const float pad = kEpsBox * (fabsf(tx) + fabsf(ty) + fabsf(tz) + fabsf(E.root_c[0]) + fabsf(E.root_c[1]) +
+                               fabsf(E.root_c[2]) + E.root_h[0] + E.root_h[1] + E.root_h[2] + E.rob_radius) + tlo_mag;
+  const float r = E.rob_radius + pad;
+  return dx * dx + dy * dy + dz * dz <= r * r * 1.000001f;
+}
+
+// Point<T>::FillRotationMatrix in FP32 (certificate stage only)
+__device__ __forceinline__ void rotation_f32(float yaw, float pitch, float roll, float *m) {
+  float sy, cy, sp, cp, sr, cr;
+  sincosf(yaw, &sy, &cy);
+  sincosf(pitch, &sp, &cp);
+  sincosf(roll, &sr, &cr);
+  m[0] = cy * cp;
+  m[1] = cy * sp * sr - sy * cr;
+  m[2] = cy * sp * cr + sy * sr;
+  m[3] = sy * cp;
+  m[4] = sy * sp * sr + cy * cr;
+  m[5] = sy * sp * cr - cy * sr;
+  m[6] = -sp;
+  m[7] = cp * sr;
+  m[8] = cp * cr;
+}
+
+__device__ __forceinline__ void stage_robot(const EnvDev &E, RobotTri *srob) {
+  const int words = E.n_robot * (int)(sizeof(RobotTri) / 4);
+  const float *g = reinterpret_cast<const float *>(E.robot);
+  float *s = reinterpret_cast<float *>(srob);
+  for (int i = threadIdx.x; i < words; i += blockDim.x) s[i] = __ldg(g + i);
+  __syncthreads();
+}
+
+__device__ __forceinline__ void flush_tally(const EnvDev &E, const Tally &t, unsigned long long poses, int lane) {
+  if (lane == 0 && E.counters) {
+    atomicAdd(E.counters + 0, poses);
+    atomicAdd(E.counters + 1, t.past_root);
+    atomicAdd(E.counters + 2, t.box);
+    atomicAdd(E.counters + 3, t.pair);
+    atomicAdd(E.counters + 4, t.exact);
+  }
+}
+
+// runs phase B over the lanes set in `alive`; returns the mask of colliding lanes (stops at the first hit when
+// `first_only`, which is what an edge needs)
+template <bool COUNT>
+__device__ __forceinline__ unsigned run_survivors(const EnvDev &E, WarpScratch &ws, const RobotTri *srob, unsigned alive,
+                                                  const float *R, double Tx, double Ty, double Tz, double yaw, double pitch,
+                                                  double roll, int lane, bool first_only, Tally &tally) {
+  unsigned hitmask = 0;
+  const float thx = (float)Tx, thy = (float)Ty, thz = (float)Tz;
+  const float tlx = (float)(Tx - (double)thx), tly = (float)(Ty - (double)thy), tlz = (float)(Tz - (double)thz);
+  while (alive) {
+    const int src = __ffs(alive) - 1;
+    alive &= alive - 1;
+    PoseU P;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) P.R[k] = __shfl_sync(kFull, R[k], src);
+    P.Thi[0] = __shfl_sync(kFull, thx, src);
+    P.Thi[1] = __shfl_sync(kFull, thy, src);
+    P.Thi[2] = __shfl_sync(kFull, thz, src);
+    P.Tlo[0] = __shfl_sync(kFull, tlx, src);
+    P.Tlo[1] = __shfl_sync(kFull, tly, src);
+    P.Tlo[2] = __shfl_sync(kFull, tlz, src);
+    if (warp_pose_hit<COUNT>(E, ws, srob, P, Tx, Ty, Tz, yaw, pitch, roll, src, lane, tally)) {
+      hitmask |= 1u << src;
+      if (first_only) break;
+    }
+  }
+  return hitmask;
+}
+
+template <bool F64, bool COUNT>
+__global__ void __launch_bounds__(kThreads) collide_poses_kernel(EnvDev E, const void *poses, long long n,
+                                                                 uint8_t *out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  RobotTri *srob = reinterpret_cast<RobotTri *>(smem);
+  stage_robot(E, srob);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + (size_t)E.n_robot * sizeof(RobotTri))[warp];
+  const long long nchunks = (n + 31) / 32;
+  Tally tally = {0, 0, 0, 0};
+  unsigned long long nposes = 0;
+  while (true) {
+    unsigned c = 0;
+    if (lane == 0) c = atomicAdd(E.work_counter, 1u);
+    c = __shfl_sync(kFull, c, 0);
+    if ((long long)c >= nchunks) break;
+    const long long i = (long long)c * 32 + lane;
+    double Tx = 0, Ty = 0, Tz = 0, yaw = 0, pitch = 0, roll = 0;
+    if (i < n) {
+      if (F64) {
+        const double2 *p = reinterpret_cast<const double2 *>(poses) + 3 * i;
+        const double2 a = p[0], b = p[1], d = p[2];
+        Tx = a.x; Ty = a.y; Tz = b.x; yaw = b.y; pitch = d.x; roll = d.y;
+      } else {
+        const float2 *p = reinterpret_cast<const float2 *>(poses) + 3 * i;
+        const float2 a = p[0], b = p[1], d = p[2];
+        Tx = a.x; Ty = a.y; Tz = b.x; yaw = b.y; pitch = d.x; roll = d.y;
+      }
+    }
+    const float thx = (float)Tx, thy = (float)Ty, thz = (float)Tz;
+    const float tlo = fabsf((float)(Tx - (double)thx)) + fabsf((float)(Ty - (double)thy)) + fabsf((float)(Tz - (double)thz));
+    const bool alive = (i < n) && E.n_obst > 0 && sphere_hits_root(E, thx, thy, thz, tlo);
+    float R[9];
+    if (alive) rotation_f32((float)yaw, (float)pitch, (float)roll, R);
+    const unsigned am = __ballot_sync(kFull, alive);
+    if (COUNT) nposes += (i < n) ? 1 : 0;
+    const unsigned hitmask = run_survivors<COUNT>(E, ws, srob, am, R, Tx, Ty, Tz, yaw, pitch, roll, lane, false, tally);
+    if (i < n) out[i] = (uint8_t)((hitmask >> lane) & 1u);
+  }
+  if (COUNT) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) nposes += __shfl_xor_sync(kFull, nposes, s);
+    flush_tally(E, tally, nposes, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// edges: Solver<T,R>::isPathFree (reference src/problemStruct.h:154-168), one warp per edge
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double wrap_pi(double a) {
+  const double pi = 3.14159265358979323846;
+  if (a < -pi) return dadd(a, dmul(2.0, pi));
+  else if (a >= pi) return dsub(a, dmul(2.0, pi));
+  return a;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kThreads) check_edges_kernel(EnvDev E, const double *starts, const double *ends,
+                                                               long long m, double sample, int rot_mode, uint8_t *free_out,
+                                                               int32_t *first_hit) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  RobotTri *srob = reinterpret_cast<RobotTri *>(smem);
+  stage_robot(E, srob);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + (size_t)E.n_robot * sizeof(RobotTri))[warp];
+  Tally tally = {0, 0, 0, 0};
+  unsigned long long nposes = 0;
+  while (true) {
+    unsigned eidx = 0;
+    if (lane == 0) eidx = atomicAdd(E.work_counter, 1u);
+    eidx = __shfl_sync(kFull, eidx, 0);
+    if ((long long)eidx >= m) break;
+    double s[6], f[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      s[k] = __ldg(starts + 6 * (size_t)eidx + k);
+      f[k] = __ldg(ends + 6 * (size_t)eidx + k);
+    }
+    // Point<T>::distance, src/primitives.h:224-235
+    double sum = 0.0, adir[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double d = dsub(s[k], f[k]);
+      sum = dadd(sum, dmul(d, d));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      adir[k] = wrap_pi(dsub(f[3 + k], s[3 + k]));
+      sum = dadd(sum, dmul(adir[k], adir[k]));
+    }
+    const double total = sqrt(sum);
+    const double parts = __ddiv_rn(total, sample);
+    const double dir[3] = {dsub(f[0], s[0]), dsub(f[1], s[1]), dsub(f[2], s[2])};
+    // indices 1 .. S with (double)index < parts
+    long long S = 0;
+    if (parts > 1.0) {
+      const double cl = ceil(parts);
+      S = (cl > 4.0e9 ? 4000000000LL : (long long)cl) - 1;
+    }
+    int hit_index = 0;
+    for (long long base = 1; base <= S && hit_index == 0; base += 32) {
+      const long long idx = base + lane;
+      const bool valid = idx <= S && E.n_obst > 0;
+      const double di = (double)idx;
+      const double Tx = dadd(s[0], __ddiv_rn(dmul(di, dir[0]), parts));
+      const double Ty = dadd(s[1], __ddiv_rn(dmul(di, dir[1]), parts));
+      const double Tz = dadd(s[2], __ddiv_rn(dmul(di, dir[2]), parts));
+      double yaw = 0.0, pitch = 0.0, roll = 0.0;
+      if (rot_mode == SFFG_ROT_INTERPOLATE) {
+        yaw = dadd(s[3], __ddiv_rn(dmul(di, adir[0]), parts));
+        pitch = dadd(s[4], __ddiv_rn(dmul(di, adir[1]), parts));
+        roll = dadd(s[5], __ddiv_rn(dmul(di, adir[2]), parts));
+      }
+      const float thx = (float)Tx, thy = (float)Ty, thz = (float)Tz;
+      const float tlo = fabsf((float)(Tx - (double)thx)) + fabsf((float)(Ty - (double)thy)) + fabsf((float)(Tz - (double)thz));
+      const bool alive = valid && sphere_hits_root(E, thx, thy, thz, tlo);
+      float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+      if (alive && rot_mode == SFFG_ROT_INTERPOLATE) rotation_f32((float)yaw, (float)pitch, (float)roll, R);
+      const unsigned am = __ballot_sync(kFull, alive);
+      if (COUNT) nposes += valid ? 1 : 0;
+      const unsigned hm = run_survivors<COUNT>(E, ws, srob, am, R, Tx, Ty, Tz, yaw, pitch, roll, lane, true, tally);
+      if (hm) hit_index = (int)(base + (__ffs(hm) - 1));
+    }
+    if (lane == 0) {
+      free_out[eidx] = hit_index == 0 ? 1 : 0;
+      if (first_hit) first_hit[eidx] = hit_index;
+    }
+  }
+  if (COUNT) {
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) nposes += __shfl_xor_sync(kFull, nposes, sft);
+    flush_tally(E, tally, nposes, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// synthetic pose stream: Philox4x32-10, bit-identical to oracle/sff_oracle.c::orc_gen_poses
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox10(unsigned long long seed, unsigned long long index, unsigned stream, unsigned *o) {
+  unsigned c0 = (unsigned)index, c1 = (unsigned)(index >> 32), c2 = stream, c3 = 0;
+  unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+__device__ __forceinline__ float u01(unsigned bits) { return __fmul_rn((float)(bits >> 8), 5.9604644775390625e-08f); }
+__device__ __forceinline__ float acos_poly(float x) {
+  const float ax = fabsf(x);
+  float p = -0.0012624911f;
+  p = __fadd_rn(__fmul_rn(p, ax), 0.0066700901f);
+  p = __fadd_rn(__fmul_rn(p, ax), -0.0170881256f);
+  p = __fadd_rn(__fmul_rn(p, ax), 0.0308918810f);
+  p = __fadd_rn(__fmul_rn(p, ax), -0.0501743046f);
+  p = __fadd_rn(__fmul_rn(p, ax), 0.0889789874f);
+  p = __fadd_rn(__fmul_rn(p, ax), -0.2145988016f);
+  p = __fadd_rn(__fmul_rn(p, ax), 1.5707963050f);
+  const float r = __fmul_rn(__fsqrt_rn(__fsub_rn(1.0f, ax)), p);
+  return x < 0.0f ? __fsub_rn(3.14159274f, r) : r;
+}
+
+__global__ void gen_poses_kernel(unsigned long long seed, unsigned long long first, long long n, float r0, float r1,
+                                 float r2, float r3, float r4, float r5, float *out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned a[4], b[4];
+  philox10(seed, first + (unsigned long long)i, 0, a);
+  philox10(seed, first + (unsigned long long)i, 1, b);
+  float *o = out + 6 * i;
+  o[0] = __fadd_rn(r0, __fmul_rn(u01(a[0]), __fsub_rn(r1, r0)));
+  o[1] = __fadd_rn(r2, __fmul_rn(u01(a[1]), __fsub_rn(r3, r2)));
+  o[2] = __fadd_rn(r4, __fmul_rn(u01(a[2]), __fsub_rn(r5, r4)));
+  o[3] = __fadd_rn(-3.14159274f, __fmul_rn(u01(a[3]), 6.28318548f));
+  float phi = __fadd_rn(acos_poly(__fsub_rn(1.0f, __fmul_rn(2.0f, u01(b[0])))), 1.57079637f);
+  if (u01(b[1]) < 0.5f) phi = __fsub_rn(phi, 3.14159274f);
+  o[4] = phi;
+  o[5] = __fadd_rn(-3.14159274f, __fmul_rn(u01(b[2]), 6.28318548f));
+}
+
+template <typename K>
+cudaError_t prep(K kernel, size_t smem) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+}  // namespace
+
+size_t collide_smem_bytes(int n_robot) {
+  return (size_t)n_robot * sizeof(RobotTri) + (size_t)kWarpsPerBlock * sizeof(WarpScratch);
+}
+
+template <typename K>
+static int grid_for(K kernel, size_t smem, const LaunchCfg &cfg) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return cfg.sm_count * per_sm;
+}
+
+cudaError_t launch_collide_poses(const EnvDev &env, const void *d_poses, bool poses_f64, int64_t n, uint8_t *d_verdict,
+                                 cudaStream_t stream, const LaunchCfg &cfg, bool count) {
+  if (n <= 0) return cudaSuccess;
+  const size_t smem = collide_smem_bytes(env.n_robot);
+  cudaError_t e = cudaMemsetAsync(env.work_counter, 0, sizeof(unsigned), stream);
+  if (e != cudaSuccess) return e;
+#define SFFG_LAUNCH(F64, CNT)                                                                          \
+  {                                                                                                    \
+    auto k = collide_poses_kernel<F64, CNT>;                                                           \
+    e = prep(k, smem);                                                                                 \
+    if (e != cudaSuccess) return e;                                                                    \
+    long long chunks = (n + 31) / 32;                                                                  \
+    long long want = (chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;                                   \
+    int grid = grid_for(k, smem, cfg);                                                                 \
+    if (want < grid) grid = (int)want;                                                                 \
+    k<<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict);                        \
+  }
+  if (poses_f64) { if (count) SFFG_LAUNCH(true, true) else SFFG_LAUNCH(true, false) }
+  else           { if (count) SFFG_LAUNCH(false, true) else SFFG_LAUNCH(false, false) }
+#undef SFFG_LAUNCH
+  return cudaGetLastError();
+}
+
+cudaError_t launch_check_edges(const EnvDev &env, const double *d_starts, const double *d_ends, int64_t m,
+                               double sample_dist, int rot_mode, uint8_t *d_free, int32_t *d_first_hit, cudaStream_t stream,
+                               const LaunchCfg &cfg, bool count) {
+  if (m <= 0) return cudaSuccess;
+  const size_t smem = collide_smem_bytes(env.n_robot);
+  cudaError_t e = cudaMemsetAsync(env.work_counter, 0, sizeof(unsigned), stream);
+  if (e != cudaSuccess) return e;
+#define SFFG_LAUNCH(CNT)                                                                               \
+  {                                                                                                    \
+    auto k = check_edges_kernel<CNT>;                                                                  \
+    e = prep(k, smem);                                                                                 \
+    if (e != cudaSuccess) return e;                                                                    \
+    long long want = (m + kWarpsPerBlock - 1) / kWarpsPerBlock;                                        \
+    int grid = grid_for(k, smem, cfg);                                                                 \
+    if (want < grid) grid = (int)want;                                                                 \
+    k<<<grid, kThreads, smem, stream>>>(env, d_starts, d_ends, (long long)m, sample_dist, rot_mode, d_free, d_first_hit); \
+  }
+  if (count) SFFG_LAUNCH(true) else SFFG_LAUNCH(false)
+#undef SFFG_LAUNCH
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gen_poses(uint64_t seed, uint64_t first, int64_t n, const float range[6], float *d_out,
+                             cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const int threads = 256;
+  const long long blocks = (n + threads - 1) / threads;
+  gen_poses_kernel<<<(unsigned)blocks, threads, 0, stream>>>(seed, first, (long long)n, range[0], range[1], range[2],
+                                                             range[3], range[4], range[5], d_out);
+  return cudaGetLastError();
+}
+
+}  // namespace sffg

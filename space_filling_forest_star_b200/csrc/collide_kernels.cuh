@@ -1,0 +1,43 @@
+// collide_kernels.cuh -- device-side view of an environment + launch wrappers (implemented in collide_kernels.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace sffg {
+
+struct EnvDev {
+  const float4 *slots;      // 2 float4 per child slot, kWide slots per node
+  const float4 *tris32;     // 3 float4 per obstacle triangle (BVH leaf order); p[0].w = representation error bound
+  const double *tris64;     // 9 doubles per obstacle triangle (BVH leaf order) -- exact stage
+  const RobotTri *robot;    // n_robot records (FP32, robot frame)
+  const double *robot64;    // 9 doubles per robot triangle -- exact stage
+  int n_robot;
+  int n_obst;
+  float root_c[3], root_h[3];   // obstacle AABB, centre / half extents (outward rounded)
+  float rob_c[3], rob_h[3];     // robot AABB in the robot frame (outward rounded)
+  float rob_radius;             // max |robot vertex| about the robot origin (rounded up)
+  unsigned long long *counters; // 5 x u64 (may be null): poses, past_root, box_tests, pair_tests, exact_tests
+  int *status;                  // device int, set non-zero on traversal-stack overflow
+  unsigned int *work_counter;   // persistent-kernel work distribution
+};
+
+struct LaunchCfg {
+  int sm_count;
+  int blocks_per_sm;
+};
+
+// verdict_out[i] = 1 if the robot at poses[i] touches the obstacle soup
+cudaError_t launch_collide_poses(const EnvDev &env, const void *d_poses, bool poses_f64, int64_t n,
+                                 uint8_t *d_verdict, cudaStream_t stream, const LaunchCfg &cfg, bool count);
+
+cudaError_t launch_check_edges(const EnvDev &env, const double *d_starts, const double *d_ends, int64_t m,
+                               double sample_dist, int rot_mode, uint8_t *d_free, int32_t *d_first_hit,
+                               cudaStream_t stream, const LaunchCfg &cfg, bool count);
+
+cudaError_t launch_gen_poses(uint64_t seed, uint64_t first, int64_t n, const float range[6], float *d_out,
+                             cudaStream_t stream);
+
+size_t collide_smem_bytes(int n_robot);
+
+}  // namespace sffg

@@ -1,0 +1,423 @@
+// knn_kernels.cu -- exact k-NN / radius search over the planner's node sets, sm_100a.
+//
+// Replaces flann::Index<D6Distance<float>>::knnSearch / radiusSearch as the planner calls them
+// (reference src/forest.h:266-267, :317; src/rrt.h:143,:166,:228) with an EXACT brute-force scan of the intended
+// metric (src/primitives.h:404-438 with `+=`): d2 = dx^2+dy^2+dz^2 + wrap(dyaw)^2 + wrap(dpitch)^2 + wrap(droll)^2
+// evaluated in float in exactly that order, no FMA contraction, so distances are bit-identical to FLANN's
+// LinearIndex with the fixed functor and neighbour ids are identical including ties (lower id first).
+//
+// A 2..6-D metric is not a dense contraction, so this is CUDA-core FP32 work: one warp owns QW queries (held in
+// registers, warp-uniform) and streams the node set 32 nodes per step (lane-per-node, coalesced SoA loads).  The
+// running top-k of every query is a sorted list spread over the lanes (KPL entries per lane); a candidate that beats
+// the current k-th distance is inserted with warp shuffles.  Small query batches are split into node slices across
+// warps and merged by a second kernel.
+#include <cfloat>
+
+#include "../../include/sffg.h"
+#include "knn_kernels.cuh"
+
+namespace sffg {
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr float kTwoPiHi = 6.28318548202514648f;      // float(2*pi)
+constexpr float kTwoPiLoNeg = 1.74845553146951715e-07f;  // float(2*pi) - 2*pi, nearest float
+
+// |wrap(b - a)| of NormalizeAngle<float> (reference src/primitives.h:277-292: the +-2*pi is done in double and
+// narrowed).  Exhaustively verified equal for every float |b - a| < 14 (tests/test_metric_wrap.py):
+//   |d| >= float(pi)  ->  |(|d| - hi) + lo'|   (first subtraction exact by Sterbenz, second correctly rounded)
+//   otherwise         ->  |d|, and min() selects between the two without a branch
+__device__ __forceinline__ float wrapped_abs(float qa, float na) {
+  const float a = fabsf(__fsub_rn(qa, na));
+  const float t = __fadd_rn(__fsub_rn(a, kTwoPiHi), kTwoPiLoNeg);
+  return fminf(a, fabsf(t));
+}
+
+template <int DIM>
+__device__ __forceinline__ float metric(const float *nd, const float *q) {
+  float d = __fsub_rn(nd[0], q[0]);
+  float r = __fmul_rn(d, d);
+  d = __fsub_rn(nd[1], q[1]);
+  r = __fadd_rn(r, __fmul_rn(d, d));
+  if (DIM == 6) {
+    d = __fsub_rn(nd[2], q[2]);
+    r = __fadd_rn(r, __fmul_rn(d, d));
+#pragma unroll
+    for (int c = 3; c < 6; ++c) {
+      const float w = wrapped_abs(q[c], nd[c]);
+      r = __fadd_rn(r, __fmul_rn(w, w));
+    }
+  }
+  return r;
+}
+
+// sorted (ascending) list of 32*KPL entries spread over the warp: position j lives in lane j / KPL, slot j % KPL
+template <int KPL>
+struct TopK {
+  float d[KPL];
+  int id[KPL];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int s = 0; s < KPL; ++s) { d[s] = INFINITY; id[s] = -1; }
+  }
+  // value at list position k-1, broadcast
+  __device__ __forceinline__ float kth(int k) const {
+    const int pos = k - 1, lane = pos / KPL, slot = pos % KPL;
+    float v = d[0];
+#pragma unroll
+    for (int s = 1; s < KPL; ++s) if (slot == s) v = d[s];
+    return __shfl_sync(kFull, v, lane);
+  }
+  // insert (cd, ci) AFTER all entries with distance <= cd (candidates arrive in ascending id order, so this is the
+  // (d2, id) order of FLANN's KNNSimpleResultSet, result_set.h:151-171).  All lanes call with identical arguments.
+  __device__ __forceinline__ void insert(float cd, int ci, int lane) {
+    float upd = __shfl_up_sync(kFull, d[KPL - 1], 1);
+    int upi = __shfl_up_sync(kFull, id[KPL - 1], 1);
+    if (lane == 0) upd = -INFINITY;
+#pragma unroll
+    for (int s = KPL - 1; s >= 0; --s) {
+      const float pd = s > 0 ? d[s - 1] : upd;
+      const int pi = s > 0 ? id[s - 1] : upi;
+      if (d[s] > cd) {
+        const bool shift = pd > cd;
+        d[s] = shift ? pd : cd;
+        id[s] = shift ? pi : ci;
+      }
+    }
+  }
+};
+
+// One warp = QW queries x one node slice.
+//   item = blockIdx.x * kWarps + warp;  group = item / slices;  slice = item % slices
+//   out_d / out_i: [nq][slices][k] when slices > 1 (partials), else the final [nq][k]
+template <int DIM, int QW, int KPL>
+__global__ void __launch_bounds__(kThreads) knn_scan_kernel(IndexDev idx, const float *__restrict__ queries, long long nq,
+                                                            int k, int slices, long long slice_len, float *out_d,
+                                                            int *out_i) {
+  const int lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const long long group = item / slices;
+  const int slice = (int)(item - group * slices);
+  if (group * QW >= nq) return;
+  float q[QW][DIM];
+  TopK<KPL> top[QW];
+  float worst[QW];
+#pragma unroll
+  for (int w = 0; w < QW; ++w) {
+    long long qi = group * QW + w;
+    if (qi >= nq) qi = nq - 1;   // duplicate work for the ragged tail, never written
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) q[w][c] = __ldg(queries + qi * DIM + c);
+    top[w].init();
+    worst[w] = INFINITY;
+  }
+  const long long begin = (long long)slice * slice_len;
+  long long end = begin + slice_len;
+  if (end > idx.n) end = idx.n;
+  const float *__restrict__ base = idx.coords;
+  for (long long b = begin; b < end; b += 32) {
+    const long long i = b + lane;
+    float nd[DIM];
+    const bool valid = i < end;
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) nd[c] = valid ? __ldg(base + (long long)c * idx.capacity + i) : 0.f;
+#pragma unroll
+    for (int w = 0; w < QW; ++w) {
+      const float d = valid ? metric<DIM>(nd, q[w]) : INFINITY;
+      unsigned mask = __ballot_sync(kFull, d < worst[w]);
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float cd = __shfl_sync(kFull, d, src);
+        if (cd < worst[w]) {
+          top[w].insert(cd, (int)(b + src), lane);
+          worst[w] = top[w].kth(k);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < QW; ++w) {
+    const long long qi = group * QW + w;
+    if (qi >= nq) break;
+#pragma unroll
+    for (int s = 0; s < KPL; ++s) {
+      const int pos = lane * KPL + s;
+      if (pos < k) {
+        const long long o = (qi * slices + slice) * k + pos;
+        out_d[o] = top[w].d[s];
+        out_i[o] = top[w].id[s];
+      }
+    }
+  }
+}
+
+// merges the per-slice partial lists of one query (one warp per query).  Slices are visited in ascending order and
+// every partial list is (d2,id)-sorted, so candidates again arrive such that "insert after equals" is the id order.
+template <int KPL>
+__global__ void __launch_bounds__(kThreads) knn_merge_kernel(const float *__restrict__ part_d, const int *__restrict__ part_i,
+                                                             long long nq, int k, int slices, float *out_d, int *out_i) {
+  const int lane = threadIdx.x & 31;
+  const long long qi = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  if (qi >= nq) return;
+  TopK<KPL> top;
+  top.init();
+  float worst = INFINITY;
+  const long long total = (long long)slices * k;
+  const float *pd = part_d + qi * total;
+  const int *pi = part_i + qi * total;
+  for (long long b = 0; b < total; b += 32) {
+    const long long i = b + lane;
+    const float d = i < total ? pd[i] : INFINITY;
+    const int id = i < total ? pi[i] : -1;
+    unsigned mask = __ballot_sync(kFull, d < worst && id >= 0);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float cd = __shfl_sync(kFull, d, src);
+      const int ci = __shfl_sync(kFull, id, src);
+      if (cd < worst) {
+        top.insert(cd, ci, lane);
+        worst = top.kth(k);
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) {
+    const int pos = lane * KPL + s;
+    if (pos < k) {
+      out_d[qi * k + pos] = top.d[s];
+      out_i[qi * k + pos] = top.id[s];
+    }
+  }
+}
+
+// ---- radius --------------------------------------------------------------------------------------------
+// FILL == false: counts[q] += #nodes with d2 < r2.   FILL == true: keys[offsets[q] + cursor[q]++] = (d2,id)
+template <int DIM, int QW, bool FILL>
+__global__ void __launch_bounds__(kThreads) radius_scan_kernel(IndexDev idx, const float *__restrict__ queries, long long nq,
+                                                               float r2, int slices, long long slice_len, int *counts,
+                                                               const long long *offsets, int *cursor,
+                                                               unsigned long long *keys) {
+  const int lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const long long group = item / slices;
+  const int slice = (int)(item - group * slices);
+  if (group * QW >= nq) return;
+  float q[QW][DIM];
+  int cnt[QW];
+#pragma unroll
+  for (int w = 0; w < QW; ++w) {
+    long long qi = group * QW + w;
+    if (qi >= nq) qi = nq - 1;
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) q[w][c] = __ldg(queries + qi * DIM + c);
+    cnt[w] = 0;
+  }
+  const long long begin = (long long)slice * slice_len;
+  long long end = begin + slice_len;
+  if (end > idx.n) end = idx.n;
+  const unsigned lt = (1u << lane) - 1u;
+  for (long long b = begin; b < end; b += 32) {
+    const long long i = b + lane;
+    float nd[DIM];
+    const bool valid = i < end;
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) nd[c] = valid ? __ldg(idx.coords + (long long)c * idx.capacity + i) : 0.f;
+#pragma unroll
+    for (int w = 0; w < QW; ++w) {
+      const float d = valid ? metric<DIM>(nd, q[w]) : INFINITY;
+      const bool in = d < r2;
+      const unsigned mask = __ballot_sync(kFull, in);
+      if (FILL) {
+        const long long qi = group * QW + w;
+        if (mask && qi < nq) {
+          int at = 0;
+          if (lane == 0) at = atomicAdd(cursor + qi, __popc(mask));
+          at = __shfl_sync(kFull, at, 0);
+          if (in)
+            keys[offsets[qi] + at + __popc(mask & lt)] =
+                ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)i;
+        }
+      } else {
+        cnt[w] += __popc(mask);
+      }
+    }
+  }
+  if (!FILL && lane == 0) {
+#pragma unroll
+    for (int w = 0; w < QW; ++w) {
+      const long long qi = group * QW + w;
+      if (qi < nq && cnt[w]) atomicAdd(counts + qi, cnt[w]);
+    }
+  }
+}
+
+// Ascending sort of one row per block with a comparator network whose exchanges all point the same way
+// (bitonic "flip + disperse" form), so positions >= len behave as +inf padding without being stored.
+constexpr int kSortSmem = 4096;
+__device__ __forceinline__ void cmpswap(unsigned long long *a, long long i, long long l) {
+  const unsigned long long x = a[i], y = a[l];
+  if (x > y) { a[i] = y; a[l] = x; }
+}
+__global__ void __launch_bounds__(kThreads) radius_sort_kernel(unsigned long long *keys, const long long *offsets,
+                                                               const int *counts, int *ids, float *d2) {
+  __shared__ unsigned long long sk[kSortSmem];
+  const long long row = blockIdx.x;
+  const long long len = counts[row];
+  if (len == 0) return;
+  unsigned long long *g = keys + offsets[row];
+  unsigned long long *a = g;
+  const bool in_smem = len <= kSortSmem;
+  if (in_smem) {
+    for (long long i = threadIdx.x; i < len; i += blockDim.x) sk[i] = g[i];
+    a = sk;
+  }
+  __syncthreads();
+  long long pow2 = 1;
+  while (pow2 < len) pow2 <<= 1;
+  for (long long k = 2; k <= pow2; k <<= 1) {
+    for (long long i = threadIdx.x; i < len; i += blockDim.x) {
+      const long long l = i ^ (k - 1);
+      if (l > i && l < len) cmpswap(a, i, l);
+    }
+    __syncthreads();
+    for (long long j = k >> 2; j > 0; j >>= 1) {
+      for (long long i = threadIdx.x; i < len; i += blockDim.x) {
+        const long long l = i ^ j;
+        if (l > i && l < len) cmpswap(a, i, l);
+      }
+      __syncthreads();
+    }
+  }
+  for (long long i = threadIdx.x; i < len; i += blockDim.x) {
+    const unsigned long long key = a[i];
+    ids[offsets[row] + i] = (int)(unsigned)(key & 0xffffffffull);
+    d2[offsets[row] + i] = __uint_as_float((unsigned)(key >> 32));
+  }
+}
+
+__global__ void index_append_kernel(float *coords, long long capacity, int dim, long long at, const float *__restrict__ pts,
+                                    long long n) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * dim) return;
+  const long long i = t / dim;
+  const int c = (int)(t - i * dim);
+  coords[(long long)c * capacity + at + i] = pts[t];
+}
+
+template <int DIM, int QW>
+cudaError_t launch_knn_kpl(const IndexDev &idx, const float *q, int64_t nq, int k, int slices, int64_t slice_len,
+                           float *od, int *oi, unsigned grid, cudaStream_t st) {
+  if (k <= 32) knn_scan_kernel<DIM, QW, 1><<<grid, kThreads, 0, st>>>(idx, q, nq, k, slices, slice_len, od, oi);
+  else if (k <= 64) knn_scan_kernel<DIM, QW, 2><<<grid, kThreads, 0, st>>>(idx, q, nq, k, slices, slice_len, od, oi);
+  else knn_scan_kernel<DIM, QW, 4><<<grid, kThreads, 0, st>>>(idx, q, nq, k, slices, slice_len, od, oi);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+KnnPlan plan_knn(int64_t nq, int64_t n, int sm_count) {
+  KnnPlan p;
+  p.qw = nq >= 4 * (int64_t)sm_count * kWarps ? 4 : 1;
+  p.groups = (nq + p.qw - 1) / p.qw;
+  const int64_t want_warps = (int64_t)sm_count * kWarps * 4;
+  int64_t slices = 1;
+  if (p.groups < want_warps) {
+    slices = (want_warps + p.groups - 1) / p.groups;
+    const int64_t max_slices = (n + 2047) / 2048;   // at least 2048 nodes per slice
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
+    if (slices > 4096) slices = 4096;
+  }
+  int64_t len = (n + slices - 1) / slices;
+  len = (len + 31) / 32 * 32;
+  if (len < 32) len = 32;
+  p.slices = (int)((n + len - 1) / len);
+  if (p.slices < 1) p.slices = 1;
+  p.slice_len = len;
+  return p;
+}
+
+size_t knn_scratch_bytes(const KnnPlan &p, int64_t nq, int k) {
+  if (p.slices <= 1) return 0;
+  return (size_t)nq * p.slices * k * 8;
+}
+
+cudaError_t launch_knn(const IndexDev &idx, const float *d_queries, int64_t nq, int k, int32_t *d_ids, float *d_d2,
+                       void *d_scratch, const KnnPlan &plan, cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  const int64_t items = plan.groups * plan.slices;
+  const unsigned grid = (unsigned)((items + kWarps - 1) / kWarps);
+  float *od = d_d2;
+  int *oi = d_ids;
+  if (plan.slices > 1) {
+    od = reinterpret_cast<float *>(d_scratch);
+    oi = reinterpret_cast<int *>(od + (size_t)nq * plan.slices * k);
+  }
+  cudaError_t e;
+  if (idx.dim == 6) {
+    if (plan.qw == 4) e = launch_knn_kpl<6, 4>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
+    else e = launch_knn_kpl<6, 1>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
+  } else {
+    if (plan.qw == 4) e = launch_knn_kpl<2, 4>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
+    else e = launch_knn_kpl<2, 1>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
+  }
+  if (e != cudaSuccess) return e;
+  if (plan.slices > 1) {
+    const unsigned mg = (unsigned)((nq + kWarps - 1) / kWarps);
+    if (k <= 32) knn_merge_kernel<1><<<mg, kThreads, 0, stream>>>(od, oi, nq, k, plan.slices, d_d2, d_ids);
+    else if (k <= 64) knn_merge_kernel<2><<<mg, kThreads, 0, stream>>>(od, oi, nq, k, plan.slices, d_d2, d_ids);
+    else knn_merge_kernel<4><<<mg, kThreads, 0, stream>>>(od, oi, nq, k, plan.slices, d_d2, d_ids);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+template <bool FILL>
+static cudaError_t launch_radius_any(const IndexDev &idx, const float *q, int64_t nq, float r2, int *counts,
+                                     const long long *offsets, int *cursor, unsigned long long *keys, const KnnPlan &plan,
+                                     cudaStream_t st) {
+  if (nq <= 0) return cudaSuccess;
+  const int64_t items = plan.groups * plan.slices;
+  const unsigned grid = (unsigned)((items + kWarps - 1) / kWarps);
+  if (idx.dim == 6) {
+    if (plan.qw == 4) radius_scan_kernel<6, 4, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys);
+    else radius_scan_kernel<6, 1, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys);
+  } else {
+    if (plan.qw == 4) radius_scan_kernel<2, 4, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys);
+    else radius_scan_kernel<2, 1, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_radius_count(const IndexDev &idx, const float *d_queries, int64_t nq, float r2, int32_t *d_counts,
+                                const KnnPlan &plan, cudaStream_t stream) {
+  return launch_radius_any<false>(idx, d_queries, nq, r2, d_counts, nullptr, nullptr, nullptr, plan, stream);
+}
+
+cudaError_t launch_radius_fill(const IndexDev &idx, const float *d_queries, int64_t nq, float r2, const int64_t *d_offsets,
+                               int32_t *d_cursor, unsigned long long *d_keys, const KnnPlan &plan, cudaStream_t stream) {
+  return launch_radius_any<true>(idx, d_queries, nq, r2, nullptr, reinterpret_cast<const long long *>(d_offsets), d_cursor,
+                                 d_keys, plan, stream);
+}
+
+cudaError_t launch_radius_sort(unsigned long long *d_keys, const int64_t *d_offsets, const int32_t *d_counts, int64_t nq,
+                               int32_t *d_ids, float *d_d2, cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  radius_sort_kernel<<<(unsigned)nq, kThreads, 0, stream>>>(d_keys, reinterpret_cast<const long long *>(d_offsets), d_counts,
+                                                            d_ids, d_d2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_index_append(float *d_coords, int64_t capacity, int dim, int64_t at, const float *d_pts, int64_t n,
+                                cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const long long total = (long long)n * dim;
+  index_append_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_coords, capacity, dim, at, d_pts, n);
+  return cudaGetLastError();
+}
+
+}  // namespace sffg

@@ -1,0 +1,46 @@
+// knn_kernels.cuh -- launch wrappers of the exact neighbour-search kernels (implemented in knn_kernels.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace sffg {
+
+// Device view of an index: struct-of-arrays, coordinate c of node i at coords[c * capacity + i]
+struct IndexDev {
+  const float *coords;
+  int64_t capacity;
+  int64_t n;
+  int dim;   // 2 or 6
+};
+
+struct KnnPlan {
+  int qw;        // queries per warp
+  int slices;    // node slices per query group
+  int64_t slice_len;
+  int64_t groups;
+};
+KnnPlan plan_knn(int64_t nq, int64_t n, int sm_count);
+
+// partial scratch: slices > 1 needs nq * slices * k (float,int) pairs = 8 bytes each
+size_t knn_scratch_bytes(const KnnPlan &p, int64_t nq, int k);
+
+cudaError_t launch_knn(const IndexDev &idx, const float *d_queries, int64_t nq, int k, int32_t *d_ids, float *d_d2,
+                       void *d_scratch, const KnnPlan &plan, cudaStream_t stream);
+
+cudaError_t launch_radius_count(const IndexDev &idx, const float *d_queries, int64_t nq, float r2, int32_t *d_counts,
+                                const KnnPlan &plan, cudaStream_t stream);
+
+// d_cursor must be zeroed [nq]; d_offsets = exclusive scan of counts [nq]; d_keys receives (d2 bits << 32 | id)
+cudaError_t launch_radius_fill(const IndexDev &idx, const float *d_queries, int64_t nq, float r2, const int64_t *d_offsets,
+                               int32_t *d_cursor, unsigned long long *d_keys, const KnnPlan &plan, cudaStream_t stream);
+
+// sorts every row of d_keys ascending and unpacks it into ids / d2
+cudaError_t launch_radius_sort(unsigned long long *d_keys, const int64_t *d_offsets, const int32_t *d_counts, int64_t nq,
+                               int32_t *d_ids, float *d_d2, cudaStream_t stream);
+
+// AoS [n][dim] -> SoA append at position `at`
+cudaError_t launch_index_append(float *d_coords, int64_t capacity, int dim, int64_t at, const float *d_pts, int64_t n,
+                                cudaStream_t stream);
+
+}  // namespace sffg

@@ -1,0 +1,643 @@
+// sffg_api.cu -- the C ABI of libsffg.so (declared in include/sffg.h).  Host-side glue only: handle lifetime,
+// HBM layout, chunked H2D / kernel / D2H pipelining on two streams.  No compute happens on the CPU and there is no
+// fallback: without a usable sm_100 device every compute entry point returns SFFG_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "collide_kernels.cuh"
+#include "common.h"
+#include "knn_kernels.cuh"
+
+namespace sffg {
+
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+int fail(int code, const std::string &msg) {
+  g_error = msg;
+  return code;
+}
+
+namespace {
+
+struct Runtime {
+  bool ready = false;
+  int device = -1;
+  int sm_count = 0;
+};
+Runtime g_rt;
+
+#define SFFG_CUDA(expr)                                                                          \
+  do {                                                                                           \
+    cudaError_t e_ = (expr);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(SFFG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));            \
+  } while (0)
+
+int ensure_runtime() {
+  if (g_rt.ready) return SFFG_OK;
+  return sffg_init(-1);
+}
+
+// grow-only device buffer
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return SFFG_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    SFFG_CUDA(cudaMalloc(&p, want));
+    cap = want;
+    return SFFG_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+bool is_device_accessible_host(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+}  // namespace sffg
+
+using namespace sffg;
+
+// ---------------------------------------------------------------------------------------------------------------
+struct sffg_env {
+  EnvDev dev{};
+  void *d_slots = nullptr, *d_tris32 = nullptr, *d_tris64 = nullptr, *d_robot = nullptr, *d_robot64 = nullptr;
+  unsigned long long *d_counters = nullptr;
+  int *d_status = nullptr;
+  unsigned *d_work = nullptr;   // ring of 8 work counters
+  int work_next = 0;
+  cudaStream_t streams[2] = {nullptr, nullptr};
+  DevBuf in[2], out[2], aux[2];
+  bool count = false;
+  sffg_env_info_t info{};
+  LaunchCfg cfg{};
+};
+
+struct sffg_index {
+  int dim = 0;
+  float *d_coords = nullptr;
+  int64_t cap = 0, n = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf q, ids, d2, scratch, counts, offsets, cursor, keys, stage;
+};
+
+extern "C" {
+
+int sffg_version(void) { return 100; }
+const char *sffg_last_error(void) { return g_error.c_str(); }
+
+int sffg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int sffg_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(SFFG_ERR_NO_DEVICE, "no CUDA device visible: the sffg engine has no CPU path and refuses to run");
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (device >= n) return fail(SFFG_ERR_ARG, "device ordinal out of range");
+  SFFG_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SFFG_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SFFG_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                        std::to_string(prop.minor) + "; libsffg.so carries sm_100a code only");
+  g_rt.device = device;
+  g_rt.sm_count = prop.multiProcessorCount;
+  g_rt.ready = true;
+  return SFFG_OK;
+}
+
+// ---- meshes -----------------------------------------------------------------------------------------------
+int sffg_mesh_load(const char *path, int is_obj, const double position[3], double scale, double **tris_out,
+                   int64_t *n_tris_out, double bbox_out[6]) {
+  if (!path || !tris_out || !n_tris_out) return fail(SFFG_ERR_ARG, "sffg_mesh_load: null argument");
+  const double zero[3] = {0, 0, 0};
+  std::vector<double> tris;
+  double bbox[6];
+  int rc = load_mesh(path, is_obj, position ? position : zero, scale, &tris, bbox);
+  if (rc != SFFG_OK) return rc;
+  double *out = (double *)std::malloc(std::max<size_t>(tris.size(), 1) * sizeof(double));
+  if (!out) return fail(SFFG_ERR_ARG, "out of host memory");
+  std::memcpy(out, tris.data(), tris.size() * sizeof(double));
+  *tris_out = out;
+  *n_tris_out = (int64_t)(tris.size() / 9);
+  if (bbox_out) std::memcpy(bbox_out, bbox, sizeof bbox);
+  return SFFG_OK;
+}
+void sffg_free(void *p) { std::free(p); }
+
+// ---- environment ------------------------------------------------------------------------------------------
+static void cross3(const double *a, const double *b, double *r) {
+  r[0] = a[1] * b[2] - a[2] * b[1];
+  r[1] = a[2] * b[0] - a[0] * b[2];
+  r[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+static void make_robot_tri(const double *t, RobotTri *o) {
+  const double *q[3] = {t, t + 3, t + 6};
+  double f[3][3], m[3], h[3][3];
+  for (int k = 0; k < 3; ++k) {
+    f[0][k] = q[1][k] - q[0][k];
+    f[1][k] = q[2][k] - q[1][k];
+    f[2][k] = q[0][k] - q[2][k];
+  }
+  cross3(f[0], f[1], m);
+  for (int j = 0; j < 3; ++j) cross3(f[j], m, h[j]);
+  double qmax = 0;
+  for (int v = 0; v < 3; ++v)
+    for (int k = 0; k < 3; ++k) {
+      o->q[v][k] = (float)q[v][k];
+      o->f[v][k] = (float)f[v][k];
+      o->h[v][k] = (float)h[v][k];
+      qmax = std::max(qmax, std::fabs(q[v][k]));
+    }
+  for (int k = 0; k < 3; ++k) o->m[k] = (float)m[k];
+  // projection intervals of the TRUE triangle on the float axes, widened and rounded outward
+  auto interval = [&](const float *axis, float *lo, float *hi) {
+    double mn = std::numeric_limits<double>::max(), mx = -mn, mag = 0;
+    for (int v = 0; v < 3; ++v) {
+      double p = (double)axis[0] * q[v][0] + (double)axis[1] * q[v][1] + (double)axis[2] * q[v][2];
+      mag = std::max(mag, std::fabs((double)axis[0] * q[v][0]) + std::fabs((double)axis[1] * q[v][1]) +
+                              std::fabs((double)axis[2] * q[v][2]));
+      mn = std::min(mn, p);
+      mx = std::max(mx, p);
+    }
+    const double slack = mag * 1e-14;
+    *lo = round_down_f32(mn - slack);
+    *hi = round_up_f32(mx + slack);
+  };
+  interval(o->m, &o->m_lo, &o->m_hi);
+  for (int j = 0; j < 3; ++j) interval(o->h[j], &o->h_lo[j], &o->h_hi[j]);
+  for (int k = 0; k < 3; ++k) {
+    o->lo[k] = round_down_f32(std::min({q[0][k], q[1][k], q[2][k]}));
+    o->hi[k] = round_up_f32(std::max({q[0][k], q[1][k], q[2][k]}));
+  }
+  o->qmax = round_up_f32(qmax);
+  o->pad[0] = o->pad[1] = o->pad[2] = 0.f;
+}
+
+int sffg_env_destroy(sffg_env *env) {
+  if (!env) return SFFG_OK;
+  for (int s = 0; s < 2; ++s) {
+    if (env->streams[s]) cudaStreamSynchronize(env->streams[s]);
+  }
+  cudaFree(env->d_slots);
+  cudaFree(env->d_tris32);
+  cudaFree(env->d_tris64);
+  cudaFree(env->d_robot);
+  cudaFree(env->d_robot64);
+  cudaFree(env->d_counters);
+  cudaFree(env->d_status);
+  cudaFree(env->d_work);
+  for (int s = 0; s < 2; ++s) {
+    env->in[s].release();
+    env->out[s].release();
+    env->aux[s].release();
+    if (env->streams[s]) cudaStreamDestroy(env->streams[s]);
+  }
+  delete env;
+  return SFFG_OK;
+}
+
+int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot_tris, int64_t n_robot, sffg_env **out) {
+  if (!out || n_obst < 0 || n_robot <= 0 || !robot_tris || (n_obst > 0 && !obst_tris))
+    return fail(SFFG_ERR_ARG, "sffg_env_create: bad arguments");
+  if (n_obst > 0x3fffffff || n_robot > 4096) return fail(SFFG_ERR_ARG, "sffg_env_create: mesh too large");
+  int rc = ensure_runtime();
+  if (rc != SFFG_OK) return rc;
+  const auto t0 = std::chrono::steady_clock::now();
+
+  sffg_env *env = new sffg_env();
+  auto bail = [&](int code) {
+    sffg_env_destroy(env);
+    return code;
+  };
+#define SFFG_ENV_CUDA(expr)                                                                                       \
+  do {                                                                                                            \
+    cudaError_t e_ = (expr);                                                                                      \
+    if (e_ != cudaSuccess) return bail(fail(SFFG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)));   \
+  } while (0)
+
+  // ---- obstacle: BVH + FP32 / FP64 triangle arrays in leaf order
+  HostBvh bvh;
+  build_wide_bvh(obst_tris, n_obst, &bvh);
+  std::vector<TriF32> t32((size_t)n_obst);
+  std::vector<double> t64(9 * (size_t)n_obst);
+  for (int64_t i = 0; i < n_obst; ++i) {
+    const double *src = obst_tris + 9 * (size_t)bvh.tri_order[(size_t)i];
+    std::memcpy(&t64[9 * (size_t)i], src, 9 * sizeof(double));
+    double err = 0;
+    for (int v = 0; v < 3; ++v) {
+      for (int k = 0; k < 3; ++k) {
+        float f = (float)src[3 * v + k];
+        t32[(size_t)i].p[v][k] = f;
+        err = std::max(err, std::fabs(src[3 * v + k] - (double)f));
+      }
+      t32[(size_t)i].p[v][3] = 0.f;
+    }
+    t32[(size_t)i].p[0][3] = round_up_f32(err * 1.0000001);
+  }
+  // ---- robot
+  std::vector<RobotTri> rob((size_t)n_robot);
+  double rlo[3] = {1e300, 1e300, 1e300}, rhi[3] = {-1e300, -1e300, -1e300}, rad2 = 0;
+  for (int64_t r = 0; r < n_robot; ++r) {
+    make_robot_tri(robot_tris + 9 * r, &rob[(size_t)r]);
+    for (int v = 0; v < 3; ++v) {
+      const double *p = robot_tris + 9 * r + 3 * v;
+      rad2 = std::max(rad2, p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+      for (int k = 0; k < 3; ++k) {
+        rlo[k] = std::min(rlo[k], p[k]);
+        rhi[k] = std::max(rhi[k], p[k]);
+      }
+    }
+  }
+  EnvDev &d = env->dev;
+  d.n_robot = (int)n_robot;
+  d.n_obst = (int)n_obst;
+  for (int k = 0; k < 3; ++k) {
+    const double c = 0.5 * (rlo[k] + rhi[k]);
+    d.rob_c[k] = (float)c;
+    d.rob_h[k] = round_up_f32(std::max(rhi[k] - (double)d.rob_c[k], (double)d.rob_c[k] - rlo[k]) * 1.0000001);
+    const double oc = 0.5 * (bvh.root_lo[k] + bvh.root_hi[k]);
+    d.root_c[k] = (float)oc;
+    d.root_h[k] = n_obst ? round_up_f32(std::max(bvh.root_hi[k] - (double)d.root_c[k], (double)d.root_c[k] - bvh.root_lo[k]) * 1.0000001) : 0.f;
+  }
+  d.rob_radius = round_up_f32(std::sqrt(rad2) * 1.000001);
+
+  size_t bytes = 0;
+  auto upload = [&](void **dst, const void *src, size_t n) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, std::max<size_t>(n, 16));
+    if (e != cudaSuccess) return e;
+    bytes += n;
+    if (n) e = cudaMemcpy(*dst, src, n, cudaMemcpyHostToDevice);
+    return e;
+  };
+  SFFG_ENV_CUDA(upload(&env->d_slots, bvh.slots.data(), bvh.slots.size() * sizeof(ChildSlot)));
+  SFFG_ENV_CUDA(upload(&env->d_tris32, t32.data(), t32.size() * sizeof(TriF32)));
+  SFFG_ENV_CUDA(upload(&env->d_tris64, t64.data(), t64.size() * sizeof(double)));
+  SFFG_ENV_CUDA(upload(&env->d_robot, rob.data(), rob.size() * sizeof(RobotTri)));
+  SFFG_ENV_CUDA(upload(&env->d_robot64, robot_tris, 9 * (size_t)n_robot * sizeof(double)));
+  SFFG_ENV_CUDA(cudaMalloc((void **)&env->d_counters, 5 * sizeof(unsigned long long)));
+  SFFG_ENV_CUDA(cudaMemset(env->d_counters, 0, 5 * sizeof(unsigned long long)));
+  SFFG_ENV_CUDA(cudaMalloc((void **)&env->d_status, sizeof(int)));
+  SFFG_ENV_CUDA(cudaMemset(env->d_status, 0, sizeof(int)));
+  SFFG_ENV_CUDA(cudaMalloc((void **)&env->d_work, 8 * sizeof(unsigned)));
+  SFFG_ENV_CUDA(cudaMemset(env->d_work, 0, 8 * sizeof(unsigned)));
+  for (int s = 0; s < 2; ++s) SFFG_ENV_CUDA(cudaStreamCreateWithFlags(&env->streams[s], cudaStreamNonBlocking));
+  d.slots = reinterpret_cast<const float4 *>(env->d_slots);
+  d.tris32 = reinterpret_cast<const float4 *>(env->d_tris32);
+  d.tris64 = reinterpret_cast<const double *>(env->d_tris64);
+  d.robot = reinterpret_cast<const RobotTri *>(env->d_robot);
+  d.robot64 = reinterpret_cast<const double *>(env->d_robot64);
+  d.counters = nullptr;
+  d.status = env->d_status;
+  d.work_counter = env->d_work;
+  env->cfg.sm_count = g_rt.sm_count;
+  env->cfg.blocks_per_sm = 0;
+
+  env->info.n_obst_tris = n_obst;
+  env->info.n_robot_tris = n_robot;
+  env->info.n_nodes = (int64_t)(bvh.slots.size() / kWide);
+  env->info.depth = bvh.depth;
+  env->info.device_bytes = (int64_t)bytes;
+  env->info.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  *out = env;
+  return SFFG_OK;
+#undef SFFG_ENV_CUDA
+}
+
+int sffg_env_info(const sffg_env *env, sffg_env_info_t *out) {
+  if (!env || !out) return fail(SFFG_ERR_ARG, "sffg_env_info: null argument");
+  *out = env->info;
+  return SFFG_OK;
+}
+
+int sffg_env_enable_counters(sffg_env *env, int on) {
+  if (!env) return fail(SFFG_ERR_ARG, "null env");
+  env->count = on != 0;
+  SFFG_CUDA(cudaMemset(env->d_counters, 0, 5 * sizeof(unsigned long long)));
+  return SFFG_OK;
+}
+
+int sffg_env_read_counters(sffg_env *env, sffg_counters_t *out) {
+  if (!env || !out) return fail(SFFG_ERR_ARG, "null argument");
+  unsigned long long h[5];
+  SFFG_CUDA(cudaDeviceSynchronize());
+  SFFG_CUDA(cudaMemcpy(h, env->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+  out->poses = (int64_t)h[0];
+  out->poses_past_root = (int64_t)h[1];
+  out->box_tests = (int64_t)h[2];
+  out->pair_tests = (int64_t)h[3];
+  out->exact_tests = (int64_t)h[4];
+  return SFFG_OK;
+}
+
+static EnvDev env_view(sffg_env *env) {
+  EnvDev v = env->dev;
+  v.counters = env->count ? env->d_counters : nullptr;
+  v.work_counter = env->d_work + (env->work_next++ & 7);
+  return v;
+}
+
+static int check_status(sffg_env *env) {
+  int st = 0;
+  SFFG_CUDA(cudaMemcpy(&st, env->d_status, sizeof st, cudaMemcpyDeviceToHost));
+  if (st != 0) {
+    cudaMemset(env->d_status, 0, sizeof(int));
+    return fail(SFFG_ERR_INTERNAL, "BVH traversal stack overflow: results of this call are invalid");
+  }
+  return SFFG_OK;
+}
+
+int sffg_env_sync_check(sffg_env *env) {
+  if (!env) return fail(SFFG_ERR_ARG, "null env");
+  SFFG_CUDA(cudaDeviceSynchronize());
+  return check_status(env);
+}
+
+int sffg_collide_poses_device(sffg_env *env, const void *d_poses, int poses_are_f64, int64_t n, uint8_t *d_verdict_out,
+                              void *stream) {
+  if (!env || n < 0 || (n > 0 && (!d_poses || !d_verdict_out))) return fail(SFFG_ERR_ARG, "sffg_collide_poses_device: bad arguments");
+  SFFG_CUDA(launch_collide_poses(env_view(env), d_poses, poses_are_f64 != 0, n, d_verdict_out, (cudaStream_t)stream, env->cfg,
+                                 env->count));
+  return SFFG_OK;
+}
+
+static int collide_poses_host(sffg_env *env, const void *poses, bool f64, int64_t n, uint8_t *verdict_out) {
+  if (!env || n < 0 || (n > 0 && (!poses || !verdict_out))) return fail(SFFG_ERR_ARG, "sffg_collide_poses: bad arguments");
+  if (n == 0) return SFFG_OK;
+  const size_t psz = f64 ? 48 : 24;
+  const int64_t chunk = 1 << 20;
+  int s = 0;
+  for (int64_t off = 0; off < n; off += chunk, s ^= 1) {
+    const int64_t cnt = std::min(chunk, n - off);
+    cudaStream_t st = env->streams[s];
+    SFFG_CUDA(cudaStreamSynchronize(st));   // buffers of this stream are free again
+    int rc = env->in[s].reserve((size_t)cnt * psz);
+    if (rc == SFFG_OK) rc = env->out[s].reserve((size_t)cnt);
+    if (rc != SFFG_OK) return rc;
+    SFFG_CUDA(cudaMemcpyAsync(env->in[s].p, (const char *)poses + (size_t)off * psz, (size_t)cnt * psz, cudaMemcpyHostToDevice, st));
+    SFFG_CUDA(launch_collide_poses(env_view(env), env->in[s].p, f64, cnt, (uint8_t *)env->out[s].p, st, env->cfg, env->count));
+    SFFG_CUDA(cudaMemcpyAsync(verdict_out + off, env->out[s].p, (size_t)cnt, cudaMemcpyDeviceToHost, st));
+  }
+  SFFG_CUDA(cudaStreamSynchronize(env->streams[0]));
+  SFFG_CUDA(cudaStreamSynchronize(env->streams[1]));
+  return check_status(env);
+}
+
+int sffg_collide_poses_f32(sffg_env *env, const float *poses, int64_t n, uint8_t *verdict_out) {
+  return collide_poses_host(env, poses, false, n, verdict_out);
+}
+int sffg_collide_poses_f64(sffg_env *env, const double *poses, int64_t n, uint8_t *verdict_out) {
+  return collide_poses_host(env, poses, true, n, verdict_out);
+}
+
+int sffg_check_edges_device(sffg_env *env, const double *d_starts, const double *d_ends, int64_t m, double sample_dist,
+                            int rot_mode, uint8_t *d_free_out, int32_t *d_first_hit_out, void *stream) {
+  if (!env || m < 0 || (m > 0 && (!d_starts || !d_ends || !d_free_out)) || !(sample_dist > 0) ||
+      (rot_mode != SFFG_ROT_REFERENCE && rot_mode != SFFG_ROT_INTERPOLATE))
+    return fail(SFFG_ERR_ARG, "sffg_check_edges_device: bad arguments");
+  SFFG_CUDA(launch_check_edges(env_view(env), d_starts, d_ends, m, sample_dist, rot_mode, d_free_out, d_first_hit_out,
+                               (cudaStream_t)stream, env->cfg, env->count));
+  return SFFG_OK;
+}
+
+int sffg_check_edges(sffg_env *env, const double *starts, const double *ends, int64_t m, double sample_dist, int rot_mode,
+                     uint8_t *free_out, int32_t *first_hit_out) {
+  if (!env || m < 0 || (m > 0 && (!starts || !ends || !free_out)) || !(sample_dist > 0) ||
+      (rot_mode != SFFG_ROT_REFERENCE && rot_mode != SFFG_ROT_INTERPOLATE))
+    return fail(SFFG_ERR_ARG, "sffg_check_edges: bad arguments");
+  if (m == 0) return SFFG_OK;
+  const int64_t chunk = 1 << 18;
+  int s = 0;
+  for (int64_t off = 0; off < m; off += chunk, s ^= 1) {
+    const int64_t cnt = std::min(chunk, m - off);
+    cudaStream_t st = env->streams[s];
+    SFFG_CUDA(cudaStreamSynchronize(st));
+    int rc = env->in[s].reserve((size_t)cnt * 96);
+    if (rc == SFFG_OK) rc = env->out[s].reserve((size_t)cnt);
+    if (rc == SFFG_OK) rc = env->aux[s].reserve((size_t)cnt * 4);
+    if (rc != SFFG_OK) return rc;
+    double *ds = (double *)env->in[s].p, *de = ds + 6 * cnt;
+    SFFG_CUDA(cudaMemcpyAsync(ds, starts + 6 * off, (size_t)cnt * 48, cudaMemcpyHostToDevice, st));
+    SFFG_CUDA(cudaMemcpyAsync(de, ends + 6 * off, (size_t)cnt * 48, cudaMemcpyHostToDevice, st));
+    SFFG_CUDA(launch_check_edges(env_view(env), ds, de, cnt, sample_dist, rot_mode, (uint8_t *)env->out[s].p,
+                                 (int32_t *)env->aux[s].p, st, env->cfg, env->count));
+    SFFG_CUDA(cudaMemcpyAsync(free_out + off, env->out[s].p, (size_t)cnt, cudaMemcpyDeviceToHost, st));
+    if (first_hit_out)
+      SFFG_CUDA(cudaMemcpyAsync(first_hit_out + off, env->aux[s].p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+  }
+  SFFG_CUDA(cudaStreamSynchronize(env->streams[0]));
+  SFFG_CUDA(cudaStreamSynchronize(env->streams[1]));
+  return check_status(env);
+}
+
+int sffg_gen_poses_device(uint64_t seed, uint64_t first_index, int64_t n, const float range[6], float *d_poses_out,
+                          void *stream) {
+  if (n < 0 || !range || (n > 0 && !d_poses_out)) return fail(SFFG_ERR_ARG, "sffg_gen_poses_device: bad arguments");
+  int rc = ensure_runtime();
+  if (rc != SFFG_OK) return rc;
+  SFFG_CUDA(launch_gen_poses(seed, first_index, n, range, d_poses_out, (cudaStream_t)stream));
+  return SFFG_OK;
+}
+
+// ---- neighbour index ------------------------------------------------------------------------------------------
+int sffg_index_create(int dim, sffg_index **out) {
+  if (!out || (dim != 2 && dim != 6)) return fail(SFFG_ERR_ARG, "sffg_index_create: dim must be 2 or 6");
+  int rc = ensure_runtime();
+  if (rc != SFFG_OK) return rc;
+  sffg_index *idx = new sffg_index();
+  idx->dim = dim;
+  cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete idx;
+    return fail(SFFG_ERR_CUDA, cudaGetErrorString(e));
+  }
+  *out = idx;
+  return SFFG_OK;
+}
+
+int sffg_index_destroy(sffg_index *idx) {
+  if (!idx) return SFFG_OK;
+  if (idx->stream) cudaStreamSynchronize(idx->stream);
+  cudaFree(idx->d_coords);
+  DevBuf *bufs[] = {&idx->q, &idx->ids, &idx->d2, &idx->scratch, &idx->counts, &idx->offsets, &idx->cursor, &idx->keys, &idx->stage};
+  for (DevBuf *b : bufs) b->release();
+  if (idx->stream) cudaStreamDestroy(idx->stream);
+  delete idx;
+  return SFFG_OK;
+}
+
+int64_t sffg_index_size(const sffg_index *idx) { return idx ? idx->n : -1; }
+
+static int index_grow(sffg_index *idx, int64_t need, cudaStream_t st) {
+  if (need <= idx->cap) return SFFG_OK;
+  int64_t ncap = std::max<int64_t>({need, idx->cap * 2, 4096});
+  ncap = (ncap + 31) / 32 * 32;
+  float *nc = nullptr;
+  SFFG_CUDA(cudaMalloc((void **)&nc, (size_t)ncap * idx->dim * sizeof(float)));
+  for (int c = 0; c < idx->dim && idx->n > 0; ++c)
+    SFFG_CUDA(cudaMemcpyAsync(nc + (size_t)c * ncap, idx->d_coords + (size_t)c * idx->cap, (size_t)idx->n * sizeof(float),
+                              cudaMemcpyDeviceToDevice, st));
+  SFFG_CUDA(cudaStreamSynchronize(st));
+  cudaFree(idx->d_coords);
+  idx->d_coords = nc;
+  idx->cap = ncap;
+  return SFFG_OK;
+}
+
+// the float metric is bit-exact against the reference only while |angle difference| < 14 rad
+static int check_angles(const float *pts, int64_t n, int dim) {
+  if (dim != 6) return SFFG_OK;
+  for (int64_t i = 0; i < n; ++i)
+    for (int c = 3; c < 6; ++c) {
+      const float a = pts[i * 6 + c];
+      if (!(a >= -7.0f && a <= 7.0f)) return fail(SFFG_ERR_DOMAIN, "angle outside [-7, 7] rad (or NaN) in point/query " + std::to_string(i));
+    }
+  return SFFG_OK;
+}
+
+int sffg_index_add_device(sffg_index *idx, const float *d_pts, int64_t n, void *stream) {
+  if (!idx || n < 0 || (n > 0 && !d_pts)) return fail(SFFG_ERR_ARG, "sffg_index_add_device: bad arguments");
+  if (n == 0) return SFFG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = index_grow(idx, idx->n + n, st);
+  if (rc != SFFG_OK) return rc;
+  SFFG_CUDA(launch_index_append(idx->d_coords, idx->cap, idx->dim, idx->n, d_pts, n, st));
+  idx->n += n;
+  return SFFG_OK;
+}
+
+int sffg_index_add(sffg_index *idx, const float *pts, int64_t n) {
+  if (!idx || n < 0 || (n > 0 && !pts)) return fail(SFFG_ERR_ARG, "sffg_index_add: bad arguments");
+  if (n == 0) return SFFG_OK;
+  int rc = check_angles(pts, n, idx->dim);
+  if (rc != SFFG_OK) return rc;
+  rc = idx->stage.reserve((size_t)n * idx->dim * sizeof(float));
+  if (rc != SFFG_OK) return rc;
+  SFFG_CUDA(cudaMemcpyAsync(idx->stage.p, pts, (size_t)n * idx->dim * sizeof(float), cudaMemcpyHostToDevice, idx->stream));
+  rc = sffg_index_add_device(idx, (const float *)idx->stage.p, n, idx->stream);
+  if (rc != SFFG_OK) return rc;
+  SFFG_CUDA(cudaStreamSynchronize(idx->stream));
+  return SFFG_OK;
+}
+
+int sffg_knn_device(sffg_index *idx, const float *d_queries, int64_t nq, int k, int32_t *d_ids_out, float *d_d2_out,
+                    void *stream) {
+  if (!idx || nq < 0 || k < 1 || k > SFFG_MAX_K || (nq > 0 && (!d_queries || !d_ids_out || !d_d2_out)))
+    return fail(SFFG_ERR_ARG, "sffg_knn_device: bad arguments (1 <= k <= 128)");
+  if (nq == 0) return SFFG_OK;
+  IndexDev v{idx->d_coords, idx->cap, idx->n, idx->dim};
+  KnnPlan plan = plan_knn(nq, idx->n, g_rt.sm_count);
+  int rc = idx->scratch.reserve(knn_scratch_bytes(plan, nq, k));
+  if (rc != SFFG_OK) return rc;
+  SFFG_CUDA(launch_knn(v, d_queries, nq, k, d_ids_out, d_d2_out, idx->scratch.p, plan, (cudaStream_t)stream));
+  return SFFG_OK;
+}
+
+int sffg_knn(sffg_index *idx, const float *queries, int64_t nq, int k, int32_t *ids_out, float *d2_out) {
+  if (!idx || nq < 0 || k < 1 || k > SFFG_MAX_K || (nq > 0 && (!queries || !ids_out || !d2_out)))
+    return fail(SFFG_ERR_ARG, "sffg_knn: bad arguments (1 <= k <= 128)");
+  if (nq == 0) return SFFG_OK;
+  int rc = check_angles(queries, nq, idx->dim);
+  if (rc != SFFG_OK) return rc;
+  const int64_t chunk = 1 << 17;
+  for (int64_t off = 0; off < nq; off += chunk) {
+    const int64_t cnt = std::min(chunk, nq - off);
+    rc = idx->q.reserve((size_t)cnt * idx->dim * 4);
+    if (rc == SFFG_OK) rc = idx->ids.reserve((size_t)cnt * k * 4);
+    if (rc == SFFG_OK) rc = idx->d2.reserve((size_t)cnt * k * 4);
+    if (rc != SFFG_OK) return rc;
+    SFFG_CUDA(cudaMemcpyAsync(idx->q.p, queries + off * idx->dim, (size_t)cnt * idx->dim * 4, cudaMemcpyHostToDevice, idx->stream));
+    rc = sffg_knn_device(idx, (const float *)idx->q.p, cnt, k, (int32_t *)idx->ids.p, (float *)idx->d2.p, idx->stream);
+    if (rc != SFFG_OK) return rc;
+    SFFG_CUDA(cudaMemcpyAsync(ids_out + off * k, idx->ids.p, (size_t)cnt * k * 4, cudaMemcpyDeviceToHost, idx->stream));
+    SFFG_CUDA(cudaMemcpyAsync(d2_out + off * k, idx->d2.p, (size_t)cnt * k * 4, cudaMemcpyDeviceToHost, idx->stream));
+    SFFG_CUDA(cudaStreamSynchronize(idx->stream));
+  }
+  return SFFG_OK;
+}
+
+int sffg_radius(sffg_index *idx, const float *queries, int64_t nq, float r2, int32_t *counts_out, int32_t *ids_out,
+                float *d2_out, int64_t capacity, int64_t *total_out) {
+  if (!idx || nq < 0 || (nq > 0 && (!queries || !counts_out)) || (ids_out && !d2_out))
+    return fail(SFFG_ERR_ARG, "sffg_radius: bad arguments");
+  if (total_out) *total_out = 0;
+  if (nq == 0) return SFFG_OK;
+  int rc = check_angles(queries, nq, idx->dim);
+  if (rc != SFFG_OK) return rc;
+  cudaStream_t st = idx->stream;
+  IndexDev v{idx->d_coords, idx->cap, idx->n, idx->dim};
+  KnnPlan plan = plan_knn(nq, idx->n, g_rt.sm_count);
+  rc = idx->q.reserve((size_t)nq * idx->dim * 4);
+  if (rc == SFFG_OK) rc = idx->counts.reserve((size_t)nq * 4);
+  if (rc != SFFG_OK) return rc;
+  SFFG_CUDA(cudaMemcpyAsync(idx->q.p, queries, (size_t)nq * idx->dim * 4, cudaMemcpyHostToDevice, st));
+  SFFG_CUDA(cudaMemsetAsync(idx->counts.p, 0, (size_t)nq * 4, st));
+  SFFG_CUDA(launch_radius_count(v, (const float *)idx->q.p, nq, r2, (int32_t *)idx->counts.p, plan, st));
+  SFFG_CUDA(cudaMemcpyAsync(counts_out, idx->counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  SFFG_CUDA(cudaStreamSynchronize(st));
+  std::vector<int64_t> offs((size_t)nq);
+  int64_t total = 0;
+  for (int64_t i = 0; i < nq; ++i) {
+    offs[(size_t)i] = total;
+    total += counts_out[i];
+  }
+  if (total_out) *total_out = total;
+  if (!ids_out || total == 0) return SFFG_OK;
+  if (capacity < total)
+    return fail(SFFG_ERR_CAPACITY, "sffg_radius: result buffers hold " + std::to_string(capacity) + " entries, " +
+                                       std::to_string(total) + " needed");
+  rc = idx->offsets.reserve((size_t)nq * 8);
+  if (rc == SFFG_OK) rc = idx->cursor.reserve((size_t)nq * 4);
+  if (rc == SFFG_OK) rc = idx->keys.reserve((size_t)total * 8);
+  if (rc == SFFG_OK) rc = idx->ids.reserve((size_t)total * 4);
+  if (rc == SFFG_OK) rc = idx->d2.reserve((size_t)total * 4);
+  if (rc != SFFG_OK) return rc;
+  SFFG_CUDA(cudaMemcpyAsync(idx->offsets.p, offs.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
+  SFFG_CUDA(cudaMemsetAsync(idx->cursor.p, 0, (size_t)nq * 4, st));
+  SFFG_CUDA(launch_radius_fill(v, (const float *)idx->q.p, nq, r2, (const int64_t *)idx->offsets.p, (int32_t *)idx->cursor.p,
+                               (unsigned long long *)idx->keys.p, plan, st));
+  SFFG_CUDA(launch_radius_sort((unsigned long long *)idx->keys.p, (const int64_t *)idx->offsets.p, (const int32_t *)idx->counts.p,
+                               nq, (int32_t *)idx->ids.p, (float *)idx->d2.p, st));
+  SFFG_CUDA(cudaMemcpyAsync(ids_out, idx->ids.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+  SFFG_CUDA(cudaMemcpyAsync(d2_out, idx->d2.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+  SFFG_CUDA(cudaStreamSynchronize(st));
+  return SFFG_OK;
+}
+
+}  // extern "C"

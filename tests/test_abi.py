@@ -1,0 +1,137 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports exactly what include/sffg.h declares, its
+host-side pieces (mesh loader) behave like the reference's, and compute refuses to run without a GPU."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = ROOT / "include" / "sffg.h"
+
+
+def declared_symbols():
+    txt = HEADER.read_text()
+    return sorted(set(re.findall(r"SFFG_API[^;(]*?\b(sffg_\w+)\s*\(", txt)))
+
+
+def test_header_library_and_binding_agree():
+    from space_filling_forest_star_b200 import _lib
+    L = _lib.load()
+    decl = declared_symbols()
+    assert len(decl) >= 26
+    assert sorted(_lib.SIGNATURES) == decl
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.lib_path())], capture_output=True, text=True, check=True).stdout
+    exported = sorted(set(re.findall(r" T (sffg_\w+)", out)))
+    assert exported == decl
+    for name in decl:
+        assert getattr(L, name) is not None
+    assert L.sffg_version() == 100
+
+
+def test_library_is_sm100a_only():
+    from space_filling_forest_star_b200 import _lib
+    _lib.load()
+    out = subprocess.run(["cuobjdump", "-lelf", str(_lib.lib_path())], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def _has_gpu():
+    from space_filling_forest_star_b200 import _lib
+    return _lib.load().sffg_device_count() > 0
+
+
+def test_no_cpu_fallback_without_gpu(meshes):
+    """the product path must fail loudly when it cannot reach a GPU"""
+    if _has_gpu():
+        pytest.skip("a GPU is present")
+    import space_filling_forest_star_b200 as S
+    with pytest.raises(S.SffgError) as ei:
+        S.Environment(meshes["triang_s10"], meshes["robot_small_s10"])
+    assert ei.value.code == 1
+    with pytest.raises(S.SffgError):
+        S.Index(dim=6)
+    with pytest.raises(S.SffgError):
+        S.init(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = ROOT / "space_filling_forest_star_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.h")) + list(pkg.rglob("*.cuh")):
+        txt = f.read_text()
+        assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, re.M), f
+        assert "sff_oracle" not in txt or f.name.endswith((".cu", ".cuh")) and "oracle/sff_oracle.c" in txt, f
+        assert "liborc" not in txt, f
+
+
+OBJ_TEXT = """# comment line
+mtllib x.mtl
+o Thing_One
+v 0 0 0
+v 1.5 0 0
+v 0 2.25 0
+v 0 0 -3
+vn 0.5 0.5 0.5
+vt 9 9 9
+s off
+f 1//1 2//1 3//1
+f 1/5/2 3/1/1 4/2/2 2/2/2
+o Thing_Two
+f 5 6 1
+"""
+
+
+def test_mesh_loader_obj_quirks(tmp_path, orc):
+    """src/environment.h:125-166: vn/vt lines are vertices, quads contribute one triangle, 'o' keeps offset 0"""
+    import space_filling_forest_star_b200 as S
+    p = tmp_path / "m.obj"
+    p.write_text(OBJ_TEXT)
+    tris, bbox = S.load_mesh(str(p), True, (1.0, -1.0, 0.5), 10.0)
+    want = orc.load_obj(p, (1.0, -1.0, 0.5), 10.0)
+    np.testing.assert_array_equal(tris, want)
+    assert tris.shape == (3, 3, 3)
+    np.testing.assert_array_equal(tris[0], (np.array([[0, 0, 0], [1.5, 0, 0], [0, 2.25, 0]]) + [1.0, -1.0, 0.5]) * 10.0)
+    np.testing.assert_array_equal(tris[1], (np.array([[0, 0, 0], [0, 2.25, 0], [0, 0, -3]]) + [1.0, -1.0, 0.5]) * 10.0)
+    np.testing.assert_array_equal(tris[2][0], (np.array([0.5, 0.5, 0.5]) + [1.0, -1.0, 0.5]) * 10.0)   # vn as vertex 5
+    np.testing.assert_array_equal(tris[2][1], (np.array([9.0, 9, 9]) + [1.0, -1.0, 0.5]) * 10.0)       # vt as vertex 6
+    assert bbox[1] == (9 + 1.0) * 10.0   # the bbox covers every parsed 'v*' line, like Obstacle::localRange
+
+
+def test_mesh_loader_tri_map(tmp_path, orc):
+    import space_filling_forest_star_b200 as S
+    p = tmp_path / "m.tri"
+    p.write_text("0 0 10 0 0 10 \n\n   \n1.5 2.5 3.5 4.5 5.5 6.5\n")   # trailing blank, blank lines
+    tris, bbox = S.load_mesh(str(p), False, (100.0, 200.0, 300.0), 2.0)
+    np.testing.assert_array_equal(tris, orc.load_tri(p, (100.0, 200.0, 300.0), 2.0))
+    assert tris.shape == (2, 3, 3) and np.all(tris[:, :, 2] == 0)       # z forced to 0 even with a z offset
+    np.testing.assert_array_equal(tris[1, 2], [(5.5 + 100) * 2, (6.5 + 200) * 2, 0])
+
+
+def test_mesh_loader_errors(tmp_path):
+    import space_filling_forest_star_b200 as S
+    with pytest.raises(S.SffgError) as ei:
+        S.load_mesh(str(tmp_path / "missing.obj"), True)
+    assert ei.value.code == 4
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 0 0 0\nv 1 0 0\nf 1 2 9\n")
+    with pytest.raises(S.SffgError):
+        S.load_mesh(str(bad), True)
+    bad.write_text("v 0  0 0\n")          # double space -> empty token, std::stod would throw in the reference
+    with pytest.raises(S.SffgError):
+        S.load_mesh(str(bad), True)
+
+
+def test_mesh_loader_matches_reference_files(meshes):
+    ref = Path("/root/reference")
+    if not ref.exists():
+        pytest.skip("reference tree not present (GPU box)")
+    import space_filling_forest_star_b200 as S
+    for key, f, is_obj, scale in [("building_s10", "maps/building.obj", True, 10.0), ("dense3d_s1", "maps/dense_3D.obj", True, 1.0),
+                                  ("triang_s10", "models/3D/triang.obj", True, 10.0), ("robot_small_s10", "models/robot_small.obj", True, 10.0),
+                                  ("robot_cyl_small_s10", "models/3D/robot_cylinder_small.obj", True, 10.0),
+                                  ("triangles_tri", "maps/triangles.tri", False, 1.0), ("dense_tri", "maps/dense.tri", False, 1.0)]:
+        tris, _ = S.load_mesh(str(ref / f), is_obj, (0, 0, 0), scale)
+        np.testing.assert_array_equal(tris, meshes[key])

@@ -1,0 +1,57 @@
+"""world_size-2 gloo test of the multi-GPU host logic (split -> local compute -> one all-gather)."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_shard_bounds_cover_everything():
+    from space_filling_forest_star_b200.sharding import shard_bounds
+    for n in (0, 1, 2, 7, 8, 9, 1000003):
+        for world in (1, 2, 3, 8):
+            seen = 0
+            for r in range(world):
+                b, e, per = shard_bounds(n, r, world)
+                assert b == seen and e - b <= per and e <= n
+                seen = e
+            assert seen == n
+
+
+def _worker(rank, world, port, n, tmp):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from space_filling_forest_star_b200.sharding import shard_bounds, sharded_rows
+    poses = torch.arange(n * 6, dtype=torch.float32).reshape(n, 6)
+
+    def compute(b, e, out):     # stands in for env.collide_device on this rank's slice
+        out[: e - b] = (poses[b:e, 0].to(torch.int64) // 6 % 3 == 0).to(torch.uint8)
+
+    got = sharded_rows(n, (), torch.uint8, "cpu", compute)
+    want = (torch.arange(n) % 3 == 0).to(torch.uint8)
+    ok = torch.equal(got, want)
+
+    def compute_rows(b, e, out):
+        out[: e - b, :, 0] = torch.arange(b, e, dtype=torch.int32)[:, None]
+        out[: e - b, :, 1] = rank
+
+    rows = sharded_rows(n, (4, 2), torch.int32, "cpu", compute_rows)
+    ok = ok and torch.equal(rows[:, 0, 0], torch.arange(n, dtype=torch.int32))
+    b, e, _ = shard_bounds(n, rank, world)
+    ok = ok and bool((rows[b:e, :, 1] == rank).all())
+    Path(tmp, f"ok{rank}").write_text(str(ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [0, 5, 64, 1001])
+def test_sharded_rows_gloo_world2(tmp_path, n):
+    port = 29500 + (os.getpid() + n) % 2000
+    mp.spawn(_worker, args=(2, port, n, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").read_text() == "True" and (tmp_path / "ok1").read_text() == "True"
