@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the collision hot path (BASELINE.json metric: collision-checked poses/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on): random 6-DoF poses of
+models/robot_small.obj (scale 10, 6 triangles) against maps/building.obj (scale 10, 26 908 triangles as the reference
+loader reads them), Philox pose stream with the distribution of RandGen::randomPointInSpace over [-70,70]^2 x [0,140].
+One step = one pass of the pose->verdict path over one batch of POSES_PER_GPU poses per GPU (weak scaling).
+
+  value      poses/s, whole job, poses already resident in HBM (402 MB per batch > 126 MB L2, so every step streams
+             from HBM); N > 1: every rank checks its own shard and the verdict bytes are all-gathered over NCCL
+  e2e        same metric through the reference-facing host call (sffg_collide_poses_f32 on pinned host buffers):
+             H2D of the poses and D2H of the verdicts inside the timed region
+  roofline   dominant kernel = collide_poses_kernel; algorithmic HBM bytes = 25 B/pose (24 B pose in + 1 B verdict out)
+  cpu_baseline / --impl reference
+             the CPU restatement of the reference path (RAPID-style OBB-tree, ALL_CONTACTS as src/environment.h:274
+             calls it) on all host cores; RAPID itself is absent from the reference, so kind = "port"
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SEED = 0x5FF5EED
+RANGE = [-70.0, 70.0, -70.0, 70.0, 0.0, 140.0]
+POSES_PER_GPU = 1 << 24
+ALGO_BYTES_PER_POSE = 25
+METRIC = "collision-checked poses/s"
+WORKLOAD = "synthetic sweep: random 6-DoF robot_small.obj poses vs building.obj (scale 10)"
+
+
+def load_meshes():
+    m = np.load(ROOT / "tests" / "golden" / "meshes.npz")
+    return m["building_s10"], m["robot_small_s10"]
+
+
+def measured_peak_hbm():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """samples SM clock + throttle reasons of one GPU during the timed region (nvidia_ml_py)"""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle port of the reference path on all host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle as O
+    O.build(ref=False)
+    obst, robot = load_meshes()
+    mo, mr = O.ObbModel(obst), O.ObbModel(robot)
+    threads = O.num_threads()
+    sample = args.cpu_sample
+    poses = O.gen_poses(SEED, 0, sample, RANGE).astype(np.float64)
+    for _ in range(args.warmup):
+        O.collide_obbtree(mo, mr, poses[: sample // 8], first_contact=False, threads=threads, want_verdicts=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.collide_obbtree(mo, mr, poses, first_contact=False, threads=threads, want_verdicts=False)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "poses_per_step": sample, "pose_seed": SEED},
+        "cpu_baseline": {"value": value, "unit": "poses/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} poses/step, RAPID-restatement OBB-tree (oracle/sff_oracle.c), ALL_CONTACTS, "
+                                   f"OpenMP over poses; RAPID 2.01 itself is not vendored in the reference"},
+        "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(sample: int):
+    import oracle as O
+    O.build(ref=False)
+    obst, robot = load_meshes()
+    mo, mr = O.ObbModel(obst), O.ObbModel(robot)
+    threads = O.num_threads()
+    poses = O.gen_poses(SEED, 0, sample, RANGE).astype(np.float64)
+    O.collide_obbtree(mo, mr, poses[: sample // 8], first_contact=False, threads=threads, want_verdicts=False)
+    t0 = time.perf_counter()
+    _, cnt = O.collide_obbtree(mo, mr, poses, first_contact=False, threads=threads, want_verdicts=False)
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    O.collide_obbtree(mo, mr, poses[: sample // 4], first_contact=False, threads=1, want_verdicts=False)
+    dt1 = time.perf_counter() - t1
+    return {"value": sample / dt, "unit": "poses/s", "cores": threads, "kind": "port",
+            "sample": f"{sample} poses of the same stream, RAPID-restatement OBB-tree, ALL_CONTACTS (as src/environment.h:274), "
+                      f"OpenMP over poses",
+            "single_core_poses_per_s": (sample // 4) / dt1,
+            "oracle_counters_per_pose": {k: v / sample for k, v in cnt.items()}}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import space_filling_forest_star_b200 as S
+    S.init(local)
+    obst, robot = load_meshes()
+    env = S.Environment(obst, robot)
+    P = args.poses_per_gpu
+    dev = torch.device("cuda", local)
+
+    # ---- device-resident leg -------------------------------------------------------------------------------
+    poses = S.gen_poses_device(SEED, rank * P, P, RANGE)
+    verdict = torch.empty(P, dtype=torch.uint8, device=dev)
+    gathered = torch.empty(world * P, dtype=torch.uint8, device=dev) if world > 1 else None
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+
+    def step(i=None):
+        if i is not None:
+            k_ev[i][0].record()
+        env.collide_device(poses, out=verdict)
+        if i is not None:
+            k_ev[i][1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, verdict)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    env.sync_check()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_beg.record()
+    for i in range(args.steps):
+        step(i)
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    env.sync_check()
+    ms = torch.tensor([t_beg.elapsed_time(t_end)], device=dev)
+    kern_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in k_ev) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    kernel_ms = float(kern_ms.item())
+    hits = int(verdict.sum().item())
+
+    # ---- end-to-end leg: pinned host buffers through the host C-ABI call ----------------------------------------
+    h_poses = torch.empty((P, 6), dtype=torch.float32, pin_memory=True)
+    h_poses.copy_(poses)
+    h_out = torch.empty(P, dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize()
+    for _ in range(max(1, args.warmup // 2)):
+        env.collide_host_buffers(h_poses.data_ptr(), False, P, h_out.data_ptr())
+    if world > 1:
+        dist.barrier()
+    e_steps = max(2, args.steps // 2)
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        env.collide_host_buffers(h_poses.data_ptr(), False, P, h_out.data_ptr())
+    e_dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * P * e_steps / float(e_dt.item())
+    e2e_hits = int(h_out.sum().item())
+    assert e2e_hits == hits, (e2e_hits, hits)
+
+    if rank == 0:
+        peak, which = measured_peak_hbm()
+        achieved = ALGO_BYTES_PER_POSE * P / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * P * args.steps / (total_ms * 1e-3), "unit": "poses/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "poses_per_gpu_per_step": P, "pose_seed": SEED, "obstacle_tris": int(len(obst)),
+                       "robot_tris": int(len(robot)), "l2_policy": "inputs larger than L2 (402 MB of poses per step)",
+                       "parallelism": f"pose-shard x{world} + NCCL all-gather of verdict bytes" if world > 1 else "single GPU",
+                       "hit_fraction": hits / P},
+            "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": P * 24, "d2h_bytes_per_step": P,
+                    "steps": e_steps, "api": "sffg_collide_poses_f32 on pinned host buffers"},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": which, "kernel": "collide_poses_kernel<f32>",
+                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_pose": ALGO_BYTES_PER_POSE,
+                         "note": "the path is FP32-issue / L2-latency bound, not HBM bound (SURVEY 8d); see DESIGN.md"},
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
+        if world == 1 and not args.no_extra:
+            line["extra"] = extra_metrics(S, env, torch)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def extra_metrics(S, env, torch):
+    """secondary numbers of the same hot path (not the headline): edges/s and exact k-NN queries/s"""
+    out = {}
+    try:
+        m = 1 << 18
+        s = S.gen_poses_device(SEED + 1, 0, m, [-45, 45, -45, 45, 0, 125]).double()
+        d = torch.randn((m, 3), device=s.device, dtype=torch.float64, generator=torch.Generator(device=s.device).manual_seed(1))
+        d = d / d.norm(dim=1, keepdim=True)
+        e = s.clone()
+        e[:, :3] += 4.0 * d
+        free = torch.empty(m, dtype=torch.uint8, device=s.device)
+        for _ in range(2):
+            env.edges_device(s, e, 0.1, 0, free_out=free)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            env.edges_device(s, e, 0.1, 0, free_out=free)
+        b.record()
+        torch.cuda.synchronize()
+        out["edges_per_s"] = 3 * m / (a.elapsed_time(b) * 1e-3)
+        out["edge_config"] = "2^18 edges of length 4 (39 samples @0.1) in building.obj, reference rotation mode"
+        out["edge_free_fraction"] = float(free.float().mean().item())
+        n, nq, k = 1_000_000, 1 << 15, 16
+        g = torch.Generator(device=s.device).manual_seed(2)
+        lo = torch.tensor([-70, -70, 0, -3.14159, -3.14159, -3.14159], device=s.device)
+        hi = torch.tensor([70, 70, 140, 3.14159, 3.14159, 3.14159], device=s.device)
+        nodes = (lo + (hi - lo) * torch.rand((n, 6), device=s.device, generator=g)).float().contiguous()
+        q = (lo + (hi - lo) * torch.rand((nq, 6), device=s.device, generator=g)).float().contiguous()
+        idx = S.Index(dim=6)
+        idx.add_device(nodes)
+        ids = torch.empty((nq, k), dtype=torch.int32, device=s.device)
+        d2 = torch.empty((nq, k), dtype=torch.float32, device=s.device)
+        idx.knn_device(q, k, ids, d2)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(3):
+            idx.knn_device(q, k, ids, d2)
+        b.record()
+        torch.cuda.synchronize()
+        sec = a.elapsed_time(b) * 1e-3 / 3
+        out["knn_queries_per_s"] = nq / sec
+        out["knn_config"] = f"N={n} 6-D nodes, Q={nq}, k={k}, exact"
+        out["knn_pair_rate_per_s"] = nq * n / sec
+    except Exception as ex:   # secondary numbers must never break the headline line
+        out["error"] = repr(ex)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--poses-per-gpu", type=int, default=POSES_PER_GPU)
+    ap.add_argument("--cpu-sample", type=int, default=1 << 22)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when started plainly with --gpus N
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500), __file__] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+"""GPU parity tests of the pose-verdict path, through the C ABI (sffg_collide_poses_*), against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import CASES, SEED
+
+pytestmark = pytest.mark.gpu
+
+
+def make_env(sff, meshes, case):
+    on, rn, _ = CASES[case]
+    return sff.Environment(meshes[on], meshes[rn])
+
+
+@pytest.mark.parametrize("case", ["B", "D", "T", "2D", "2Dd"])
+def test_golden_verdicts_bit_exact(sff, meshes, gold_collision, case):
+    """committed fixture: all-pairs double SAT verdicts incl. poses sampled near surfaces; no tolerance"""
+    env = make_env(sff, meshes, case)
+    poses = gold_collision[f"{case}_poses"]
+    gold = gold_collision[f"{case}_verdict"]
+    got = env.Collide(poses)                       # dtype of the fixture (f32 for 3-D cases, f64 for 2-D)
+    bad = np.nonzero(got != gold)[0]
+    assert len(bad) == 0, (case, bad[:10], gold_collision[f"{case}_margin"][bad[:10]])
+    got64 = env.Collide(poses.astype(np.float64))  # the double entry point sees the same values
+    np.testing.assert_array_equal(got64, gold)
+
+
+@pytest.mark.parametrize("case,n", [("B", 400000), ("D", 200000), ("T", 100000)])
+def test_seeded_sweep_vs_obbtree_oracle(sff, orc, meshes, case, n):
+    """SURVEY 8d sweep shape at a size the CPU oracle finishes in seconds; mismatches are enumerated with margins"""
+    on, rn, rng = CASES[case]
+    env = make_env(sff, meshes, case)
+    poses = orc.gen_poses(SEED, 12345, n, rng)
+    env.enable_counters(True)
+    got = env.Collide(poses)
+    cnt = env.read_counters()
+    want, _ = orc.collide_obbtree(orc.ObbModel(meshes[on]), orc.ObbModel(meshes[rn]), poses.astype(np.float64))
+    bad = np.nonzero(got != want)[0]
+    margins = orc.pose_margin(meshes[on], meshes[rn], poses[bad].astype(np.float64)) if len(bad) else []
+    assert len(bad) == 0, f"{case}: {len(bad)} mismatches; poses {bad[:8]}, oracle margins {margins[:8]}"
+    assert cnt["poses"] == n and 0 < cnt["poses_past_root"] <= n
+    # the FP64 stage must stay the exception, not the rule
+    assert cnt["exact_tests"] <= 0.2 * max(cnt["pair_tests"], 1)
+    assert 0.001 < want.mean() < 0.9
+
+
+def test_ragged_sizes_and_empty(sff, orc, meshes):
+    env = make_env(sff, meshes, "T")
+    on, rn, rng = CASES["T"]
+    mo, mr = orc.ObbModel(meshes[on]), orc.ObbModel(meshes[rn])
+    assert env.Collide(np.zeros((0, 6), dtype=np.float32)).shape == (0,)
+    for n in (1, 31, 32, 33, 255, 257, 1025):
+        poses = orc.gen_poses(SEED + n, 0, n, rng)
+        want, _ = orc.collide_obbtree(mo, mr, poses.astype(np.float64))
+        np.testing.assert_array_equal(env.Collide(poses), want)
+
+
+def test_chunked_host_path_large_batch(sff, orc, meshes):
+    """> 1 chunk (2^20 poses) through the host entry point: checks the two-stream pipeline stitches correctly"""
+    on, rn, rng = CASES["B"]
+    env = make_env(sff, meshes, "B")
+    n = (1 << 21) + 777
+    poses = orc.gen_poses(SEED, 0, n, rng)
+    got = env.Collide(poses)
+    idx = np.random.RandomState(0).choice(n, 60000, replace=False)
+    idx = np.concatenate([idx, np.arange((1 << 20) - 64, (1 << 20) + 64), np.arange(n - 64, n)])
+    want, _ = orc.collide_obbtree(orc.ObbModel(meshes[on]), orc.ObbModel(meshes[rn]), poses[idx].astype(np.float64))
+    np.testing.assert_array_equal(got[idx], want)
+    # size-independent properties at full size: far-away poses never collide; the result is idempotent
+    far = poses.copy()
+    far[:, 2] += 1000.0
+    assert env.Collide(far).sum() == 0
+    np.testing.assert_array_equal(env.Collide(poses), got)
+
+
+def test_no_map_never_collides(sff, meshes):
+    # Environment<T>::Collide with HasMap == false (src/environment.h:307-309)
+    env = sff.Environment(np.zeros((0, 3, 3)), meshes["robot_small_s10"])
+    assert env.Collide(np.random.RandomState(0).uniform(-5, 5, (1000, 6)).astype(np.float32)).sum() == 0
+
+
+def test_device_entry_point_and_generator(sff, orc, meshes):
+    """sffg_collide_poses_device + sffg_gen_poses_device: the device pose stream is bit-identical to the oracle's"""
+    import torch
+    on, rn, rng = CASES["B"]
+    env = make_env(sff, meshes, "B")
+    n = 300000
+    d_poses = sff.gen_poses_device(SEED, 777, n, rng)
+    out = env.collide_device(d_poses)
+    torch.cuda.synchronize()
+    env.sync_check()
+    h_poses = orc.gen_poses(SEED, 777, n, rng)
+    np.testing.assert_array_equal(d_poses.cpu().numpy().view(np.uint32), h_poses.view(np.uint32))
+    want, _ = orc.collide_obbtree(orc.ObbModel(meshes[on]), orc.ObbModel(meshes[rn]), h_poses.astype(np.float64))
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
+def test_translated_world_far_from_origin(sff, orc, meshes):
+    """coordinates ~1e4: the FP32 stage loses precision, the error bounds must push near calls to the exact stage"""
+    on, rn, rng = CASES["T"]
+    shift = np.array([12345.678, -9876.543, 4321.0])
+    obst = meshes[on] + shift
+    env = sff.Environment(obst, meshes[rn])
+    poses = orc.gen_poses(SEED, 0, 60000, rng).astype(np.float64)
+    poses[:, :3] += shift
+    want, _ = orc.collide_obbtree(orc.ObbModel(obst), orc.ObbModel(meshes[rn]), poses)
+    got = env.Collide(poses)
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, (bad[:10], orc.pose_margin(obst, meshes[rn], poses[bad[:10]]))

@@ -1,0 +1,111 @@
+"""GPU parity tests of exact k-NN / radius search through sffg_knn / sffg_radius."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def cloud(n, dim, seed):
+    r = np.random.RandomState(seed)
+    if dim == 6:
+        return np.concatenate([r.uniform([-70, -70, 0], [70, 70, 140], (n, 3)), r.uniform(-np.pi, np.pi, (n, 3))], 1).astype(np.float32)
+    return r.uniform([-10, -10], [1010, 710], (n, 2)).astype(np.float32)
+
+
+@pytest.mark.parametrize("dim", [6, 2])
+def test_knn_golden_real_flann(sff, gold_knn, dim):
+    """fixtures produced by the reference's vendored FLANN LinearIndex: ids AND distances bit-exact"""
+    idx = sff.Index(gold_knn[f"nodes{dim}"])
+    idx.buildIndex()
+    q = gold_knn[f"queries{dim}"]
+    for k in (1, 4, 16, 32, 50, 128):
+        ids, d2 = idx.knnSearch(q, k)
+        np.testing.assert_array_equal(ids, gold_knn[f"ids{dim}_k{k}"])
+        np.testing.assert_array_equal(d2.view(np.uint32), gold_knn[f"d2{dim}_k{k}"].view(np.uint32))
+
+
+@pytest.mark.parametrize("dim", [6, 2])
+def test_radius_golden_real_flann(sff, gold_knn, dim):
+    idx = sff.Index(gold_knn[f"nodes{dim}"])
+    c, off, ids, d2 = idx.radiusSearch(gold_knn[f"queries{dim}"], float(gold_knn[f"rad{dim}_r2"]))
+    np.testing.assert_array_equal(c, gold_knn[f"rad{dim}_counts"])
+    np.testing.assert_array_equal(ids, gold_knn[f"rad{dim}_ids"])
+    np.testing.assert_array_equal(d2.view(np.uint32), gold_knn[f"rad{dim}_d2"].view(np.uint32))
+
+
+@pytest.mark.parametrize("n,nq,k", [(100000, 3000, 16), (100000, 7, 27), (1000, 50000, 8), (33, 5, 32), (5, 3, 8), (200000, 1, 32)])
+def test_knn_vs_oracle_shapes(sff, orc, n, nq, k):
+    """big-Q (4 queries per warp), small-Q (sliced + merge), index smaller than k (padded rows)"""
+    nodes, q = cloud(n, 6, 1), cloud(nq, 6, 2)
+    idx = sff.Index(nodes)
+    ids, d2 = idx.knnSearch(q, k)
+    wi, wd = orc.knn_linear(nodes, q, k)
+    np.testing.assert_array_equal(ids, wi)
+    np.testing.assert_array_equal(d2.view(np.uint32), wd.view(np.uint32))
+
+
+def test_incremental_add_like_the_planner(sff, orc):
+    """src/forest.h:72-73 + :367: one root point, then one addPoints per expansion; ids = insertion order"""
+    nodes = cloud(3000, 6, 5)
+    idx = sff.Index(nodes[:1])
+    idx.buildIndex()
+    for i in range(1, 40):
+        idx.addPoints(nodes[i:i + 1])
+    idx.addPoints(nodes[40:3000])
+    assert idx.size() == 3000
+    q = cloud(100, 6, 6)
+    for k in (1, 21):
+        ids, d2 = idx.knnSearch(q, k)
+        wi, wd = orc.knn_linear(nodes, q, k)
+        np.testing.assert_array_equal(ids, wi)
+    c, off, ids, d2 = idx.radiusSearch(q, 169.0)
+    wc, woff, wids, wd2 = orc.radius_linear(nodes, q, 169.0)
+    np.testing.assert_array_equal(c, wc)
+    np.testing.assert_array_equal(ids, wids)
+
+
+def test_radius_large_rows_and_empty_rows(sff, orc):
+    """2-D planner radius (r^2 = 67600) returns thousands of hits per row -> global-memory sort path"""
+    nodes, q = cloud(30000, 2, 8), cloud(40, 2, 9)
+    q[0] = [1e6, 1e6]   # nothing in range
+    idx = sff.Index(nodes)
+    c, off, ids, d2 = idx.radiusSearch(q, 67600.0)
+    wc, woff, wids, wd2 = orc.radius_linear(nodes, q, 67600.0)
+    assert c[0] == 0 and c.max() > 4096
+    np.testing.assert_array_equal(c, wc)
+    np.testing.assert_array_equal(ids, wids)
+    np.testing.assert_array_equal(d2.view(np.uint32), wd2.view(np.uint32))
+    # rows are sorted by (d2, id) and strictly inside the radius
+    for i in range(len(q)):
+        row = d2[off[i]:off[i + 1]]
+        assert np.all(np.diff(row) >= 0) and np.all(row < 67600.0)
+
+
+def test_argument_and_domain_errors(sff):
+    idx = sff.Index(cloud(10, 6, 1))
+    with pytest.raises(sff.SffgError) as ei:
+        idx.knnSearch(cloud(2, 6, 2), 0)
+    assert ei.value.code == 3
+    with pytest.raises(sff.SffgError) as ei:
+        idx.knnSearch(cloud(2, 6, 2), 129)
+    assert ei.value.code == 3
+    bad = cloud(2, 6, 2)
+    bad[1, 4] = 9.0
+    with pytest.raises(sff.SffgError) as ei:
+        idx.addPoints(bad)
+    assert ei.value.code == 6
+    with pytest.raises(sff.SffgError):
+        sff.Index(dim=3)
+
+
+def test_knn_device_and_sharded_single_rank(sff, orc):
+    import torch
+    from space_filling_forest_star_b200.sharding import sharded_knn
+    nodes, q = cloud(50000, 6, 3), cloud(2000, 6, 4)
+    idx = sff.Index(dim=6)
+    idx.add_device(torch.from_numpy(nodes).cuda())
+    ids, d2 = sharded_knn(idx, torch.from_numpy(q).cuda(), 16)
+    torch.cuda.synchronize()
+    wi, wd = orc.knn_linear(nodes, q, 16)
+    np.testing.assert_array_equal(ids.cpu().numpy(), wi)
+    np.testing.assert_array_equal(d2.cpu().numpy().view(np.uint32), wd.view(np.uint32))
