@@ -82,6 +82,9 @@ SFFG_API int sffg_env_info(const sffg_env *env, sffg_env_info_t *out);
  *      = RAPID_Collide(I, 0, obstacle, R(pose), T(pose), robot) != 0 contacts, :269-276 ---------------------- */
 SFFG_API int sffg_collide_poses_f32(sffg_env *env, const float *poses, int64_t n, uint8_t *verdict_out);
 SFFG_API int sffg_collide_poses_f64(sffg_env *env, const double *poses, int64_t n, uint8_t *verdict_out);
+/* RAPID_Collide's own argument form: rt = [n][12] doubles, R2 row-major (9) then T2 (3); obstacle at identity.
+ * This is what a RAPID.H shim forwards (src/environment.h:274). */
+SFFG_API int sffg_collide_transforms_f64(sffg_env *env, const double *rt, int64_t n, uint8_t *verdict_out);
 SFFG_API int sffg_collide_poses_device(sffg_env *env, const void *d_poses, int poses_are_f64, int64_t n,
                               uint8_t *d_verdict_out, void *stream);
 

@@ -46,6 +46,7 @@ SIGNATURES = {
     "sffg_env_info": (C.c_int, [_p, C.POINTER(EnvInfo)]),
     "sffg_collide_poses_f32": (C.c_int, [_p, _p, C.c_int64, _p]),
     "sffg_collide_poses_f64": (C.c_int, [_p, _p, C.c_int64, _p]),
+    "sffg_collide_transforms_f64": (C.c_int, [_p, _p, C.c_int64, _p]),
     "sffg_collide_poses_device": (C.c_int, [_p, _p, C.c_int, C.c_int64, _p, _p]),
     "sffg_check_edges": (C.c_int, [_p, _p, _p, C.c_int64, C.c_double, C.c_int, _p, _p]),
     "sffg_check_edges_device": (C.c_int, [_p, _p, _p, C.c_int64, C.c_double, C.c_int, _p, _p, _p]),
@@ -74,7 +75,9 @@ def load() -> C.CDLL:
     """Load (building first if needed) libsffg.so.  Raises if it cannot be built -- never falls back."""
     global _lib
     if _lib is None:
-        path = _build.build_native()
+        import os
+        variant = os.environ.get("SFFG_LIB")   # tuning variants built by scripts/; the default is the in-tree library
+        path = Path(variant) if variant else _build.build_native()
         L = C.CDLL(str(path))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)   # AttributeError here = header and library out of sync

@@ -221,6 +221,38 @@ struct Collapser {
 
 }  // namespace
 
+void top_cut(const HostBvh &bvh, std::vector<ChildSlot> *out) {
+  out->clear();
+  if (bvh.slots.empty()) return;
+  auto push_node = [&](int node) {
+    for (int i = 0; i < kWide; ++i) {
+      const ChildSlot &s = bvh.slots[(size_t)node * kWide + i];
+      if (s.child != kEmptyChild) out->push_back(s);
+    }
+  };
+  push_node(0);
+  while (true) {
+    int pick = -1;
+    float best = -1.f;
+    for (int i = 0; i < (int)out->size(); ++i) {
+      const ChildSlot &s = (*out)[i];
+      if (s.child < 0) continue;
+      int kids = 0;
+      for (int c = 0; c < kWide; ++c) kids += bvh.slots[(size_t)s.child * kWide + c].child != kEmptyChild;
+      if ((int)out->size() - 1 + kids > 32) continue;
+      const float area = s.hx * s.hy + s.hy * s.hz + s.hz * s.hx;
+      if (area > best) {
+        best = area;
+        pick = i;
+      }
+    }
+    if (pick < 0) break;
+    const int node = (*out)[pick].child;
+    out->erase(out->begin() + pick);
+    push_node(node);
+  }
+}
+
 void build_wide_bvh(const double *tris, int64_t n, HostBvh *out) {
   out->slots.clear();
   out->tri_order.clear();

@@ -29,14 +29,18 @@ constexpr int kStackCap = 384;   // node ids pending for one pose
 constexpr int kTriCap = 64;      // candidate triangles pending for one pose
 constexpr int kTriFlush = 12;    // run the triangle stage once this many candidates are pending
 constexpr unsigned kFull = 0xffffffffu;
+#ifndef SFFG_MIN_BLOCKS
+#define SFFG_MIN_BLOCKS 2
+#endif
 constexpr float kEpsBox = 1.52587890625e-05f;   // 2^-16, relative slack of the box culls   (>= 140 ulp)
 constexpr float kEpsSat = 1.52587890625e-05f;   // 2^-16, relative position error of the FP32 SAT stage
 
-struct XTri {        // obstacle triangle in the robot frame (FP32), 48 B
+struct XTri {        // obstacle triangle in the robot frame (FP32); 13 words = odd stride, bank-conflict free
   float v[9];
   float err;         // absolute position error bound of these 9 values
   float mabs;        // max |v|
   int tri;           // triangle index (leaf order) for the exact stage
+  int pad;
 };
 
 struct WarpScratch {
@@ -136,12 +140,16 @@ __device__ __forceinline__ void dcross(double *r, const double *a, const double 
   r[2] = dsub(dmul(a[0], b[1]), dmul(a[1], b[0]));
 }
 
-// Point<T>::FillRotationMatrix (reference src/primitives.h:252-262), double
-__device__ void rotation_f64(double yaw, double pitch, double roll, double *m) {
-  double sy, cy, sp, cp, sr, cr;
-  sincos(yaw, &sy, &cy);
-  sincos(pitch, &sp, &cp);
-  sincos(roll, &sr, &cr);
+// Point<T>::FillRotationMatrix (reference src/primitives.h:252-262), double.  The three sincos calls are spread over
+// lanes 0..2 (every lane runs one call) and exchanged by shuffle; all lanes return the same matrix.
+__device__ void rotation_f64_warp(double yaw, double pitch, double roll, double *m, int lane) {
+  const int sel = lane % 3;
+  const double ang = sel == 0 ? yaw : (sel == 1 ? pitch : roll);
+  double s, c;
+  sincos(ang, &s, &c);
+  const double sy = __shfl_sync(kFull, s, 0), cy = __shfl_sync(kFull, c, 0);
+  const double sp = __shfl_sync(kFull, s, 1), cp = __shfl_sync(kFull, c, 1);
+  const double sr = __shfl_sync(kFull, s, 2), cr = __shfl_sync(kFull, c, 2);
   m[0] = dmul(cy, cp);
   m[1] = dsub(dmul(dmul(cy, sp), sr), dmul(sy, cr));
   m[2] = dadd(dmul(dmul(cy, sp), cr), dmul(sy, sr));
@@ -214,6 +222,117 @@ __device__ __noinline__ bool exact_pair_contact(const double *R2, const double *
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// pose formats.  Each lane keeps its own pose in the narrowest form that loses nothing; the exact stage fetches the
+// double pose of lane `src` on demand (rare), so the FP32 fast path of an f32 batch never touches the FP64 pipe.
+// ---------------------------------------------------------------------------------------------------------
+enum { kFmtEulerF32 = 0, kFmtEulerF64 = 1, kFmtMatrixF64 = 2 };
+
+template <int FMT> struct LanePose;
+
+template <> struct LanePose<kFmtEulerF32> {
+  float t[3], a[3];
+  __device__ __forceinline__ void load(const void *base, long long i) {
+    const float2 *p = reinterpret_cast<const float2 *>(base) + 3 * i;
+    const float2 x = p[0], y = p[1], z = p[2];
+    t[0] = x.x; t[1] = x.y; t[2] = y.x; a[0] = y.y; a[1] = z.x; a[2] = z.y;
+  }
+  __device__ __forceinline__ void clear() { t[0] = t[1] = t[2] = a[0] = a[1] = a[2] = 0.f; }
+  __device__ __forceinline__ void split(float *hi, float *lo) const {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { hi[k] = t[k]; lo[k] = 0.f; }
+  }
+  __device__ __forceinline__ void rot32(float *R) const;
+  __device__ __forceinline__ void exact(int src, double *R2, double *T2, int lane) const {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) T2[k] = (double)__shfl_sync(kFull, t[k], src);
+    rotation_f64_warp((double)__shfl_sync(kFull, a[0], src), (double)__shfl_sync(kFull, a[1], src),
+                      (double)__shfl_sync(kFull, a[2], src), R2, lane);
+  }
+};
+
+template <> struct LanePose<kFmtEulerF64> {
+  double t[3], a[3];
+  bool identity;   // edge samples in reference mode: R = I exactly, no trigonometry anywhere
+  __device__ __forceinline__ void load(const void *base, long long i) {
+    const double2 *p = reinterpret_cast<const double2 *>(base) + 3 * i;
+    const double2 x = p[0], y = p[1], z = p[2];
+    t[0] = x.x; t[1] = x.y; t[2] = y.x; a[0] = y.y; a[1] = z.x; a[2] = z.y;
+    identity = false;
+  }
+  __device__ __forceinline__ void clear() { t[0] = t[1] = t[2] = a[0] = a[1] = a[2] = 0.0; identity = false; }
+  __device__ __forceinline__ void split(float *hi, float *lo) const {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { hi[k] = (float)t[k]; lo[k] = (float)(t[k] - (double)hi[k]); }
+  }
+  __device__ __forceinline__ void rot32(float *R) const;
+  __device__ __forceinline__ void exact(int src, double *R2, double *T2, int lane) const {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) T2[k] = __shfl_sync(kFull, t[k], src);
+    if (__shfl_sync(kFull, (int)identity, src)) {
+      // FillRotationMatrix at zero angles: identity with m[2][0] = -sin(0) = -0.0
+      R2[0] = 1.0; R2[1] = 0.0; R2[2] = 0.0; R2[3] = 0.0; R2[4] = 1.0; R2[5] = 0.0; R2[6] = -0.0; R2[7] = 0.0; R2[8] = 1.0;
+    } else {
+      rotation_f64_warp(__shfl_sync(kFull, a[0], src), __shfl_sync(kFull, a[1], src), __shfl_sync(kFull, a[2], src), R2, lane);
+    }
+  }
+};
+
+template <> struct LanePose<kFmtMatrixF64> {
+  double t[3], r[9];   // RAPID_Collide's own arguments: R2 row-major, T2
+  __device__ __forceinline__ void load(const void *base, long long i) {
+    const double *p = reinterpret_cast<const double *>(base) + 12 * i;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) r[k] = p[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t[k] = p[9 + k];
+  }
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) r[k] = 0.0;
+    t[0] = t[1] = t[2] = 0.0;
+  }
+  __device__ __forceinline__ void split(float *hi, float *lo) const {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { hi[k] = (float)t[k]; lo[k] = (float)(t[k] - (double)hi[k]); }
+  }
+  __device__ __forceinline__ void rot32(float *R) const {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = (float)r[k];
+  }
+  __device__ __forceinline__ void exact(int src, double *R2, double *T2, int) const {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) T2[k] = __shfl_sync(kFull, t[k], src);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R2[k] = __shfl_sync(kFull, r[k], src);
+  }
+};
+
+// Point<T>::FillRotationMatrix in FP32 (certificate stage only)
+__device__ __forceinline__ void rotation_f32(float yaw, float pitch, float roll, float *m) {
+  float sy, cy, sp, cp, sr, cr;
+  sincosf(yaw, &sy, &cy);
+  sincosf(pitch, &sp, &cp);
+  sincosf(roll, &sr, &cr);
+  m[0] = cy * cp;
+  m[1] = cy * sp * sr - sy * cr;
+  m[2] = cy * sp * cr + sy * sr;
+  m[3] = sy * cp;
+  m[4] = sy * sp * sr + cy * cr;
+  m[5] = sy * sp * cr - cy * sr;
+  m[6] = -sp;
+  m[7] = cp * sr;
+  m[8] = cp * cr;
+}
+__device__ __forceinline__ void LanePose<kFmtEulerF32>::rot32(float *R) const { rotation_f32(a[0], a[1], a[2], R); }
+__device__ __forceinline__ void LanePose<kFmtEulerF64>::rot32(float *R) const {
+  if (identity) {
+    R[0] = 1.f; R[1] = 0.f; R[2] = 0.f; R[3] = 0.f; R[4] = 1.f; R[5] = 0.f; R[6] = 0.f; R[7] = 0.f; R[8] = 1.f;
+  } else {
+    rotation_f32((float)a[0], (float)a[1], (float)a[2], R);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // per-pose warp traversal
 // ---------------------------------------------------------------------------------------------------------
 struct PoseU {          // warp-uniform copy of one pose
@@ -223,61 +342,75 @@ struct PoseU {          // warp-uniform copy of one pose
 
 struct Tally { unsigned long long past_root, box, pair, exact; };
 
-template <bool COUNT>
+struct BoxTest {        // per-pose constants of the oriented-box test
+  float o[3], ra[3], rob_sz;
+};
+
+// robot oriented box (centre T + R c, axes R, half extents h) against an AABB slot; conservative
+__device__ __forceinline__ bool slot_overlaps(const EnvDev &E, const PoseU &P, const BoxTest &bt, const float4 a, const float4 b) {
+  const float tx = (a.x - P.Thi[0]) - bt.o[0], ty = (a.y - P.Thi[1]) - bt.o[1], tz = (a.z - P.Thi[2]) - bt.o[2];
+  const float pad = kEpsBox * (fabsf(tx) + fabsf(ty) + fabsf(tz) + b.x + b.y + b.z + bt.rob_sz);
+  if (fabsf(tx) > b.x + bt.ra[0] + pad || fabsf(ty) > b.y + bt.ra[1] + pad || fabsf(tz) > b.z + bt.ra[2] + pad) return false;
+  bool ov = true;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float s_j = P.R[j] * tx + P.R[3 + j] * ty + P.R[6 + j] * tz;
+    const float rb = fabsf(P.R[j]) * b.x + fabsf(P.R[3 + j]) * b.y + fabsf(P.R[6 + j]) * b.z;
+    const float hj = j == 0 ? E.rob_h[0] : (j == 1 ? E.rob_h[1] : E.rob_h[2]);
+    if (fabsf(s_j) > hj + rb + pad) ov = false;
+  }
+  return ov;
+}
+
+template <int FMT, bool COUNT>
 __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *srob, const PoseU &P,
-                              double Tdx, double Tdy, double Tdz, double yaw, double pitch, double roll, int src,
-                              int lane, Tally &tally) {
-  // ---- per-pose constants of the oriented-box test
-  float o[3], ra[3];
+                              const LanePose<FMT> &lp, int src, int lane, Tally &tally) {
+  BoxTest bt;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    o[k] = P.R[3 * k] * E.rob_c[0] + P.R[3 * k + 1] * E.rob_c[1] + P.R[3 * k + 2] * E.rob_c[2] + P.Tlo[k];
-    ra[k] = fabsf(P.R[3 * k]) * E.rob_h[0] + fabsf(P.R[3 * k + 1]) * E.rob_h[1] + fabsf(P.R[3 * k + 2]) * E.rob_h[2];
+    bt.o[k] = P.R[3 * k] * E.rob_c[0] + P.R[3 * k + 1] * E.rob_c[1] + P.R[3 * k + 2] * E.rob_c[2] + P.Tlo[k];
+    bt.ra[k] = fabsf(P.R[3 * k]) * E.rob_h[0] + fabsf(P.R[3 * k + 1]) * E.rob_h[1] + fabsf(P.R[3 * k + 2]) * E.rob_h[2];
   }
-  const float rob_sz = 2.0f * E.rob_radius + fabsf(P.Tlo[0]) + fabsf(P.Tlo[1]) + fabsf(P.Tlo[2]);
+  bt.rob_sz = 2.0f * E.rob_radius + fabsf(P.Tlo[0]) + fabsf(P.Tlo[1]) + fabsf(P.Tlo[2]);
   const unsigned lt = (1u << lane) - 1u;
 
-  int sp = 1, ntri = 0;
-  if (lane == 0) ws.stack[0] = 0;
-  __syncwarp();
+  int sp = 0, ntri = 0;
   bool hit = false;
   bool have_R2 = false;
   double R2[9], T2[3];
   if (COUNT) tally.past_root += 1;
 
+  bool first = true;   // step 0 tests the precomputed <=32-box cut of the top of the hierarchy with all lanes
   while (true) {
-    if (sp > 0 && ntri <= kTriCap - 32) {
-      const int take = sp < 4 ? sp : 4;
-      const int grp = lane >> 3;
-      const bool active = grp < take;
-      const int node = active ? ws.stack[sp - 1 - grp] : 0;
-      __syncwarp();
-      sp -= take;
+    if (first || (sp > 0 && ntri <= kTriCap - 32)) {
       bool ov = false;
       int child = kEmptyChild;
-      if (active) {
-        const float4 *s = E.slots + ((size_t)node * kWide + (lane & 7)) * 2;
-        const float4 a = __ldg(s), b = __ldg(s + 1);
-        child = __float_as_int(a.w);
-        if (child != kEmptyChild) {
-          const float tx = (a.x - P.Thi[0]) - o[0], ty = (a.y - P.Thi[1]) - o[1], tz = (a.z - P.Thi[2]) - o[2];
-          const float pad = kEpsBox * (fabsf(tx) + fabsf(ty) + fabsf(tz) + b.x + b.y + b.z + rob_sz);
-          ov = !(fabsf(tx) > b.x + ra[0] + pad) && !(fabsf(ty) > b.y + ra[1] + pad) && !(fabsf(tz) > b.z + ra[2] + pad);
-          if (ov) {
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const float s_j = P.R[j] * tx + P.R[3 + j] * ty + P.R[6 + j] * tz;
-              const float rb = fabsf(P.R[j]) * b.x + fabsf(P.R[3 + j]) * b.y + fabsf(P.R[6 + j]) * b.z;
-              const float hj = j == 0 ? E.rob_h[0] : (j == 1 ? E.rob_h[1] : E.rob_h[2]);
-              if (fabsf(s_j) > hj + rb + pad) ov = false;
-            }
-          }
+      bool active;
+      if (first) {
+        active = lane < E.n_top;
+        if (active) {
+          const float4 a = __ldg(E.top + 2 * lane), b = __ldg(E.top + 2 * lane + 1);
+          child = __float_as_int(a.w);
+          ov = slot_overlaps(E, P, bt, a, b);
+        }
+        first = false;
+      } else {
+        const int take = sp < 4 ? sp : 4;
+        const int grp = lane >> 3;
+        active = grp < take;
+        const int node = active ? ws.stack[sp - 1 - grp] : 0;
+        __syncwarp();
+        sp -= take;
+        if (active) {
+          const float4 *s = E.slots + ((size_t)node * kWide + (lane & 7)) * 2;
+          const float4 a = __ldg(s), b = __ldg(s + 1);
+          child = __float_as_int(a.w);
+          if (child != kEmptyChild) ov = slot_overlaps(E, P, bt, a, b);
         }
       }
-      const unsigned m_tested = COUNT ? __ballot_sync(kFull, active && child != kEmptyChild) : 0u;
       const unsigned m_int = __ballot_sync(kFull, ov && child >= 0);
       const unsigned m_leaf = __ballot_sync(kFull, ov && child < 0);
-      if (COUNT) tally.box += __popc(m_tested);
+      if (COUNT) tally.box += __popc(__ballot_sync(kFull, active && child != kEmptyChild));
       if (ov && child >= 0) {
         const int pos = sp + __popc(m_int & lt);
         if (pos < kStackCap) ws.stack[pos] = child;
@@ -320,6 +453,7 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *
         x.err = v0.w;
         x.mabs = mabs;
         x.tri = t;
+        x.pad = 0;
         const float padT = 2.0f * x.err + kEpsSat * fmaxf(mabs, E.rob_radius);
         keep = true;
 #pragma unroll
@@ -352,12 +486,7 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *
           const int l = __ffs(um) - 1;
           um &= um - 1;
           if (!have_R2) {
-            const double ty_ = __shfl_sync(kFull, yaw, src), tp_ = __shfl_sync(kFull, pitch, src),
-                         tr_ = __shfl_sync(kFull, roll, src);
-            T2[0] = __shfl_sync(kFull, Tdx, src);
-            T2[1] = __shfl_sync(kFull, Tdy, src);
-            T2[2] = __shfl_sync(kFull, Tdz, src);
-            rotation_f64(ty_, tp_, tr_, R2);
+            lp.exact(src, R2, T2, lane);
             have_R2 = true;
           }
           const int pp = pb + l;
@@ -389,23 +518,6 @@ __device__ __forceinline__ bool sphere_hits_root(const EnvDev &E, float tx, floa
   return dx * dx + dy * dy + dz * dz <= r * r * 1.000001f;
 }
 
-// Point<T>::FillRotationMatrix in FP32 (certificate stage only)
-__device__ __forceinline__ void rotation_f32(float yaw, float pitch, float roll, float *m) {
-  float sy, cy, sp, cp, sr, cr;
-  sincosf(yaw, &sy, &cy);
-  sincosf(pitch, &sp, &cp);
-  sincosf(roll, &sr, &cr);
-  m[0] = cy * cp;
-  m[1] = cy * sp * sr - sy * cr;
-  m[2] = cy * sp * cr + sy * sr;
-  m[3] = sy * cp;
-  m[4] = sy * sp * sr + cy * cr;
-  m[5] = sy * sp * cr - cy * sr;
-  m[6] = -sp;
-  m[7] = cp * sr;
-  m[8] = cp * cr;
-}
-
 __device__ __forceinline__ void stage_robot(const EnvDev &E, RobotTri *srob) {
   const int words = E.n_robot * (int)(sizeof(RobotTri) / 4);
   const float *g = reinterpret_cast<const float *>(E.robot);
@@ -424,28 +536,30 @@ __device__ __forceinline__ void flush_tally(const EnvDev &E, const Tally &t, uns
   }
 }
 
-// runs phase B over the lanes set in `alive`; returns the mask of colliding lanes (stops at the first hit when
-// `first_only`, which is what an edge needs)
-template <bool COUNT>
-__device__ __forceinline__ unsigned run_survivors(const EnvDev &E, WarpScratch &ws, const RobotTri *srob, unsigned alive,
-                                                  const float *R, double Tx, double Ty, double Tz, double yaw, double pitch,
-                                                  double roll, int lane, bool first_only, Tally &tally) {
+// phase A (lane-per-pose cull + rotation) then phase B over the surviving lanes; returns the mask of colliding lanes
+// (stops at the first hit when `first_only`, which is what an edge needs)
+template <int FMT, bool COUNT>
+__device__ __forceinline__ unsigned check_32_poses(const EnvDev &E, WarpScratch &ws, const RobotTri *srob, bool valid,
+                                                   const LanePose<FMT> &lp, int lane, bool first_only, Tally &tally) {
+  float thi[3], tlo[3], R[9];
+  lp.split(thi, tlo);
+  const bool alive = valid && E.n_obst > 0 &&
+                     sphere_hits_root(E, thi[0], thi[1], thi[2], fabsf(tlo[0]) + fabsf(tlo[1]) + fabsf(tlo[2]));
+  if (alive) lp.rot32(R);
+  unsigned todo = __ballot_sync(kFull, alive);
   unsigned hitmask = 0;
-  const float thx = (float)Tx, thy = (float)Ty, thz = (float)Tz;
-  const float tlx = (float)(Tx - (double)thx), tly = (float)(Ty - (double)thy), tlz = (float)(Tz - (double)thz);
-  while (alive) {
-    const int src = __ffs(alive) - 1;
-    alive &= alive - 1;
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
     PoseU P;
 #pragma unroll
     for (int k = 0; k < 9; ++k) P.R[k] = __shfl_sync(kFull, R[k], src);
-    P.Thi[0] = __shfl_sync(kFull, thx, src);
-    P.Thi[1] = __shfl_sync(kFull, thy, src);
-    P.Thi[2] = __shfl_sync(kFull, thz, src);
-    P.Tlo[0] = __shfl_sync(kFull, tlx, src);
-    P.Tlo[1] = __shfl_sync(kFull, tly, src);
-    P.Tlo[2] = __shfl_sync(kFull, tlz, src);
-    if (warp_pose_hit<COUNT>(E, ws, srob, P, Tx, Ty, Tz, yaw, pitch, roll, src, lane, tally)) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      P.Thi[k] = __shfl_sync(kFull, thi[k], src);
+      P.Tlo[k] = FMT == kFmtEulerF32 ? 0.f : __shfl_sync(kFull, tlo[k], src);
+    }
+    if (warp_pose_hit<FMT, COUNT>(E, ws, srob, P, lp, src, lane, tally)) {
       hitmask |= 1u << src;
       if (first_only) break;
     }
@@ -453,9 +567,9 @@ __device__ __forceinline__ unsigned run_survivors(const EnvDev &E, WarpScratch &
   return hitmask;
 }
 
-template <bool F64, bool COUNT>
-__global__ void __launch_bounds__(kThreads) collide_poses_kernel(EnvDev E, const void *poses, long long n,
-                                                                 uint8_t *out) {
+template <int FMT, bool COUNT>
+__global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) collide_poses_kernel(EnvDev E, const void *poses, long long n,
+                                                                                  uint8_t *out) {
   extern __shared__ __align__(16) unsigned char smem[];
   RobotTri *srob = reinterpret_cast<RobotTri *>(smem);
   stage_robot(E, srob);
@@ -470,26 +584,11 @@ __global__ void __launch_bounds__(kThreads) collide_poses_kernel(EnvDev E, const
     c = __shfl_sync(kFull, c, 0);
     if ((long long)c >= nchunks) break;
     const long long i = (long long)c * 32 + lane;
-    double Tx = 0, Ty = 0, Tz = 0, yaw = 0, pitch = 0, roll = 0;
-    if (i < n) {
-      if (F64) {
-        const double2 *p = reinterpret_cast<const double2 *>(poses) + 3 * i;
-        const double2 a = p[0], b = p[1], d = p[2];
-        Tx = a.x; Ty = a.y; Tz = b.x; yaw = b.y; pitch = d.x; roll = d.y;
-      } else {
-        const float2 *p = reinterpret_cast<const float2 *>(poses) + 3 * i;
-        const float2 a = p[0], b = p[1], d = p[2];
-        Tx = a.x; Ty = a.y; Tz = b.x; yaw = b.y; pitch = d.x; roll = d.y;
-      }
-    }
-    const float thx = (float)Tx, thy = (float)Ty, thz = (float)Tz;
-    const float tlo = fabsf((float)(Tx - (double)thx)) + fabsf((float)(Ty - (double)thy)) + fabsf((float)(Tz - (double)thz));
-    const bool alive = (i < n) && E.n_obst > 0 && sphere_hits_root(E, thx, thy, thz, tlo);
-    float R[9];
-    if (alive) rotation_f32((float)yaw, (float)pitch, (float)roll, R);
-    const unsigned am = __ballot_sync(kFull, alive);
+    LanePose<FMT> lp;
+    if (i < n) lp.load(poses, i);
+    else lp.clear();
     if (COUNT) nposes += (i < n) ? 1 : 0;
-    const unsigned hitmask = run_survivors<COUNT>(E, ws, srob, am, R, Tx, Ty, Tz, yaw, pitch, roll, lane, false, tally);
+    const unsigned hitmask = check_32_poses<FMT, COUNT>(E, ws, srob, i < n, lp, lane, false, tally);
     if (i < n) out[i] = (uint8_t)((hitmask >> lane) & 1u);
   }
   if (COUNT) {
@@ -510,9 +609,10 @@ __device__ __forceinline__ double wrap_pi(double a) {
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kThreads) check_edges_kernel(EnvDev E, const double *starts, const double *ends,
-                                                               long long m, double sample, int rot_mode, uint8_t *free_out,
-                                                               int32_t *first_hit) {
+__global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(EnvDev E, const double *starts,
+                                                                                const double *ends, long long m, double sample,
+                                                                                int rot_mode, uint8_t *free_out,
+                                                                                int32_t *first_hit) {
   extern __shared__ __align__(16) unsigned char smem[];
   RobotTri *srob = reinterpret_cast<RobotTri *>(smem);
   stage_robot(E, srob);
@@ -555,25 +655,19 @@ __global__ void __launch_bounds__(kThreads) check_edges_kernel(EnvDev E, const d
     int hit_index = 0;
     for (long long base = 1; base <= S && hit_index == 0; base += 32) {
       const long long idx = base + lane;
-      const bool valid = idx <= S && E.n_obst > 0;
+      const bool valid = idx <= S;
       const double di = (double)idx;
-      const double Tx = dadd(s[0], __ddiv_rn(dmul(di, dir[0]), parts));
-      const double Ty = dadd(s[1], __ddiv_rn(dmul(di, dir[1]), parts));
-      const double Tz = dadd(s[2], __ddiv_rn(dmul(di, dir[2]), parts));
-      double yaw = 0.0, pitch = 0.0, roll = 0.0;
+      LanePose<kFmtEulerF64> lp;
+      lp.clear();
+      lp.identity = rot_mode != SFFG_ROT_INTERPOLATE;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) lp.t[k] = dadd(s[k], __ddiv_rn(dmul(di, dir[k]), parts));
       if (rot_mode == SFFG_ROT_INTERPOLATE) {
-        yaw = dadd(s[3], __ddiv_rn(dmul(di, adir[0]), parts));
-        pitch = dadd(s[4], __ddiv_rn(dmul(di, adir[1]), parts));
-        roll = dadd(s[5], __ddiv_rn(dmul(di, adir[2]), parts));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) lp.a[k] = dadd(s[3 + k], __ddiv_rn(dmul(di, adir[k]), parts));
       }
-      const float thx = (float)Tx, thy = (float)Ty, thz = (float)Tz;
-      const float tlo = fabsf((float)(Tx - (double)thx)) + fabsf((float)(Ty - (double)thy)) + fabsf((float)(Tz - (double)thz));
-      const bool alive = valid && sphere_hits_root(E, thx, thy, thz, tlo);
-      float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
-      if (alive && rot_mode == SFFG_ROT_INTERPOLATE) rotation_f32((float)yaw, (float)pitch, (float)roll, R);
-      const unsigned am = __ballot_sync(kFull, alive);
       if (COUNT) nposes += valid ? 1 : 0;
-      const unsigned hm = run_survivors<COUNT>(E, ws, srob, am, R, Tx, Ty, Tz, yaw, pitch, roll, lane, true, tally);
+      const unsigned hm = check_32_poses<kFmtEulerF64, COUNT>(E, ws, srob, valid, lp, lane, true, tally);
       if (hm) hit_index = (int)(base + (__ffs(hm) - 1));
     }
     if (lane == 0) {
@@ -644,10 +738,6 @@ cudaError_t prep(K kernel, size_t smem) {
 
 }  // namespace
 
-size_t collide_smem_bytes(int n_robot) {
-  return (size_t)n_robot * sizeof(RobotTri) + (size_t)kWarpsPerBlock * sizeof(WarpScratch);
-}
-
 template <typename K>
 static int grid_for(K kernel, size_t smem, const LaunchCfg &cfg) {
   int per_sm = 0;
@@ -655,27 +745,45 @@ static int grid_for(K kernel, size_t smem, const LaunchCfg &cfg) {
   return cfg.sm_count * per_sm;
 }
 
-cudaError_t launch_collide_poses(const EnvDev &env, const void *d_poses, bool poses_f64, int64_t n, uint8_t *d_verdict,
+size_t collide_smem_bytes(int n_robot) {
+  return (size_t)n_robot * sizeof(RobotTri) + (size_t)kWarpsPerBlock * sizeof(WarpScratch);
+}
+
+
+template <int FMT>
+static cudaError_t launch_poses_fmt(const EnvDev &env, const void *d_poses, int64_t n, uint8_t *d_verdict, cudaStream_t stream,
+                                    const LaunchCfg &cfg, bool count) {
+  const size_t smem = collide_smem_bytes(env.n_robot);
+  const long long chunks = (n + 31) / 32;
+  const long long want = (chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  cudaError_t e;
+  if (count) {
+    auto k = collide_poses_kernel<FMT, true>;
+    if ((e = prep(k, smem)) != cudaSuccess) return e;
+    int grid = grid_for(k, smem, cfg);
+    if (want < grid) grid = (int)want;
+    k<<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict);
+  } else {
+    auto k = collide_poses_kernel<FMT, false>;
+    if ((e = prep(k, smem)) != cudaSuccess) return e;
+    int grid = grid_for(k, smem, cfg);
+    if (want < grid) grid = (int)want;
+    k<<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_collide_poses(const EnvDev &env, const void *d_poses, int pose_fmt, int64_t n, uint8_t *d_verdict,
                                  cudaStream_t stream, const LaunchCfg &cfg, bool count) {
   if (n <= 0) return cudaSuccess;
-  const size_t smem = collide_smem_bytes(env.n_robot);
   cudaError_t e = cudaMemsetAsync(env.work_counter, 0, sizeof(unsigned), stream);
   if (e != cudaSuccess) return e;
-#define SFFG_LAUNCH(F64, CNT)                                                                          \
-  {                                                                                                    \
-    auto k = collide_poses_kernel<F64, CNT>;                                                           \
-    e = prep(k, smem);                                                                                 \
-    if (e != cudaSuccess) return e;                                                                    \
-    long long chunks = (n + 31) / 32;                                                                  \
-    long long want = (chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;                                   \
-    int grid = grid_for(k, smem, cfg);                                                                 \
-    if (want < grid) grid = (int)want;                                                                 \
-    k<<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict);                        \
+  switch (pose_fmt) {
+    case 0: return launch_poses_fmt<kFmtEulerF32>(env, d_poses, n, d_verdict, stream, cfg, count);
+    case 1: return launch_poses_fmt<kFmtEulerF64>(env, d_poses, n, d_verdict, stream, cfg, count);
+    case 2: return launch_poses_fmt<kFmtMatrixF64>(env, d_poses, n, d_verdict, stream, cfg, count);
   }
-  if (poses_f64) { if (count) SFFG_LAUNCH(true, true) else SFFG_LAUNCH(true, false) }
-  else           { if (count) SFFG_LAUNCH(false, true) else SFFG_LAUNCH(false, false) }
-#undef SFFG_LAUNCH
-  return cudaGetLastError();
+  return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_check_edges(const EnvDev &env, const double *d_starts, const double *d_ends, int64_t m,

@@ -8,6 +8,8 @@ namespace sffg {
 
 struct EnvDev {
   const float4 *slots;      // 2 float4 per child slot, kWide slots per node
+  const float4 *top;        // <= 32 slots: a cut through the top of the hierarchy, tested by all lanes in step 0
+  int n_top;
   const float4 *tris32;     // 3 float4 per obstacle triangle (BVH leaf order); p[0].w = representation error bound
   const double *tris64;     // 9 doubles per obstacle triangle (BVH leaf order) -- exact stage
   const RobotTri *robot;    // n_robot records (FP32, robot frame)
@@ -28,7 +30,8 @@ struct LaunchCfg {
 };
 
 // verdict_out[i] = 1 if the robot at poses[i] touches the obstacle soup
-cudaError_t launch_collide_poses(const EnvDev &env, const void *d_poses, bool poses_f64, int64_t n,
+// pose_fmt: 0 = float [n][6] x y z yaw pitch roll, 1 = double [n][6], 2 = double [n][12] (R row-major, then T)
+cudaError_t launch_collide_poses(const EnvDev &env, const void *d_poses, int pose_fmt, int64_t n,
                                  uint8_t *d_verdict, cudaStream_t stream, const LaunchCfg &cfg, bool count);
 
 cudaError_t launch_check_edges(const EnvDev &env, const double *d_starts, const double *d_ends, int64_t m,

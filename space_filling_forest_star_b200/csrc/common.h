@@ -44,7 +44,7 @@ struct RobotTri {
   float h_lo[3], h_hi[3];   // same for the three h axes
   float lo[3], hi[3]; // AABB in the robot frame (rounded outward)
   float qmax;         // max |coordinate| of the three vertices (rounded up)
-  float pad[3];
+  float pad[7];       // 52 words per record: stride 20 mod 32 banks -> 6 consecutive records never share a bank
 };
 static_assert(sizeof(RobotTri) % 16 == 0, "RobotTri must be 16-byte granular");
 
@@ -54,6 +54,9 @@ struct HostBvh {
   int depth = 0;
   double root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
 };
+
+// picks <= 32 slots forming a cut through the top of the hierarchy (largest boxes expanded first)
+void top_cut(const HostBvh &bvh, std::vector<ChildSlot> *out);
 
 // builds an 8-wide AABB BVH over a double triangle soup; leaves are single triangles; slots refer to triangles by
 // their position in tri_order

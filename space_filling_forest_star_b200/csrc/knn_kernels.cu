@@ -35,8 +35,9 @@ __device__ __forceinline__ float wrapped_abs(float qa, float na) {
   return fminf(a, fabsf(t));
 }
 
+// translational part (all of the metric for DIM == 2): ((dx^2 + dy^2) + dz^2), float, unfused
 template <int DIM>
-__device__ __forceinline__ float metric(const float *nd, const float *q) {
+__device__ __forceinline__ float metric_lin(const float *nd, const float *q) {
   float d = __fsub_rn(nd[0], q[0]);
   float r = __fmul_rn(d, d);
   d = __fsub_rn(nd[1], q[1]);
@@ -44,12 +45,24 @@ __device__ __forceinline__ float metric(const float *nd, const float *q) {
   if (DIM == 6) {
     d = __fsub_rn(nd[2], q[2]);
     r = __fadd_rn(r, __fmul_rn(d, d));
-#pragma unroll
-    for (int c = 3; c < 6; ++c) {
-      const float w = wrapped_abs(q[c], nd[c]);
-      r = __fadd_rn(r, __fmul_rn(w, w));
-    }
   }
+  return r;
+}
+// angular part continues the same accumulator: (((r + wy^2) + wp^2) + wr^2).  Every term is >= 0 and round-to-nearest
+// addition is monotone, so metric_lin() is a lower bound of the full distance: a 32-node block whose translational
+// parts all reach the current k-th distance cannot contain a candidate and its angles are never loaded.
+__device__ __forceinline__ float metric_ang(float r, const float *na, const float *q) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float w = wrapped_abs(q[3 + c], na[c]);
+    r = __fadd_rn(r, __fmul_rn(w, w));
+  }
+  return r;
+}
+template <int DIM>
+__device__ __forceinline__ float metric(const float *nd, const float *q) {
+  float r = metric_lin<DIM>(nd, q);
+  if (DIM == 6) r = metric_ang(r, nd + 3, q);
   return r;
 }
 
@@ -92,6 +105,9 @@ struct TopK {
 // One warp = QW queries x one node slice.
 //   item = blockIdx.x * kWarps + warp;  group = item / slices;  slice = item % slices
 //   out_d / out_i: [nq][slices][k] when slices > 1 (partials), else the final [nq][k]
+// The node stream is software-pipelined: the next 32-node block is loaded into registers while the current one is
+// evaluated against the QW queries (QW independent dependency chains give the ILP), and one warp vote decides whether
+// any of the QW queries has a candidate in this block before the per-query ballots are taken.
 template <int DIM, int QW, int KPL>
 __global__ void __launch_bounds__(kThreads) knn_scan_kernel(IndexDev idx, const float *__restrict__ queries, long long nq,
                                                             int k, int slices, long long slice_len, float *out_d,
@@ -116,27 +132,58 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(IndexDev idx, const 
   const long long begin = (long long)slice * slice_len;
   long long end = begin + slice_len;
   if (end > idx.n) end = idx.n;
-  const float *__restrict__ base = idx.coords;
-  for (long long b = begin; b < end; b += 32) {
-    const long long i = b + lane;
-    float nd[DIM];
-    const bool valid = i < end;
+  const long long nblocks = end > begin ? (end - begin + 31) / 32 : 0;
+  constexpr int LIN = DIM == 6 ? 3 : 2;   // coordinates streamed for every block; the 3 angles only on demand
+  const float *ptr[LIN];
 #pragma unroll
-    for (int c = 0; c < DIM; ++c) nd[c] = valid ? __ldg(base + (long long)c * idx.capacity + i) : 0.f;
+  for (int c = 0; c < LIN; ++c) ptr[c] = idx.coords + (long long)c * idx.capacity + begin + lane;
+  float cur[LIN], nxt[LIN];
+  // capacity is a multiple of 32 and slices start at multiples of 32, so a whole block is always addressable; lanes
+  // past `end` read stale-but-allocated floats and are masked below
+#pragma unroll
+  for (int c = 0; c < LIN; ++c) cur[c] = nblocks > 0 ? __ldg(ptr[c]) : 0.f;
+  for (long long blk = 0; blk < nblocks; ++blk) {
+    const long long b = begin + blk * 32;
+    if (blk + 1 < nblocks) {
+#pragma unroll
+      for (int c = 0; c < LIN; ++c) {
+        ptr[c] += 32;
+        nxt[c] = __ldg(ptr[c]);
+      }
+    }
+    const bool valid = b + lane < end;
+    float d[QW];
+    bool any = false;
 #pragma unroll
     for (int w = 0; w < QW; ++w) {
-      const float d = valid ? metric<DIM>(nd, q[w]) : INFINITY;
-      unsigned mask = __ballot_sync(kFull, d < worst[w]);
-      while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const float cd = __shfl_sync(kFull, d, src);
-        if (cd < worst[w]) {
-          top[w].insert(cd, (int)(b + src), lane);
-          worst[w] = top[w].kth(k);
+      d[w] = metric_lin<DIM>(cur, q[w]);
+      d[w] = valid ? d[w] : INFINITY;
+      any |= d[w] < worst[w];
+    }
+    if (__any_sync(kFull, any)) {
+      if (DIM == 6) {
+        float ang[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ang[c] = __ldg(idx.coords + (long long)(3 + c) * idx.capacity + b + lane);
+#pragma unroll
+        for (int w = 0; w < QW; ++w) d[w] = valid ? metric_ang(d[w], ang, q[w]) : INFINITY;
+      }
+#pragma unroll
+      for (int w = 0; w < QW; ++w) {
+        unsigned mask = __ballot_sync(kFull, d[w] < worst[w]);
+        while (mask) {
+          const int src = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float cd = __shfl_sync(kFull, d[w], src);
+          if (cd < worst[w]) {
+            top[w].insert(cd, (int)(b + src), lane);
+            worst[w] = top[w].kth(k);
+          }
         }
       }
     }
+#pragma unroll
+    for (int c = 0; c < LIN; ++c) cur[c] = nxt[c];
   }
 #pragma unroll
   for (int w = 0; w < QW; ++w) {
@@ -321,7 +368,7 @@ cudaError_t launch_knn_kpl(const IndexDev &idx, const float *q, int64_t nq, int 
 
 KnnPlan plan_knn(int64_t nq, int64_t n, int sm_count) {
   KnnPlan p;
-  p.qw = nq >= 4 * (int64_t)sm_count * kWarps ? 4 : 1;
+  p.qw = nq >= 8192 ? 8 : (nq >= 1024 ? 4 : 1);
   p.groups = (nq + p.qw - 1) / p.qw;
   const int64_t want_warps = (int64_t)sm_count * kWarps * 4;
   int64_t slices = 1;
@@ -359,10 +406,12 @@ cudaError_t launch_knn(const IndexDev &idx, const float *d_queries, int64_t nq, 
   }
   cudaError_t e;
   if (idx.dim == 6) {
-    if (plan.qw == 4) e = launch_knn_kpl<6, 4>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
+    if (plan.qw == 8) e = launch_knn_kpl<6, 8>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
+    else if (plan.qw == 4) e = launch_knn_kpl<6, 4>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
     else e = launch_knn_kpl<6, 1>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
   } else {
-    if (plan.qw == 4) e = launch_knn_kpl<2, 4>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
+    if (plan.qw == 8) e = launch_knn_kpl<2, 8>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
+    else if (plan.qw == 4) e = launch_knn_kpl<2, 4>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
     else e = launch_knn_kpl<2, 1>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
   }
   if (e != cudaSuccess) return e;
@@ -378,9 +427,14 @@ cudaError_t launch_knn(const IndexDev &idx, const float *d_queries, int64_t nq, 
 
 template <bool FILL>
 static cudaError_t launch_radius_any(const IndexDev &idx, const float *q, int64_t nq, float r2, int *counts,
-                                     const long long *offsets, int *cursor, unsigned long long *keys, const KnnPlan &plan,
+                                     const long long *offsets, int *cursor, unsigned long long *keys, const KnnPlan &plan_in,
                                      cudaStream_t st) {
   if (nq <= 0) return cudaSuccess;
+  KnnPlan plan = plan_in;
+  if (plan.qw == 8) {   // the radius kernels are instantiated for 1 and 4 queries per warp
+    plan.qw = 4;
+    plan.groups = (nq + 3) / 4;
+  }
   const int64_t items = plan.groups * plan.slices;
   const unsigned grid = (unsigned)((items + kWarps - 1) / kWarps);
   if (idx.dim == 6) {

@@ -84,7 +84,7 @@ using namespace sffg;
 // ---------------------------------------------------------------------------------------------------------------
 struct sffg_env {
   EnvDev dev{};
-  void *d_slots = nullptr, *d_tris32 = nullptr, *d_tris64 = nullptr, *d_robot = nullptr, *d_robot64 = nullptr;
+  void *d_slots = nullptr, *d_top = nullptr, *d_tris32 = nullptr, *d_tris64 = nullptr, *d_robot = nullptr, *d_robot64 = nullptr;
   unsigned long long *d_counters = nullptr;
   int *d_status = nullptr;
   unsigned *d_work = nullptr;   // ring of 8 work counters
@@ -216,6 +216,7 @@ int sffg_env_destroy(sffg_env *env) {
     if (env->streams[s]) cudaStreamSynchronize(env->streams[s]);
   }
   cudaFree(env->d_slots);
+  cudaFree(env->d_top);
   cudaFree(env->d_tris32);
   cudaFree(env->d_tris64);
   cudaFree(env->d_robot);
@@ -307,6 +308,9 @@ int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot
     return e;
   };
   SFFG_ENV_CUDA(upload(&env->d_slots, bvh.slots.data(), bvh.slots.size() * sizeof(ChildSlot)));
+  std::vector<ChildSlot> top;
+  top_cut(bvh, &top);
+  SFFG_ENV_CUDA(upload(&env->d_top, top.data(), top.size() * sizeof(ChildSlot)));
   SFFG_ENV_CUDA(upload(&env->d_tris32, t32.data(), t32.size() * sizeof(TriF32)));
   SFFG_ENV_CUDA(upload(&env->d_tris64, t64.data(), t64.size() * sizeof(double)));
   SFFG_ENV_CUDA(upload(&env->d_robot, rob.data(), rob.size() * sizeof(RobotTri)));
@@ -319,6 +323,8 @@ int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot
   SFFG_ENV_CUDA(cudaMemset(env->d_work, 0, 8 * sizeof(unsigned)));
   for (int s = 0; s < 2; ++s) SFFG_ENV_CUDA(cudaStreamCreateWithFlags(&env->streams[s], cudaStreamNonBlocking));
   d.slots = reinterpret_cast<const float4 *>(env->d_slots);
+  d.top = reinterpret_cast<const float4 *>(env->d_top);
+  d.n_top = (int)top.size();
   d.tris32 = reinterpret_cast<const float4 *>(env->d_tris32);
   d.tris64 = reinterpret_cast<const double *>(env->d_tris64);
   d.robot = reinterpret_cast<const RobotTri *>(env->d_robot);
@@ -392,15 +398,15 @@ int sffg_env_sync_check(sffg_env *env) {
 int sffg_collide_poses_device(sffg_env *env, const void *d_poses, int poses_are_f64, int64_t n, uint8_t *d_verdict_out,
                               void *stream) {
   if (!env || n < 0 || (n > 0 && (!d_poses || !d_verdict_out))) return fail(SFFG_ERR_ARG, "sffg_collide_poses_device: bad arguments");
-  SFFG_CUDA(launch_collide_poses(env_view(env), d_poses, poses_are_f64 != 0, n, d_verdict_out, (cudaStream_t)stream, env->cfg,
+  SFFG_CUDA(launch_collide_poses(env_view(env), d_poses, poses_are_f64 ? 1 : 0, n, d_verdict_out, (cudaStream_t)stream, env->cfg,
                                  env->count));
   return SFFG_OK;
 }
 
-static int collide_poses_host(sffg_env *env, const void *poses, bool f64, int64_t n, uint8_t *verdict_out) {
+static int collide_poses_host(sffg_env *env, const void *poses, int fmt, int64_t n, uint8_t *verdict_out) {
   if (!env || n < 0 || (n > 0 && (!poses || !verdict_out))) return fail(SFFG_ERR_ARG, "sffg_collide_poses: bad arguments");
   if (n == 0) return SFFG_OK;
-  const size_t psz = f64 ? 48 : 24;
+  const size_t psz = fmt == 0 ? 24 : (fmt == 1 ? 48 : 96);
   const int64_t chunk = 1 << 20;
   int s = 0;
   for (int64_t off = 0; off < n; off += chunk, s ^= 1) {
@@ -411,7 +417,7 @@ static int collide_poses_host(sffg_env *env, const void *poses, bool f64, int64_
     if (rc == SFFG_OK) rc = env->out[s].reserve((size_t)cnt);
     if (rc != SFFG_OK) return rc;
     SFFG_CUDA(cudaMemcpyAsync(env->in[s].p, (const char *)poses + (size_t)off * psz, (size_t)cnt * psz, cudaMemcpyHostToDevice, st));
-    SFFG_CUDA(launch_collide_poses(env_view(env), env->in[s].p, f64, cnt, (uint8_t *)env->out[s].p, st, env->cfg, env->count));
+    SFFG_CUDA(launch_collide_poses(env_view(env), env->in[s].p, fmt, cnt, (uint8_t *)env->out[s].p, st, env->cfg, env->count));
     SFFG_CUDA(cudaMemcpyAsync(verdict_out + off, env->out[s].p, (size_t)cnt, cudaMemcpyDeviceToHost, st));
   }
   SFFG_CUDA(cudaStreamSynchronize(env->streams[0]));
@@ -420,10 +426,13 @@ static int collide_poses_host(sffg_env *env, const void *poses, bool f64, int64_
 }
 
 int sffg_collide_poses_f32(sffg_env *env, const float *poses, int64_t n, uint8_t *verdict_out) {
-  return collide_poses_host(env, poses, false, n, verdict_out);
+  return collide_poses_host(env, poses, 0, n, verdict_out);
 }
 int sffg_collide_poses_f64(sffg_env *env, const double *poses, int64_t n, uint8_t *verdict_out) {
-  return collide_poses_host(env, poses, true, n, verdict_out);
+  return collide_poses_host(env, poses, 1, n, verdict_out);
+}
+int sffg_collide_transforms_f64(sffg_env *env, const double *rt, int64_t n, uint8_t *verdict_out) {
+  return collide_poses_host(env, rt, 2, n, verdict_out);
 }
 
 int sffg_check_edges_device(sffg_env *env, const double *d_starts, const double *d_ends, int64_t m, double sample_dist,

@@ -102,6 +102,15 @@ class Environment:
         check(fn(self._h, _ptr(p) if len(p) else None, len(p), _ptr(out) if len(p) else None))
         return out
 
+    def CollideTransforms(self, R, T) -> np.ndarray:
+        """RAPID_Collide's own argument form: R [n][3][3] row-major rotation of the robot, T [n][3] -> uint8[n]."""
+        R = np.asarray(R, dtype=np.float64).reshape(-1, 9)
+        T = np.asarray(T, dtype=np.float64).reshape(-1, 3)
+        rt = np.ascontiguousarray(np.concatenate([R, T], axis=1))
+        out = np.empty(len(rt), dtype=np.uint8)
+        check(self._L.sffg_collide_transforms_f64(self._h, _ptr(rt) if len(rt) else None, len(rt), _ptr(out) if len(rt) else None))
+        return out
+
     def collide_host_buffers(self, poses_ptr: int, is_f64: bool, n: int, out_ptr: int) -> None:
         """Raw host-pointer form of Collide (pinned buffers from the caller), used by bench.py's e2e leg."""
         fn = self._L.sffg_collide_poses_f64 if is_f64 else self._L.sffg_collide_poses_f32

@@ -107,3 +107,12 @@ def test_translated_world_far_from_origin(sff, orc, meshes):
     got = env.Collide(poses)
     bad = np.nonzero(got != want)[0]
     assert len(bad) == 0, (bad[:10], orc.pose_margin(obst, meshes[rn], poses[bad[:10]]))
+
+
+def test_transform_entry_point_matches_euler(sff, orc, meshes, gold_collision):
+    """sffg_collide_transforms_f64 takes what RAPID_Collide takes (R2, T2): same verdicts as the Euler form"""
+    env = make_env(sff, meshes, "B")
+    poses = gold_collision["B_poses"].astype(np.float64)
+    R = np.stack([orc.rotation(p) for p in poses])
+    got = env.CollideTransforms(R, poses[:, :3])
+    np.testing.assert_array_equal(got, gold_collision["B_verdict"])
