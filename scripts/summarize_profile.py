@@ -74,7 +74,7 @@ def main():
     txt = launches(tag)
     if txt:
         (OUT / f"{tag}_launches.txt").write_text(txt)
-    kernels = {"collide": "collide_poses_kernelILb0ELb0", "knn": "knn_scan_kernelILi6", "edges": "check_edges_kernelILb0"}
+    kernels = {"collide": "collide_poses_kernelILi0ELb0", "knn": "knn_scan_kernelILi6", "edges": "check_edges_kernelILb0"}
     for name, key in kernels.items():
         rep = SRC / f"{tag}_{name}.ncu-rep"
         if not rep.exists():
