@@ -148,11 +148,16 @@ static double tri_pair_margin(const double P1[3], const double P2[3], const doub
  * ---------------------------------------------------------------------------------------------- */
 typedef struct { double mR[3][3]; double mT[3]; double R2[3][3]; double T2[3]; } orc_xform;
 
+static void finish_xform(orc_xform *x);
 static void make_xform(const double pose[6], orc_xform *x) {
-    static const double R1[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    const double T1[3] = {0, 0, 0};
     orc_rotation(pose, x->R2);
     x->T2[0] = pose[0]; x->T2[1] = pose[1]; x->T2[2] = pose[2];
+    finish_xform(x);
+}
+/* x->R2, x->T2 given -> mR, mT */
+static void finish_xform(orc_xform *x) {
+    static const double R1[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    const double T1[3] = {0, 0, 0};
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j)
             x->mR[i][j] = x->R2[0][i] * R1[0][j] + x->R2[1][i] * R1[1][j] + x->R2[2][i] * R1[2][j];
@@ -529,10 +534,25 @@ static void collide_rec(orc_query *q, int b1i, int b2i, const double R[3][3], co
     }
 }
 
+static int collide_obbtree_x(const orc_model *obst, const orc_model *robot, const orc_xform *xp, int first_contact,
+                             int64_t counters[4]);
 /* RAPID_Collide(I, 0, obstacle, R(pose), T(pose), robot, flag).  counters[4] += {box, tri, desc, contacts} */
 ORC_API int orc_collide_obbtree(const orc_model *obst, const orc_model *robot, const double pose[6],
                                 int first_contact, int64_t counters[4]) {
     orc_xform x; make_xform(pose, &x);
+    return collide_obbtree_x(obst, robot, &x, first_contact, counters);
+}
+/* same, but with RAPID_Collide's own arguments (R2 row-major, T2): what the CPU RAPID.H stand-in forwards */
+ORC_API int orc_collide_obbtree_rt(const orc_model *obst, const orc_model *robot, const double R2[3][3], const double T2[3],
+                                   int first_contact, int64_t counters[4]) {
+    orc_xform x;
+    memcpy(x.R2, R2, sizeof x.R2); memcpy(x.T2, T2, sizeof x.T2);
+    finish_xform(&x);
+    return collide_obbtree_x(obst, robot, &x, first_contact, counters);
+}
+static int collide_obbtree_x(const orc_model *obst, const orc_model *robot, const orc_xform *xp, int first_contact,
+                             int64_t counters[4]) {
+    orc_xform x = *xp;
     static const double R1[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
     const double T1[3] = {0, 0, 0};
     double tR1[3][3], tR2[3][3], tT1[3], tT2[3], R[3][3], T[3], u[3];

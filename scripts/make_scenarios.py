@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Writes runnable planner scenarios (mesh files + XML configs in the reference's schema, README.md:45-274) into a
+directory, from the committed triangle soups in tests/golden/meshes.npz.
+
+    python scripts/make_scenarios.py <out_dir>
+
+The reference's own mesh files cannot travel to the GPU box, so the soups (already offset+scaled by the reference
+loader) are written back as OBJ / .tri text with 17 significant digits and every config uses scale="1" with lengths
+pre-multiplied: both the reference host and the engine then load bit-identical triangles.  All three shipped configs
+are rejected by the reference's own validation, hence solver="sff" variants.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def write_obj(path, tris):
+    with open(path, "w") as f:
+        f.write("o soup\n")
+        for t in tris.reshape(-1, 3):
+            f.write("v %.17g %.17g %.17g\n" % tuple(t))
+        for i in range(len(tris)):
+            f.write("f %d %d %d\n" % (3 * i + 1, 3 * i + 2, 3 * i + 3))
+
+
+def write_tri(path, tris):
+    with open(path, "w") as f:
+        for t in tris:
+            f.write(" ".join("%.17g %.17g" % (v[0], v[1]) for v in t) + "\n")
+
+
+CONFIG = """<?xml version="1.0" ?>
+<Problem solver="{solver}" optimize="{optimize}" smoothing="false" scale="1" dim="{dim}">
+  <ObjectDelimiters standard=" " name="_"/>
+  <Robot file="{robot}" is_obj="true"/>
+  <Environment collision="0.1">
+    <Obstacle file="{obstacle}" is_obj="{obst_is_obj}" position="[0; 0; 0]"/>
+  </Environment>
+  <Points>
+{points}
+  </Points>
+  <Range autoDetect="false">
+    <RangeX min="{r[0]}" max="{r[1]}" />
+    <RangeY min="{r[2]}" max="{r[3]}" />
+    <RangeZ min="{r[4]}" max="{r[5]}" />
+  </Range>
+  <Distances dtree="{dtree}" circum="{circum}"/>
+  <Improvements priorityBias="0"/>
+  <Thresholds standard="5"/>
+  <MaxIterations value="{maxiter}"/>
+  <Save>
+    <Params file="output//params_{name}.csv" id="{name}"/>
+  </Save>
+</Problem>
+"""
+
+SCENARIOS = {
+    # test_building.xml:9-23 (points, range, dtree 0.5, circum 0.4, all x scale 10), solver sff
+    "building": dict(dim="3D", robot="robot_small_s10.obj", obstacle="building_s10.obj", obst_is_obj="true",
+                     points=[[-53.76207930019596, -53.38214644384135, 7.519141368058615],
+                             [53.09629695920314, -53.435510614853206, 22.25339932086428],
+                             [-54.45894591081855, 49.42949264187298, 80.34669391216193],
+                             [34.004901456614443, 3.800196290706541, 100.0],
+                             [3.0319967716688234, 0.57430173261578954, 70.0]],
+                     r=[-70, 70, -70, 70, 0, 140], dtree=5, circum=4, maxiter=100000),
+    # test_triang.xml:8-22 (x scale 10), solver sff, robot_small as BASELINE.json names it
+    "triang": dict(dim="3D", robot="robot_small_s10.obj", obstacle="triang_s10.obj", obst_is_obj="true",
+                   points=[[-15, 40, 30], [29, 3, 70], [27, -34, 50], [-39.6, -24, 10], [42, 35, 10], [-43, 35, 80]],
+                   r=[-100, 100, -100, 100, 0, 100], dtree=5, circum=4, maxiter=100000),
+    # BASELINE.json configs[0]: 2-D SFF* on maps/triangles.tri (test_2D.xml distances: dtree 100, circum 80)
+    "2d": dict(dim="2D", robot="robot_small_s1.obj", obstacle="triangles.tri", obst_is_obj="false",
+               points=[[60, 60, 0], [950, 650, 0], [80, 640, 0], [930, 70, 0]],
+               r=[-10, 1010, -10, 710, 0, 0], dtree=100, circum=80, maxiter=100000),
+}
+
+
+def main():
+    out = Path(sys.argv[1] if len(sys.argv) > 1 else "scenarios")
+    out.mkdir(parents=True, exist_ok=True)
+    (out / "output").mkdir(exist_ok=True)
+    m = np.load(ROOT / "tests" / "golden" / "meshes.npz")
+    write_obj(out / "building_s10.obj", m["building_s10"])
+    write_obj(out / "triang_s10.obj", m["triang_s10"])
+    write_obj(out / "robot_small_s10.obj", m["robot_small_s10"])
+    write_obj(out / "robot_small_s1.obj", m["robot_small_s1"])
+    write_obj(out / "robot_cyl_small_s10.obj", m["robot_cyl_small_s10"])
+    write_tri(out / "triangles.tri", m["triangles_tri"])
+    for name, sc in SCENARIOS.items():
+        for solver, optimize in (("sff", "true"), ("sff", "false"), ("rrt", "true")):
+            if solver == "rrt" and len(sc["points"]) > 1:
+                continue   # the reference rejects multi-root RRT* (src/main.cpp:286-287)
+            tag = f"{name}_{solver}{'star' if optimize == 'true' else ''}"
+            pts = "\n".join('    <Point coord="[%.17g; %.17g; %.17g]"/>' % tuple(p) for p in sc["points"])
+            cfg = CONFIG.format(solver=solver, optimize=optimize, name=tag, points=pts, **{k: v for k, v in sc.items() if k != "points"})
+            (out / f"{tag}.xml").write_text(cfg)
+    print("scenarios written to", out)
+
+
+if __name__ == "__main__":
+    main()
