@@ -419,7 +419,7 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *
       sp += __popc(m_int);
       ntri += __popc(m_leaf);
       if (sp > kStackCap) {     // never silently drop work: flag the launch as failed
-        if (lane == 0) atomicExch(E.status, 1);
+        if (lane == 0) *reinterpret_cast<volatile int *>(E.status) = 1;
         sp = kStackCap;
       }
       __syncwarp();
@@ -569,27 +569,30 @@ __device__ __forceinline__ unsigned check_32_poses(const EnvDev &E, WarpScratch 
 
 template <int FMT, bool COUNT>
 __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) collide_poses_kernel(EnvDev E, const void *poses, long long n,
-                                                                                  uint8_t *out) {
+                                                                                  uint8_t *out, int chunk) {
   extern __shared__ __align__(16) unsigned char smem[];
   RobotTri *srob = reinterpret_cast<RobotTri *>(smem);
   stage_robot(E, srob);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + (size_t)E.n_robot * sizeof(RobotTri))[warp];
-  const long long nchunks = (n + 31) / 32;
+  // a work unit is `chunk` (1..32) consecutive poses: 32 for large batches (full lanes in phase A), fewer when the
+  // batch is too small to give every resident warp a unit (planner-sized calls are latency-, not throughput-bound)
+  const long long nchunks = (n + chunk - 1) / chunk;
   Tally tally = {0, 0, 0, 0};
   unsigned long long nposes = 0;
   while (true) {
     unsigned c = 0;
-    if (lane == 0) c = atomicAdd(E.work_counter, 1u);
+    if (lane == 0) c = atomicAdd(E.work_counter, 1u) - E.work_base;
     c = __shfl_sync(kFull, c, 0);
     if ((long long)c >= nchunks) break;
-    const long long i = (long long)c * 32 + lane;
+    const long long i = (long long)c * chunk + lane;
+    const bool mine = lane < chunk && i < n;
     LanePose<FMT> lp;
-    if (i < n) lp.load(poses, i);
+    if (mine) lp.load(poses, i);
     else lp.clear();
-    if (COUNT) nposes += (i < n) ? 1 : 0;
-    const unsigned hitmask = check_32_poses<FMT, COUNT>(E, ws, srob, i < n, lp, lane, false, tally);
-    if (i < n) out[i] = (uint8_t)((hitmask >> lane) & 1u);
+    if (COUNT) nposes += mine ? 1 : 0;
+    const unsigned hitmask = check_32_poses<FMT, COUNT>(E, ws, srob, mine, lp, lane, false, tally);
+    if (mine) out[i] = (uint8_t)((hitmask >> lane) & 1u);
   }
   if (COUNT) {
 #pragma unroll
@@ -608,11 +611,18 @@ __device__ __forceinline__ double wrap_pi(double a) {
   return a;
 }
 
+// `split` (power of two) warps share one edge: warp j of an edge takes the samples with (index - 1) % split == j, so a
+// planner-sized batch still occupies the whole GPU and the serial phase B of one warp covers 1/split of the samples.
+// With split > 1 the per-edge minimum colliding index is combined with atomicMin in `fh` (pre-set to kNoHit) and warps
+// stop as soon as an earlier hit than anything they could still find is published; finalize_edges_kernel then writes
+// the outputs.  split == 1 writes them directly.
+constexpr int kNoHit = 0x7f7f7f7f;   // what cudaMemsetAsync(..., 0x7f, ...) produces
+
 template <bool COUNT>
 __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(EnvDev E, const double *starts,
                                                                                 const double *ends, long long m, double sample,
                                                                                 int rot_mode, uint8_t *free_out,
-                                                                                int32_t *first_hit) {
+                                                                                int32_t *first_hit, int split, int *fh) {
   extern __shared__ __align__(16) unsigned char smem[];
   RobotTri *srob = reinterpret_cast<RobotTri *>(smem);
   stage_robot(E, srob);
@@ -620,11 +630,14 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(
   WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + (size_t)E.n_robot * sizeof(RobotTri))[warp];
   Tally tally = {0, 0, 0, 0};
   unsigned long long nposes = 0;
+  const long long units = m * split;
   while (true) {
-    unsigned eidx = 0;
-    if (lane == 0) eidx = atomicAdd(E.work_counter, 1u);
-    eidx = __shfl_sync(kFull, eidx, 0);
-    if ((long long)eidx >= m) break;
+    unsigned u = 0;
+    if (lane == 0) u = atomicAdd(E.work_counter, 1u) - E.work_base;
+    u = __shfl_sync(kFull, u, 0);
+    if ((long long)u >= units) break;
+    const unsigned eidx = u / (unsigned)split;
+    const int part = (int)(u - eidx * (unsigned)split);
     double s[6], f[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -650,11 +663,12 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(
     long long S = 0;
     if (parts > 1.0) {
       const double cl = ceil(parts);
-      S = (cl > 4.0e9 ? 4000000000LL : (long long)cl) - 1;
+      S = (cl > 2.0e9 ? 2000000000LL : (long long)cl) - 1;
     }
     int hit_index = 0;
-    for (long long base = 1; base <= S && hit_index == 0; base += 32) {
-      const long long idx = base + lane;
+    for (long long base = 1 + part; base <= S && hit_index == 0; base += 32LL * split) {
+      if (split > 1 && *reinterpret_cast<volatile int *>(fh + eidx) < base) break;   // an earlier hit is already known
+      const long long idx = base + (long long)lane * split;
       const bool valid = idx <= S;
       const double di = (double)idx;
       LanePose<kFmtEulerF64> lp;
@@ -668,11 +682,15 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(
       }
       if (COUNT) nposes += valid ? 1 : 0;
       const unsigned hm = check_32_poses<kFmtEulerF64, COUNT>(E, ws, srob, valid, lp, lane, true, tally);
-      if (hm) hit_index = (int)(base + (__ffs(hm) - 1));
+      if (hm) hit_index = (int)(base + (long long)(__ffs(hm) - 1) * split);
     }
     if (lane == 0) {
-      free_out[eidx] = hit_index == 0 ? 1 : 0;
-      if (first_hit) first_hit[eidx] = hit_index;
+      if (split > 1) {
+        if (hit_index) atomicMin(fh + eidx, hit_index);
+      } else {
+        free_out[eidx] = hit_index == 0 ? 1 : 0;
+        if (first_hit) first_hit[eidx] = hit_index;
+      }
     }
   }
   if (COUNT) {
@@ -680,6 +698,14 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(
     for (int sft = 16; sft > 0; sft >>= 1) nposes += __shfl_xor_sync(kFull, nposes, sft);
     flush_tally(E, tally, nposes, lane);
   }
+}
+
+__global__ void finalize_edges_kernel(const int *fh, long long m, uint8_t *free_out, int32_t *first_hit) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int v = fh[i];
+  free_out[i] = v == kNoHit ? 1 : 0;
+  if (first_hit) first_hit[i] = v == kNoHit ? 0 : v;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -731,18 +757,28 @@ __global__ void gen_poses_kernel(unsigned long long seed, unsigned long long fir
   o[5] = __fadd_rn(-3.14159274f, __fmul_rn(u01(b[2]), 6.28318548f));
 }
 
-template <typename K>
-cudaError_t prep(K kernel, size_t smem) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-}
 
 }  // namespace
 
-template <typename K>
-static int grid_for(K kernel, size_t smem, const LaunchCfg &cfg) {
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-  return cfg.sm_count * per_sm;
+// cudaFuncSetAttribute + occupancy are queried once per kernel instantiation (and per shared-memory size)
+struct KernelCfg {
+  size_t smem = ~size_t(0);
+  int per_sm = 1;
+  cudaError_t err = cudaSuccess;
+};
+template <auto Kernel>
+static const KernelCfg &kernel_cfg(size_t smem) {
+  static KernelCfg c;
+  if (c.smem != smem) {
+    c.smem = smem;
+    c.err = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    if (c.err == cudaSuccess &&
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, Kernel, kThreads, smem) != cudaSuccess || per_sm < 1))
+      per_sm = 1;
+    c.per_sm = per_sm < 1 ? 1 : per_sm;
+  }
+  return c;
 }
 
 size_t collide_smem_bytes(int n_robot) {
@@ -752,60 +788,89 @@ size_t collide_smem_bytes(int n_robot) {
 
 template <int FMT>
 static cudaError_t launch_poses_fmt(const EnvDev &env, const void *d_poses, int64_t n, uint8_t *d_verdict, cudaStream_t stream,
-                                    const LaunchCfg &cfg, bool count) {
+                                    const LaunchCfg &cfg, bool count, int chunk, int *grid_out) {
   const size_t smem = collide_smem_bytes(env.n_robot);
-  const long long chunks = (n + 31) / 32;
+  const long long chunks = (n + chunk - 1) / chunk;
   const long long want = (chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
   cudaError_t e;
   if (count) {
-    auto k = collide_poses_kernel<FMT, true>;
-    if ((e = prep(k, smem)) != cudaSuccess) return e;
-    int grid = grid_for(k, smem, cfg);
+    const KernelCfg &kc = kernel_cfg<collide_poses_kernel<FMT, true>>(smem);
+    if ((e = kc.err) != cudaSuccess) return e;
+    int grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;
-    k<<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict);
+    *grid_out = grid;
+    collide_poses_kernel<FMT, true><<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict, chunk);
   } else {
-    auto k = collide_poses_kernel<FMT, false>;
-    if ((e = prep(k, smem)) != cudaSuccess) return e;
-    int grid = grid_for(k, smem, cfg);
+    const KernelCfg &kc = kernel_cfg<collide_poses_kernel<FMT, false>>(smem);
+    if ((e = kc.err) != cudaSuccess) return e;
+    int grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;
-    k<<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict);
+    *grid_out = grid;
+    collide_poses_kernel<FMT, false><<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict, chunk);
   }
   return cudaGetLastError();
 }
 
-cudaError_t launch_collide_poses(const EnvDev &env, const void *d_poses, int pose_fmt, int64_t n, uint8_t *d_verdict,
-                                 cudaStream_t stream, const LaunchCfg &cfg, bool count) {
+// every warp of the grid leaves its loop through exactly one failing fetch, so a launch consumes
+// (units + grid * warps) values of the shared counter; the host advances the base instead of resetting the counter
+cudaError_t launch_collide_poses(const EnvDev &env_in, const void *d_poses, int pose_fmt, int64_t n, uint8_t *d_verdict,
+                                 cudaStream_t stream, const LaunchCfg &cfg, bool count, unsigned *work_base_io) {
   if (n <= 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(env.work_counter, 0, sizeof(unsigned), stream);
-  if (e != cudaSuccess) return e;
+  EnvDev env = env_in;
+  env.work_base = *work_base_io;
+  int grid = 0;
+  // poses per work unit: enough units for ~2 per resident warp (at 2 CTAs/SM), capped at a full warp
+  int chunk = 32;
+  const long long warps = (long long)cfg.sm_count * 2 * kWarpsPerBlock * 2;
+  while (chunk > 1 && (n + chunk - 1) / chunk < warps) chunk >>= 1;
+  cudaError_t e = cudaErrorInvalidValue;
   switch (pose_fmt) {
-    case 0: return launch_poses_fmt<kFmtEulerF32>(env, d_poses, n, d_verdict, stream, cfg, count);
-    case 1: return launch_poses_fmt<kFmtEulerF64>(env, d_poses, n, d_verdict, stream, cfg, count);
-    case 2: return launch_poses_fmt<kFmtMatrixF64>(env, d_poses, n, d_verdict, stream, cfg, count);
+    case 0: e = launch_poses_fmt<kFmtEulerF32>(env, d_poses, n, d_verdict, stream, cfg, count, chunk, &grid); break;
+    case 1: e = launch_poses_fmt<kFmtEulerF64>(env, d_poses, n, d_verdict, stream, cfg, count, chunk, &grid); break;
+    case 2: e = launch_poses_fmt<kFmtMatrixF64>(env, d_poses, n, d_verdict, stream, cfg, count, chunk, &grid); break;
   }
-  return cudaErrorInvalidValue;
+  if (e == cudaSuccess) *work_base_io += (unsigned)((n + chunk - 1) / chunk) + (unsigned)grid * kWarpsPerBlock;
+  return e;
 }
 
-cudaError_t launch_check_edges(const EnvDev &env, const double *d_starts, const double *d_ends, int64_t m,
+cudaError_t launch_check_edges(const EnvDev &env_in, const double *d_starts, const double *d_ends, int64_t m,
                                double sample_dist, int rot_mode, uint8_t *d_free, int32_t *d_first_hit, cudaStream_t stream,
-                               const LaunchCfg &cfg, bool count) {
+                               const LaunchCfg &cfg, bool count, unsigned *work_base_io, int *d_fh_scratch) {
   if (m <= 0) return cudaSuccess;
+  EnvDev env = env_in;
+  env.work_base = *work_base_io;
   const size_t smem = collide_smem_bytes(env.n_robot);
-  cudaError_t e = cudaMemsetAsync(env.work_counter, 0, sizeof(unsigned), stream);
-  if (e != cudaSuccess) return e;
-#define SFFG_LAUNCH(CNT)                                                                               \
-  {                                                                                                    \
-    auto k = check_edges_kernel<CNT>;                                                                  \
-    e = prep(k, smem);                                                                                 \
-    if (e != cudaSuccess) return e;                                                                    \
-    long long want = (m + kWarpsPerBlock - 1) / kWarpsPerBlock;                                        \
-    int grid = grid_for(k, smem, cfg);                                                                 \
-    if (want < grid) grid = (int)want;                                                                 \
-    k<<<grid, kThreads, smem, stream>>>(env, d_starts, d_ends, (long long)m, sample_dist, rot_mode, d_free, d_first_hit); \
+  // warps per edge: enough units for ~2 per resident warp, at most 32 (needs the scratch array)
+  int split = 1;
+  const long long warps = (long long)cfg.sm_count * 2 * kWarpsPerBlock * 2;
+  if (d_fh_scratch)
+    while (split < 32 && m * split < warps) split <<= 1;
+  const long long units = m * split;
+  const long long want = (units + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  cudaError_t e;
+  if (split > 1 && (e = cudaMemsetAsync(d_fh_scratch, 0x7f, (size_t)m * sizeof(int), stream)) != cudaSuccess) return e;
+  int grid;
+  if (count) {
+    const KernelCfg &kc = kernel_cfg<check_edges_kernel<true>>(smem);
+    if ((e = kc.err) != cudaSuccess) return e;
+    grid = cfg.sm_count * kc.per_sm;
+    if (want < grid) grid = (int)want;
+    check_edges_kernel<true><<<grid, kThreads, smem, stream>>>(env, d_starts, d_ends, (long long)m, sample_dist, rot_mode, d_free, d_first_hit, split, d_fh_scratch);
+  } else {
+    const KernelCfg &kc = kernel_cfg<check_edges_kernel<false>>(smem);
+    if ((e = kc.err) != cudaSuccess) return e;
+    grid = cfg.sm_count * kc.per_sm;
+    if (want < grid) grid = (int)want;
+    check_edges_kernel<false><<<grid, kThreads, smem, stream>>>(env, d_starts, d_ends, (long long)m, sample_dist, rot_mode, d_free, d_first_hit, split, d_fh_scratch);
   }
-  if (count) SFFG_LAUNCH(true) else SFFG_LAUNCH(false)
-#undef SFFG_LAUNCH
-  return cudaGetLastError();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  *work_base_io += (unsigned)units + (unsigned)grid * kWarpsPerBlock;
+  if (split > 1) {
+    finalize_edges_kernel<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(d_fh_scratch, (long long)m, d_free, d_first_hit);
+    e = cudaGetLastError();
+  }
+  return e;
 }
 
 cudaError_t launch_gen_poses(uint64_t seed, uint64_t first, int64_t n, const float range[6], float *d_out,

@@ -21,7 +21,8 @@ struct EnvDev {
   float rob_radius;             // max |robot vertex| about the robot origin (rounded up)
   unsigned long long *counters; // 5 x u64 (may be null): poses, past_root, box_tests, pair_tests, exact_tests
   int *status;                  // device int, set non-zero on traversal-stack overflow
-  unsigned int *work_counter;   // persistent-kernel work distribution
+  unsigned int *work_counter;   // persistent-kernel work distribution: never reset, units are (fetched value - work_base)
+  unsigned int work_base;
 };
 
 struct LaunchCfg {
@@ -32,11 +33,13 @@ struct LaunchCfg {
 // verdict_out[i] = 1 if the robot at poses[i] touches the obstacle soup
 // pose_fmt: 0 = float [n][6] x y z yaw pitch roll, 1 = double [n][6], 2 = double [n][12] (R row-major, then T)
 cudaError_t launch_collide_poses(const EnvDev &env, const void *d_poses, int pose_fmt, int64_t n,
-                                 uint8_t *d_verdict, cudaStream_t stream, const LaunchCfg &cfg, bool count);
+                                 uint8_t *d_verdict, cudaStream_t stream, const LaunchCfg &cfg, bool count,
+                                 unsigned *work_base_io);
 
 cudaError_t launch_check_edges(const EnvDev &env, const double *d_starts, const double *d_ends, int64_t m,
                                double sample_dist, int rot_mode, uint8_t *d_free, int32_t *d_first_hit,
-                               cudaStream_t stream, const LaunchCfg &cfg, bool count);
+                               cudaStream_t stream, const LaunchCfg &cfg, bool count, unsigned *work_base_io,
+                               int *d_fh_scratch /* m ints, or null to force one warp per edge */);
 
 cudaError_t launch_gen_poses(uint64_t seed, uint64_t first, int64_t n, const float range[6], float *d_out,
                              cudaStream_t stream);

@@ -27,6 +27,9 @@ int fail(int code, const std::string &msg) {
 
 namespace {
 
+constexpr size_t kSmallBytes = 1 << 20;        // staging for small calls: inputs in the first 3/4, outputs in the last 1/4
+constexpr size_t kSmallIn = 768 << 10;
+
 struct Runtime {
   bool ready = false;
   int device = -1;
@@ -86,11 +89,13 @@ struct sffg_env {
   EnvDev dev{};
   void *d_slots = nullptr, *d_top = nullptr, *d_tris32 = nullptr, *d_tris64 = nullptr, *d_robot = nullptr, *d_robot64 = nullptr;
   unsigned long long *d_counters = nullptr;
-  int *d_status = nullptr;
-  unsigned *d_work = nullptr;   // ring of 8 work counters
+  int *h_status = nullptr;      // pinned + device-mapped: the kernels raise it, the host reads it without a copy
+  unsigned *d_work = nullptr;   // ring of 8 work counters (never reset; see launch_collide_poses)
+  unsigned work_base[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int work_next = 0;
+  unsigned char *h_small = nullptr;   // pinned + device-mapped staging for small calls (planner-sized batches)
   cudaStream_t streams[2] = {nullptr, nullptr};
-  DevBuf in[2], out[2], aux[2];
+  DevBuf in[2], out[2], aux[2], fh;   // fh: per-edge first-hit scratch of small edge batches
   bool count = false;
   sffg_env_info_t info{};
   LaunchCfg cfg{};
@@ -102,6 +107,7 @@ struct sffg_index {
   int64_t cap = 0, n = 0;
   cudaStream_t stream = nullptr;
   DevBuf q, ids, d2, scratch, counts, offsets, cursor, keys, stage;
+  unsigned char *h_small = nullptr;   // pinned + device-mapped staging for planner-sized queries
 };
 
 extern "C" {
@@ -222,12 +228,14 @@ int sffg_env_destroy(sffg_env *env) {
   cudaFree(env->d_robot);
   cudaFree(env->d_robot64);
   cudaFree(env->d_counters);
-  cudaFree(env->d_status);
+  if (env->h_status) cudaFreeHost(env->h_status);
+  if (env->h_small) cudaFreeHost(env->h_small);
   cudaFree(env->d_work);
   for (int s = 0; s < 2; ++s) {
     env->in[s].release();
     env->out[s].release();
     env->aux[s].release();
+    env->fh.release();
     if (env->streams[s]) cudaStreamDestroy(env->streams[s]);
   }
   delete env;
@@ -317,8 +325,9 @@ int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot
   SFFG_ENV_CUDA(upload(&env->d_robot64, robot_tris, 9 * (size_t)n_robot * sizeof(double)));
   SFFG_ENV_CUDA(cudaMalloc((void **)&env->d_counters, 5 * sizeof(unsigned long long)));
   SFFG_ENV_CUDA(cudaMemset(env->d_counters, 0, 5 * sizeof(unsigned long long)));
-  SFFG_ENV_CUDA(cudaMalloc((void **)&env->d_status, sizeof(int)));
-  SFFG_ENV_CUDA(cudaMemset(env->d_status, 0, sizeof(int)));
+  SFFG_ENV_CUDA(cudaHostAlloc((void **)&env->h_status, sizeof(int), cudaHostAllocMapped));
+  *env->h_status = 0;
+  SFFG_ENV_CUDA(cudaHostAlloc((void **)&env->h_small, kSmallBytes, cudaHostAllocMapped));
   SFFG_ENV_CUDA(cudaMalloc((void **)&env->d_work, 8 * sizeof(unsigned)));
   SFFG_ENV_CUDA(cudaMemset(env->d_work, 0, 8 * sizeof(unsigned)));
   for (int s = 0; s < 2; ++s) SFFG_ENV_CUDA(cudaStreamCreateWithFlags(&env->streams[s], cudaStreamNonBlocking));
@@ -330,7 +339,7 @@ int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot
   d.robot = reinterpret_cast<const RobotTri *>(env->d_robot);
   d.robot64 = reinterpret_cast<const double *>(env->d_robot64);
   d.counters = nullptr;
-  d.status = env->d_status;
+  d.status = env->h_status;   // unified addressing: the mapped host pointer is valid on the device
   d.work_counter = env->d_work;
   env->cfg.sm_count = g_rt.sm_count;
   env->cfg.blocks_per_sm = 0;
@@ -372,18 +381,20 @@ int sffg_env_read_counters(sffg_env *env, sffg_counters_t *out) {
   return SFFG_OK;
 }
 
-static EnvDev env_view(sffg_env *env) {
+// picks the next work counter of the ring; *base_io points at the host-side base that the launch advances
+static EnvDev env_view(sffg_env *env, unsigned **base_io) {
   EnvDev v = env->dev;
+  const int slot = env->work_next++ & 7;
   v.counters = env->count ? env->d_counters : nullptr;
-  v.work_counter = env->d_work + (env->work_next++ & 7);
+  v.work_counter = env->d_work + slot;
+  *base_io = &env->work_base[slot];
   return v;
 }
 
+// call after the streams were synchronised
 static int check_status(sffg_env *env) {
-  int st = 0;
-  SFFG_CUDA(cudaMemcpy(&st, env->d_status, sizeof st, cudaMemcpyDeviceToHost));
-  if (st != 0) {
-    cudaMemset(env->d_status, 0, sizeof(int));
+  if (*reinterpret_cast<volatile int *>(env->h_status) != 0) {
+    *env->h_status = 0;
     return fail(SFFG_ERR_INTERNAL, "BVH traversal stack overflow: results of this call are invalid");
   }
   return SFFG_OK;
@@ -398,8 +409,10 @@ int sffg_env_sync_check(sffg_env *env) {
 int sffg_collide_poses_device(sffg_env *env, const void *d_poses, int poses_are_f64, int64_t n, uint8_t *d_verdict_out,
                               void *stream) {
   if (!env || n < 0 || (n > 0 && (!d_poses || !d_verdict_out))) return fail(SFFG_ERR_ARG, "sffg_collide_poses_device: bad arguments");
-  SFFG_CUDA(launch_collide_poses(env_view(env), d_poses, poses_are_f64 ? 1 : 0, n, d_verdict_out, (cudaStream_t)stream, env->cfg,
-                                 env->count));
+  unsigned *base;
+  EnvDev v = env_view(env, &base);
+  SFFG_CUDA(launch_collide_poses(v, d_poses, poses_are_f64 ? 1 : 0, n, d_verdict_out, (cudaStream_t)stream, env->cfg,
+                                 env->count, base));
   return SFFG_OK;
 }
 
@@ -407,6 +420,17 @@ static int collide_poses_host(sffg_env *env, const void *poses, int fmt, int64_t
   if (!env || n < 0 || (n > 0 && (!poses || !verdict_out))) return fail(SFFG_ERR_ARG, "sffg_collide_poses: bad arguments");
   if (n == 0) return SFFG_OK;
   const size_t psz = fmt == 0 ? 24 : (fmt == 1 ? 48 : 96);
+  unsigned *base;
+  if ((size_t)n * psz <= kSmallIn && (size_t)n <= kSmallBytes - kSmallIn) {
+    // planner-sized call: one kernel reading/writing pinned mapped memory, one synchronisation, no DMA copies
+    cudaStream_t st = env->streams[0];
+    std::memcpy(env->h_small, poses, (size_t)n * psz);
+    EnvDev v = env_view(env, &base);
+    SFFG_CUDA(launch_collide_poses(v, env->h_small, fmt, n, env->h_small + kSmallIn, st, env->cfg, env->count, base));
+    SFFG_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(verdict_out, env->h_small + kSmallIn, (size_t)n);
+    return check_status(env);
+  }
   const int64_t chunk = 1 << 20;
   int s = 0;
   for (int64_t off = 0; off < n; off += chunk, s ^= 1) {
@@ -417,7 +441,8 @@ static int collide_poses_host(sffg_env *env, const void *poses, int fmt, int64_t
     if (rc == SFFG_OK) rc = env->out[s].reserve((size_t)cnt);
     if (rc != SFFG_OK) return rc;
     SFFG_CUDA(cudaMemcpyAsync(env->in[s].p, (const char *)poses + (size_t)off * psz, (size_t)cnt * psz, cudaMemcpyHostToDevice, st));
-    SFFG_CUDA(launch_collide_poses(env_view(env), env->in[s].p, fmt, cnt, (uint8_t *)env->out[s].p, st, env->cfg, env->count));
+    EnvDev v = env_view(env, &base);
+    SFFG_CUDA(launch_collide_poses(v, env->in[s].p, fmt, cnt, (uint8_t *)env->out[s].p, st, env->cfg, env->count, base));
     SFFG_CUDA(cudaMemcpyAsync(verdict_out + off, env->out[s].p, (size_t)cnt, cudaMemcpyDeviceToHost, st));
   }
   SFFG_CUDA(cudaStreamSynchronize(env->streams[0]));
@@ -440,8 +465,16 @@ int sffg_check_edges_device(sffg_env *env, const double *d_starts, const double 
   if (!env || m < 0 || (m > 0 && (!d_starts || !d_ends || !d_free_out)) || !(sample_dist > 0) ||
       (rot_mode != SFFG_ROT_REFERENCE && rot_mode != SFFG_ROT_INTERPOLATE))
     return fail(SFFG_ERR_ARG, "sffg_check_edges_device: bad arguments");
-  SFFG_CUDA(launch_check_edges(env_view(env), d_starts, d_ends, m, sample_dist, rot_mode, d_free_out, d_first_hit_out,
-                               (cudaStream_t)stream, env->cfg, env->count));
+  unsigned *base;
+  EnvDev v = env_view(env, &base);
+  int *scratch = nullptr;
+  if (m < 8192) {   // small batches: several warps per edge (needs a scratch word per edge)
+    int rc = env->fh.reserve((size_t)m * sizeof(int));
+    if (rc != SFFG_OK) return rc;
+    scratch = (int *)env->fh.p;
+  }
+  SFFG_CUDA(launch_check_edges(v, d_starts, d_ends, m, sample_dist, rot_mode, d_free_out, d_first_hit_out,
+                               (cudaStream_t)stream, env->cfg, env->count, base, scratch));
   return SFFG_OK;
 }
 
@@ -451,6 +484,28 @@ int sffg_check_edges(sffg_env *env, const double *starts, const double *ends, in
       (rot_mode != SFFG_ROT_REFERENCE && rot_mode != SFFG_ROT_INTERPOLATE))
     return fail(SFFG_ERR_ARG, "sffg_check_edges: bad arguments");
   if (m == 0) return SFFG_OK;
+  unsigned *base;
+  if ((size_t)m * 96 <= kSmallIn && (size_t)m * 5 <= kSmallBytes - kSmallIn) {
+    // planner-sized call.  The endpoints are re-read by every warp that shares an edge, so they go to device memory with
+    // one DMA from the pinned staging area; the results are written straight into pinned mapped memory.
+    cudaStream_t st = env->streams[0];
+    int rc = env->in[0].reserve((size_t)m * 96);
+    if (rc == SFFG_OK) rc = env->fh.reserve((size_t)m * sizeof(int));
+    if (rc != SFFG_OK) return rc;
+    std::memcpy(env->h_small, starts, (size_t)m * 48);
+    std::memcpy(env->h_small + (size_t)m * 48, ends, (size_t)m * 48);
+    double *ds = (double *)env->in[0].p, *de = ds + 6 * m;
+    SFFG_CUDA(cudaMemcpyAsync(ds, env->h_small, (size_t)m * 96, cudaMemcpyHostToDevice, st));
+    int32_t *h_first = reinterpret_cast<int32_t *>(env->h_small + kSmallIn);
+    uint8_t *h_free = env->h_small + kSmallIn + (size_t)m * 4;
+    EnvDev v = env_view(env, &base);
+    SFFG_CUDA(launch_check_edges(v, ds, de, m, sample_dist, rot_mode, h_free, h_first, st, env->cfg, env->count, base,
+                                 (int *)env->fh.p));
+    SFFG_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(free_out, h_free, (size_t)m);
+    if (first_hit_out) std::memcpy(first_hit_out, h_first, (size_t)m * 4);
+    return check_status(env);
+  }
   const int64_t chunk = 1 << 18;
   int s = 0;
   for (int64_t off = 0; off < m; off += chunk, s ^= 1) {
@@ -464,8 +519,9 @@ int sffg_check_edges(sffg_env *env, const double *starts, const double *ends, in
     double *ds = (double *)env->in[s].p, *de = ds + 6 * cnt;
     SFFG_CUDA(cudaMemcpyAsync(ds, starts + 6 * off, (size_t)cnt * 48, cudaMemcpyHostToDevice, st));
     SFFG_CUDA(cudaMemcpyAsync(de, ends + 6 * off, (size_t)cnt * 48, cudaMemcpyHostToDevice, st));
-    SFFG_CUDA(launch_check_edges(env_view(env), ds, de, cnt, sample_dist, rot_mode, (uint8_t *)env->out[s].p,
-                                 (int32_t *)env->aux[s].p, st, env->cfg, env->count));
+    EnvDev v = env_view(env, &base);
+    SFFG_CUDA(launch_check_edges(v, ds, de, cnt, sample_dist, rot_mode, (uint8_t *)env->out[s].p,
+                                 (int32_t *)env->aux[s].p, st, env->cfg, env->count, base, nullptr));
     SFFG_CUDA(cudaMemcpyAsync(free_out + off, env->out[s].p, (size_t)cnt, cudaMemcpyDeviceToHost, st));
     if (first_hit_out)
       SFFG_CUDA(cudaMemcpyAsync(first_hit_out + off, env->aux[s].p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
@@ -492,7 +548,9 @@ int sffg_index_create(int dim, sffg_index **out) {
   sffg_index *idx = new sffg_index();
   idx->dim = dim;
   cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaHostAlloc((void **)&idx->h_small, kSmallBytes, cudaHostAllocMapped);
   if (e != cudaSuccess) {
+    if (idx->stream) cudaStreamDestroy(idx->stream);
     delete idx;
     return fail(SFFG_ERR_CUDA, cudaGetErrorString(e));
   }
@@ -506,6 +564,7 @@ int sffg_index_destroy(sffg_index *idx) {
   cudaFree(idx->d_coords);
   DevBuf *bufs[] = {&idx->q, &idx->ids, &idx->d2, &idx->scratch, &idx->counts, &idx->offsets, &idx->cursor, &idx->keys, &idx->stage};
   for (DevBuf *b : bufs) b->release();
+  if (idx->h_small) cudaFreeHost(idx->h_small);
   if (idx->stream) cudaStreamDestroy(idx->stream);
   delete idx;
   return SFFG_OK;
@@ -584,6 +643,19 @@ int sffg_knn(sffg_index *idx, const float *queries, int64_t nq, int k, int32_t *
   if (nq == 0) return SFFG_OK;
   int rc = check_angles(queries, nq, idx->dim);
   if (rc != SFFG_OK) return rc;
+  const size_t qbytes = (size_t)nq * idx->dim * 4, obytes = (size_t)nq * k * 4;
+  if (qbytes <= (64 << 10) && 2 * obytes <= kSmallBytes - (64 << 10)) {
+    // planner-sized call: queries and results live in pinned mapped memory, one synchronisation
+    std::memcpy(idx->h_small, queries, qbytes);
+    int32_t *h_ids = reinterpret_cast<int32_t *>(idx->h_small + (64 << 10));
+    float *h_d2 = reinterpret_cast<float *>(idx->h_small + (64 << 10) + obytes);
+    rc = sffg_knn_device(idx, reinterpret_cast<const float *>(idx->h_small), nq, k, h_ids, h_d2, idx->stream);
+    if (rc != SFFG_OK) return rc;
+    SFFG_CUDA(cudaStreamSynchronize(idx->stream));
+    std::memcpy(ids_out, h_ids, obytes);
+    std::memcpy(d2_out, h_d2, obytes);
+    return SFFG_OK;
+  }
   const int64_t chunk = 1 << 17;
   for (int64_t off = 0; off < nq; off += chunk) {
     const int64_t cnt = std::min(chunk, nq - off);
