@@ -53,6 +53,25 @@ def build_native(force: bool = False, verbose: bool = False, defines=(), out: Pa
     return target
 
 
+HOST_SRC = PKG / "host" / "sff_planner.cpp"
+HOST_BIN = PKG / "host" / "sff_planner"
+
+
+def build_host(force: bool = False) -> Path:
+    """The restructured (batched) planner host: plain C++17 on top of the C ABI, linked against libsffg.so."""
+    lib = build_native()
+    if not force and HOST_BIN.exists() and HOST_BIN.stat().st_mtime > max(HOST_SRC.stat().st_mtime, lib.stat().st_mtime):
+        return HOST_BIN
+    cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-I", str(PKG.parent / "include"), str(HOST_SRC), "-L", str(PKG), "-l:libsffg.so",
+           "-Wl,-rpath,$ORIGIN/..", "-o", str(HOST_BIN)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host build failed:\n" + res.stdout + res.stderr)
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     import sys
     print(build_native(force=True, verbose="-v" in sys.argv))
+    print(build_host(force=True))

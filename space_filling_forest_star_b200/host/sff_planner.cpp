@@ -1,0 +1,896 @@
+// sff_planner.cpp -- restructured host of the Space-Filling Forest / SFF* planner on top of the engine's C ABI.
+//
+// This is row (f)-1 of SURVEY.md section 8: the reference's expansion loop (SpaceForest<T,R>::Solve / expandNode,
+// reference src/forest.h:112-376) evaluates one pose, one edge or one query at a time behind short-circuit conditions.
+// Here the same decisions are taken over *rounds*: a round picks up to B frontier nodes, draws every node's
+// ThresholdMisses candidate points at once and pushes all poses, edges and neighbour queries the sequential logic could
+// possibly need through the GPU in five batched calls; the accept / reject / rewire rules are then replayed on the
+// host over the returned flags in the reference's order.  Speculation changes the amount of work, never a rule:
+//   candidate validity      limits, Environment::Collide(newPoint), isPathFree(expanded, newPoint)      (forest.h:244-248)
+//   crowding / border rules radius search r = dtree + 2*circum over all trees, same-tree-closer-with-free-path rejects,
+//                           other-tree-within-dtree records a border link and rejects                    (forest.h:255-303)
+//   SFF* parent choice and rewiring over k = 2e*log10(#nodes) nearest nodes of the same tree               (forest.h:306-351)
+//   frontier / closed list, ThresholdMisses, termination                                                   (forest.h:122-206)
+//   path extraction: best border link per tree pair, composition through third trees                       (forest.h:420-463,
+//                                                                                        problemStruct.h:183-253)
+// Differences to the reference, all deliberate: neighbour search is exact with the intended metric (the reference's
+// FLANN setup is approximate and its functor assigns instead of accumulating); expansions of one round
+// do not see each other (a candidate that would interact with a node created in the same round is deferred to the
+// next round); stored angles are normalised into [-pi, pi); the RNG is seedable.  Only solver="sff" without a goal and without priority bias is covered.
+//
+//   sff_planner <config.xml> [run-id] [--seed S] [--batch B] [--paths file] [--quiet]
+//
+// Output: one line appended to the Params file in the reference's format (problemStruct.h:391-429):
+//   id,run,iterations,solved|unsolved,[connected tree ids],[pairwise path lengths],elapsed seconds
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <random>
+#include <sstream>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "sffg.h"
+
+namespace {
+
+constexpr double kTol = 1e-9;          // TOLERANCE, src/primitives.h:45
+constexpr double kSample = 0.1;        // Solver::collisionSampleSize, src/problemStruct.h:121
+
+[[noreturn]] void die(const std::string &msg) {
+  std::cout << "Problem loading error: " << msg << "\n";
+  std::exit(1);
+}
+void check(int rc) {
+  if (rc != SFFG_OK) {
+    std::cout << "engine error: " << sffg_last_error() << "\n";
+    std::exit(3);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// configuration (same XML schema as the reference, README.md:45-274)
+// ---------------------------------------------------------------------------------------------------------------
+struct Tag {
+  std::string name;
+  std::map<std::string, std::string> attr;
+};
+
+std::vector<Tag> scan_tags(const std::string &t) {
+  std::vector<Tag> out;
+  size_t i = 0;
+  while ((i = t.find('<', i)) != std::string::npos) {
+    ++i;
+    if (i >= t.size()) break;
+    if (t[i] == '?' || t[i] == '/') continue;
+    if (t.compare(i, 3, "!--") == 0) {
+      size_t e = t.find("-->", i);
+      i = e == std::string::npos ? t.size() : e + 3;
+      continue;
+    }
+    Tag tag;
+    while (i < t.size() && !std::isspace((unsigned char)t[i]) && t[i] != '>' && t[i] != '/') tag.name += t[i++];
+    while (i < t.size() && t[i] != '>') {
+      while (i < t.size() && (std::isspace((unsigned char)t[i]) || t[i] == '/')) ++i;
+      if (i >= t.size() || t[i] == '>') break;
+      std::string key;
+      while (i < t.size() && t[i] != '=' && !std::isspace((unsigned char)t[i]) && t[i] != '>') key += t[i++];
+      while (i < t.size() && t[i] != '"' && t[i] != '\'' && t[i] != '>') ++i;
+      if (i >= t.size() || t[i] == '>') break;
+      const char q = t[i++];
+      std::string val;
+      while (i < t.size() && t[i] != q) val += t[i++];
+      ++i;
+      tag.attr[key] = val;
+    }
+    out.push_back(tag);
+  }
+  return out;
+}
+
+bool parse_point(const std::string &s, double scale, double out[3]) {
+  // "[x; y; z]"  (Point<T>(const std::string&, T scale), src/primitives.h:104-114)
+  size_t a = s.find('['), b = s.find(']');
+  if (a == std::string::npos || b == std::string::npos) return false;
+  std::string body = s.substr(a + 1, b - a - 1);
+  for (char &c : body)
+    if (c == ';') c = ' ';
+  std::istringstream is(body);
+  for (int i = 0; i < 3; ++i) {
+    if (!(is >> out[i])) return false;
+    out[i] *= scale;
+  }
+  return true;
+}
+
+struct MeshRef {
+  std::string file;
+  bool is_obj = false;
+  double pos[3] = {0, 0, 0};
+};
+
+struct Config {
+  std::string solver = "sff";
+  bool optimize = false;
+  int dim = 6;              // 2 or 6 (Dimensions, src/primitives.h:76-79)
+  double scale = 1;
+  MeshRef robot;
+  std::vector<MeshRef> obstacles;
+  bool has_map = true;
+  std::vector<std::array<double, 3>> roots;
+  bool auto_range = false;
+  double range[6] = {0, 0, 0, 0, 0, 0};
+  double dtree = 0, circum = 1;
+  double priority_bias = 0;
+  int threshold_misses = 3;   // DEFAULT_THRES_MISS
+  long max_iterations = 0;
+  std::string params_file, id;
+};
+
+Config load_config(const std::string &path) {
+  std::ifstream f(path);
+  if (!f.good()) die("cannot open " + path);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  std::vector<Tag> tags = scan_tags(ss.str());
+  Config c;
+  bool seen_problem = false, seen_range = false, seen_dist = false, seen_iter = false, seen_robot = false, in_save = false;
+  for (const Tag &t : tags) {
+    auto get = [&](const char *k) -> const std::string * {
+      auto it = t.attr.find(k);
+      return it == t.attr.end() ? nullptr : &it->second;
+    };
+    if (t.name == "Problem") {
+      seen_problem = true;
+      if (auto v = get("solver")) c.solver = *v; else die("invalid solver attribute in Problem node!");
+      if (auto v = get("optimize")) c.optimize = *v == "true"; else die("invalid optimize attribute in Problem node!");
+      if (auto v = get("scale")) c.scale = std::stod(*v);
+      if (auto v = get("dim")) {
+        if (*v == "2D" || *v == "2d") c.dim = 2;
+        else if (*v == "3D" || *v == "3d") c.dim = 6;
+        else die("invalid dim attribute!");
+      }
+    } else if (t.name == "Robot") {
+      seen_robot = true;
+      if (auto v = get("file")) c.robot.file = *v; else die("invalid file node in Robot node!");
+      if (auto v = get("is_obj")) c.robot.is_obj = *v == "true";
+    } else if (t.name == "Obstacle") {
+      MeshRef m;
+      if (auto v = get("file")) m.file = *v; else die("invalid file attribute in Obstacle node!");
+      if (auto v = get("is_obj")) m.is_obj = *v == "true";
+      if (auto v = get("position")) if (!parse_point(*v, 1.0, m.pos)) die("Unknown format of point");
+      c.obstacles.push_back(m);
+    } else if (t.name == "Point") {
+      std::array<double, 3> p;
+      auto v = get("coord");
+      if (!v || !parse_point(*v, c.scale, p.data())) die("invalid coord attribute in Point node!");
+      c.roots.push_back(p);
+    } else if (t.name == "Goal") {
+      die("single-goal planning is not covered by the batched host (use the reference host with the shims)");
+    } else if (t.name == "Range") {
+      seen_range = true;
+      if (auto v = get("autoDetect")) c.auto_range = *v == "true";
+    } else if (t.name == "RangeX" || t.name == "RangeY" || t.name == "RangeZ") {
+      const int ax = t.name[5] - 'X';
+      auto lo = get("min"), hi = get("max");
+      if (!lo || !hi) die("invalid min/max attribute in range node");
+      c.range[2 * ax] = c.scale * std::stod(*lo);
+      c.range[2 * ax + 1] = c.scale * std::stod(*hi);
+    } else if (t.name == "Distances") {
+      seen_dist = true;
+      auto a = get("dtree"), b = get("circum");
+      if (!a || !b) die("invalid Distances node!");
+      c.dtree = c.scale * std::stod(*a);
+      c.circum = c.scale * std::stod(*b);
+    } else if (t.name == "Improvements") {
+      if (auto v = get("priorityBias")) c.priority_bias = std::stod(*v);
+    } else if (t.name == "Thresholds") {
+      if (auto v = get("standard")) c.threshold_misses = std::stoi(*v);
+    } else if (t.name == "MaxIterations") {
+      seen_iter = true;
+      if (auto v = get("value")) c.max_iterations = std::stol(*v); else die("invalid MaxIterations node!");
+    } else if (t.name == "Save") {
+      in_save = true;
+    } else if (t.name == "Params" && in_save) {
+      if (auto v = get("file")) c.params_file = *v;
+      if (auto v = get("id")) c.id = *v;
+    }
+  }
+  if (!seen_problem) die("invalid root node!");
+  if (!seen_robot) die("invalid Robot node!");
+  if (!seen_range) die("invalid range node");
+  if (!seen_dist) die("invalid Distances node!");
+  if (!seen_iter) die("invalid MaxIterations node!");
+  if (c.roots.empty()) die("invalid Points node - insert at least one point!");
+  if (c.solver != "sff") die("the batched host covers solver=\"sff\" only (sff / sff*)");
+  if (c.priority_bias != 0) die("priorityBias != 0 is not covered by the batched host");
+  c.has_map = !c.obstacles.empty();
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// geometry helpers (double, same operation order as the reference)
+// ---------------------------------------------------------------------------------------------------------------
+inline double wrap(double a) {   // NormalizeAngle, src/primitives.h:277-286
+  if (a < -M_PI) return a + 2 * M_PI;
+  if (a >= M_PI) return a - 2 * M_PI;
+  return a;
+}
+inline double dist6(const double *a, const double *b) {   // Point<T>::distance, src/primitives.h:224-235
+  double sum = 0;
+  for (int i = 0; i < 3; ++i) {
+    const double d = a[i] - b[i];
+    sum += d * d;
+  }
+  for (int i = 3; i < 6; ++i) {
+    const double d = wrap(b[i] - a[i]);
+    sum += d * d;
+  }
+  return std::sqrt(sum);
+}
+
+struct Node {
+  double p[6];
+  int tree;
+  int parent;              // global id, -1 for a root
+  double d_parent, d_root;
+  std::vector<int> children;
+  bool force_children = false;
+  long generation = 0;
+};
+
+struct Border {
+  int a, b;   // global node ids, a < b
+};
+
+struct EdgeBatch {
+  std::vector<double> s, e;
+  std::vector<uint8_t> free_flag;
+  int add(const double *a, const double *b) {
+    s.insert(s.end(), a, a + 6);
+    e.insert(e.end(), b, b + 6);
+    return (int)(s.size() / 6) - 1;
+  }
+  void run(sffg_env *env) {
+    const int64_t m = (int64_t)(s.size() / 6);
+    free_flag.assign((size_t)m, 1);
+    if (m) check(sffg_check_edges(env, s.data(), e.data(), m, kSample, SFFG_ROT_REFERENCE, free_flag.data(), nullptr));
+  }
+  void clear() {
+    s.clear();
+    e.clear();
+    free_flag.clear();
+  }
+};
+
+struct Cand {
+  int exp = -1;             // expanded node (global id)
+  double p[6];
+  bool in_limits = false, alive = false, rejected = false;
+  double parent_dist = 0;
+  int e_first = -1;         // edge expanded -> candidate
+  // crowding / border stage
+  std::vector<int> nb;                      // radius neighbours in (d2, id) order
+  std::vector<int> nb_edge;                 // edge index per neighbour or -1
+  int border_nb = -1;                       // neighbour that recorded a border link when this attempt is replayed
+  // SFF* stage
+  std::vector<int> knn;                     // same-tree neighbours, ascending distance
+  std::vector<int> e_parent, e_rewire;      // edge index per knn entry or -1
+};
+
+class Planner {
+ public:
+  Planner(const Config &cfg, uint64_t seed, int batch, bool quiet) : cfg_(cfg), rng_(seed), batch_(batch), quiet_(quiet) {}
+
+  void load() {
+    double *tris = nullptr;
+    int64_t n = 0;
+    double bbox[6];
+    const double zero[3] = {0, 0, 0};
+    check(sffg_mesh_load(cfg_.robot.file.c_str(), cfg_.robot.is_obj, zero, cfg_.scale, &tris, &n, bbox));
+    std::vector<double> robot(tris, tris + 9 * n);
+    sffg_free(tris);
+    std::vector<double> obst;
+    double lim[6] = {1e308, -1e308, 1e308, -1e308, 1e308, -1e308};
+    for (const MeshRef &m : cfg_.obstacles) {
+      check(sffg_mesh_load(m.file.c_str(), m.is_obj, m.pos, cfg_.scale, &tris, &n, bbox));
+      obst.insert(obst.end(), tris, tris + 9 * n);
+      sffg_free(tris);
+      for (int k = 0; k < 3; ++k) {   // Environment::processLimits, src/environment.h:46-53
+        lim[2 * k] = std::min(lim[2 * k], bbox[2 * k]);
+        lim[2 * k + 1] = std::max(lim[2 * k + 1], bbox[2 * k + 1]);
+      }
+    }
+    if (cfg_.auto_range)
+      for (int k = 0; k < 6; ++k) cfg_.range[k] = lim[k];
+    check(sffg_env_create(obst.empty() ? nullptr : obst.data(), (int64_t)(obst.size() / 9), robot.data(), (int64_t)(robot.size() / 9), &env_));
+    const int T = (int)cfg_.roots.size();
+    members_.resize(T);
+    tree_idx_.resize(T, nullptr);
+    check(sffg_index_create(cfg_.dim, &global_idx_));
+    for (int t = 0; t < T; ++t) {
+      check(sffg_index_create(cfg_.dim, &tree_idx_[t]));
+      Node nd{};
+      for (int k = 0; k < 3; ++k) nd.p[k] = cfg_.roots[t][k];
+      nd.tree = t;
+      nd.parent = -1;
+      nd.d_parent = nd.d_root = 0;
+      const int id = add_node(nd);
+      frontier_.push_back(id);
+    }
+    flush_index_appends();
+  }
+
+  void solve() {
+    const auto t0 = std::chrono::steady_clock::now();
+    bool solved = false;
+    const int T = (int)cfg_.roots.size();
+    while (!solved && iter_ < cfg_.max_iterations) {
+      const bool from_closed = frontier_.empty();
+      std::vector<int> &pool = from_closed ? closed_ : frontier_;
+      if (pool.empty()) break;
+      const int B = (int)std::min<size_t>((size_t)batch_, pool.size());
+      // B distinct pool positions (partial Fisher-Yates over a position array)
+      std::vector<int> pos(pool.size());
+      for (size_t i = 0; i < pos.size(); ++i) pos[i] = (int)i;
+      for (int i = 0; i < B; ++i) {
+        std::uniform_int_distribution<int> pick(i, (int)pos.size() - 1);
+        std::swap(pos[i], pos[pick(rng_)]);
+      }
+      std::vector<int> chosen(pos.begin(), pos.begin() + B);
+      std::vector<int> chosen_nodes(B);
+      for (int i = 0; i < B; ++i) chosen_nodes[i] = pool[chosen[i]];
+      std::vector<char> exhausted(B, 0);
+      run_round(chosen_nodes, exhausted);
+      if (!from_closed) {
+        // nodes whose every attempt failed leave the frontier for the closed list (forest.h:160-180)
+        std::vector<int> drop;
+        for (int i = 0; i < B; ++i)
+          if (exhausted[i]) {
+            nodes_[chosen_nodes[i]].force_children = true;
+            closed_.push_back(chosen_nodes[i]);
+            drop.push_back(chosen[i]);
+          }
+        std::sort(drop.begin(), drop.end(), std::greater<int>());
+        for (int d : drop) {
+          frontier_[d] = frontier_.back();
+          frontier_.pop_back();
+        }
+      }
+      const bool connected = max_connected() == T;
+      solved = frontier_.empty() && connected;   // (!hasGoal && emptyFrontier && connected), forest.h:199-201
+      ++rounds_;
+    }
+    elapsed_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!solved) solved = max_connected() == T;   // forest.h:204-206
+    solved_ = solved;
+    max_connected();
+    build_paths();
+  }
+
+  void save_params(const std::string &run_id) const {
+    if (cfg_.params_file.empty()) return;
+    std::ofstream out(cfg_.params_file, std::ios_base::app);
+    if (!out.good()) {
+      std::cout << "Cannot create file at: " << cfg_.params_file << "\n";
+      return;
+    }
+    out << cfg_.id << "," << run_id << "," << iter_ << "," << (solved_ ? "solved" : "unsolved") << ",[";
+    for (size_t i = 0; i < connected_.size(); ++i) out << connected_[i] << (i + 1 != connected_.size() ? ";" : "");
+    out << "],[";
+    const int n = (int)connected_.size();
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < i; ++j) {
+        out << link(connected_[i], connected_[j]).distance / cfg_.scale;
+        if (i + 1 != n || j + 1 != i) out << ";";
+      }
+    out << "]," << elapsed_ << "\n";
+  }
+
+  // every plan as "treeA treeB length n  x y z yaw pitch roll ..." so that tests can re-validate each segment
+  // (the role of Solver::checkDistances, src/problemStruct.h:370-389)
+  void save_paths(const std::string &file) const {
+    std::ofstream out(file);
+    out.precision(17);
+    for (const auto &kv : links_) {
+      const Link &l = kv.second;
+      if (!l.exists()) continue;
+      out << kv.first.first << " " << kv.first.second << " " << l.distance << " " << l.plan.size();
+      for (int id : l.plan)
+        for (int c = 0; c < 6; ++c) out << " " << nodes_[id].p[c];
+      out << "\n";
+    }
+  }
+
+  void report() const {
+    if (quiet_) return;
+    std::cout << "nodes " << nodes_.size() << ", iterations " << iter_ << ", rounds " << rounds_ << ", "
+              << (solved_ ? "solved" : "unsolved") << ", connected trees " << connected_.size() << ", elapsed " << elapsed_
+              << " s, engine calls " << calls_ << ", poses " << n_poses_ << ", edges " << n_edges_ << ", queries " << n_queries_
+              << "\n";
+  }
+
+  ~Planner() {
+    for (sffg_index *i : tree_idx_) sffg_index_destroy(i);
+    sffg_index_destroy(global_idx_);
+    sffg_env_destroy(env_);
+  }
+
+ private:
+  struct Link {
+    int n1 = -1, n2 = -1;
+    double distance = std::numeric_limits<double>::max();
+    std::vector<int> plan;
+    bool exists() const { return n1 >= 0; }
+  };
+
+  int add_node(const Node &nd) {
+    const int id = (int)nodes_.size();
+    nodes_.push_back(nd);
+    members_[nd.tree].push_back(id);
+    pending_.push_back(id);
+    return id;
+  }
+
+  // new nodes become searchable at the end of a round: one append per tree index + one for the global index
+  void flush_index_appends() {
+    if (pending_.empty()) return;
+    const int dim = cfg_.dim;
+    std::vector<float> rows(pending_.size() * (size_t)dim);
+    for (size_t i = 0; i < pending_.size(); ++i)
+      for (int c = 0; c < dim; ++c) rows[i * dim + c] = (float)nodes_[pending_[i]].p[c];   // double -> float, forest.h:258-260
+    check(sffg_index_add(global_idx_, rows.data(), (int64_t)pending_.size()));
+    const int T = (int)tree_idx_.size();
+    for (int t = 0; t < T; ++t) {
+      std::vector<float> tr;
+      for (size_t i = 0; i < pending_.size(); ++i)
+        if (nodes_[pending_[i]].tree == t) tr.insert(tr.end(), rows.begin() + i * dim, rows.begin() + (i + 1) * dim);
+      if (!tr.empty()) check(sffg_index_add(tree_idx_[t], tr.data(), (int64_t)(tr.size() / dim)));
+    }
+    calls_ += 1 + T;
+    pending_.clear();
+  }
+
+  // RandGen<T>::randomPointInDistance, src/randGen.h:69-109
+  bool sample_around(const double *center, double *out) {
+    std::uniform_real_distribution<double> ang(-M_PI, M_PI), prob(0, 1);
+    const double distance = cfg_.circum;
+    double tmp[6] = {0, 0, 0, 0, 0, 0};
+    double phi = ang(rng_);
+    if (cfg_.dim == 2) {
+      out[0] = center[0] + std::cos(phi) * distance;
+      out[1] = center[1] + std::sin(phi) * distance;
+      out[2] = out[3] = out[4] = out[5] = 0;
+    } else {
+      const double theta = ang(rng_);
+      tmp[0] = center[0] + std::cos(theta) * std::sin(phi) * distance;
+      tmp[1] = center[1] + std::sin(theta) * std::sin(phi) * distance;
+      tmp[2] = center[2] + std::cos(phi) * distance;
+      tmp[3] = ang(rng_);
+      phi = std::acos(1 - 2 * prob(rng_)) + M_PI_2;
+      if (prob(rng_) < 0.5) phi += phi < 0 ? M_PI : -M_PI;
+      tmp[4] = phi;
+      tmp[5] = ang(rng_);
+      // Point<T>::getStateInDistance, src/primitives.h:237-250 (angles are not re-normalised)
+      const double real = dist6(center, tmp);
+      for (int i = 0; i < 3; ++i) out[i] = center[i] + (tmp[i] - center[i]) * (distance / real);
+      for (int i = 3; i < 6; ++i) {
+        // the reference leaves the stepped angles unnormalised, so they random-walk away from [-pi, pi) and its
+        // single-wrap metric degrades; here every stored angle is brought back into [-pi, pi) (same rotation)
+        const double a = center[i] + wrap(tmp[i] - center[i]) * (distance / real);
+        out[i] = a - 2 * M_PI * std::floor((a + M_PI) / (2 * M_PI));
+      }
+    }
+    return out[0] >= cfg_.range[0] && out[0] <= cfg_.range[1] && out[1] >= cfg_.range[2] && out[1] <= cfg_.range[3] &&
+           out[2] >= cfg_.range[4] && out[2] <= cfg_.range[5];
+  }
+
+  void run_round(const std::vector<int> &chosen, std::vector<char> &exhausted) {
+    const int B = (int)chosen.size(), A = cfg_.threshold_misses, dim = cfg_.dim;
+    std::vector<Cand> cand((size_t)B * A);
+    // ---- stage 1: candidate points, pose + first-edge verdicts
+    std::vector<double> poses;
+    std::vector<int> pose_of;
+    EdgeBatch eb;
+    for (int b = 0; b < B; ++b)
+      for (int a = 0; a < A; ++a) {
+        Cand &c = cand[(size_t)b * A + a];
+        c.exp = chosen[b];
+        c.in_limits = sample_around(nodes_[c.exp].p, c.p);
+        if (!c.in_limits) continue;
+        poses.insert(poses.end(), c.p, c.p + 6);
+        pose_of.push_back(b * A + a);
+        c.e_first = eb.add(nodes_[c.exp].p, c.p);
+      }
+    std::vector<uint8_t> hit(pose_of.size(), 0);
+    if (!pose_of.empty() && cfg_.has_map) {
+      check(sffg_collide_poses_f64(env_, poses.data(), (int64_t)pose_of.size(), hit.data()));
+      eb.run(env_);
+      calls_ += 2;
+      n_poses_ += (long)pose_of.size();
+      n_edges_ += (long)pose_of.size();
+    } else {
+      eb.free_flag.assign(pose_of.size(), 1);
+    }
+    std::vector<int> alive;
+    for (size_t i = 0; i < pose_of.size(); ++i) {
+      Cand &c = cand[pose_of[i]];
+      c.alive = !hit[i] && eb.free_flag[c.e_first];
+      if (c.alive) {
+        c.parent_dist = dist6(nodes_[c.exp].p, c.p);
+        alive.push_back(pose_of[i]);
+      }
+    }
+    // ---- stage 2: radius search over every tree (one global index == union of the per-tree searches)
+    const double check_dist = cfg_.dtree + 2 * cfg_.circum;
+    const float r2 = (float)(check_dist * check_dist);
+    if (!alive.empty()) {
+      std::vector<float> q(alive.size() * (size_t)dim);
+      for (size_t i = 0; i < alive.size(); ++i)
+        for (int k = 0; k < dim; ++k) q[i * dim + k] = (float)cand[alive[i]].p[k];
+      std::vector<int32_t> counts(alive.size());
+      int64_t total = 0;
+      check(sffg_radius(global_idx_, q.data(), (int64_t)alive.size(), r2, counts.data(), nullptr, nullptr, 0, &total));
+      std::vector<int32_t> ids((size_t)std::max<int64_t>(total, 1));
+      std::vector<float> d2((size_t)std::max<int64_t>(total, 1));
+      if (total) check(sffg_radius(global_idx_, q.data(), (int64_t)alive.size(), r2, counts.data(), ids.data(), d2.data(), total, &total));
+      calls_ += 2;
+      n_queries_ += (long)alive.size();
+      size_t off = 0;
+      for (size_t i = 0; i < alive.size(); ++i) {
+        Cand &c = cand[alive[i]];
+        c.nb.assign(ids.begin() + off, ids.begin() + off + counts[i]);
+        off += (size_t)counts[i];
+        // the reference searches tree after tree (forest.h:262): tree-major order, (d2, id) order inside a tree
+        std::stable_sort(c.nb.begin(), c.nb.end(), [&](int x, int y) { return nodes_[x].tree < nodes_[y].tree; });
+      }
+    }
+    // ---- stage 3: edges the crowding / border rules may ask for (forest.h:270-302), in neighbour order
+    eb.clear();
+    for (int ci : alive) {
+      Cand &c = cand[ci];
+      const Node &ex = nodes_[c.exp];
+      c.nb_edge.assign(c.nb.size(), -1);
+      for (size_t j = 0; j < c.nb.size(); ++j) {
+        const Node &nb = nodes_[c.nb[j]];
+        const double real = dist6(nb.p, c.p);
+        if (!ex.force_children && real < c.parent_dist - kTol && nb.tree == ex.tree) c.nb_edge[j] = eb.add(nb.p, c.p);
+        if (nb.tree != ex.tree && real < cfg_.dtree - kTol) {
+          c.nb_edge[j] = eb.add(ex.p, nb.p);
+          c.nb.resize(j + 1);       // this neighbour always ends the scan
+          c.nb_edge.resize(j + 1);
+          break;
+        }
+      }
+    }
+    if (cfg_.has_map) {
+      eb.run(env_);
+      if (!eb.s.empty()) ++calls_;
+    } else {
+      eb.free_flag.assign(eb.s.size() / 6, 1);
+    }
+    n_edges_ += (long)(eb.s.size() / 6);
+    for (int ci : alive) {
+      Cand &c = cand[ci];
+      const Node &ex = nodes_[c.exp];
+      for (size_t j = 0; j < c.nb.size() && !c.rejected; ++j) {
+        if (c.nb_edge[j] < 0) continue;
+        const Node &nb = nodes_[c.nb[j]];
+        if (nb.tree == ex.tree) {
+          if (eb.free_flag[c.nb_edge[j]]) c.rejected = true;             // a closer node of the same tree sees the point
+        } else {
+          if (eb.free_flag[c.nb_edge[j]]) c.border_nb = c.nb[j];          // trees meet: remember the link
+          c.rejected = true;
+        }
+      }
+    }
+    // ---- stage 4 + 5 (SFF*): k nearest nodes of the same tree for the first surviving attempt of every node
+    std::vector<int> winners(B, -1);
+    for (int b = 0; b < B; ++b)
+      for (int a = 0; a < A; ++a) {
+        const Cand &c = cand[(size_t)b * A + a];
+        if (c.alive && !c.rejected) {
+          winners[b] = b * A + a;
+          break;
+        }
+      }
+    EdgeBatch eb2;
+    if (cfg_.optimize) {
+      const int k = (int)std::min<double>(2 * M_E * std::log10((double)nodes_.size()), (double)SFFG_MAX_K);   // forest.h:309
+      const int T = (int)tree_idx_.size();
+      if (k >= 1) {
+        for (int t = 0; t < T; ++t) {
+          std::vector<int> who;
+          for (int b = 0; b < B; ++b)
+            if (winners[b] >= 0 && nodes_[cand[winners[b]].exp].tree == t) who.push_back(winners[b]);
+          if (who.empty()) continue;
+          std::vector<float> q(who.size() * (size_t)dim);
+          for (size_t i = 0; i < who.size(); ++i)
+            for (int c = 0; c < dim; ++c) q[i * dim + c] = (float)cand[who[i]].p[c];
+          std::vector<int32_t> ids(who.size() * (size_t)k);
+          std::vector<float> d2(who.size() * (size_t)k);
+          check(sffg_knn(tree_idx_[t], q.data(), (int64_t)who.size(), k, ids.data(), d2.data()));
+          ++calls_;
+          n_queries_ += (long)who.size();
+          for (size_t i = 0; i < who.size(); ++i) {
+            Cand &c = cand[who[i]];
+            for (int j = 0; j < k && ids[i * k + j] >= 0; ++j) c.knn.push_back(members_[t][ids[i * k + j]]);
+          }
+        }
+      }
+      for (int b = 0; b < B; ++b) {
+        if (winners[b] < 0) continue;
+        Cand &c = cand[winners[b]];
+        const Node &ex = nodes_[c.exp];
+        const double best0 = c.parent_dist + ex.d_root;
+        double low = best0;
+        c.e_parent.assign(c.knn.size(), -1);
+        c.e_rewire.assign(c.knn.size(), -1);
+        for (size_t j = 0; j < c.knn.size(); ++j) {
+          const Node &nb = nodes_[c.knn[j]];
+          const double nd = dist6(c.p, nb.p) + nb.d_root;
+          if (nd < best0 - kTol) {
+            c.e_parent[j] = eb2.add(c.p, nb.p);
+            low = std::min(low, nd);
+          }
+        }
+        for (size_t j = 0; j < c.knn.size(); ++j) {
+          const Node &nb = nodes_[c.knn[j]];
+          if (low + dist6(nb.p, c.p) < nb.d_root - kTol) c.e_rewire[j] = eb2.add(nb.p, c.p);
+        }
+      }
+      if (cfg_.has_map) {
+        eb2.run(env_);
+        if (!eb2.s.empty()) ++calls_;
+      } else {
+        eb2.free_flag.assign(eb2.s.size() / 6, 1);
+      }
+      n_edges_ += (long)(eb2.s.size() / 6);
+    }
+    // ---- stage 6: replay in the reference's order
+    std::vector<int> added;
+    for (int b = 0; b < B && iter_ < cfg_.max_iterations; ++b) {
+      bool success = false, deferred = false;
+      for (int a = 0; a < A && !success && !deferred && iter_ < cfg_.max_iterations; ++a) {
+        Cand &c = cand[(size_t)b * A + a];
+        if (c.alive && !c.rejected) {
+          // interaction with a node created earlier in this round was not evaluated: postpone this frontier node
+          const Node &ex = nodes_[c.exp];
+          for (int id : added) {
+            const Node &o = nodes_[id];
+            const double d = dist6(o.p, c.p);
+            if ((o.tree == ex.tree && d < c.parent_dist - kTol) || (o.tree != ex.tree && d < cfg_.dtree - kTol)) {
+              deferred = true;
+              break;
+            }
+          }
+          if (deferred) break;
+        }
+        ++iter_;
+        if (!c.alive) continue;
+        if (c.rejected) {
+          if (c.border_nb >= 0) add_border(c.border_nb, c.exp);
+          continue;
+        }
+        added.push_back(commit(c, eb2));
+        success = true;
+      }
+      exhausted[b] = !success && !deferred;
+    }
+    flush_index_appends();
+  }
+
+  // creates the node of an accepted candidate: SFF* parent choice + rewiring (forest.h:306-351) or plain SFF (:352-356)
+  int commit(Cand &c, const EdgeBatch &eb2) {
+    int parent = c.exp;
+    double best = c.parent_dist + nodes_[c.exp].d_root;
+    if (cfg_.optimize) {
+      for (size_t j = 0; j < c.knn.size(); ++j) {
+        const Node &nb = nodes_[c.knn[j]];
+        const double nd = dist6(c.p, nb.p) + nb.d_root;
+        if (nd < best - kTol && c.e_parent[j] >= 0 && eb2.free_flag[c.e_parent[j]]) {
+          best = nd;
+          parent = c.knn[j];
+        }
+      }
+    }
+    Node nd{};
+    std::memcpy(nd.p, c.p, sizeof nd.p);
+    nd.tree = nodes_[c.exp].tree;
+    nd.parent = parent;
+    nd.d_parent = dist6(c.p, nodes_[parent].p);
+    nd.d_root = best;
+    nd.generation = iter_;
+    const int id = add_node(nd);
+    nodes_[parent].children.push_back(id);
+    if (cfg_.optimize) {
+      for (size_t j = 0; j < c.knn.size(); ++j) {
+        Node &nb = nodes_[c.knn[j]];
+        const double d = dist6(nb.p, c.p);
+        const double proposed = best + d;
+        if (proposed < nb.d_root - kTol && c.e_rewire[j] >= 0 && eb2.free_flag[c.e_rewire[j]] && nb.parent >= 0) {
+          std::vector<int> &ch = nodes_[nb.parent].children;
+          auto it = std::find(ch.begin(), ch.end(), c.knn[j]);
+          if (it != ch.end()) ch.erase(it);
+          nb.parent = id;
+          nb.d_parent = d;
+          nb.d_root = proposed;                 // descendants keep their stored cost, as in the reference
+          nodes_[id].children.push_back(c.knn[j]);
+        }
+      }
+    }
+    frontier_.push_back(id);
+    return id;
+  }
+
+  std::vector<Border> &borders(int t1, int t2) { return borders_[{std::min(t1, t2), std::max(t1, t2)}]; }
+
+  void add_border(int n1, int n2) {
+    Border bd{std::min(n1, n2), std::max(n1, n2)};
+    std::vector<Border> &v = borders(nodes_[n1].tree, nodes_[n2].tree);
+    for (const Border &o : v)
+      if (o.a == bd.a && o.b == bd.b) return;
+    v.push_back(bd);
+  }
+
+  // SpaceForest::maxConnected, forest.h:378-418
+  int max_connected() {
+    const int T = (int)cfg_.roots.size();
+    std::vector<char> seen(T, 0);
+    int max_conn = 0, remaining = T, start = 0;
+    while (max_conn < remaining) {
+      connected_.clear();
+      std::vector<int> stack{start};
+      seen[start] = 1;
+      while (!stack.empty()) {
+        const int r = stack.front();
+        stack.erase(stack.begin());
+        connected_.push_back(r);
+        for (int i = 0; i < T; ++i)
+          if (i != r && !seen[i] && !borders(r, i).empty()) {
+            seen[i] = 1;
+            stack.insert(stack.begin(), i);
+          }
+      }
+      max_conn = (int)connected_.size();
+      for (int i = 0; i < T; ++i)
+        if (!seen[i]) {
+          start = i;
+          break;
+        }
+      remaining -= max_conn;
+    }
+    return max_conn;
+  }
+
+  Link &link(int i, int j) { return links_[{std::min(i, j), std::max(i, j)}]; }
+  const Link &link(int i, int j) const {
+    static const Link none;
+    auto it = links_.find({std::min(i, j), std::max(i, j)});
+    return it == links_.end() ? none : it->second;
+  }
+
+  double plan_length(const std::vector<int> &plan) const {
+    double d = 0;
+    for (size_t i = 1; i < plan.size(); ++i) d += dist6(nodes_[plan[i - 1]].p, nodes_[plan[i]].p);
+    return d;
+  }
+
+  // SpaceForest::getPaths (forest.h:420-463) + Solver::getAllPaths (problemStruct.h:183-253)
+  void build_paths() {
+    const int T = (int)cfg_.roots.size();
+    for (int i = 0; i < T; ++i)
+      for (int j = i + 1; j < T; ++j) {
+        const std::vector<Border> &bs = borders(i, j);
+        if (bs.empty()) continue;
+        Link best;
+        double best_d = -1;
+        for (const Border &b : bs) {
+          const double d = nodes_[b.a].d_root + nodes_[b.b].d_root + dist6(nodes_[b.a].p, nodes_[b.b].p);
+          if (best_d == -1 || d < best_d - kTol) {
+            best_d = d;
+            best.n1 = b.a;
+            best.n2 = b.b;
+            best.distance = d;
+          }
+        }
+        // plan: root of n1's tree ... n1, n2 ... root of n2's tree
+        std::vector<int> left, right;
+        for (int n = best.n1; n >= 0; n = nodes_[n].parent) left.insert(left.begin(), n);
+        for (int n = best.n2; n >= 0; n = nodes_[n].parent) right.push_back(n);
+        best.plan = left;
+        best.plan.insert(best.plan.end(), right.begin(), right.end());
+        link(i, j) = best;
+      }
+    const std::vector<int> &ct = connected_;
+    for (int id3 : ct)
+      for (int id1 : ct) {
+        if (id1 == id3 || !link(id1, id3).exists()) continue;
+        for (int id2 : ct) {
+          if (id1 == id2 || id2 == id3 || !link(id2, id3).exists()) continue;
+          const Link &h1 = link(id1, id3), &h2 = link(id2, id3);
+          std::vector<int> p1 = h1.plan, p2 = h2.plan;
+          if (nodes_[p1.front()].tree != id1) std::reverse(p1.begin(), p1.end());
+          if (nodes_[p2.front()].tree != id2) std::reverse(p2.begin(), p2.end());
+          int last = -1;
+          while (!p1.empty() && !p2.empty() && p1.back() == p2.back()) {   // drop the shared tail towards root id3
+            last = p1.back();
+            p1.pop_back();
+            p2.pop_back();
+          }
+          if (last < 0) continue;
+          std::vector<int> plan = p1;
+          plan.push_back(last);
+          plan.insert(plan.end(), p2.rbegin(), p2.rend());
+          const double d = plan_length(plan);
+          Link &direct = link(id1, id2);
+          if (d < direct.distance - kTol) {
+            direct.n1 = plan.front();
+            direct.n2 = plan.back();
+            direct.distance = d;
+            direct.plan = plan;
+          }
+        }
+      }
+  }
+
+  Config cfg_;
+  std::mt19937_64 rng_;
+  int batch_;
+  bool quiet_;
+  sffg_env *env_ = nullptr;
+  sffg_index *global_idx_ = nullptr;
+  std::vector<sffg_index *> tree_idx_;
+  std::vector<Node> nodes_;
+  std::vector<std::vector<int>> members_;   // per tree: local index id -> global node id
+  std::vector<int> pending_;
+  std::vector<int> frontier_, closed_;
+  std::map<std::pair<int, int>, std::vector<Border>> borders_;
+  std::map<std::pair<int, int>, Link> links_;
+  std::vector<int> connected_;
+  long iter_ = 0, rounds_ = 0, calls_ = 0, n_poses_ = 0, n_edges_ = 0, n_queries_ = 0;
+  bool solved_ = false;
+  double elapsed_ = 0;
+};
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  if (argc < 2) {
+    std::cout << "Missing problem configuration file!\n";
+    return 1;
+  }
+  std::string run_id = "0";
+  uint64_t seed = (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count();
+  int batch = 128;
+  bool quiet = false;
+  std::string paths_file;
+  int positional = 0;
+  for (int i = 2; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (a == "--seed" && i + 1 < argc) seed = std::strtoull(argv[++i], nullptr, 10);
+    else if (a == "--batch" && i + 1 < argc) batch = std::max(1, std::atoi(argv[++i]));
+    else if (a == "--quiet") quiet = true;
+    else if (a == "--paths" && i + 1 < argc) paths_file = argv[++i];
+    else if (positional++ == 0) run_id = a;
+  }
+  Config cfg = load_config(argv[1]);
+  check(sffg_init(-1));
+  Planner planner(cfg, seed, batch, quiet);
+  planner.load();
+  planner.solve();
+  planner.save_params(run_id);
+  if (!paths_file.empty()) planner.save_paths(paths_file);
+  planner.report();
+  return 0;
+}

@@ -1,0 +1,70 @@
+"""GPU test of the restructured (batched) SFF* host: every reported path is re-validated with the CPU oracle."""
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def run_planner(tmp_path, scenario, seed, max_iter=None, batch=128):
+    subprocess.run([sys.executable, str(ROOT / "scripts" / "make_scenarios.py"), str(tmp_path)], check=True, capture_output=True)
+    from space_filling_forest_star_b200 import build as B
+    exe = B.build_host()
+    cfg = tmp_path / f"{scenario}.xml"
+    if max_iter:
+        cfg.write_text(cfg.read_text().replace('MaxIterations value="100000"', f'MaxIterations value="{max_iter}"'))
+    paths = tmp_path / "paths.txt"
+    p = subprocess.run([str(exe), cfg.name, "0", "--seed", str(seed), "--batch", str(batch), "--paths", str(paths)], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    row = (tmp_path / "output" / f"params_{scenario}.csv").read_text().strip().splitlines()[-1]
+    plans = []
+    for line in paths.read_text().splitlines():
+        v = line.split()
+        n = int(v[3])
+        plans.append((int(v[0]), int(v[1]), float(v[2]), np.array(v[4:4 + 6 * n], dtype=np.float64).reshape(n, 6)))
+    return row, plans, p.stdout
+
+
+def validate_plans(orc, obst, robot, plans, roots):
+    assert plans
+    for a, b, length, pts in plans:
+        # endpoints are the two roots; the length is the sum of the 6-D segment lengths
+        ends = {tuple(np.round(pts[0, :3], 9)), tuple(np.round(pts[-1, :3], 9))}
+        assert ends == {tuple(np.round(roots[a], 9)), tuple(np.round(roots[b], 9))}
+        seg = sum(orc.distance6(pts[i], pts[i + 1]) for i in range(len(pts) - 1))
+        assert seg == pytest.approx(length, rel=1e-9)
+        # every node is collision free and every segment passes the reference local planner in at least one direction
+        assert orc.collide_brute(obst, robot, pts).sum() == 0
+        f1, _, _ = orc.edges_free(obst, robot, pts[:-1], pts[1:], 0.1, 0)
+        f2, _, _ = orc.edges_free(obst, robot, pts[1:], pts[:-1], 0.1, 0)
+        assert np.all((f1 | f2) == 1), (a, b, np.nonzero((f1 | f2) == 0)[0])
+
+
+def test_sffstar_2d_solves_and_paths_are_valid(tmp_path, orc, meshes):
+    sys.path.insert(0, str(ROOT / "scripts"))
+    import make_scenarios as MS
+    row, plans, out = run_planner(tmp_path, "2d_sffstar", seed=7)
+    assert ",solved," in row, row
+    assert len(plans) == 6   # 4 roots -> 6 pairs, all connected
+    validate_plans(orc, meshes["triangles_tri"], meshes["robot_small_s1"], plans, np.array(MS.SCENARIOS["2d"]["points"], dtype=float))
+    # reproducible for a fixed seed
+    row2, _, _ = run_planner(tmp_path, "2d_sffstar", seed=7)
+    assert row.split(",")[2:6] == row2.split(",")[2:6]
+
+
+def test_sffstar_3d_paths_are_valid(tmp_path, orc, meshes):
+    sys.path.insert(0, str(ROOT / "scripts"))
+    import make_scenarios as MS
+    row, plans, out = run_planner(tmp_path, "triang_sffstar", seed=3, max_iter=30000)
+    validate_plans(orc, meshes["triang_s10"], meshes["robot_small_s10"], plans, np.array(MS.SCENARIOS["triang"]["points"], dtype=float))
+
+
+def test_batch_size_one_equals_sequential_semantics(tmp_path, orc, meshes):
+    """B = 1 is the reference's one-node-at-a-time loop; it must solve the 2-D problem as well"""
+    row, plans, out = run_planner(tmp_path, "2d_sffstar", seed=11, batch=1)
+    assert ",solved," in row, row
