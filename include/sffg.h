@@ -101,7 +101,11 @@ SFFG_API int sffg_check_edges_device(sffg_env *env, const double *d_starts, cons
 
 /* work counters of the last call on this env (debug/roofline): poses past the root cull, BVH child-box tests,
  * triangle-pair FP32 SAT tests, FP64 exact re-tests                                                          */
-typedef struct { int64_t poses, poses_past_root, box_tests, pair_tests, exact_tests; } sffg_counters_t;
+typedef struct {
+  int64_t poses, poses_past_root, box_tests, pair_tests, exact_tests;
+  int64_t traversal_steps, triangle_passes, triangles_transformed;   /* warp-level steps of the two inner loops */
+  int64_t exact_run;   /* FP64 pair tests actually executed (exact_tests counts pairs FP32 SAT left undecided) */
+} sffg_counters_t;
 SFFG_API int sffg_env_enable_counters(sffg_env *env, int on);
 /* after *_device calls: waits for the device and reports a traversal failure (SFFG_ERR_INTERNAL) if one was flagged */
 SFFG_API int sffg_env_sync_check(sffg_env *env);

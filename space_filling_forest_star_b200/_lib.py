@@ -29,7 +29,8 @@ class EnvInfo(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("poses", C.c_int64), ("poses_past_root", C.c_int64), ("box_tests", C.c_int64), ("pair_tests", C.c_int64),
-                ("exact_tests", C.c_int64)]
+                ("exact_tests", C.c_int64), ("traversal_steps", C.c_int64), ("triangle_passes", C.c_int64),
+                ("triangles_transformed", C.c_int64), ("exact_run", C.c_int64)]
 
 
 # name -> (restype, argtypes); mirrors include/sffg.h one to one (tests/test_abi.py checks the header against this)

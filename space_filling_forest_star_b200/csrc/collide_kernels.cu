@@ -125,6 +125,44 @@ __device__ bool pair_certified_disjoint(const XTri &x, const RobotTri &rt) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// FP32 contact certificate.  A pair the separating-axis stage could not clear is usually a deep contact; proving it
+// in FP32 saves the FP64 stage.  Sufficient condition: an edge of one triangle pierces the interior of the other --
+// its endpoints lie strictly on opposite sides of the other triangle's plane and the three signed volumes
+// [(c_k - a) x (c_{k+1} - a)] . (b - a) share a sign -- with every quantity clear of a rigorous error bound
+// (positions are off by at most errpos; a bilinear / trilinear form of vectors bounded by 2M then moves by less than
+// 150 * errpos * M^2, allotted 256).  Lane j < 6 checks one (edge, triangle) combination; any lane suffices.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool edge_pierces(const float *a, const float *b, const float *c0, const float *c1, const float *c2,
+                                             float bound) {
+  const float u[3] = {c1[0] - c0[0], c1[1] - c0[1], c1[2] - c0[2]}, v[3] = {c2[0] - c0[0], c2[1] - c0[1], c2[2] - c0[2]};
+  const float n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+  const float da = n[0] * (a[0] - c0[0]) + n[1] * (a[1] - c0[1]) + n[2] * (a[2] - c0[2]);
+  const float db = n[0] * (b[0] - c0[0]) + n[1] * (b[1] - c0[1]) + n[2] * (b[2] - c0[2]);
+  if (!((da > bound && db < -bound) || (da < -bound && db > bound))) return false;
+  const float d[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+  const float w0[3] = {c0[0] - a[0], c0[1] - a[1], c0[2] - a[2]}, w1[3] = {c1[0] - a[0], c1[1] - a[1], c1[2] - a[2]},
+              w2[3] = {c2[0] - a[0], c2[1] - a[1], c2[2] - a[2]};
+  const float v0 = (w0[1] * w1[2] - w0[2] * w1[1]) * d[0] + (w0[2] * w1[0] - w0[0] * w1[2]) * d[1] + (w0[0] * w1[1] - w0[1] * w1[0]) * d[2];
+  const float v1 = (w1[1] * w2[2] - w1[2] * w2[1]) * d[0] + (w1[2] * w2[0] - w1[0] * w2[2]) * d[1] + (w1[0] * w2[1] - w1[1] * w2[0]) * d[2];
+  const float v2 = (w2[1] * w0[2] - w2[2] * w0[1]) * d[0] + (w2[2] * w0[0] - w2[0] * w0[2]) * d[1] + (w2[0] * w0[1] - w2[1] * w0[0]) * d[2];
+  return (v0 > bound && v1 > bound && v2 > bound) || (v0 < -bound && v1 < -bound && v2 < -bound);
+}
+
+// all lanes call with the same pair; returns (warp-uniform) true when a contact is PROVEN
+__device__ __forceinline__ bool pair_certified_contact(const XTri &x, const RobotTri &rt, int lane) {
+  const float errpos = 2.0f * x.err + kEpsSat * fmaxf(x.mabs, rt.qmax);
+  const float M = fmaxf(x.mabs, rt.qmax);
+  const float bound = 256.0f * errpos * M * M;
+  bool ok = false;
+  if (lane < 6) {
+    const int e = lane < 3 ? lane : lane - 3, e1 = e == 2 ? 0 : e + 1;
+    if (lane < 3) ok = edge_pierces(x.v + 3 * e, x.v + 3 * e1, rt.q[0], rt.q[1], rt.q[2], bound);
+    else ok = edge_pierces(rt.q[e], rt.q[e1], x.v, x.v + 3, x.v + 6, bound);
+  }
+  return __any_sync(kFull, ok);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // FP64 exact stage -- operation order of oracle/sff_oracle.c (make_xform, xform_point, orc_tri_contact).
 // Explicit *_rn intrinsics keep ptxas from contracting a*b+c into an FMA, which the CPU oracle does not do.
 // ---------------------------------------------------------------------------------------------------------
@@ -340,7 +378,7 @@ struct PoseU {          // warp-uniform copy of one pose
   float Thi[3], Tlo[3]; // T = Thi + Tlo (+ negligible)
 };
 
-struct Tally { unsigned long long past_root, box, pair, exact; };
+struct Tally { unsigned long long past_root, box, pair, exact, steps, tri_passes, tris, exact_run; };
 
 struct BoxTest {        // per-pose constants of the oriented-box test
   float o[3], ra[3], rob_sz;
@@ -395,7 +433,9 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *
         }
         first = false;
       } else {
-        const int take = sp < 4 ? sp : 4;
+        // 4 nodes per step while there is room; near the cap fall back to strict depth-first (1 node per step grows the
+        // stack by at most 7 per level), which keeps any hierarchy of depth <= 45 inside the stack
+        const int take = sp > kStackCap - 64 ? 1 : (sp < 4 ? sp : 4);
         const int grp = lane >> 3;
         active = grp < take;
         const int node = active ? ws.stack[sp - 1 - grp] : 0;
@@ -410,7 +450,7 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *
       }
       const unsigned m_int = __ballot_sync(kFull, ov && child >= 0);
       const unsigned m_leaf = __ballot_sync(kFull, ov && child < 0);
-      if (COUNT) tally.box += __popc(__ballot_sync(kFull, active && child != kEmptyChild));
+      if (COUNT) { tally.box += __popc(__ballot_sync(kFull, active && child != kEmptyChild)); tally.steps += 1; }
       if (ov && child >= 0) {
         const int pos = sp + __popc(m_int & lt);
         if (pos < kStackCap) ws.stack[pos] = child;
@@ -466,6 +506,7 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *
       }
       const unsigned km = __ballot_sync(kFull, keep);
       const int nx = __popc(km);
+      if (COUNT) { tally.tri_passes += 1; tally.tris += cnt; }
       if (keep) ws.xt[__popc(km & lt)] = x;
       __syncwarp();
       const int npairs = nx * E.n_robot;
@@ -480,17 +521,22 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *
         if (COUNT) {
           const int np = (npairs - pb) < 32 ? (npairs - pb) : 32;
           tally.pair += np;
-          tally.exact += __popc(um);
+          tally.exact += __popc(um);   // pairs the FP32 separating-axis stage left undecided
         }
         while (um) {
           const int l = __ffs(um) - 1;
           um &= um - 1;
+          const int pp = pb + l;
+          const int xi = pp / E.n_robot, r = pp - xi * E.n_robot;
+          if (pair_certified_contact(ws.xt[xi], srob[r], lane)) {
+            hit = true;
+            break;
+          }
+          if (COUNT) tally.exact_run += 1;
           if (!have_R2) {
             lp.exact(src, R2, T2, lane);
             have_R2 = true;
           }
-          const int pp = pb + l;
-          const int xi = pp / E.n_robot, r = pp - xi * E.n_robot;
           const int t = ws.xt[xi].tri;
           if (exact_pair_contact(R2, T2, E.tris64 + 9 * (size_t)t, E.robot64 + 9 * (size_t)r, lane)) {
             hit = true;
@@ -533,6 +579,10 @@ __device__ __forceinline__ void flush_tally(const EnvDev &E, const Tally &t, uns
     atomicAdd(E.counters + 2, t.box);
     atomicAdd(E.counters + 3, t.pair);
     atomicAdd(E.counters + 4, t.exact);
+    atomicAdd(E.counters + 8, t.exact_run);
+    atomicAdd(E.counters + 5, t.steps);
+    atomicAdd(E.counters + 6, t.tri_passes);
+    atomicAdd(E.counters + 7, t.tris);
   }
 }
 
@@ -578,7 +628,7 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) collide_poses_kerne
   // a work unit is `chunk` (1..32) consecutive poses: 32 for large batches (full lanes in phase A), fewer when the
   // batch is too small to give every resident warp a unit (planner-sized calls are latency-, not throughput-bound)
   const long long nchunks = (n + chunk - 1) / chunk;
-  Tally tally = {0, 0, 0, 0};
+  Tally tally = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long nposes = 0;
   while (true) {
     unsigned c = 0;
@@ -628,7 +678,7 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(
   stage_robot(E, srob);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + (size_t)E.n_robot * sizeof(RobotTri))[warp];
-  Tally tally = {0, 0, 0, 0};
+  Tally tally = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long nposes = 0;
   const long long units = m * split;
   while (true) {

@@ -323,8 +323,8 @@ int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot
   SFFG_ENV_CUDA(upload(&env->d_tris64, t64.data(), t64.size() * sizeof(double)));
   SFFG_ENV_CUDA(upload(&env->d_robot, rob.data(), rob.size() * sizeof(RobotTri)));
   SFFG_ENV_CUDA(upload(&env->d_robot64, robot_tris, 9 * (size_t)n_robot * sizeof(double)));
-  SFFG_ENV_CUDA(cudaMalloc((void **)&env->d_counters, 5 * sizeof(unsigned long long)));
-  SFFG_ENV_CUDA(cudaMemset(env->d_counters, 0, 5 * sizeof(unsigned long long)));
+  SFFG_ENV_CUDA(cudaMalloc((void **)&env->d_counters, 9 * sizeof(unsigned long long)));
+  SFFG_ENV_CUDA(cudaMemset(env->d_counters, 0, 9 * sizeof(unsigned long long)));
   SFFG_ENV_CUDA(cudaHostAlloc((void **)&env->h_status, sizeof(int), cudaHostAllocMapped));
   *env->h_status = 0;
   SFFG_ENV_CUDA(cudaHostAlloc((void **)&env->h_small, kSmallBytes, cudaHostAllocMapped));
@@ -364,13 +364,13 @@ int sffg_env_info(const sffg_env *env, sffg_env_info_t *out) {
 int sffg_env_enable_counters(sffg_env *env, int on) {
   if (!env) return fail(SFFG_ERR_ARG, "null env");
   env->count = on != 0;
-  SFFG_CUDA(cudaMemset(env->d_counters, 0, 5 * sizeof(unsigned long long)));
+  SFFG_CUDA(cudaMemset(env->d_counters, 0, 9 * sizeof(unsigned long long)));
   return SFFG_OK;
 }
 
 int sffg_env_read_counters(sffg_env *env, sffg_counters_t *out) {
   if (!env || !out) return fail(SFFG_ERR_ARG, "null argument");
-  unsigned long long h[5];
+  unsigned long long h[9];
   SFFG_CUDA(cudaDeviceSynchronize());
   SFFG_CUDA(cudaMemcpy(h, env->d_counters, sizeof h, cudaMemcpyDeviceToHost));
   out->poses = (int64_t)h[0];
@@ -378,6 +378,10 @@ int sffg_env_read_counters(sffg_env *env, sffg_counters_t *out) {
   out->box_tests = (int64_t)h[2];
   out->pair_tests = (int64_t)h[3];
   out->exact_tests = (int64_t)h[4];
+  out->traversal_steps = (int64_t)h[5];
+  out->triangle_passes = (int64_t)h[6];
+  out->triangles_transformed = (int64_t)h[7];
+  out->exact_run = (int64_t)h[8];
   return SFFG_OK;
 }
 
