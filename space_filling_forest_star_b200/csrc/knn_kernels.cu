@@ -132,58 +132,77 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(IndexDev idx, const 
   const long long begin = (long long)slice * slice_len;
   long long end = begin + slice_len;
   if (end > idx.n) end = idx.n;
-  const long long nblocks = end > begin ? (end - begin + 31) / 32 : 0;
   constexpr int LIN = DIM == 6 ? 3 : 2;   // coordinates streamed for every block; the 3 angles only on demand
+  // 32-bit bookkeeping in the hot loop (node ids fit in 31 bits).  Two 32-node blocks per iteration, both prefetched
+  // one iteration (2 blocks) ahead; the index capacity is padded by 96 nodes so the prefetch never needs a bounds branch.
+  const int nvalid = end > begin ? (int)(end - begin) : 0;
+  const int nsteps = (nvalid + 63) / 64;
   const float *ptr[LIN];
 #pragma unroll
   for (int c = 0; c < LIN; ++c) ptr[c] = idx.coords + (long long)c * idx.capacity + begin + lane;
-  float cur[LIN], nxt[LIN];
-  // capacity is a multiple of 32 and slices start at multiples of 32, so a whole block is always addressable; lanes
-  // past `end` read stale-but-allocated floats and are masked below
+  const float *ang_base = idx.coords + 3LL * idx.capacity + lane;
+  float cur[2][LIN], nxt[2][LIN];
 #pragma unroll
-  for (int c = 0; c < LIN; ++c) cur[c] = nblocks > 0 ? __ldg(ptr[c]) : 0.f;
-  for (long long blk = 0; blk < nblocks; ++blk) {
-    const long long b = begin + blk * 32;
-    if (blk + 1 < nblocks) {
+  for (int c = 0; c < LIN; ++c) {
+    cur[0][c] = __ldg(ptr[c]);
+    cur[1][c] = __ldg(ptr[c] + 32);
+  }
+  int b = (int)begin;
+  int left = nvalid;   // valid nodes from block `b` on
+  for (int it = 0; it < nsteps; ++it) {
 #pragma unroll
-      for (int c = 0; c < LIN; ++c) {
-        ptr[c] += 32;
-        nxt[c] = __ldg(ptr[c]);
-      }
+    for (int c = 0; c < LIN; ++c) {
+      ptr[c] += 64;
+      nxt[0][c] = __ldg(ptr[c]);
+      nxt[1][c] = __ldg(ptr[c] + 32);
     }
-    const bool valid = b + lane < end;
-    float d[QW];
-    bool any = false;
 #pragma unroll
-    for (int w = 0; w < QW; ++w) {
-      d[w] = metric_lin<DIM>(cur, q[w]);
-      d[w] = valid ? d[w] : INFINITY;
-      any |= d[w] < worst[w];
-    }
-    if (__any_sync(kFull, any)) {
-      if (DIM == 6) {
-        float ang[3];
+    for (int h = 0; h < 2; ++h, b += 32, left -= 32) {
+      float d[QW];
+      bool any = false;
+      if (left >= 32) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) ang[c] = __ldg(idx.coords + (long long)(3 + c) * idx.capacity + b + lane);
+        for (int w = 0; w < QW; ++w) {
+          d[w] = metric_lin<DIM>(cur[h], q[w]);
+          any |= d[w] < worst[w];
+        }
+      } else {
+        const bool valid = lane < left;
 #pragma unroll
-        for (int w = 0; w < QW; ++w) d[w] = valid ? metric_ang(d[w], ang, q[w]) : INFINITY;
+        for (int w = 0; w < QW; ++w) {
+          d[w] = valid ? metric_lin<DIM>(cur[h], q[w]) : INFINITY;
+          any |= d[w] < worst[w];
+        }
       }
+      if (__any_sync(kFull, any)) {
+        if (DIM == 6) {
+          const bool valid = lane < left;
+          float ang[3];
 #pragma unroll
-      for (int w = 0; w < QW; ++w) {
-        unsigned mask = __ballot_sync(kFull, d[w] < worst[w]);
-        while (mask) {
-          const int src = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const float cd = __shfl_sync(kFull, d[w], src);
-          if (cd < worst[w]) {
-            top[w].insert(cd, (int)(b + src), lane);
-            worst[w] = top[w].kth(k);
+          for (int c = 0; c < 3; ++c) ang[c] = __ldg(ang_base + (long long)c * idx.capacity + b);
+#pragma unroll
+          for (int w = 0; w < QW; ++w) d[w] = valid ? metric_ang(d[w], ang, q[w]) : INFINITY;
+        }
+#pragma unroll
+        for (int w = 0; w < QW; ++w) {
+          unsigned mask = __ballot_sync(kFull, d[w] < worst[w]);
+          while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float cd = __shfl_sync(kFull, d[w], src);
+            if (cd < worst[w]) {
+              top[w].insert(cd, b + src, lane);
+              worst[w] = top[w].kth(k);
+            }
           }
         }
       }
     }
 #pragma unroll
-    for (int c = 0; c < LIN; ++c) cur[c] = nxt[c];
+    for (int c = 0; c < LIN; ++c) {
+      cur[0][c] = nxt[0][c];
+      cur[1][c] = nxt[1][c];
+    }
   }
 #pragma unroll
   for (int w = 0; w < QW; ++w) {

@@ -553,8 +553,14 @@ int sffg_index_create(int dim, sffg_index **out) {
   idx->dim = dim;
   cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaHostAlloc((void **)&idx->h_small, kSmallBytes, cudaHostAllocMapped);
+  if (e == cudaSuccess) {   // storage exists from the start: the scan kernels may touch the first block of an empty index
+    idx->cap = 4096 + 128;
+    e = cudaMalloc((void **)&idx->d_coords, (size_t)idx->cap * dim * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(idx->d_coords, 0, (size_t)idx->cap * dim * sizeof(float));
+  }
   if (e != cudaSuccess) {
     if (idx->stream) cudaStreamDestroy(idx->stream);
+    if (idx->h_small) cudaFreeHost(idx->h_small);
     delete idx;
     return fail(SFFG_ERR_CUDA, cudaGetErrorString(e));
   }
@@ -577,9 +583,9 @@ int sffg_index_destroy(sffg_index *idx) {
 int64_t sffg_index_size(const sffg_index *idx) { return idx ? idx->n : -1; }
 
 static int index_grow(sffg_index *idx, int64_t need, cudaStream_t st) {
-  if (need <= idx->cap) return SFFG_OK;
+  if (need + 128 <= idx->cap) return SFFG_OK;
   int64_t ncap = std::max<int64_t>({need, idx->cap * 2, 4096});
-  ncap = (ncap + 31) / 32 * 32;
+  ncap = (ncap + 31) / 32 * 32 + 128;   // spare blocks: the scan kernels prefetch up to 3 blocks past the end of a slice
   float *nc = nullptr;
   SFFG_CUDA(cudaMalloc((void **)&nc, (size_t)ncap * idx->dim * sizeof(float)));
   for (int c = 0; c < idx->dim && idx->n > 0; ++c)

@@ -109,3 +109,19 @@ def test_knn_device_and_sharded_single_rank(sff, orc):
     wi, wd = orc.knn_linear(nodes, q, 16)
     np.testing.assert_array_equal(ids.cpu().numpy(), wi)
     np.testing.assert_array_equal(d2.cpu().numpy().view(np.uint32), wd.view(np.uint32))
+
+
+def test_empty_index_and_growth_boundaries(sff, orc):
+    idx = sff.Index(dim=6)
+    ids, d2 = idx.knnSearch(cloud(3, 6, 1), 4)
+    assert (ids == -1).all() and np.isinf(d2).all()
+    c, off, rid, rd = idx.radiusSearch(cloud(3, 6, 1), 100.0)
+    assert c.sum() == 0
+    nodes = cloud(9000, 6, 2)
+    for lo, hi in ((0, 1), (1, 31), (31, 33), (33, 4095), (4095, 4129), (4129, 9000)):   # cross every capacity / block edge
+        idx.addPoints(nodes[lo:hi])
+        q = cloud(5, 6, hi)
+        ids, d2 = idx.knnSearch(q, 8)
+        wi, wd = orc.knn_linear(nodes[:hi], q, 8)
+        np.testing.assert_array_equal(ids, wi)
+        np.testing.assert_array_equal(d2.view(np.uint32), wd.view(np.uint32))
