@@ -122,6 +122,7 @@ struct MeshRef {
 struct Config {
   std::string solver = "sff";
   bool optimize = false;
+  bool smoothing = false;
   int dim = 6;              // 2 or 6 (Dimensions, src/primitives.h:76-79)
   double scale = 1;
   MeshRef robot;
@@ -154,6 +155,7 @@ Config load_config(const std::string &path) {
       seen_problem = true;
       if (auto v = get("solver")) c.solver = *v; else die("invalid solver attribute in Problem node!");
       if (auto v = get("optimize")) c.optimize = *v == "true"; else die("invalid optimize attribute in Problem node!");
+      if (auto v = get("smoothing")) c.smoothing = *v == "true";
       if (auto v = get("scale")) c.scale = std::stod(*v);
       if (auto v = get("dim")) {
         if (*v == "2D" || *v == "2d") c.dim = 2;
@@ -376,6 +378,8 @@ class Planner {
     solved_ = solved;
     max_connected();
     build_paths();
+    if (cfg_.smoothing) smooth_paths();
+    verify_paths();
   }
 
   void save_params(const std::string &run_id) const {
@@ -417,7 +421,7 @@ class Planner {
     std::cout << "nodes " << nodes_.size() << ", iterations " << iter_ << ", rounds " << rounds_ << ", "
               << (solved_ ? "solved" : "unsolved") << ", connected trees " << connected_.size() << ", elapsed " << elapsed_
               << " s, engine calls " << calls_ << ", poses " << n_poses_ << ", edges " << n_edges_ << ", queries " << n_queries_
-              << "\n";
+              << ", smoothed plans " << smoothed_ << ", verified segments " << verified_segments_ << "\n";
   }
 
   ~Planner() {
@@ -844,6 +848,68 @@ class Planner {
       }
   }
 
+  // SpaceForest::smoothPaths (forest.h:465-511): walking back from the far end of a plan, connect the current target to
+  // the EARLIEST node of the plan that sees it and drop everything in between.  All L(L-1)/2 candidate shortcuts of a
+  // plan are evaluated in one batched edge call; the greedy choice is replayed on the host.
+  void smooth_paths() {
+    for (auto &kv : links_) {
+      Link &l = kv.second;
+      if (!l.exists() || l.plan.size() < 3) continue;
+      const int L = (int)l.plan.size();
+      EdgeBatch eb;
+      std::vector<int> eid((size_t)L * L, -1);
+      for (int g = 2; g < L; ++g)
+        for (int t = 0; t + 1 < g; ++t) eid[(size_t)t * L + g] = eb.add(nodes_[l.plan[t]].p, nodes_[l.plan[g]].p);
+      if (cfg_.has_map) {
+        eb.run(env_);
+        ++calls_;
+      } else {
+        eb.free_flag.assign(eb.s.size() / 6, 1);
+      }
+      n_edges_ += (long)(eb.s.size() / 6);
+      std::vector<int> keep;   // built from the back
+      int g = L - 1;
+      keep.push_back(l.plan[g]);
+      while (g > 0) {
+        int t = g - 1;
+        for (int c = 0; c + 1 < g; ++c)
+          if (eb.free_flag[eid[(size_t)c * L + g]]) {
+            t = c;
+            break;
+          }
+        keep.push_back(l.plan[t]);
+        g = t;
+      }
+      std::reverse(keep.begin(), keep.end());
+      l.plan = keep;
+      l.distance = plan_length(keep);
+      ++smoothed_;
+    }
+  }
+
+  // Solver::checkDistances (problemStruct.h:370-389) as an always-on verifier: every segment of every reported plan
+  // must pass the local planner (either direction: parent edges were validated child->parent or parent->child)
+  void verify_paths() {
+    EdgeBatch fwd, bwd;
+    for (const auto &kv : links_) {
+      const Link &l = kv.second;
+      for (size_t i = 1; i < l.plan.size(); ++i) {
+        fwd.add(nodes_[l.plan[i - 1]].p, nodes_[l.plan[i]].p);
+        bwd.add(nodes_[l.plan[i]].p, nodes_[l.plan[i - 1]].p);
+      }
+    }
+    if (fwd.s.empty() || !cfg_.has_map) return;
+    fwd.run(env_);
+    bwd.run(env_);
+    calls_ += 2;
+    for (size_t i = 0; i < fwd.free_flag.size(); ++i)
+      if (!fwd.free_flag[i] && !bwd.free_flag[i]) {
+        std::cout << "Error: a segment of a reported path is not collision free\n";
+        std::exit(1);
+      }
+    verified_segments_ = (long)fwd.free_flag.size();
+  }
+
   Config cfg_;
   std::mt19937_64 rng_;
   int batch_;
@@ -858,7 +924,7 @@ class Planner {
   std::map<std::pair<int, int>, std::vector<Border>> borders_;
   std::map<std::pair<int, int>, Link> links_;
   std::vector<int> connected_;
-  long iter_ = 0, rounds_ = 0, calls_ = 0, n_poses_ = 0, n_edges_ = 0, n_queries_ = 0;
+  long iter_ = 0, rounds_ = 0, calls_ = 0, n_poses_ = 0, n_edges_ = 0, n_queries_ = 0, smoothed_ = 0, verified_segments_ = 0;
   bool solved_ = false;
   double elapsed_ = 0;
 };

@@ -68,3 +68,26 @@ def test_batch_size_one_equals_sequential_semantics(tmp_path, orc, meshes):
     """B = 1 is the reference's one-node-at-a-time loop; it must solve the 2-D problem as well"""
     row, plans, out = run_planner(tmp_path, "2d_sffstar", seed=11, batch=1)
     assert ",solved," in row, row
+
+
+def test_smoothing_shortens_and_stays_valid(tmp_path, orc, meshes):
+    """smoothing="true": SpaceForest::smoothPaths on the batched edge kernel; paths stay valid and never get longer"""
+    sys.path.insert(0, str(ROOT / "scripts"))
+    import make_scenarios as MS
+    row, plans, _ = run_planner(tmp_path, "2d_sffstar", seed=5)
+    cfg = tmp_path / "2d_sffstar.xml"
+    cfg.write_text(cfg.read_text().replace('smoothing="false"', 'smoothing="true"'))
+    from space_filling_forest_star_b200 import build as B
+    paths = tmp_path / "paths_s.txt"
+    p = subprocess.run([str(B.build_host()), cfg.name, "1", "--seed", "5", "--paths", str(paths)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    smooth = []
+    for line in paths.read_text().splitlines():
+        v = line.split()
+        n = int(v[3])
+        smooth.append((int(v[0]), int(v[1]), float(v[2]), np.array(v[4:4 + 6 * n], dtype=np.float64).reshape(n, 6)))
+    validate_plans(orc, meshes["triangles_tri"], meshes["robot_small_s1"], smooth, np.array(MS.SCENARIOS["2d"]["points"], dtype=float))
+    raw = {(a, b): (d, len(pts)) for a, b, d, pts in plans}
+    for a, b, d, pts in smooth:
+        assert d <= raw[(a, b)][0] + 1e-9 and len(pts) <= raw[(a, b)][1]
+    assert sum(d for _, _, d, _ in smooth) < sum(v[0] for v in raw.values())
