@@ -135,3 +135,23 @@ def test_mesh_loader_matches_reference_files(meshes):
                                   ("triangles_tri", "maps/triangles.tri", False, 1.0), ("dense_tri", "maps/dense.tri", False, 1.0)]:
         tris, _ = S.load_mesh(str(ref / f), is_obj, (0, 0, 0), scale)
         np.testing.assert_array_equal(tris, meshes[key])
+
+
+def test_host_planner_builds_and_refuses_without_gpu(tmp_path):
+    """the restructured C++ host links against the C ABI only and exits loudly when there is no GPU"""
+    import sys
+    from space_filling_forest_star_b200 import build as B
+    exe = B.build_host()
+    out = subprocess.run(["nm", "-D", "--undefined-only", str(exe)], capture_output=True, text=True, check=True).stdout
+    used = set(re.findall(r" U (sffg_\w+)", out))
+    assert used and used <= set(declared_symbols())
+    subprocess.run([sys.executable, str(ROOT / "scripts" / "make_scenarios.py"), str(tmp_path)], check=True, capture_output=True)
+    p = subprocess.run([str(exe), "2d_sffstar.xml", "0", "--seed", "1"], cwd=tmp_path, capture_output=True, text=True)
+    if _has_gpu():
+        assert p.returncode == 0
+    else:
+        assert p.returncode == 3 and "no CUDA device" in p.stdout
+    bad = tmp_path / "bad.xml"
+    bad.write_text((tmp_path / "2d_sffstar.xml").read_text().replace('solver="sff"', 'solver="lazy"'))
+    p = subprocess.run([str(exe), "bad.xml"], cwd=tmp_path, capture_output=True, text=True)
+    assert p.returncode == 1 and "Problem loading error" in p.stdout
