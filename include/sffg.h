@@ -132,6 +132,11 @@ SFFG_API int sffg_knn(sffg_index *idx, const float *queries, int64_t nq, int k, 
 SFFG_API int sffg_knn_device(sffg_index *idx, const float *d_queries, int64_t nq, int k, int32_t *d_ids_out, float *d2_out,
                     void *stream);
 
+/* several indices in one call (the planner keeps one index per tree, src/forest.h:72): queries are concatenated in index
+ * order, nq_per[i] rows for idx[i]; one upload, one kernel per index on one stream, one download, one synchronisation. */
+SFFG_API int sffg_knn_multi(sffg_index *const *idx, const int64_t *nq_per, int n_idx, const float *queries, int k,
+                            int32_t *ids_out, float *d2_out);
+
 /* all points with d2 < r2 (strict), each row sorted by (d2,id); rows packed in query order.
  * counts_out[nq] is always written; *total_out = sum(counts).  Pass ids_out == NULL to size the buffers
  * (two-call protocol); otherwise capacity must be >= total or SFFG_ERR_CAPACITY is returned.                */

@@ -683,6 +683,56 @@ int sffg_knn(sffg_index *idx, const float *queries, int64_t nq, int k, int32_t *
   return SFFG_OK;
 }
 
+int sffg_knn_multi(sffg_index *const *idx, const int64_t *nq_per, int n_idx, const float *queries, int k, int32_t *ids_out,
+                   float *d2_out) {
+  if (!idx || !nq_per || n_idx < 1 || k < 1 || k > SFFG_MAX_K) return fail(SFFG_ERR_ARG, "sffg_knn_multi: bad arguments");
+  int64_t total = 0;
+  const int dim = idx[0] ? idx[0]->dim : 0;
+  for (int i = 0; i < n_idx; ++i) {
+    if (!idx[i] || idx[i]->dim != dim || nq_per[i] < 0) return fail(SFFG_ERR_ARG, "sffg_knn_multi: bad index / count");
+    total += nq_per[i];
+  }
+  if (total == 0) return SFFG_OK;
+  if (!queries || !ids_out || !d2_out) return fail(SFFG_ERR_ARG, "sffg_knn_multi: null buffers");
+  int rc = check_angles(queries, total, dim);
+  if (rc != SFFG_OK) return rc;
+  sffg_index *lead = idx[0];   // its stream and staging carry the whole call
+  cudaStream_t st = lead->stream;
+  const size_t qbytes = (size_t)total * dim * 4, obytes = (size_t)total * k * 4;
+  const bool small = qbytes <= (64 << 10) && 2 * obytes <= kSmallBytes - (64 << 10);
+  rc = lead->q.reserve(qbytes);
+  if (rc == SFFG_OK) rc = lead->ids.reserve(obytes);
+  if (rc == SFFG_OK) rc = lead->d2.reserve(obytes);
+  if (rc != SFFG_OK) return rc;
+  if (small) {
+    std::memcpy(lead->h_small, queries, qbytes);
+    SFFG_CUDA(cudaMemcpyAsync(lead->q.p, lead->h_small, qbytes, cudaMemcpyHostToDevice, st));
+  } else {
+    SFFG_CUDA(cudaMemcpyAsync(lead->q.p, queries, qbytes, cudaMemcpyHostToDevice, st));
+  }
+  int64_t off = 0;
+  for (int i = 0; i < n_idx; ++i) {
+    if (nq_per[i] == 0) continue;
+    rc = sffg_knn_device(idx[i], (const float *)lead->q.p + off * dim, nq_per[i], k, (int32_t *)lead->ids.p + off * k,
+                         (float *)lead->d2.p + off * k, st);
+    if (rc != SFFG_OK) return rc;
+    off += nq_per[i];
+  }
+  if (small) {
+    unsigned char *ho = lead->h_small + (64 << 10);
+    SFFG_CUDA(cudaMemcpyAsync(ho, lead->ids.p, obytes, cudaMemcpyDeviceToHost, st));
+    SFFG_CUDA(cudaMemcpyAsync(ho + obytes, lead->d2.p, obytes, cudaMemcpyDeviceToHost, st));
+    SFFG_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(ids_out, ho, obytes);
+    std::memcpy(d2_out, ho + obytes, obytes);
+  } else {
+    SFFG_CUDA(cudaMemcpyAsync(ids_out, lead->ids.p, obytes, cudaMemcpyDeviceToHost, st));
+    SFFG_CUDA(cudaMemcpyAsync(d2_out, lead->d2.p, obytes, cudaMemcpyDeviceToHost, st));
+    SFFG_CUDA(cudaStreamSynchronize(st));
+  }
+  return SFFG_OK;
+}
+
 int sffg_radius(sffg_index *idx, const float *queries, int64_t nq, float r2, int32_t *counts_out, int32_t *ids_out,
                 float *d2_out, int64_t capacity, int64_t *total_out) {
   if (!idx || nq < 0 || (nq > 0 && (!queries || !counts_out)) || (ids_out && !d2_out))
@@ -694,14 +744,25 @@ int sffg_radius(sffg_index *idx, const float *queries, int64_t nq, float r2, int
   cudaStream_t st = idx->stream;
   IndexDev v{idx->d_coords, idx->cap, idx->n, idx->dim};
   KnnPlan plan = plan_knn(nq, idx->n, g_rt.sm_count);
-  rc = idx->q.reserve((size_t)nq * idx->dim * 4);
-  if (rc == SFFG_OK) rc = idx->counts.reserve((size_t)nq * 4);
+  const size_t qbytes = (size_t)nq * idx->dim * 4, cbytes = (size_t)nq * 4;
+  // planner-sized calls stage through pinned memory so that every copy is an asynchronous DMA
+  const bool small = qbytes <= (64 << 10) && cbytes <= (64 << 10);
+  unsigned char *hq = idx->h_small, *hc = idx->h_small + (64 << 10), *hr = idx->h_small + (128 << 10);
+  const size_t hr_bytes = kSmallBytes - (128 << 10);
+  rc = idx->q.reserve(qbytes);
+  if (rc == SFFG_OK) rc = idx->counts.reserve(cbytes);
   if (rc != SFFG_OK) return rc;
-  SFFG_CUDA(cudaMemcpyAsync(idx->q.p, queries, (size_t)nq * idx->dim * 4, cudaMemcpyHostToDevice, st));
-  SFFG_CUDA(cudaMemsetAsync(idx->counts.p, 0, (size_t)nq * 4, st));
+  if (small) {
+    std::memcpy(hq, queries, qbytes);
+    SFFG_CUDA(cudaMemcpyAsync(idx->q.p, hq, qbytes, cudaMemcpyHostToDevice, st));
+  } else {
+    SFFG_CUDA(cudaMemcpyAsync(idx->q.p, queries, qbytes, cudaMemcpyHostToDevice, st));
+  }
+  SFFG_CUDA(cudaMemsetAsync(idx->counts.p, 0, cbytes, st));
   SFFG_CUDA(launch_radius_count(v, (const float *)idx->q.p, nq, r2, (int32_t *)idx->counts.p, plan, st));
-  SFFG_CUDA(cudaMemcpyAsync(counts_out, idx->counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  SFFG_CUDA(cudaMemcpyAsync(small ? (void *)hc : (void *)counts_out, idx->counts.p, cbytes, cudaMemcpyDeviceToHost, st));
   SFFG_CUDA(cudaStreamSynchronize(st));
+  if (small) std::memcpy(counts_out, hc, cbytes);
   std::vector<int64_t> offs((size_t)nq);
   int64_t total = 0;
   for (int64_t i = 0; i < nq; ++i) {
@@ -714,20 +775,34 @@ int sffg_radius(sffg_index *idx, const float *queries, int64_t nq, float r2, int
     return fail(SFFG_ERR_CAPACITY, "sffg_radius: result buffers hold " + std::to_string(capacity) + " entries, " +
                                        std::to_string(total) + " needed");
   rc = idx->offsets.reserve((size_t)nq * 8);
-  if (rc == SFFG_OK) rc = idx->cursor.reserve((size_t)nq * 4);
+  if (rc == SFFG_OK) rc = idx->cursor.reserve(cbytes);
   if (rc == SFFG_OK) rc = idx->keys.reserve((size_t)total * 8);
   if (rc == SFFG_OK) rc = idx->ids.reserve((size_t)total * 4);
   if (rc == SFFG_OK) rc = idx->d2.reserve((size_t)total * 4);
   if (rc != SFFG_OK) return rc;
-  SFFG_CUDA(cudaMemcpyAsync(idx->offsets.p, offs.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
-  SFFG_CUDA(cudaMemsetAsync(idx->cursor.p, 0, (size_t)nq * 4, st));
+  const bool small_out = small && (size_t)nq * 8 <= (64 << 10) && (size_t)total * 8 <= hr_bytes;
+  if (small_out) {
+    std::memcpy(hq, offs.data(), (size_t)nq * 8);   // the query staging area is free again
+    SFFG_CUDA(cudaMemcpyAsync(idx->offsets.p, hq, (size_t)nq * 8, cudaMemcpyHostToDevice, st));
+  } else {
+    SFFG_CUDA(cudaMemcpyAsync(idx->offsets.p, offs.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
+  }
+  SFFG_CUDA(cudaMemsetAsync(idx->cursor.p, 0, cbytes, st));
   SFFG_CUDA(launch_radius_fill(v, (const float *)idx->q.p, nq, r2, (const int64_t *)idx->offsets.p, (int32_t *)idx->cursor.p,
                                (unsigned long long *)idx->keys.p, plan, st));
   SFFG_CUDA(launch_radius_sort((unsigned long long *)idx->keys.p, (const int64_t *)idx->offsets.p, (const int32_t *)idx->counts.p,
                                nq, (int32_t *)idx->ids.p, (float *)idx->d2.p, st));
-  SFFG_CUDA(cudaMemcpyAsync(ids_out, idx->ids.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-  SFFG_CUDA(cudaMemcpyAsync(d2_out, idx->d2.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-  SFFG_CUDA(cudaStreamSynchronize(st));
+  if (small_out) {
+    SFFG_CUDA(cudaMemcpyAsync(hr, idx->ids.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+    SFFG_CUDA(cudaMemcpyAsync(hr + (size_t)total * 4, idx->d2.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+    SFFG_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(ids_out, hr, (size_t)total * 4);
+    std::memcpy(d2_out, hr + (size_t)total * 4, (size_t)total * 4);
+  } else {
+    SFFG_CUDA(cudaMemcpyAsync(ids_out, idx->ids.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+    SFFG_CUDA(cudaMemcpyAsync(d2_out, idx->d2.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+    SFFG_CUDA(cudaStreamSynchronize(st));
+  }
   return SFFG_OK;
 }
 

@@ -290,6 +290,17 @@ struct Cand {
   std::vector<int> e_parent, e_rewire;      // edge index per knn entry or -1
 };
 
+struct StageClock {
+  double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::chrono::steady_clock::time_point last;
+  void start() { last = std::chrono::steady_clock::now(); }
+  void lap(int i) {
+    auto now = std::chrono::steady_clock::now();
+    t[i] += std::chrono::duration<double>(now - last).count();
+    last = now;
+  }
+};
+
 class Planner {
  public:
   Planner(const Config &cfg, uint64_t seed, int batch, bool quiet) : cfg_(cfg), rng_(seed), batch_(batch), quiet_(quiet) {}
@@ -421,7 +432,9 @@ class Planner {
     std::cout << "nodes " << nodes_.size() << ", iterations " << iter_ << ", rounds " << rounds_ << ", "
               << (solved_ ? "solved" : "unsolved") << ", connected trees " << connected_.size() << ", elapsed " << elapsed_
               << " s, engine calls " << calls_ << ", poses " << n_poses_ << ", edges " << n_edges_ << ", queries " << n_queries_
-              << ", smoothed plans " << smoothed_ << ", verified segments " << verified_segments_ << "\n";
+              << "\nstage seconds: sample " << clk_.t[0] << ", pose+edge " << clk_.t[1] << ", radius " << clk_.t[2] << ", crowd edges "
+              << clk_.t[3] << ", knn+rewire edges " << clk_.t[4] << ", replay " << clk_.t[5] << ", index append " << clk_.t[6]
+              << "\nsmoothed plans " << smoothed_ << ", verified segments " << verified_segments_ << "\n";
   }
 
   ~Planner() {
@@ -502,6 +515,7 @@ class Planner {
   void run_round(const std::vector<int> &chosen, std::vector<char> &exhausted) {
     const int B = (int)chosen.size(), A = cfg_.threshold_misses, dim = cfg_.dim;
     std::vector<Cand> cand((size_t)B * A);
+    clk_.start();
     // ---- stage 1: candidate points, pose + first-edge verdicts
     std::vector<double> poses;
     std::vector<int> pose_of;
@@ -516,6 +530,7 @@ class Planner {
         pose_of.push_back(b * A + a);
         c.e_first = eb.add(nodes_[c.exp].p, c.p);
       }
+    clk_.lap(0);
     std::vector<uint8_t> hit(pose_of.size(), 0);
     if (!pose_of.empty() && cfg_.has_map) {
       check(sffg_collide_poses_f64(env_, poses.data(), (int64_t)pose_of.size(), hit.data()));
@@ -535,30 +550,46 @@ class Planner {
         alive.push_back(pose_of[i]);
       }
     }
-    // ---- stage 2: radius search over every tree (one global index == union of the per-tree searches)
-    const double check_dist = cfg_.dtree + 2 * cfg_.circum;
-    const float r2 = (float)(check_dist * check_dist);
+    clk_.lap(1);
+    // ---- stage 2: radius search over every tree (one global index == union of the per-tree searches).
+    // The reference asks for everything within dtree + 2*circum (forest.h:261-267) but its rules only ever fire for
+    // neighbours closer than max(parentDistance, dtree) (forest.h:276, :283); with an exact search the smaller radius
+    // returns exactly the neighbours that can matter (plus a float-rounding margin; the rules re-test in double).
     if (!alive.empty()) {
       std::vector<float> q(alive.size() * (size_t)dim);
-      for (size_t i = 0; i < alive.size(); ++i)
+      double reach = cfg_.dtree;
+      for (size_t i = 0; i < alive.size(); ++i) {
         for (int k = 0; k < dim; ++k) q[i * dim + k] = (float)cand[alive[i]].p[k];
+        reach = std::max(reach, cand[alive[i]].parent_dist);
+      }
+      reach = reach * (1.0 + 1e-5) + 1e-4 * (1.0 + std::fabs(cfg_.range[1]) + std::fabs(cfg_.range[3]) + std::fabs(cfg_.range[5]));
+      const float r2 = (float)(reach * reach);
       std::vector<int32_t> counts(alive.size());
       int64_t total = 0;
-      check(sffg_radius(global_idx_, q.data(), (int64_t)alive.size(), r2, counts.data(), nullptr, nullptr, 0, &total));
-      std::vector<int32_t> ids((size_t)std::max<int64_t>(total, 1));
-      std::vector<float> d2((size_t)std::max<int64_t>(total, 1));
-      if (total) check(sffg_radius(global_idx_, q.data(), (int64_t)alive.size(), r2, counts.data(), ids.data(), d2.data(), total, &total));
-      calls_ += 2;
+      radius_ids_.resize(std::max<size_t>(radius_ids_.size(), alive.size() * 32));
+      radius_d2_.resize(radius_ids_.size());
+      int rc = sffg_radius(global_idx_, q.data(), (int64_t)alive.size(), r2, counts.data(), radius_ids_.data(), radius_d2_.data(),
+                           (int64_t)radius_ids_.size(), &total);
+      ++calls_;
+      if (rc == SFFG_ERR_CAPACITY) {   // optimistic buffer too small: grow to the reported size and repeat once
+        radius_ids_.resize((size_t)total * 2);
+        radius_d2_.resize(radius_ids_.size());
+        rc = sffg_radius(global_idx_, q.data(), (int64_t)alive.size(), r2, counts.data(), radius_ids_.data(), radius_d2_.data(),
+                         (int64_t)radius_ids_.size(), &total);
+        ++calls_;
+      }
+      check(rc);
       n_queries_ += (long)alive.size();
       size_t off = 0;
       for (size_t i = 0; i < alive.size(); ++i) {
         Cand &c = cand[alive[i]];
-        c.nb.assign(ids.begin() + off, ids.begin() + off + counts[i]);
+        c.nb.assign(radius_ids_.begin() + off, radius_ids_.begin() + off + counts[i]);
         off += (size_t)counts[i];
         // the reference searches tree after tree (forest.h:262): tree-major order, (d2, id) order inside a tree
         std::stable_sort(c.nb.begin(), c.nb.end(), [&](int x, int y) { return nodes_[x].tree < nodes_[y].tree; });
       }
     }
+    clk_.lap(2);
     // ---- stage 3: edges the crowding / border rules may ask for (forest.h:270-302), in neighbour order
     eb.clear();
     for (int ci : alive) {
@@ -598,6 +629,7 @@ class Planner {
         }
       }
     }
+    clk_.lap(3);
     // ---- stage 4 + 5 (SFF*): k nearest nodes of the same tree for the first surviving attempt of every node
     std::vector<int> winners(B, -1);
     for (int b = 0; b < B; ++b)
@@ -613,21 +645,27 @@ class Planner {
       const int k = (int)std::min<double>(2 * M_E * std::log10((double)nodes_.size()), (double)SFFG_MAX_K);   // forest.h:309
       const int T = (int)tree_idx_.size();
       if (k >= 1) {
-        for (int t = 0; t < T; ++t) {
-          std::vector<int> who;
+        // one engine call for all trees: queries concatenated in tree order (sffg_knn_multi)
+        std::vector<int> who;
+        std::vector<int64_t> per(T, 0);
+        for (int t = 0; t < T; ++t)
           for (int b = 0; b < B; ++b)
-            if (winners[b] >= 0 && nodes_[cand[winners[b]].exp].tree == t) who.push_back(winners[b]);
-          if (who.empty()) continue;
+            if (winners[b] >= 0 && nodes_[cand[winners[b]].exp].tree == t) {
+              who.push_back(winners[b]);
+              ++per[t];
+            }
+        if (!who.empty()) {
           std::vector<float> q(who.size() * (size_t)dim);
           for (size_t i = 0; i < who.size(); ++i)
             for (int c = 0; c < dim; ++c) q[i * dim + c] = (float)cand[who[i]].p[c];
           std::vector<int32_t> ids(who.size() * (size_t)k);
           std::vector<float> d2(who.size() * (size_t)k);
-          check(sffg_knn(tree_idx_[t], q.data(), (int64_t)who.size(), k, ids.data(), d2.data()));
+          check(sffg_knn_multi(tree_idx_.data(), per.data(), T, q.data(), k, ids.data(), d2.data()));
           ++calls_;
           n_queries_ += (long)who.size();
           for (size_t i = 0; i < who.size(); ++i) {
             Cand &c = cand[who[i]];
+            const int t = nodes_[c.exp].tree;
             for (int j = 0; j < k && ids[i * k + j] >= 0; ++j) c.knn.push_back(members_[t][ids[i * k + j]]);
           }
         }
@@ -661,6 +699,7 @@ class Planner {
       }
       n_edges_ += (long)(eb2.s.size() / 6);
     }
+    clk_.lap(4);
     // ---- stage 6: replay in the reference's order
     std::vector<int> added;
     for (int b = 0; b < B && iter_ < cfg_.max_iterations; ++b) {
@@ -691,7 +730,9 @@ class Planner {
       }
       exhausted[b] = !success && !deferred;
     }
+    clk_.lap(5);
     flush_index_appends();
+    clk_.lap(6);
   }
 
   // creates the node of an accepted candidate: SFF* parent choice + rewiring (forest.h:306-351) or plain SFF (:352-356)
@@ -910,6 +951,7 @@ class Planner {
     verified_segments_ = (long)fwd.free_flag.size();
   }
 
+  StageClock clk_;
   Config cfg_;
   std::mt19937_64 rng_;
   int batch_;
@@ -920,6 +962,8 @@ class Planner {
   std::vector<Node> nodes_;
   std::vector<std::vector<int>> members_;   // per tree: local index id -> global node id
   std::vector<int> pending_;
+  std::vector<int32_t> radius_ids_;
+  std::vector<float> radius_d2_;
   std::vector<int> frontier_, closed_;
   std::map<std::pair<int, int>, std::vector<Border>> borders_;
   std::map<std::pair<int, int>, Link> links_;
