@@ -23,14 +23,20 @@
 namespace sffg {
 namespace {
 
-constexpr int kWarpsPerBlock = 8;
+#ifndef SFFG_WARPS
+#define SFFG_WARPS 16
+#endif
+#ifndef SFFG_TRI_FLUSH
+#define SFFG_TRI_FLUSH 1
+#endif
+constexpr int kWarpsPerBlock = SFFG_WARPS;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kStackCap = 384;   // node ids pending for one pose
 constexpr int kTriCap = 64;      // candidate triangles pending for one pose
-constexpr int kTriFlush = 12;    // run the triangle stage once this many candidates are pending
+constexpr int kTriFlush = SFFG_TRI_FLUSH;    // run the triangle stage once this many candidates are pending
 constexpr unsigned kFull = 0xffffffffu;
 #ifndef SFFG_MIN_BLOCKS
-#define SFFG_MIN_BLOCKS 2
+#define SFFG_MIN_BLOCKS 1
 #endif
 constexpr float kEpsBox = 1.52587890625e-05f;   // 2^-16, relative slack of the box culls   (>= 140 ulp)
 constexpr float kEpsSat = 1.52587890625e-05f;   // 2^-16, relative position error of the FP32 SAT stage

@@ -39,8 +39,10 @@ def test_seeded_sweep_vs_obbtree_oracle(sff, orc, meshes, case, n):
     margins = orc.pose_margin(meshes[on], meshes[rn], poses[bad].astype(np.float64)) if len(bad) else []
     assert len(bad) == 0, f"{case}: {len(bad)} mismatches; poses {bad[:8]}, oracle margins {margins[:8]}"
     assert cnt["poses"] == n and 0 < cnt["poses_past_root"] <= n
-    # the FP64 stage must stay the exception, not the rule
-    assert cnt["exact_tests"] <= 0.2 * max(cnt["pair_tests"], 1)
+    # the FP64 stage must stay the exception, not the rule: well under one executed FP64 pair test per pose that gets
+    # past the root cull (exact_tests = pairs the FP32 axis stage left undecided; most are proven contacts in FP32)
+    assert cnt["exact_run"] <= cnt["exact_tests"]
+    assert cnt["exact_run"] <= 0.6 * cnt["poses_past_root"]
     assert 0.001 < want.mean() < 0.9
 
 
