@@ -46,6 +46,18 @@ def load_meshes():
     return m["building_s10"], m["robot_small_s10"]
 
 
+def measured_traffic(poses_per_launch):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json)"""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        t = json.loads(p.read_text())
+        if int(t["poses_per_launch"]) == int(poses_per_launch):
+            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"]), t
+    except Exception:
+        pass
+    return None, None
+
+
 def measured_peak_hbm():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -239,6 +251,7 @@ def run_ours(args):
     if rank == 0:
         peak, which = measured_peak_hbm()
         achieved = ALGO_BYTES_PER_POSE * P / (kernel_ms * 1e-3) / 1e9
+        traffic, tinfo = measured_traffic(P)
         line = {
             "metric": METRIC, "value": world * P * args.steps / (total_ms * 1e-3), "unit": "poses/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -252,9 +265,13 @@ def run_ours(args):
             "gpu_launches": args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": which, "kernel": "collide_poses_kernel<f32>",
+                         "traffic": traffic, "peak_source": which, "kernel": "collide_poses_kernel<f32>",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_pose": ALGO_BYTES_PER_POSE,
-                         "note": "the path is FP32-issue / L2-latency bound, not HBM bound (SURVEY 8d); see DESIGN.md"},
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POSE * P,
+                         "ncu": ({"warp_instructions_per_pose": tinfo["warp_instructions"] / tinfo["poses_per_launch"],
+                                  "issue_slots_active_pct": tinfo["issue_active_pct"], "source": tinfo["source"]} if tinfo else None),
+                         "note": "the path is instruction-issue / L2-latency bound, not HBM bound (SURVEY 8d): the informative "
+                                 "fraction is issue_slots_active_pct; see DESIGN.md 4.1"},
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
