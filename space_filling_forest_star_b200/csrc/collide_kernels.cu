@@ -85,11 +85,12 @@ __device__ __forceinline__ bool axis_certifies_pre(const float *a, const float *
   return gap > bound;
 }
 
-// returns true when the pair is PROVEN disjoint in FP32; false = undecided (exact stage must look at it)
-__device__ bool pair_certified_disjoint(const XTri &x, const RobotTri &rt) {
+// Stage P1, lane-per-pair: the 8 most selective certificates -- AABB in the robot frame, the two face normals and the
+// six in-plane edge normals (robot-side intervals precomputed on the host).
+// Returns true when the pair is PROVEN disjoint; false = still open (stage P2 looks at it).
+__device__ bool pair_quick_disjoint(const XTri &x, const RobotTri &rt) {
   const float *p = x.v;
   const float errpos = 2.0f * x.err + kEpsSat * fmaxf(x.mabs, rt.qmax);
-  // AABB prefilter in the robot frame
   {
     float lo0 = min3f(p[0], p[3], p[6]) - errpos, hi0 = max3f(p[0], p[3], p[6]) + errpos;
     float lo1 = min3f(p[1], p[4], p[7]) - errpos, hi1 = max3f(p[1], p[4], p[7]) + errpos;
@@ -97,36 +98,18 @@ __device__ bool pair_certified_disjoint(const XTri &x, const RobotTri &rt) {
     if (lo0 > rt.hi[0] || hi0 < rt.lo[0] || lo1 > rt.hi[1] || hi1 < rt.lo[1] || lo2 > rt.hi[2] || hi2 < rt.lo[2])
       return true;
   }
-  // robot face normal, then obstacle face normal: these two reject most pairs
   if (axis_certifies_pre(rt.m, p, rt.m_lo, rt.m_hi, errpos)) return true;
-  float e[3][3];
-  e[0][0] = p[3] - p[0]; e[0][1] = p[4] - p[1]; e[0][2] = p[5] - p[2];
-  e[1][0] = p[6] - p[3]; e[1][1] = p[7] - p[4]; e[1][2] = p[8] - p[5];
-  e[2][0] = p[0] - p[6]; e[2][1] = p[1] - p[7]; e[2][2] = p[2] - p[8];
-  float n[3];
-  n[0] = e[0][1] * e[1][2] - e[0][2] * e[1][1];
-  n[1] = e[0][2] * e[1][0] - e[0][0] * e[1][2];
-  n[2] = e[0][0] * e[1][1] - e[0][1] * e[1][0];
-  if (axis_certifies(n[0], n[1], n[2], p, rt.q, errpos)) return true;
+  const float e0[3] = {p[3] - p[0], p[4] - p[1], p[5] - p[2]}, e1[3] = {p[6] - p[3], p[7] - p[4], p[8] - p[5]};
+  const float n0 = e0[1] * e1[2] - e0[2] * e1[1], n1 = e0[2] * e1[0] - e0[0] * e1[2], n2 = e0[0] * e1[1] - e0[1] * e1[0];
+  if (axis_certifies(n0, n1, n2, p, rt.q, errpos)) return true;
 #pragma unroll
   for (int k = 0; k < 3; ++k)
     if (axis_certifies_pre(rt.h[k], p, rt.h_lo[k], rt.h_hi[k], errpos)) return true;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    float gx = e[i][1] * n[2] - e[i][2] * n[1];
-    float gy = e[i][2] * n[0] - e[i][0] * n[2];
-    float gz = e[i][0] * n[1] - e[i][1] * n[0];
-    if (axis_certifies(gx, gy, gz, p, rt.q, errpos)) return true;
-  }
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      float cx = e[i][1] * rt.f[j][2] - e[i][2] * rt.f[j][1];
-      float cy = e[i][2] * rt.f[j][0] - e[i][0] * rt.f[j][2];
-      float cz = e[i][0] * rt.f[j][1] - e[i][1] * rt.f[j][0];
-      if (axis_certifies(cx, cy, cz, p, rt.q, errpos)) return true;
-    }
+  // obstacle in-plane edge normals e_i x n: what separates a robot lying in the plane of a big triangle but beyond an edge
+  const float e2[3] = {p[0] - p[6], p[1] - p[7], p[2] - p[8]};
+  if (axis_certifies(e0[1] * n2 - e0[2] * n1, e0[2] * n0 - e0[0] * n2, e0[0] * n1 - e0[1] * n0, p, rt.q, errpos)) return true;
+  if (axis_certifies(e1[1] * n2 - e1[2] * n1, e1[2] * n0 - e1[0] * n2, e1[0] * n1 - e1[1] * n0, p, rt.q, errpos)) return true;
+  if (axis_certifies(e2[1] * n2 - e2[2] * n1, e2[2] * n0 - e2[0] * n2, e2[0] * n1 - e2[1] * n0, p, rt.q, errpos)) return true;
   return false;
 }
 
@@ -154,18 +137,29 @@ __device__ __forceinline__ bool edge_pierces(const float *a, const float *b, con
   return (v0 > bound && v1 > bound && v2 > bound) || (v0 < -bound && v1 < -bound && v2 < -bound);
 }
 
-// all lanes call with the same pair; returns (warp-uniform) true when a contact is PROVEN
-__device__ __forceinline__ bool pair_certified_contact(const XTri &x, const RobotTri &rt, int lane) {
-  const float errpos = 2.0f * x.err + kEpsSat * fmaxf(x.mabs, rt.qmax);
+// Stage P2, warp-per-pair (all lanes call with the same pair): the nine edge x edge axes e_i x f_j on lanes 0..8 and the
+// six edge-pierces-triangle contact certificates on lanes 9..14, all at once.
+// Returns 0 = proven disjoint, 1 = proven contact, 2 = undecided (FP64 stage).
+__device__ __forceinline__ int pair_cooperative_verdict(const XTri &x, const RobotTri &rt, int lane) {
+  const float *p = x.v;
   const float M = fmaxf(x.mabs, rt.qmax);
-  const float bound = 256.0f * errpos * M * M;
-  bool ok = false;
-  if (lane < 6) {
-    const int e = lane < 3 ? lane : lane - 3, e1 = e == 2 ? 0 : e + 1;
-    if (lane < 3) ok = edge_pierces(x.v + 3 * e, x.v + 3 * e1, rt.q[0], rt.q[1], rt.q[2], bound);
-    else ok = edge_pierces(rt.q[e], rt.q[e1], x.v, x.v + 3, x.v + 6, bound);
+  const float errpos = 2.0f * x.err + kEpsSat * M;
+  bool sep = false, con = false;
+  if (lane < 9) {
+    const int i = lane / 3, j = lane - 3 * i, i1 = i == 2 ? 0 : i + 1;
+    const float e[3] = {p[3 * i1] - p[3 * i], p[3 * i1 + 1] - p[3 * i + 1], p[3 * i1 + 2] - p[3 * i + 2]};
+    const float ax = e[1] * rt.f[j][2] - e[2] * rt.f[j][1], ay = e[2] * rt.f[j][0] - e[0] * rt.f[j][2],
+                az = e[0] * rt.f[j][1] - e[1] * rt.f[j][0];
+    sep = axis_certifies(ax, ay, az, p, rt.q, errpos);
+  } else if (lane < 15) {
+    const float bound = 256.0f * errpos * M * M;
+    const int c = lane - 9, ed = c < 3 ? c : c - 3, ed1 = ed == 2 ? 0 : ed + 1;
+    if (c < 3) con = edge_pierces(x.v + 3 * ed, x.v + 3 * ed1, rt.q[0], rt.q[1], rt.q[2], bound);
+    else con = edge_pierces(rt.q[ed], rt.q[ed1], x.v, x.v + 3, x.v + 6, bound);
   }
-  return __any_sync(kFull, ok);
+  if (__any_sync(kFull, sep)) return 0;
+  if (__any_sync(kFull, con)) return 1;
+  return 2;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -390,20 +384,20 @@ struct BoxTest {        // per-pose constants of the oriented-box test
   float o[3], ra[3], rob_sz;
 };
 
-// robot oriented box (centre T + R c, axes R, half extents h) against an AABB slot; conservative
+// robot oriented box (centre T + R c, axes R, half extents h) against an AABB slot; conservative.  Straight-line code:
+// lanes of one step almost never agree on an early exit, so all six axes are evaluated and combined without branches.
 __device__ __forceinline__ bool slot_overlaps(const EnvDev &E, const PoseU &P, const BoxTest &bt, const float4 a, const float4 b) {
   const float tx = (a.x - P.Thi[0]) - bt.o[0], ty = (a.y - P.Thi[1]) - bt.o[1], tz = (a.z - P.Thi[2]) - bt.o[2];
   const float pad = kEpsBox * (fabsf(tx) + fabsf(ty) + fabsf(tz) + b.x + b.y + b.z + bt.rob_sz);
-  if (fabsf(tx) > b.x + bt.ra[0] + pad || fabsf(ty) > b.y + bt.ra[1] + pad || fabsf(tz) > b.z + bt.ra[2] + pad) return false;
-  bool ov = true;
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const float s_j = P.R[j] * tx + P.R[3 + j] * ty + P.R[6 + j] * tz;
-    const float rb = fabsf(P.R[j]) * b.x + fabsf(P.R[3 + j]) * b.y + fabsf(P.R[6 + j]) * b.z;
-    const float hj = j == 0 ? E.rob_h[0] : (j == 1 ? E.rob_h[1] : E.rob_h[2]);
-    if (fabsf(s_j) > hj + rb + pad) ov = false;
-  }
-  return ov;
+  const float s0 = P.R[0] * tx + P.R[3] * ty + P.R[6] * tz, s1 = P.R[1] * tx + P.R[4] * ty + P.R[7] * tz,
+              s2 = P.R[2] * tx + P.R[5] * ty + P.R[8] * tz;
+  const float r0 = fabsf(P.R[0]) * b.x + fabsf(P.R[3]) * b.y + fabsf(P.R[6]) * b.z,
+              r1 = fabsf(P.R[1]) * b.x + fabsf(P.R[4]) * b.y + fabsf(P.R[7]) * b.z,
+              r2 = fabsf(P.R[2]) * b.x + fabsf(P.R[5]) * b.y + fabsf(P.R[8]) * b.z;
+  // the largest excess over the allowed distance on any axis; overlap iff none is positive
+  const float ex = fmaxf(fmaxf(fabsf(tx) - (b.x + bt.ra[0]), fabsf(ty) - (b.y + bt.ra[1])), fabsf(tz) - (b.z + bt.ra[2]));
+  const float eb = fmaxf(fmaxf(fabsf(s0) - (E.rob_h[0] + r0), fabsf(s1) - (E.rob_h[1] + r1)), fabsf(s2) - (E.rob_h[2] + r2));
+  return !(fmaxf(ex, eb) > pad);
 }
 
 template <int FMT, bool COUNT>
@@ -521,20 +515,22 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *
         bool undecided = false;
         if (pidx < npairs) {
           const int xi = pidx / E.n_robot, r = pidx - xi * E.n_robot;
-          undecided = !pair_certified_disjoint(ws.xt[xi], srob[r]);
+          undecided = !pair_quick_disjoint(ws.xt[xi], srob[r]);
         }
         unsigned um = __ballot_sync(kFull, undecided);
         if (COUNT) {
           const int np = (npairs - pb) < 32 ? (npairs - pb) : 32;
           tally.pair += np;
-          tally.exact += __popc(um);   // pairs the FP32 separating-axis stage left undecided
+          tally.exact += __popc(um);   // pairs the lane-per-pair stage P1 left open
         }
         while (um) {
           const int l = __ffs(um) - 1;
           um &= um - 1;
           const int pp = pb + l;
           const int xi = pp / E.n_robot, r = pp - xi * E.n_robot;
-          if (pair_certified_contact(ws.xt[xi], srob[r], lane)) {
+          const int verdict = pair_cooperative_verdict(ws.xt[xi], srob[r], lane);
+          if (verdict == 0) continue;
+          if (verdict == 1) {
             hit = true;
             break;
           }
