@@ -74,7 +74,9 @@ typedef struct {
   int64_t n_nodes;          /* 8-wide BVH nodes                                                               */
   int32_t depth;            /* levels of the wide BVH                                                         */
   int64_t device_bytes;     /* HBM held by this environment                                                   */
-  double build_ms;          /* host BVH build + upload                                                        */
+  double build_ms;          /* host BVH build + upload + clearance grid                                       */
+  int64_t grid_cells;       /* cells of the free-space (clearance) grid, 0 when disabled                      */
+  double grid_cell_size;
 } sffg_env_info_t;
 SFFG_API int sffg_env_info(const sffg_env *env, sffg_env_info_t *out);
 
@@ -105,6 +107,7 @@ typedef struct {
   int64_t poses, poses_past_root, box_tests, pair_tests, exact_tests;
   int64_t traversal_steps, triangle_passes, triangles_transformed;   /* warp-level steps of the two inner loops */
   int64_t exact_run;   /* FP64 pair tests actually executed (exact_tests counts pairs FP32 SAT left undecided) */
+  int64_t poses_past_grid;   /* poses neither culled by the obstacle AABB nor proven free by the clearance grid */
 } sffg_counters_t;
 SFFG_API int sffg_env_enable_counters(sffg_env *env, int on);
 /* after *_device calls: waits for the device and reports a traversal failure (SFFG_ERR_INTERNAL) if one was flagged */

@@ -17,4 +17,4 @@ for on, rn, rng in (("building_s10", "robot_small_s10", [-70, 70, -70, 70, 0, 14
     v = env.Collide(poses)
     c = env.read_counters()
     pr = max(c["poses_past_root"], 1)
-    print(on, rn, env.info, json.dumps({"hit": float(v.mean()), "past_root_frac": c["poses_past_root"] / n, "per_past_root": {k: c[k] / pr for k in c if k not in ("poses", "poses_past_root")}}))
+    print(on, rn, env.info, json.dumps({"hit": float(v.mean()), "past_root_frac": c["poses_past_root"] / n, "past_grid_frac": c["poses_past_grid"] / n, "per_past_root": {k: c[k] / pr for k in c if k not in ("poses", "poses_past_root")}}))

@@ -24,13 +24,13 @@ class SffgError(RuntimeError):
 
 class EnvInfo(C.Structure):
     _fields_ = [("n_obst_tris", C.c_int64), ("n_robot_tris", C.c_int64), ("n_nodes", C.c_int64), ("depth", C.c_int32),
-                ("device_bytes", C.c_int64), ("build_ms", C.c_double)]
+                ("device_bytes", C.c_int64), ("build_ms", C.c_double), ("grid_cells", C.c_int64), ("grid_cell_size", C.c_double)]
 
 
 class Counters(C.Structure):
     _fields_ = [("poses", C.c_int64), ("poses_past_root", C.c_int64), ("box_tests", C.c_int64), ("pair_tests", C.c_int64),
                 ("exact_tests", C.c_int64), ("traversal_steps", C.c_int64), ("triangle_passes", C.c_int64),
-                ("triangles_transformed", C.c_int64), ("exact_run", C.c_int64)]
+                ("triangles_transformed", C.c_int64), ("exact_run", C.c_int64), ("poses_past_grid", C.c_int64)]
 
 
 # name -> (restype, argtypes); mirrors include/sffg.h one to one (tests/test_abi.py checks the header against this)

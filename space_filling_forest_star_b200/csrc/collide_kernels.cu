@@ -378,7 +378,7 @@ struct PoseU {          // warp-uniform copy of one pose
   float Thi[3], Tlo[3]; // T = Thi + Tlo (+ negligible)
 };
 
-struct Tally { unsigned long long past_root, box, pair, exact, steps, tri_passes, tris, exact_run; };
+struct Tally { unsigned long long past_root, box, pair, exact, steps, tri_passes, tris, exact_run, past_grid; };
 
 struct BoxTest {        // per-pose constants of the oriented-box test
   float o[3], ra[3], rob_sz;
@@ -555,6 +555,17 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *
   return hit;
 }
 
+// O(1) free-space test: the cell of the clearance grid that holds the robot origin.  A clear bit proves that no obstacle
+// triangle comes within the robot's bounding radius of any point of the cell (the build inflates the reach by the cell's
+// half diagonal plus rounding margins), so the pose is free whatever its orientation.
+__device__ __forceinline__ bool clearance_says_free(const EnvDev &E, float tx, float ty, float tz) {
+  const float fx = (tx - E.grid_o[0]) * E.grid_inv_h, fy = (ty - E.grid_o[1]) * E.grid_inv_h, fz = (tz - E.grid_o[2]) * E.grid_inv_h;
+  if (!(fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)E.grid_n[0] && fy < (float)E.grid_n[1] && fz < (float)E.grid_n[2]))
+    return false;
+  const unsigned cell = ((unsigned)fz * (unsigned)E.grid_n[1] + (unsigned)fy) * (unsigned)E.grid_n[0] + (unsigned)fx;
+  return ((__ldg(E.clear_bits + (cell >> 5)) >> (cell & 31)) & 1u) == 0u;
+}
+
 // lane-per-pose cull: robot bounding sphere (about the robot origin) against the obstacle AABB
 __device__ __forceinline__ bool sphere_hits_root(const EnvDev &E, float tx, float ty, float tz, float tlo_mag) {
   const float dx = fmaxf(fabsf(tx - E.root_c[0]) - E.root_h[0], 0.f);
@@ -582,6 +593,7 @@ __device__ __forceinline__ void flush_tally(const EnvDev &E, const Tally &t, uns
     atomicAdd(E.counters + 3, t.pair);
     atomicAdd(E.counters + 4, t.exact);
     atomicAdd(E.counters + 8, t.exact_run);
+    atomicAdd(E.counters + 9, t.past_grid);
     atomicAdd(E.counters + 5, t.steps);
     atomicAdd(E.counters + 6, t.tri_passes);
     atomicAdd(E.counters + 7, t.tris);
@@ -595,8 +607,10 @@ __device__ __forceinline__ unsigned check_32_poses(const EnvDev &E, WarpScratch 
                                                    const LanePose<FMT> &lp, int lane, bool first_only, Tally &tally) {
   float thi[3], tlo[3], R[9];
   lp.split(thi, tlo);
-  const bool alive = valid && E.n_obst > 0 &&
-                     sphere_hits_root(E, thi[0], thi[1], thi[2], fabsf(tlo[0]) + fabsf(tlo[1]) + fabsf(tlo[2]));
+  bool alive = valid && E.n_obst > 0 &&
+               sphere_hits_root(E, thi[0], thi[1], thi[2], fabsf(tlo[0]) + fabsf(tlo[1]) + fabsf(tlo[2]));
+  if (alive && E.grid_n[0] > 0) alive = !clearance_says_free(E, thi[0], thi[1], thi[2]);
+  if (COUNT) tally.past_grid += __popc(__ballot_sync(kFull, alive));
   if (alive) lp.rot32(R);
   unsigned todo = __ballot_sync(kFull, alive);
   unsigned hitmask = 0;
@@ -630,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) collide_poses_kerne
   // a work unit is `chunk` (1..32) consecutive poses: 32 for large batches (full lanes in phase A), fewer when the
   // batch is too small to give every resident warp a unit (planner-sized calls are latency-, not throughput-bound)
   const long long nchunks = (n + chunk - 1) / chunk;
-  Tally tally = {0, 0, 0, 0, 0, 0, 0, 0};
+  Tally tally = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long nposes = 0;
   while (true) {
     unsigned c = 0;
@@ -680,7 +694,7 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(
   stage_robot(E, srob);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + (size_t)E.n_robot * sizeof(RobotTri))[warp];
-  Tally tally = {0, 0, 0, 0, 0, 0, 0, 0};
+  Tally tally = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long nposes = 0;
   const long long units = m * split;
   while (true) {
@@ -758,6 +772,83 @@ __global__ void finalize_edges_kernel(const int *fh, long long m, uint8_t *free_
   const int v = fh[i];
   free_out[i] = v == kNoHit ? 1 : 0;
   if (first_hit) first_hit[i] = v == kNoHit ? 0 : v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// clearance grid build: one warp per obstacle triangle marks the cells whose centre lies within `reach` of the triangle
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float point_tri_dist2(const float *p, const float *a, const float *b, const float *c) {
+  // closest point on a triangle (Voronoi-region walk), squared distance
+  const float ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+  const float ap[3] = {p[0] - a[0], p[1] - a[1], p[2] - a[2]};
+  const float d1 = ab[0] * ap[0] + ab[1] * ap[1] + ab[2] * ap[2], d2 = ac[0] * ap[0] + ac[1] * ap[1] + ac[2] * ap[2];
+  float q[3];
+  if (d1 <= 0.f && d2 <= 0.f) { q[0] = a[0]; q[1] = a[1]; q[2] = a[2]; }
+  else {
+    const float bp[3] = {p[0] - b[0], p[1] - b[1], p[2] - b[2]};
+    const float d3 = ab[0] * bp[0] + ab[1] * bp[1] + ab[2] * bp[2], d4 = ac[0] * bp[0] + ac[1] * bp[1] + ac[2] * bp[2];
+    if (d3 >= 0.f && d4 <= d3) { q[0] = b[0]; q[1] = b[1]; q[2] = b[2]; }
+    else {
+      const float vc = d1 * d4 - d3 * d2;
+      if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) {
+        const float v = d1 / (d1 - d3);
+        q[0] = a[0] + v * ab[0]; q[1] = a[1] + v * ab[1]; q[2] = a[2] + v * ab[2];
+      } else {
+        const float cp[3] = {p[0] - c[0], p[1] - c[1], p[2] - c[2]};
+        const float d5 = ab[0] * cp[0] + ab[1] * cp[1] + ab[2] * cp[2], d6 = ac[0] * cp[0] + ac[1] * cp[1] + ac[2] * cp[2];
+        if (d6 >= 0.f && d5 <= d6) { q[0] = c[0]; q[1] = c[1]; q[2] = c[2]; }
+        else {
+          const float vb = d5 * d2 - d1 * d6;
+          if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) {
+            const float w = d2 / (d2 - d6);
+            q[0] = a[0] + w * ac[0]; q[1] = a[1] + w * ac[1]; q[2] = a[2] + w * ac[2];
+          } else {
+            const float va = d3 * d6 - d5 * d4;
+            if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+              const float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+              q[0] = b[0] + w * (c[0] - b[0]); q[1] = b[1] + w * (c[1] - b[1]); q[2] = b[2] + w * (c[2] - b[2]);
+            } else {
+              const float den = 1.f / (va + vb + vc), v = vb * den, w = vc * den;
+              q[0] = a[0] + ab[0] * v + ac[0] * w; q[1] = a[1] + ab[1] * v + ac[1] * w; q[2] = a[2] + ab[2] * v + ac[2] * w;
+            }
+          }
+        }
+      }
+    }
+  }
+  const float dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
+  return dx * dx + dy * dy + dz * dz;
+}
+
+__global__ void build_clearance_kernel(const float4 *__restrict__ tris, int n_tris, float ox, float oy, float oz, float h, int nx,
+                                       int ny, int nz, float reach, unsigned *bits) {
+  const int lane = threadIdx.x & 31;
+  const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (t >= n_tris) return;
+  const float4 v0 = __ldg(tris + 3 * (size_t)t), v1 = __ldg(tris + 3 * (size_t)t + 1), v2 = __ldg(tris + 3 * (size_t)t + 2);
+  const float a[3] = {v0.x, v0.y, v0.z}, b[3] = {v1.x, v1.y, v1.z}, c[3] = {v2.x, v2.y, v2.z};
+  const float inv = 1.0f / h;
+  int lo[3], hi[3];
+  const float o[3] = {ox, oy, oz};
+  const int n[3] = {nx, ny, nz};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float mn = fminf(a[k], fminf(b[k], c[k])) - reach, mx = fmaxf(a[k], fmaxf(b[k], c[k])) + reach;
+    lo[k] = max(0, (int)floorf((mn - o[k]) * inv) - 1);
+    hi[k] = min(n[k] - 1, (int)floorf((mx - o[k]) * inv) + 1);
+  }
+  const int sx = hi[0] - lo[0] + 1, sy = hi[1] - lo[1] + 1, sz = hi[2] - lo[2] + 1;
+  if (sx <= 0 || sy <= 0 || sz <= 0) return;
+  const long long total = (long long)sx * sy * sz;
+  const float r2 = reach * reach;
+  for (long long i = lane; i < total; i += 32) {
+    const int ix = lo[0] + (int)(i % sx), iy = lo[1] + (int)((i / sx) % sy), iz = lo[2] + (int)(i / ((long long)sx * sy));
+    const float p[3] = {ox + (ix + 0.5f) * h, oy + (iy + 0.5f) * h, oz + (iz + 0.5f) * h};
+    if (!(point_tri_dist2(p, a, b, c) > r2)) {   // NaN (degenerate triangle) marks the cell: never optimistic
+      const unsigned cell = ((unsigned)iz * (unsigned)ny + (unsigned)iy) * (unsigned)nx + (unsigned)ix;
+      atomicOr(bits + (cell >> 5), 1u << (cell & 31));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -923,6 +1014,16 @@ cudaError_t launch_check_edges(const EnvDev &env_in, const double *d_starts, con
     e = cudaGetLastError();
   }
   return e;
+}
+
+cudaError_t launch_build_clearance(const float4 *d_tris32, int n_tris, const float origin[3], float h, const int n[3], float reach,
+                                   unsigned *d_bits, cudaStream_t stream) {
+  if (n_tris <= 0) return cudaSuccess;
+  const int threads = 256;
+  const long long blocks = ((long long)n_tris * 32 + threads - 1) / threads;
+  build_clearance_kernel<<<(unsigned)blocks, threads, 0, stream>>>(d_tris32, n_tris, origin[0], origin[1], origin[2], h, n[0], n[1],
+                                                                    n[2], reach, d_bits);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_gen_poses(uint64_t seed, uint64_t first, int64_t n, const float range[6], float *d_out,

@@ -19,6 +19,12 @@ struct EnvDev {
   float root_c[3], root_h[3];   // obstacle AABB, centre / half extents (outward rounded)
   float rob_c[3], rob_h[3];     // robot AABB in the robot frame (outward rounded)
   float rob_radius;             // max |robot vertex| about the robot origin (rounded up)
+  // free-space (clearance) grid: bit = 1 -> some obstacle triangle may be within rob_radius of a robot origin placed in
+  // that cell; bit = 0 -> every pose with its origin in the cell is collision free.  grid_n[0] == 0 disables it.
+  const unsigned *clear_bits;
+  float grid_o[3];
+  float grid_inv_h;
+  int grid_n[3];
   unsigned long long *counters; // 5 x u64 (may be null): poses, past_root, box_tests, pair_tests, exact_tests
   int *status;                  // device int, set non-zero on traversal-stack overflow
   unsigned int *work_counter;   // persistent-kernel work distribution: never reset, units are (fetched value - work_base)
@@ -45,5 +51,9 @@ cudaError_t launch_gen_poses(uint64_t seed, uint64_t first, int64_t n, const flo
                              cudaStream_t stream);
 
 size_t collide_smem_bytes(int n_robot);
+
+// marks every cell whose centre is within `reach` of an obstacle triangle (one warp per triangle)
+cudaError_t launch_build_clearance(const float4 *d_tris32, int n_tris, const float origin[3], float h, const int n[3], float reach,
+                                   unsigned *d_bits, cudaStream_t stream);
 
 }  // namespace sffg

@@ -87,7 +87,7 @@ using namespace sffg;
 // ---------------------------------------------------------------------------------------------------------------
 struct sffg_env {
   EnvDev dev{};
-  void *d_slots = nullptr, *d_top = nullptr, *d_tris32 = nullptr, *d_tris64 = nullptr, *d_robot = nullptr, *d_robot64 = nullptr;
+  void *d_slots = nullptr, *d_top = nullptr, *d_clear = nullptr, *d_tris32 = nullptr, *d_tris64 = nullptr, *d_robot = nullptr, *d_robot64 = nullptr;
   unsigned long long *d_counters = nullptr;
   int *h_status = nullptr;      // pinned + device-mapped: the kernels raise it, the host reads it without a copy
   unsigned *d_work = nullptr;   // ring of 8 work counters (never reset; see launch_collide_poses)
@@ -223,6 +223,7 @@ int sffg_env_destroy(sffg_env *env) {
   }
   cudaFree(env->d_slots);
   cudaFree(env->d_top);
+  cudaFree(env->d_clear);
   cudaFree(env->d_tris32);
   cudaFree(env->d_tris64);
   cudaFree(env->d_robot);
@@ -323,14 +324,54 @@ int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot
   SFFG_ENV_CUDA(upload(&env->d_tris64, t64.data(), t64.size() * sizeof(double)));
   SFFG_ENV_CUDA(upload(&env->d_robot, rob.data(), rob.size() * sizeof(RobotTri)));
   SFFG_ENV_CUDA(upload(&env->d_robot64, robot_tris, 9 * (size_t)n_robot * sizeof(double)));
-  SFFG_ENV_CUDA(cudaMalloc((void **)&env->d_counters, 9 * sizeof(unsigned long long)));
-  SFFG_ENV_CUDA(cudaMemset(env->d_counters, 0, 9 * sizeof(unsigned long long)));
+  SFFG_ENV_CUDA(cudaMalloc((void **)&env->d_counters, 10 * sizeof(unsigned long long)));
+  SFFG_ENV_CUDA(cudaMemset(env->d_counters, 0, 10 * sizeof(unsigned long long)));
   SFFG_ENV_CUDA(cudaHostAlloc((void **)&env->h_status, sizeof(int), cudaHostAllocMapped));
   *env->h_status = 0;
   SFFG_ENV_CUDA(cudaHostAlloc((void **)&env->h_small, kSmallBytes, cudaHostAllocMapped));
   SFFG_ENV_CUDA(cudaMalloc((void **)&env->d_work, 8 * sizeof(unsigned)));
   SFFG_ENV_CUDA(cudaMemset(env->d_work, 0, 8 * sizeof(unsigned)));
   for (int s = 0; s < 2; ++s) SFFG_ENV_CUDA(cudaStreamCreateWithFlags(&env->streams[s], cudaStreamNonBlocking));
+  // ---- clearance grid (free-space bitmap) over the obstacle AABB dilated by the robot's reach
+  d.clear_bits = nullptr;
+  d.grid_n[0] = d.grid_n[1] = d.grid_n[2] = 0;
+  d.grid_inv_h = 0.f;
+  d.grid_o[0] = d.grid_o[1] = d.grid_o[2] = 0.f;
+  const char *grid_env = std::getenv("SFFG_CLEARANCE_GRID");
+  if (n_obst > 0 && !(grid_env && grid_env[0] == '0')) {
+    const double rho = d.rob_radius;
+    double h = rho / 4.0;
+    double ext[3], maxc = 0;
+    for (int k = 0; k < 3; ++k) {
+      ext[k] = (bvh.root_hi[k] - bvh.root_lo[k]) + 2.0 * rho;
+      maxc = std::max({maxc, std::fabs(bvh.root_lo[k]) + rho, std::fabs(bvh.root_hi[k]) + rho});
+    }
+    // cap the grid at 2^24 cells (2 MB of bits, L2-resident)
+    while ((ext[0] / h + 1) * (ext[1] / h + 1) * (ext[2] / h + 1) > double(1 << 24)) h *= 1.25;
+    int gn[3];
+    float go[3];
+    for (int k = 0; k < 3; ++k) {
+      go[k] = (float)(bvh.root_lo[k] - rho);
+      gn[k] = std::max(1, (int)std::ceil(ext[k] / h));
+    }
+    // reach = bounding radius + half cell diagonal + margins for float rounding of vertices, cell lookup and distances
+    const double reach = (rho + 0.8661 * h) * 1.002 + 1e-3 * h + maxc * 3.9e-6;
+    const size_t words = ((size_t)gn[0] * gn[1] * gn[2] + 31) / 32;
+    SFFG_ENV_CUDA(cudaMalloc(&env->d_clear, words * sizeof(unsigned)));
+    SFFG_ENV_CUDA(cudaMemset(env->d_clear, 0, words * sizeof(unsigned)));
+    SFFG_ENV_CUDA(launch_build_clearance(reinterpret_cast<const float4 *>(env->d_tris32), (int)n_obst, go, (float)h, gn, (float)reach,
+                                         (unsigned *)env->d_clear, env->streams[0]));
+    SFFG_ENV_CUDA(cudaStreamSynchronize(env->streams[0]));
+    bytes += words * sizeof(unsigned);
+    d.clear_bits = reinterpret_cast<const unsigned *>(env->d_clear);
+    for (int k = 0; k < 3; ++k) {
+      d.grid_o[k] = go[k];
+      d.grid_n[k] = gn[k];
+    }
+    d.grid_inv_h = (float)(1.0 / h);
+    env->info.grid_cells = (int64_t)gn[0] * gn[1] * gn[2];
+    env->info.grid_cell_size = h;
+  }
   d.slots = reinterpret_cast<const float4 *>(env->d_slots);
   d.top = reinterpret_cast<const float4 *>(env->d_top);
   d.n_top = (int)top.size();
@@ -364,13 +405,13 @@ int sffg_env_info(const sffg_env *env, sffg_env_info_t *out) {
 int sffg_env_enable_counters(sffg_env *env, int on) {
   if (!env) return fail(SFFG_ERR_ARG, "null env");
   env->count = on != 0;
-  SFFG_CUDA(cudaMemset(env->d_counters, 0, 9 * sizeof(unsigned long long)));
+  SFFG_CUDA(cudaMemset(env->d_counters, 0, 10 * sizeof(unsigned long long)));
   return SFFG_OK;
 }
 
 int sffg_env_read_counters(sffg_env *env, sffg_counters_t *out) {
   if (!env || !out) return fail(SFFG_ERR_ARG, "null argument");
-  unsigned long long h[9];
+  unsigned long long h[10];
   SFFG_CUDA(cudaDeviceSynchronize());
   SFFG_CUDA(cudaMemcpy(h, env->d_counters, sizeof h, cudaMemcpyDeviceToHost));
   out->poses = (int64_t)h[0];
@@ -382,6 +423,7 @@ int sffg_env_read_counters(sffg_env *env, sffg_counters_t *out) {
   out->triangle_passes = (int64_t)h[6];
   out->triangles_transformed = (int64_t)h[7];
   out->exact_run = (int64_t)h[8];
+  out->poses_past_grid = (int64_t)h[9];
   return SFFG_OK;
 }
 
