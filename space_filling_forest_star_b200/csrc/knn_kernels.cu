@@ -14,93 +14,13 @@
 #include <cfloat>
 
 #include "../../include/sffg.h"
+#include "knn_common.cuh"
 #include "knn_kernels.cuh"
 
 namespace sffg {
 namespace {
 
-constexpr unsigned kFull = 0xffffffffu;
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * 32;
-constexpr float kTwoPiHi = 6.28318548202514648f;      // float(2*pi)
-constexpr float kTwoPiLoNeg = 1.74845553146951715e-07f;  // float(2*pi) - 2*pi, nearest float
-
-// |wrap(b - a)| of NormalizeAngle<float> (reference src/primitives.h:277-292: the +-2*pi is done in double and
-// narrowed).  Exhaustively verified equal for every float |b - a| < 14 (tests/test_metric_wrap.py):
-//   |d| >= float(pi)  ->  |(|d| - hi) + lo'|   (first subtraction exact by Sterbenz, second correctly rounded)
-//   otherwise         ->  |d|, and min() selects between the two without a branch
-__device__ __forceinline__ float wrapped_abs(float qa, float na) {
-  const float a = fabsf(__fsub_rn(qa, na));
-  const float t = __fadd_rn(__fsub_rn(a, kTwoPiHi), kTwoPiLoNeg);
-  return fminf(a, fabsf(t));
-}
-
-// translational part (all of the metric for DIM == 2): ((dx^2 + dy^2) + dz^2), float, unfused
-template <int DIM>
-__device__ __forceinline__ float metric_lin(const float *nd, const float *q) {
-  float d = __fsub_rn(nd[0], q[0]);
-  float r = __fmul_rn(d, d);
-  d = __fsub_rn(nd[1], q[1]);
-  r = __fadd_rn(r, __fmul_rn(d, d));
-  if (DIM == 6) {
-    d = __fsub_rn(nd[2], q[2]);
-    r = __fadd_rn(r, __fmul_rn(d, d));
-  }
-  return r;
-}
-// angular part continues the same accumulator: (((r + wy^2) + wp^2) + wr^2).  Every term is >= 0 and round-to-nearest
-// addition is monotone, so metric_lin() is a lower bound of the full distance: a 32-node block whose translational
-// parts all reach the current k-th distance cannot contain a candidate and its angles are never loaded.
-__device__ __forceinline__ float metric_ang(float r, const float *na, const float *q) {
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float w = wrapped_abs(q[3 + c], na[c]);
-    r = __fadd_rn(r, __fmul_rn(w, w));
-  }
-  return r;
-}
-template <int DIM>
-__device__ __forceinline__ float metric(const float *nd, const float *q) {
-  float r = metric_lin<DIM>(nd, q);
-  if (DIM == 6) r = metric_ang(r, nd + 3, q);
-  return r;
-}
-
-// sorted (ascending) list of 32*KPL entries spread over the warp: position j lives in lane j / KPL, slot j % KPL
-template <int KPL>
-struct TopK {
-  float d[KPL];
-  int id[KPL];
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int s = 0; s < KPL; ++s) { d[s] = INFINITY; id[s] = -1; }
-  }
-  // value at list position k-1, broadcast
-  __device__ __forceinline__ float kth(int k) const {
-    const int pos = k - 1, lane = pos / KPL, slot = pos % KPL;
-    float v = d[0];
-#pragma unroll
-    for (int s = 1; s < KPL; ++s) if (slot == s) v = d[s];
-    return __shfl_sync(kFull, v, lane);
-  }
-  // insert (cd, ci) AFTER all entries with distance <= cd (candidates arrive in ascending id order, so this is the
-  // (d2, id) order of FLANN's KNNSimpleResultSet, result_set.h:151-171).  All lanes call with identical arguments.
-  __device__ __forceinline__ void insert(float cd, int ci, int lane) {
-    float upd = __shfl_up_sync(kFull, d[KPL - 1], 1);
-    int upi = __shfl_up_sync(kFull, id[KPL - 1], 1);
-    if (lane == 0) upd = -INFINITY;
-#pragma unroll
-    for (int s = KPL - 1; s >= 0; --s) {
-      const float pd = s > 0 ? d[s - 1] : upd;
-      const int pi = s > 0 ? id[s - 1] : upi;
-      if (d[s] > cd) {
-        const bool shift = pd > cd;
-        d[s] = shift ? pd : cd;
-        id[s] = shift ? pi : ci;
-      }
-    }
-  }
-};
+using namespace knn;
 
 // One warp = QW queries x one node slice.
 //   item = blockIdx.x * kWarps + warp;  group = item / slices;  slice = item % slices
@@ -111,7 +31,7 @@ struct TopK {
 template <int DIM, int QW, int KPL>
 __global__ void __launch_bounds__(kThreads) knn_scan_kernel(IndexDev idx, const float *__restrict__ queries, long long nq,
                                                             int k, int slices, long long slice_len, float *out_d,
-                                                            int *out_i) {
+                                                            int *out_i, long long first, int slot_base, int slots_total) {
   const int lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   const long long group = item / slices;
@@ -129,7 +49,8 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(IndexDev idx, const 
     top[w].init();
     worst[w] = INFINITY;
   }
-  const long long begin = (long long)slice * slice_len;
+  // the scan covers nodes [first, idx.n): the whole index, or the not-yet-sorted tail behind a sorted view
+  const long long begin = first + (long long)slice * slice_len;
   long long end = begin + slice_len;
   if (end > idx.n) end = idx.n;
   constexpr int LIN = DIM == 6 ? 3 : 2;   // coordinates streamed for every block; the 3 angles only on demand
@@ -212,7 +133,7 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(IndexDev idx, const 
     for (int s = 0; s < KPL; ++s) {
       const int pos = lane * KPL + s;
       if (pos < k) {
-        const long long o = (qi * slices + slice) * k + pos;
+        const long long o = (qi * slots_total + slot_base + slice) * k + pos;
         out_d[o] = top[w].d[s];
         out_i[o] = top[w].id[s];
       }
@@ -220,8 +141,8 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(IndexDev idx, const 
   }
 }
 
-// merges the per-slice partial lists of one query (one warp per query).  Slices are visited in ascending order and
-// every partial list is (d2,id)-sorted, so candidates again arrive such that "insert after equals" is the id order.
+// merges the partial lists of one query (one warp per query) with the (d2, id)-keyed insert: lists may come from node
+// slices, from the spatially sorted view and from the unsorted tail, in any id order.
 template <int KPL>
 __global__ void __launch_bounds__(kThreads) knn_merge_kernel(const float *__restrict__ part_d, const int *__restrict__ part_i,
                                                              long long nq, int k, int slices, float *out_d, int *out_i) {
@@ -231,6 +152,7 @@ __global__ void __launch_bounds__(kThreads) knn_merge_kernel(const float *__rest
   TopK<KPL> top;
   top.init();
   float worst = INFINITY;
+  int worst_id = -1;
   const long long total = (long long)slices * k;
   const float *pd = part_d + qi * total;
   const int *pi = part_i + qi * total;
@@ -238,15 +160,16 @@ __global__ void __launch_bounds__(kThreads) knn_merge_kernel(const float *__rest
     const long long i = b + lane;
     const float d = i < total ? pd[i] : INFINITY;
     const int id = i < total ? pi[i] : -1;
-    unsigned mask = __ballot_sync(kFull, d < worst && id >= 0);
+    unsigned mask = __ballot_sync(kFull, id >= 0 && (d < worst || (d == worst && (unsigned)id < (unsigned)worst_id)));
     while (mask) {
       const int src = __ffs(mask) - 1;
       mask &= mask - 1;
       const float cd = __shfl_sync(kFull, d, src);
       const int ci = __shfl_sync(kFull, id, src);
-      if (cd < worst) {
-        top.insert(cd, ci, lane);
+      if (cd < worst || (cd == worst && (unsigned)ci < (unsigned)worst_id)) {
+        top.insert_keyed(cd, ci, lane);
         worst = top.kth(k);
+        worst_id = top.kth_id(k);
       }
     }
   }
@@ -266,7 +189,7 @@ template <int DIM, int QW, bool FILL>
 __global__ void __launch_bounds__(kThreads) radius_scan_kernel(IndexDev idx, const float *__restrict__ queries, long long nq,
                                                                float r2, int slices, long long slice_len, int *counts,
                                                                const long long *offsets, int *cursor,
-                                                               unsigned long long *keys) {
+                                                               unsigned long long *keys, long long first) {
   const int lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   const long long group = item / slices;
@@ -282,7 +205,7 @@ __global__ void __launch_bounds__(kThreads) radius_scan_kernel(IndexDev idx, con
     for (int c = 0; c < DIM; ++c) q[w][c] = __ldg(queries + qi * DIM + c);
     cnt[w] = 0;
   }
-  const long long begin = (long long)slice * slice_len;
+  const long long begin = first + (long long)slice * slice_len;
   long long end = begin + slice_len;
   if (end > idx.n) end = idx.n;
   const unsigned lt = (1u << lane) - 1u;
@@ -376,10 +299,10 @@ __global__ void index_append_kernel(float *coords, long long capacity, int dim, 
 
 template <int DIM, int QW>
 cudaError_t launch_knn_kpl(const IndexDev &idx, const float *q, int64_t nq, int k, int slices, int64_t slice_len,
-                           float *od, int *oi, unsigned grid, cudaStream_t st) {
-  if (k <= 32) knn_scan_kernel<DIM, QW, 1><<<grid, kThreads, 0, st>>>(idx, q, nq, k, slices, slice_len, od, oi);
-  else if (k <= 64) knn_scan_kernel<DIM, QW, 2><<<grid, kThreads, 0, st>>>(idx, q, nq, k, slices, slice_len, od, oi);
-  else knn_scan_kernel<DIM, QW, 4><<<grid, kThreads, 0, st>>>(idx, q, nq, k, slices, slice_len, od, oi);
+                           float *od, int *oi, unsigned grid, cudaStream_t st, long long first, int slot_base, int slots_total) {
+  if (k <= 32) knn_scan_kernel<DIM, QW, 1><<<grid, kThreads, 0, st>>>(idx, q, nq, k, slices, slice_len, od, oi, first, slot_base, slots_total);
+  else if (k <= 64) knn_scan_kernel<DIM, QW, 2><<<grid, kThreads, 0, st>>>(idx, q, nq, k, slices, slice_len, od, oi, first, slot_base, slots_total);
+  else knn_scan_kernel<DIM, QW, 4><<<grid, kThreads, 0, st>>>(idx, q, nq, k, slices, slice_len, od, oi, first, slot_base, slots_total);
   return cudaGetLastError();
 }
 
@@ -412,42 +335,54 @@ size_t knn_scratch_bytes(const KnnPlan &p, int64_t nq, int k) {
   return (size_t)nq * p.slices * k * 8;
 }
 
+// brute-force scan of nodes [first, idx.n) in `slices` pieces; partial list of slice s goes to slot slot_base + s of
+// slots_total (slots_total == 1: od / oi are the final [nq][k] outputs)
+cudaError_t launch_knn_scan_range(const IndexDev &idx, const float *d_queries, int64_t nq, int k, int qw, int slices,
+                                  int64_t slice_len, int64_t first, float *od, int *oi, int slot_base, int slots_total,
+                                  cudaStream_t stream) {
+  if (nq <= 0 || slices <= 0) return cudaSuccess;
+  const int64_t groups = (nq + qw - 1) / qw;
+  const int64_t items = groups * slices;
+  const unsigned grid = (unsigned)((items + kWarps - 1) / kWarps);
+  if (idx.dim == 6) {
+    if (qw == 8) return launch_knn_kpl<6, 8>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total);
+    if (qw == 4) return launch_knn_kpl<6, 4>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total);
+    return launch_knn_kpl<6, 1>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total);
+  }
+  if (qw == 8) return launch_knn_kpl<2, 8>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total);
+  if (qw == 4) return launch_knn_kpl<2, 4>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total);
+  return launch_knn_kpl<2, 1>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total);
+}
+
+cudaError_t launch_knn_merge(const float *part_d, const int *part_i, int64_t nq, int k, int slots, float *d_d2, int32_t *d_ids,
+                             cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  const unsigned mg = (unsigned)((nq + kWarps - 1) / kWarps);
+  if (k <= 32) knn_merge_kernel<1><<<mg, kThreads, 0, stream>>>(part_d, part_i, nq, k, slots, d_d2, d_ids);
+  else if (k <= 64) knn_merge_kernel<2><<<mg, kThreads, 0, stream>>>(part_d, part_i, nq, k, slots, d_d2, d_ids);
+  else knn_merge_kernel<4><<<mg, kThreads, 0, stream>>>(part_d, part_i, nq, k, slots, d_d2, d_ids);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_knn(const IndexDev &idx, const float *d_queries, int64_t nq, int k, int32_t *d_ids, float *d_d2,
                        void *d_scratch, const KnnPlan &plan, cudaStream_t stream) {
   if (nq <= 0) return cudaSuccess;
-  const int64_t items = plan.groups * plan.slices;
-  const unsigned grid = (unsigned)((items + kWarps - 1) / kWarps);
   float *od = d_d2;
   int *oi = d_ids;
   if (plan.slices > 1) {
     od = reinterpret_cast<float *>(d_scratch);
     oi = reinterpret_cast<int *>(od + (size_t)nq * plan.slices * k);
   }
-  cudaError_t e;
-  if (idx.dim == 6) {
-    if (plan.qw == 8) e = launch_knn_kpl<6, 8>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
-    else if (plan.qw == 4) e = launch_knn_kpl<6, 4>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
-    else e = launch_knn_kpl<6, 1>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
-  } else {
-    if (plan.qw == 8) e = launch_knn_kpl<2, 8>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
-    else if (plan.qw == 4) e = launch_knn_kpl<2, 4>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
-    else e = launch_knn_kpl<2, 1>(idx, d_queries, nq, k, plan.slices, plan.slice_len, od, oi, grid, stream);
-  }
+  cudaError_t e = launch_knn_scan_range(idx, d_queries, nq, k, plan.qw, plan.slices, plan.slice_len, 0, od, oi, 0, plan.slices, stream);
   if (e != cudaSuccess) return e;
-  if (plan.slices > 1) {
-    const unsigned mg = (unsigned)((nq + kWarps - 1) / kWarps);
-    if (k <= 32) knn_merge_kernel<1><<<mg, kThreads, 0, stream>>>(od, oi, nq, k, plan.slices, d_d2, d_ids);
-    else if (k <= 64) knn_merge_kernel<2><<<mg, kThreads, 0, stream>>>(od, oi, nq, k, plan.slices, d_d2, d_ids);
-    else knn_merge_kernel<4><<<mg, kThreads, 0, stream>>>(od, oi, nq, k, plan.slices, d_d2, d_ids);
-    e = cudaGetLastError();
-  }
+  if (plan.slices > 1) e = launch_knn_merge(od, oi, nq, k, plan.slices, d_d2, d_ids, stream);
   return e;
 }
 
 template <bool FILL>
 static cudaError_t launch_radius_any(const IndexDev &idx, const float *q, int64_t nq, float r2, int *counts,
                                      const long long *offsets, int *cursor, unsigned long long *keys, const KnnPlan &plan_in,
-                                     cudaStream_t st) {
+                                     cudaStream_t st, long long first) {
   if (nq <= 0) return cudaSuccess;
   KnnPlan plan = plan_in;
   if (plan.qw == 8) {   // the radius kernels are instantiated for 1 and 4 queries per warp
@@ -457,24 +392,25 @@ static cudaError_t launch_radius_any(const IndexDev &idx, const float *q, int64_
   const int64_t items = plan.groups * plan.slices;
   const unsigned grid = (unsigned)((items + kWarps - 1) / kWarps);
   if (idx.dim == 6) {
-    if (plan.qw == 4) radius_scan_kernel<6, 4, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys);
-    else radius_scan_kernel<6, 1, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys);
+    if (plan.qw == 4) radius_scan_kernel<6, 4, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys, first);
+    else radius_scan_kernel<6, 1, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys, first);
   } else {
-    if (plan.qw == 4) radius_scan_kernel<2, 4, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys);
-    else radius_scan_kernel<2, 1, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys);
+    if (plan.qw == 4) radius_scan_kernel<2, 4, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys, first);
+    else radius_scan_kernel<2, 1, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys, first);
   }
   return cudaGetLastError();
 }
 
 cudaError_t launch_radius_count(const IndexDev &idx, const float *d_queries, int64_t nq, float r2, int32_t *d_counts,
-                                const KnnPlan &plan, cudaStream_t stream) {
-  return launch_radius_any<false>(idx, d_queries, nq, r2, d_counts, nullptr, nullptr, nullptr, plan, stream);
+                                const KnnPlan &plan, cudaStream_t stream, int64_t first) {
+  return launch_radius_any<false>(idx, d_queries, nq, r2, d_counts, nullptr, nullptr, nullptr, plan, stream, first);
 }
 
 cudaError_t launch_radius_fill(const IndexDev &idx, const float *d_queries, int64_t nq, float r2, const int64_t *d_offsets,
-                               int32_t *d_cursor, unsigned long long *d_keys, const KnnPlan &plan, cudaStream_t stream) {
+                               int32_t *d_cursor, unsigned long long *d_keys, const KnnPlan &plan, cudaStream_t stream,
+                               int64_t first) {
   return launch_radius_any<true>(idx, d_queries, nq, r2, nullptr, reinterpret_cast<const long long *>(d_offsets), d_cursor,
-                                 d_keys, plan, stream);
+                                 d_keys, plan, stream, first);
 }
 
 cudaError_t launch_radius_sort(unsigned long long *d_keys, const int64_t *d_offsets, const int32_t *d_counts, int64_t nq,

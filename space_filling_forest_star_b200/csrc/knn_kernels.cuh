@@ -28,12 +28,20 @@ size_t knn_scratch_bytes(const KnnPlan &p, int64_t nq, int k);
 cudaError_t launch_knn(const IndexDev &idx, const float *d_queries, int64_t nq, int k, int32_t *d_ids, float *d_d2,
                        void *d_scratch, const KnnPlan &plan, cudaStream_t stream);
 
+cudaError_t launch_knn_scan_range(const IndexDev &idx, const float *d_queries, int64_t nq, int k, int qw, int slices,
+                                  int64_t slice_len, int64_t first, float *od, int *oi, int slot_base, int slots_total,
+                                  cudaStream_t stream);
+cudaError_t launch_knn_merge(const float *part_d, const int *part_i, int64_t nq, int k, int slots, float *d_d2, int32_t *d_ids,
+                             cudaStream_t stream);
+
+// the radius scans cover nodes [first, idx.n); counts are accumulated with atomicAdd (zero them first)
 cudaError_t launch_radius_count(const IndexDev &idx, const float *d_queries, int64_t nq, float r2, int32_t *d_counts,
-                                const KnnPlan &plan, cudaStream_t stream);
+                                const KnnPlan &plan, cudaStream_t stream, int64_t first = 0);
 
 // d_cursor must be zeroed [nq]; d_offsets = exclusive scan of counts [nq]; d_keys receives (d2 bits << 32 | id)
 cudaError_t launch_radius_fill(const IndexDev &idx, const float *d_queries, int64_t nq, float r2, const int64_t *d_offsets,
-                               int32_t *d_cursor, unsigned long long *d_keys, const KnnPlan &plan, cudaStream_t stream);
+                               int32_t *d_cursor, unsigned long long *d_keys, const KnnPlan &plan, cudaStream_t stream,
+                               int64_t first = 0);
 
 // sorts every row of d_keys ascending and unpacks it into ids / d2
 cudaError_t launch_radius_sort(unsigned long long *d_keys, const int64_t *d_offsets, const int32_t *d_counts, int64_t nq,

@@ -15,6 +15,7 @@
 #include "collide_kernels.cuh"
 #include "common.h"
 #include "knn_kernels.cuh"
+#include "knn_pruned.cuh"
 
 namespace sffg {
 
@@ -108,6 +109,10 @@ struct sffg_index {
   cudaStream_t stream = nullptr;
   DevBuf q, ids, d2, scratch, counts, offsets, cursor, keys, stage;
   unsigned char *h_small = nullptr;   // pinned + device-mapped staging for planner-sized queries
+  // spatially sorted view (knn_pruned.cu): covers nodes [0, n_sorted); rebuilt when the unsorted tail grows too long
+  DevBuf s_coords, s_ids, s_bb, s_keys, s_vals, s_temp, s_bounds;
+  int64_t n_sorted = 0, s_cap = 0, s_nblk_cap = 0;
+  bool pruning = true;
 };
 
 extern "C" {
@@ -593,6 +598,8 @@ int sffg_index_create(int dim, sffg_index **out) {
   if (rc != SFFG_OK) return rc;
   sffg_index *idx = new sffg_index();
   idx->dim = dim;
+  const char *pr = std::getenv("SFFG_KNN_PRUNING");
+  idx->pruning = !(pr && pr[0] == '0');
   cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaHostAlloc((void **)&idx->h_small, kSmallBytes, cudaHostAllocMapped);
   if (e == cudaSuccess) {   // storage exists from the start: the scan kernels may touch the first block of an empty index
@@ -614,7 +621,8 @@ int sffg_index_destroy(sffg_index *idx) {
   if (!idx) return SFFG_OK;
   if (idx->stream) cudaStreamSynchronize(idx->stream);
   cudaFree(idx->d_coords);
-  DevBuf *bufs[] = {&idx->q, &idx->ids, &idx->d2, &idx->scratch, &idx->counts, &idx->offsets, &idx->cursor, &idx->keys, &idx->stage};
+  DevBuf *bufs[] = {&idx->q, &idx->ids, &idx->d2, &idx->scratch, &idx->counts, &idx->offsets, &idx->cursor, &idx->keys, &idx->stage,
+                    &idx->s_coords, &idx->s_ids, &idx->s_bb, &idx->s_keys, &idx->s_vals, &idx->s_temp, &idx->s_bounds};
   for (DevBuf *b : bufs) b->release();
   if (idx->h_small) cudaFreeHost(idx->h_small);
   if (idx->stream) cudaStreamDestroy(idx->stream);
@@ -676,16 +684,84 @@ int sffg_index_add(sffg_index *idx, const float *pts, int64_t n) {
   return SFFG_OK;
 }
 
+constexpr int64_t kSortMinNodes = 8192;   // below this the exhaustive scan is already latency-bound
+
+// (re)builds the Morton-sorted view when the index is large and too many nodes were appended since the last build
+static int ensure_sorted(sffg_index *idx, cudaStream_t st) {
+  if (!idx->pruning || idx->n < kSortMinNodes) return SFFG_OK;
+  const int64_t tail = idx->n - idx->n_sorted;
+  if (idx->n_sorted > 0 && tail <= std::max<int64_t>(2048, idx->n_sorted / 4)) return SFFG_OK;
+  const int n = (int)idx->n;
+  const int lin = idx->dim == 6 ? 3 : 2;
+  if (n > idx->s_cap) {
+    idx->s_cap = ((int64_t)n * 3 / 2 + 31) / 32 * 32 + 128;
+    idx->s_nblk_cap = idx->s_cap / 32 + 32;
+    idx->s_coords.release();
+    idx->s_ids.release();
+    idx->s_bb.release();
+    idx->s_keys.release();
+    idx->s_vals.release();
+  }
+  int rc = idx->s_coords.reserve((size_t)idx->s_cap * idx->dim * 4);
+  if (rc == SFFG_OK) rc = idx->s_ids.reserve((size_t)idx->s_cap * 4);
+  if (rc == SFFG_OK) rc = idx->s_bb.reserve((size_t)idx->s_nblk_cap * 2 * lin * 4);
+  if (rc == SFFG_OK) rc = idx->s_keys.reserve((size_t)idx->s_cap * 8);
+  if (rc == SFFG_OK) rc = idx->s_vals.reserve((size_t)idx->s_cap * 8);
+  if (rc == SFFG_OK) rc = idx->s_temp.reserve(sorted_build_temp_bytes((int)idx->s_cap));
+  if (rc == SFFG_OK) rc = idx->s_bounds.reserve(64);
+  if (rc != SFFG_OK) return rc;
+  SortedBuildBuffers b;
+  b.bounds = (int *)idx->s_bounds.p;
+  b.keys_in = (unsigned *)idx->s_keys.p;
+  b.keys_out = b.keys_in + idx->s_cap;
+  b.vals_in = (unsigned *)idx->s_vals.p;
+  b.vals_out = b.vals_in + idx->s_cap;
+  b.temp = idx->s_temp.p;
+  b.temp_bytes = idx->s_temp.cap;
+  b.s_coords = (float *)idx->s_coords.p;
+  b.cap_s = idx->s_cap;
+  b.s_ids = (int *)idx->s_ids.p;
+  b.bb = (float *)idx->s_bb.p;
+  b.nblk_cap = idx->s_nblk_cap;
+  IndexDev v{idx->d_coords, idx->cap, idx->n, idx->dim};
+  SFFG_CUDA(launch_sorted_build(v, n, b, st));
+  idx->n_sorted = n;
+  return SFFG_OK;
+}
+
+static SortedDev sorted_view(const sffg_index *idx) {
+  SortedDev sv;
+  sv.coords = (const float *)idx->s_coords.p;
+  sv.ids = (const int *)idx->s_ids.p;
+  sv.bb = (const float *)idx->s_bb.p;
+  sv.cap_s = idx->s_cap;
+  sv.nblk_cap = idx->s_nblk_cap;
+  sv.n_sorted = (int)idx->n_sorted;
+  sv.nblk = (int)((idx->n_sorted + 31) / 32);
+  return sv;
+}
+
 int sffg_knn_device(sffg_index *idx, const float *d_queries, int64_t nq, int k, int32_t *d_ids_out, float *d_d2_out,
                     void *stream) {
   if (!idx || nq < 0 || k < 1 || k > SFFG_MAX_K || (nq > 0 && (!d_queries || !d_ids_out || !d_d2_out)))
     return fail(SFFG_ERR_ARG, "sffg_knn_device: bad arguments (1 <= k <= 128)");
   if (nq == 0) return SFFG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
   IndexDev v{idx->d_coords, idx->cap, idx->n, idx->dim};
-  KnnPlan plan = plan_knn(nq, idx->n, g_rt.sm_count);
-  int rc = idx->scratch.reserve(knn_scratch_bytes(plan, nq, k));
+  int rc = ensure_sorted(idx, st);
   if (rc != SFFG_OK) return rc;
-  SFFG_CUDA(launch_knn(v, d_queries, nq, k, d_ids_out, d_d2_out, idx->scratch.p, plan, (cudaStream_t)stream));
+  if (idx->n_sorted > 0) {
+    const SortedDev sv = sorted_view(idx);
+    const PrunedPlan plan = plan_pruned(nq, sv, idx->n - idx->n_sorted, g_rt.sm_count);
+    rc = idx->scratch.reserve(pruned_scratch_bytes(plan, nq, k));
+    if (rc != SFFG_OK) return rc;
+    SFFG_CUDA(launch_knn_pruned(v, sv, d_queries, nq, k, d_ids_out, d_d2_out, idx->scratch.p, plan, st));
+    return SFFG_OK;
+  }
+  KnnPlan plan = plan_knn(nq, idx->n, g_rt.sm_count);
+  rc = idx->scratch.reserve(knn_scratch_bytes(plan, nq, k));
+  if (rc != SFFG_OK) return rc;
+  SFFG_CUDA(launch_knn(v, d_queries, nq, k, d_ids_out, d_d2_out, idx->scratch.p, plan, st));
   return SFFG_OK;
 }
 
@@ -801,7 +877,12 @@ int sffg_radius(sffg_index *idx, const float *queries, int64_t nq, float r2, int
     SFFG_CUDA(cudaMemcpyAsync(idx->q.p, queries, qbytes, cudaMemcpyHostToDevice, st));
   }
   SFFG_CUDA(cudaMemsetAsync(idx->counts.p, 0, cbytes, st));
-  SFFG_CUDA(launch_radius_count(v, (const float *)idx->q.p, nq, r2, (int32_t *)idx->counts.p, plan, st));
+  rc = ensure_sorted(idx, st);
+  if (rc != SFFG_OK) return rc;
+  const bool pruned = idx->n_sorted > 0;
+  const SortedDev sv = sorted_view(idx);
+  if (pruned) SFFG_CUDA(launch_radius_count_pruned(v, sv, (const float *)idx->q.p, nq, r2, (int32_t *)idx->counts.p, g_rt.sm_count, st));
+  else SFFG_CUDA(launch_radius_count(v, (const float *)idx->q.p, nq, r2, (int32_t *)idx->counts.p, plan, st));
   SFFG_CUDA(cudaMemcpyAsync(small ? (void *)hc : (void *)counts_out, idx->counts.p, cbytes, cudaMemcpyDeviceToHost, st));
   SFFG_CUDA(cudaStreamSynchronize(st));
   if (small) std::memcpy(counts_out, hc, cbytes);
@@ -830,8 +911,12 @@ int sffg_radius(sffg_index *idx, const float *queries, int64_t nq, float r2, int
     SFFG_CUDA(cudaMemcpyAsync(idx->offsets.p, offs.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
   }
   SFFG_CUDA(cudaMemsetAsync(idx->cursor.p, 0, cbytes, st));
-  SFFG_CUDA(launch_radius_fill(v, (const float *)idx->q.p, nq, r2, (const int64_t *)idx->offsets.p, (int32_t *)idx->cursor.p,
-                               (unsigned long long *)idx->keys.p, plan, st));
+  if (pruned)
+    SFFG_CUDA(launch_radius_fill_pruned(v, sv, (const float *)idx->q.p, nq, r2, (const int64_t *)idx->offsets.p, (int32_t *)idx->cursor.p,
+                                        (unsigned long long *)idx->keys.p, g_rt.sm_count, st));
+  else
+    SFFG_CUDA(launch_radius_fill(v, (const float *)idx->q.p, nq, r2, (const int64_t *)idx->offsets.p, (int32_t *)idx->cursor.p,
+                                 (unsigned long long *)idx->keys.p, plan, st));
   SFFG_CUDA(launch_radius_sort((unsigned long long *)idx->keys.p, (const int64_t *)idx->offsets.p, (const int32_t *)idx->counts.p,
                                nq, (int32_t *)idx->ids.p, (float *)idx->d2.p, st));
   if (small_out) {

@@ -125,3 +125,40 @@ def test_empty_index_and_growth_boundaries(sff, orc):
         wi, wd = orc.knn_linear(nodes[:hi], q, 8)
         np.testing.assert_array_equal(ids, wi)
         np.testing.assert_array_equal(d2.view(np.uint32), wd.view(np.uint32))
+
+
+def test_sorted_view_tail_and_rebuild(sff, orc):
+    """large indices keep a Morton-sorted, block-pruned view: results must stay bit-identical to the exhaustive oracle
+    right after a build, with an unsorted tail behind the view, and after the tail forces a rebuild (k-NN and radius)"""
+    nodes = cloud(40000, 6, 21)
+    nodes[5000:5100] = nodes[100:200]            # ties across the sorted part
+    nodes[30500:30600] = nodes[100:200]          # ... and between sorted part and tail
+    q = cloud(300, 6, 22)
+    q[:20] = nodes[100:120]
+    idx = sff.Index(nodes[:30000])
+    steps = [(30000, "view just built"), (31500, "1 500-node tail"), (36000, "tail too long -> rebuild"), (40000, "tail again")]
+    have = 30000
+    for upto, what in steps:
+        if upto > have:
+            idx.addPoints(nodes[have:upto])
+            have = upto
+        for k in (1, 16, 40):
+            ids, d2 = idx.knnSearch(q, k)
+            wi, wd = orc.knn_linear(nodes[:have], q, k)
+            assert np.array_equal(ids, wi), (what, k)
+            assert np.array_equal(d2.view(np.uint32), wd.view(np.uint32)), (what, k)
+        ids1, _ = idx.knnSearch(q[:3], 16)       # small batch: sliced path + merge
+        np.testing.assert_array_equal(ids1, orc.knn_linear(nodes[:have], q[:3], 16)[0])
+        c, off, rid, rd = idx.radiusSearch(q, 60.0)
+        wc, woff, wid, wd2 = orc.radius_linear(nodes[:have], q, 60.0)
+        assert np.array_equal(c, wc) and np.array_equal(rid, wid), what
+        assert np.array_equal(rd.view(np.uint32), wd2.view(np.uint32)), what
+
+
+def test_pruning_can_be_disabled(sff, orc, monkeypatch):
+    monkeypatch.setenv("SFFG_KNN_PRUNING", "0")
+    nodes, q = cloud(20000, 2, 31), cloud(200, 2, 32)
+    idx = sff.Index(nodes)
+    ids, d2 = idx.knnSearch(q, 8)
+    wi, wd = orc.knn_linear(nodes, q, 8)
+    np.testing.assert_array_equal(ids, wi)
