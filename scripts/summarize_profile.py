@@ -47,7 +47,7 @@ def launches(tag):
     out = [f"# {tag}: ncu launch list of `python bench.py --steps 5 --warmup 3 --no-cpu` (gpu__time_duration.sum, --clock-control none)",
            "# per-launch times are cold-cache and serialised: compare SHARES, not absolutes",
            "# the timed region of `value` launches collide_poses_kernel only (1 launch per step = 100 % of the step);",
-           "# the remaining collide launches are the chunked e2e leg (16 chunks per host call), knn_scan / check_edges /",
+           "# the remaining collide launches are the chunked e2e leg (16 chunks per host call), knn_pruned / check_edges /",
            "# knn_merge belong to the untimed `extra` block of the JSON line", ""]
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f"{t / 1e6:10.3f} ms  {n:4d} launches  {100 * t / tot:5.1f} %  {k}")
@@ -77,7 +77,7 @@ def main():
     txt = launches(tag)
     if txt:
         (OUT / f"{tag}_launches.txt").write_text(txt)
-    kernels = {"collide": "collide_poses_kernelILi0ELb0", "knn": "knn_scan_kernelILi6", "edges": "check_edges_kernelILb0"}
+    kernels = {"collide": "collide_poses_kernelILi0ELb0", "knn": "knn_pruned_kernel", "edges": "check_edges_kernelILb0"}
     for name, key in kernels.items():
         rep = SRC / f"{tag}_{name}.ncu-rep"
         if not rep.exists():
