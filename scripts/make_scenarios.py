@@ -42,13 +42,13 @@ CONFIG = """<?xml version="1.0" ?>
   <Points>
 {points}
   </Points>
-  <Range autoDetect="false">
+{goal}  <Range autoDetect="false">
     <RangeX min="{r[0]}" max="{r[1]}" />
     <RangeY min="{r[2]}" max="{r[3]}" />
     <RangeZ min="{r[4]}" max="{r[5]}" />
   </Range>
   <Distances dtree="{dtree}" circum="{circum}"/>
-  <Improvements priorityBias="0"/>
+  <Improvements priorityBias="{bias}"/>
   <Thresholds standard="5"/>
   <MaxIterations value="{maxiter}"/>
   <Save>
@@ -89,13 +89,23 @@ def main():
     write_obj(out / "robot_cyl_small_s10.obj", m["robot_cyl_small_s10"])
     write_tri(out / "triangles.tri", m["triangles_tri"])
     for name, sc in SCENARIOS.items():
-        for solver, optimize in (("sff", "true"), ("sff", "false"), ("rrt", "true")):
-            if solver == "rrt" and len(sc["points"]) > 1:
-                continue   # the reference rejects multi-root RRT* (src/main.cpp:286-287)
+        fmt = lambda pts: "\n".join('    <Point coord="[%.17g; %.17g; %.17g]"/>' % tuple(p) for p in pts)
+        rest = {k: v for k, v in sc.items() if k != "points"}
+        for solver, optimize in (("sff", "true"), ("sff", "false")):
             tag = f"{name}_{solver}{'star' if optimize == 'true' else ''}"
-            pts = "\n".join('    <Point coord="[%.17g; %.17g; %.17g]"/>' % tuple(p) for p in sc["points"])
-            cfg = CONFIG.format(solver=solver, optimize=optimize, name=tag, points=pts, **{k: v for k, v in sc.items() if k != "points"})
-            (out / f"{tag}.xml").write_text(cfg)
+            (out / f"{tag}.xml").write_text(CONFIG.format(solver=solver, optimize=optimize, name=tag, points=fmt(sc["points"]),
+                                                          goal="", bias="0", **rest))
+        # Multi-T-RRT: every root grows its own RRT, trees merge when they meet (src/rrt.h:219-317); the reference rejects
+        # the optimal variant with several roots (src/main.cpp:286-287)
+        tag = f"{name}_mtrrt"
+        (out / f"{tag}.xml").write_text(CONFIG.format(solver="rrt", optimize="false", name=tag, points=fmt(sc["points"]), goal="",
+                                                      bias="0", **rest))
+        # single-query RRT / RRT*: first point = start, second point = goal, goal bias 0.05
+        goal = '  <Goal coord="[%.17g; %.17g; %.17g]"/>\n' % tuple(sc["points"][1])
+        for optimize in ("true", "false"):
+            tag = f"{name}_rrt{'star' if optimize == 'true' else ''}_goal"
+            (out / f"{tag}.xml").write_text(CONFIG.format(solver="rrt", optimize=optimize, name=tag, points=fmt(sc["points"][:1]),
+                                                          goal=goal, bias="0.05", **rest))
     print("scenarios written to", out)
 
 

@@ -60,7 +60,8 @@ HOST_BIN = PKG / "host" / "sff_planner"
 def build_host(force: bool = False) -> Path:
     """The restructured (batched) planner host: plain C++17 on top of the C ABI, linked against libsffg.so."""
     lib = build_native()
-    if not force and HOST_BIN.exists() and HOST_BIN.stat().st_mtime > max(HOST_SRC.stat().st_mtime, lib.stat().st_mtime):
+    newest = max([f.stat().st_mtime for f in HOST_SRC.parent.glob("*.h")] + [HOST_SRC.stat().st_mtime, lib.stat().st_mtime])
+    if not force and HOST_BIN.exists() and HOST_BIN.stat().st_mtime > newest:
         return HOST_BIN
     cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
     cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-I", str(PKG.parent / "include"), str(HOST_SRC), "-L", str(PKG), "-l:libsffg.so",

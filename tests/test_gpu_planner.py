@@ -1,5 +1,5 @@
-"""GPU test of the restructured (batched) SFF* host: every reported path is re-validated with the CPU oracle."""
-import subprocess
+"""GPU tests of the restructured (batched) planner hosts on the real engine: every reported path is re-validated with
+the CPU oracle.  (The same host logic runs against the engine test double in tests/test_planner_host_cpu.py.)"""
 import sys
 from pathlib import Path
 
@@ -7,87 +7,80 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
-ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "scripts"))
+import make_scenarios as MS  # noqa: E402
+import planner_util as PU  # noqa: E402
 
 
-def run_planner(tmp_path, scenario, seed, max_iter=None, batch=128):
-    subprocess.run([sys.executable, str(ROOT / "scripts" / "make_scenarios.py"), str(tmp_path)], check=True, capture_output=True)
+@pytest.fixture(scope="module")
+def exe():
     from space_filling_forest_star_b200 import build as B
-    exe = B.build_host()
-    cfg = tmp_path / f"{scenario}.xml"
-    if max_iter:
-        cfg.write_text(cfg.read_text().replace('MaxIterations value="100000"', f'MaxIterations value="{max_iter}"'))
-    paths = tmp_path / "paths.txt"
-    p = subprocess.run([str(exe), cfg.name, "0", "--seed", str(seed), "--batch", str(batch), "--paths", str(paths)], cwd=tmp_path,
-                       capture_output=True, text=True, timeout=600)
-    assert p.returncode == 0, p.stdout + p.stderr
-    row = (tmp_path / "output" / f"params_{scenario}.csv").read_text().strip().splitlines()[-1]
-    plans = []
-    for line in paths.read_text().splitlines():
-        v = line.split()
-        n = int(v[3])
-        plans.append((int(v[0]), int(v[1]), float(v[2]), np.array(v[4:4 + 6 * n], dtype=np.float64).reshape(n, 6)))
-    return row, plans, p.stdout
+    return B.build_host()
 
 
-def validate_plans(orc, obst, robot, plans, roots):
-    assert plans
-    for a, b, length, pts in plans:
-        # endpoints are the two roots; the length is the sum of the 6-D segment lengths
-        ends = {tuple(np.round(pts[0, :3], 9)), tuple(np.round(pts[-1, :3], 9))}
-        assert ends == {tuple(np.round(roots[a], 9)), tuple(np.round(roots[b], 9))}
-        seg = sum(orc.distance6(pts[i], pts[i + 1]) for i in range(len(pts) - 1))
-        assert seg == pytest.approx(length, rel=1e-9)
-        # every node is collision free and every segment passes the reference local planner in at least one direction
-        assert orc.collide_brute(obst, robot, pts).sum() == 0
-        f1, _, _ = orc.edges_free(obst, robot, pts[:-1], pts[1:], 0.1, 0)
-        f2, _, _ = orc.edges_free(obst, robot, pts[1:], pts[:-1], 0.1, 0)
-        assert np.all((f1 | f2) == 1), (a, b, np.nonzero((f1 | f2) == 0)[0])
+def roots_of(name, with_goal=False):
+    pts = np.array(MS.SCENARIOS[name]["points"], dtype=float)
+    return pts[:2] if with_goal else pts
 
 
-def test_sffstar_2d_solves_and_paths_are_valid(tmp_path, orc, meshes):
-    sys.path.insert(0, str(ROOT / "scripts"))
-    import make_scenarios as MS
-    row, plans, out = run_planner(tmp_path, "2d_sffstar", seed=7)
+def test_sffstar_2d_solves_and_paths_are_valid(exe, tmp_path, orc, meshes):
+    row, plans, out = PU.run_planner(exe, tmp_path, "2d_sffstar", seed=7)
     assert ",solved," in row, row
     assert len(plans) == 6   # 4 roots -> 6 pairs, all connected
-    validate_plans(orc, meshes["triangles_tri"], meshes["robot_small_s1"], plans, np.array(MS.SCENARIOS["2d"]["points"], dtype=float))
+    PU.validate_plans(orc, meshes["triangles_tri"], meshes["robot_small_s1"], plans, roots_of("2d"))
     # reproducible for a fixed seed
-    row2, _, _ = run_planner(tmp_path, "2d_sffstar", seed=7)
+    row2, _, _ = PU.run_planner(exe, tmp_path, "2d_sffstar", seed=7, run_id="1")
     assert row.split(",")[2:6] == row2.split(",")[2:6]
 
 
-def test_sffstar_3d_paths_are_valid(tmp_path, orc, meshes):
-    sys.path.insert(0, str(ROOT / "scripts"))
-    import make_scenarios as MS
-    row, plans, out = run_planner(tmp_path, "triang_sffstar", seed=3, max_iter=30000)
-    validate_plans(orc, meshes["triang_s10"], meshes["robot_small_s10"], plans, np.array(MS.SCENARIOS["triang"]["points"], dtype=float))
+def test_sffstar_3d_paths_are_valid(exe, tmp_path, orc, meshes):
+    row, plans, out = PU.run_planner(exe, tmp_path, "triang_sffstar", seed=3, max_iter=30000)
+    PU.validate_plans(orc, meshes["triang_s10"], meshes["robot_small_s10"], plans, roots_of("triang"))
 
 
-def test_batch_size_one_equals_sequential_semantics(tmp_path, orc, meshes):
+def test_batch_size_one_equals_sequential_semantics(exe, tmp_path, orc, meshes):
     """B = 1 is the reference's one-node-at-a-time loop; it must solve the 2-D problem as well"""
-    row, plans, out = run_planner(tmp_path, "2d_sffstar", seed=11, batch=1)
+    row, plans, out = PU.run_planner(exe, tmp_path, "2d_sffstar", seed=11, batch=1)
     assert ",solved," in row, row
 
 
-def test_smoothing_shortens_and_stays_valid(tmp_path, orc, meshes):
+def test_smoothing_shortens_and_stays_valid(exe, tmp_path, orc, meshes):
     """smoothing="true": SpaceForest::smoothPaths on the batched edge kernel; paths stay valid and never get longer"""
-    sys.path.insert(0, str(ROOT / "scripts"))
-    import make_scenarios as MS
-    row, plans, _ = run_planner(tmp_path, "2d_sffstar", seed=5)
-    cfg = tmp_path / "2d_sffstar.xml"
-    cfg.write_text(cfg.read_text().replace('smoothing="false"', 'smoothing="true"'))
-    from space_filling_forest_star_b200 import build as B
-    paths = tmp_path / "paths_s.txt"
-    p = subprocess.run([str(B.build_host()), cfg.name, "1", "--seed", "5", "--paths", str(paths)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
-    assert p.returncode == 0, p.stdout + p.stderr
-    smooth = []
-    for line in paths.read_text().splitlines():
-        v = line.split()
-        n = int(v[3])
-        smooth.append((int(v[0]), int(v[1]), float(v[2]), np.array(v[4:4 + 6 * n], dtype=np.float64).reshape(n, 6)))
-    validate_plans(orc, meshes["triangles_tri"], meshes["robot_small_s1"], smooth, np.array(MS.SCENARIOS["2d"]["points"], dtype=float))
+    row, plans, _ = PU.run_planner(exe, tmp_path, "2d_sffstar", seed=5)
+    _, smooth, _ = PU.run_planner(exe, tmp_path, "2d_sffstar", seed=5, smoothing=True, run_id="s")
+    PU.validate_plans(orc, meshes["triangles_tri"], meshes["robot_small_s1"], smooth, roots_of("2d"))
     raw = {(a, b): (d, len(pts)) for a, b, d, pts in plans}
     for a, b, d, pts in smooth:
         assert d <= raw[(a, b)][0] + 1e-9 and len(pts) <= raw[(a, b)][1]
     assert sum(d for _, _, d, _ in smooth) < sum(v[0] for v in raw.values())
+
+
+@pytest.mark.parametrize("scenario,mesh,robot,name", [
+    ("2d_rrtstar_goal", "triangles_tri", "robot_small_s1", "2d"),
+    ("triang_rrtstar_goal", "triang_s10", "robot_small_s10", "triang"),
+    ("building_rrtstar_goal", "building_s10", "robot_small_s10", "building"),
+])
+def test_rrtstar_to_goal(exe, tmp_path, orc, meshes, scenario, mesh, robot, name):
+    """RRT* from one root to a goal (BASELINE.json configs[2] names RRT* in building.obj); rrt.h:127-235"""
+    row, plans, out = PU.run_planner(exe, tmp_path, scenario, seed=4)
+    assert ",solved,[1;0]," in row, row + out
+    PU.validate_plans(orc, meshes[mesh], meshes[robot], plans, roots_of(name, True))
+
+
+def test_multi_t_rrt_3d(exe, tmp_path, orc, meshes):
+    """Multi-T-RRT: six trees merge into one (rrt.h:219-317); all 15 root pairs get a valid plan"""
+    row, plans, _ = PU.run_planner(exe, tmp_path, "triang_mtrrt", seed=1)
+    assert ",solved," in row, row
+    assert len(plans) == 15
+    PU.validate_plans(orc, meshes["triang_s10"], meshes["robot_small_s10"], plans, roots_of("triang"))
+
+
+def test_engine_and_double_agree_on_a_fixed_seed(exe, tmp_path):
+    """same host, same seed: the engine (GPU) and the CPU double behind the same ABI must produce the same params row
+    (iterations, solved flag, connected trees, path lengths) -- an end-to-end parity check of verdicts and neighbours"""
+    dbl = PU.build_double_host()
+    for scenario in ("2d_mtrrt", "2d_rrtstar_goal", "2d_sffstar"):
+        row_g, _, _ = PU.run_planner(exe, tmp_path, scenario, seed=9, run_id="g")
+        row_c, _, _ = PU.run_planner(dbl, tmp_path, scenario, seed=9, run_id="c")
+        assert row_g.split(",")[2:6] == row_c.split(",")[2:6], (scenario, row_g, row_c)

@@ -1,0 +1,113 @@
+"""Host logic of the batched planners (SFF / SFF*, RRT / RRT* / Multi-T-RRT) without a GPU.
+
+The hosts sit strictly above the C ABI (include/sffg.h), so here they are linked against tests/engine_double (the CPU
+oracle behind the same ABI -- test infrastructure, never shipped) instead of libsffg.so.  What is checked is the host
+side: the replayed accept / rewire / merge rules terminate, report the reference's params row, and every reported plan
+is valid under the reference's own local planner (re-validated independently with the brute-force oracle).
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "scripts"))
+import make_scenarios as MS  # noqa: E402
+import planner_util as PU  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def exe():
+    return PU.build_double_host()
+
+
+def roots_of(name, with_goal=False):
+    pts = np.array(MS.SCENARIOS[name]["points"], dtype=float)
+    return pts[:2] if with_goal else pts
+
+
+def test_double_is_not_the_engine(exe):
+    """the double lives under oracle/_build and reports a negative version; the product library is never this file"""
+    import ctypes
+    lib = ctypes.CDLL(str(PU.BUILD / "libsffg_double.so"))
+    assert lib.sffg_version() < 0
+    from space_filling_forest_star_b200 import _lib
+    assert "double" not in Path(_lib.lib_path()).name and "oracle" not in str(_lib.lib_path())
+
+
+def test_sffstar_2d(exe, tmp_path, orc, meshes):
+    row, plans, _ = PU.run_planner(exe, tmp_path, "2d_sffstar", seed=7)
+    assert ",solved," in row, row
+    assert len(plans) == 6
+    PU.validate_plans(orc, meshes["triangles_tri"], meshes["robot_small_s1"], plans, roots_of("2d"))
+
+
+@pytest.mark.parametrize("scenario", ["2d_rrt_goal", "2d_rrtstar_goal"])
+def test_rrt_single_query_2d(exe, tmp_path, orc, meshes, scenario):
+    """RRT / RRT* from one root to a goal (rrt.h:64-81, :130-134): solved at the first link to the goal tree"""
+    row, plans, out = PU.run_planner(exe, tmp_path, scenario, seed=3)
+    assert ",solved,[1;0]," in row, row
+    assert len(plans) == 1 and (plans[0][0], plans[0][1]) == (0, 1)
+    PU.validate_plans(orc, meshes["triangles_tri"], meshes["robot_small_s1"], plans, roots_of("2d", True))
+    # reproducible for a fixed seed
+    row2, _, _ = PU.run_planner(exe, tmp_path, scenario, seed=3, run_id="1")
+    assert row.split(",")[2:6] == row2.split(",")[2:6]
+
+
+def test_rrtstar_is_not_longer_than_rrt_on_average(exe, tmp_path):
+    """parent choice + rewiring (rrt.h:153-201) shorten the tree paths: compare mean path length over a few seeds"""
+    def mean_len(scenario):
+        tot = 0.0
+        for seed in range(1, 9):
+            _, plans, _ = PU.run_planner(exe, tmp_path, scenario, seed=seed, run_id=str(seed))
+            tot += plans[0][2]
+        return tot / 8
+    assert mean_len("2d_rrtstar_goal") < mean_len("2d_rrt_goal")
+
+
+def test_multi_t_rrt_2d_merges_all_trees(exe, tmp_path, orc, meshes):
+    """Multi-T-RRT (rrt.h:219-317): trees merge on contact until one is left; all 6 root pairs get a plan"""
+    row, plans, _ = PU.run_planner(exe, tmp_path, "2d_mtrrt", seed=5)
+    assert ",solved," in row, row
+    assert sorted(int(t) for t in row.split("[")[1].split("]")[0].split(";")) == [0, 1, 2, 3]
+    assert len(plans) == 6
+    PU.validate_plans(orc, meshes["triangles_tri"], meshes["robot_small_s1"], plans, roots_of("2d"))
+
+
+def test_multi_t_rrt_batch_one_is_sequential(exe, tmp_path, orc, meshes):
+    """batch 1 = the reference's one-sample-at-a-time loop (no carried samples, no snapshot effects)"""
+    row, plans, out = PU.run_planner(exe, tmp_path, "2d_mtrrt", seed=5, batch=1)
+    assert ",solved," in row and "carried samples 0," in out
+    PU.validate_plans(orc, meshes["triangles_tri"], meshes["robot_small_s1"], plans, roots_of("2d"))
+
+
+def test_rrtstar_3d_goal_with_smoothing(exe, tmp_path, orc, meshes):
+    """6-DoF RRT* to a goal in triang.obj, then RapidExpTree::smoothPaths (rrt.h:353-379) on the batched edge call"""
+    row, plans, _ = PU.run_planner(exe, tmp_path, "triang_rrtstar_goal", seed=2)
+    assert ",solved," in row, row
+    PU.validate_plans(orc, meshes["triang_s10"], meshes["robot_small_s10"], plans, roots_of("triang", True))
+    _, smooth, _ = PU.run_planner(exe, tmp_path, "triang_rrtstar_goal", seed=2, smoothing=True, run_id="s")
+    PU.validate_plans(orc, meshes["triang_s10"], meshes["robot_small_s10"], smooth, roots_of("triang", True))
+    assert smooth[0][2] <= plans[0][2] + 1e-9 and len(smooth[0][3]) <= len(plans[0][3])
+
+
+def test_multi_t_rrt_3d(exe, tmp_path, orc, meshes):
+    row, plans, _ = PU.run_planner(exe, tmp_path, "triang_mtrrt", seed=1)
+    assert ",solved," in row, row
+    assert len(plans) == 15   # 6 roots
+    PU.validate_plans(orc, meshes["triang_s10"], meshes["robot_small_s10"], plans, roots_of("triang"))
+
+
+def test_reference_validation_rules(exe, tmp_path):
+    """the reference rejects Multi-T-RRT* and biased Multi-T-RRT (src/main.cpp:286-288, :327-329); so does the host"""
+    import subprocess
+    PU.run_planner(exe, tmp_path, "2d_mtrrt", seed=1)
+    cfg = tmp_path / "2d_mtrrt.xml"
+    bad = tmp_path / "bad.xml"
+    bad.write_text(cfg.read_text().replace('optimize="false"', 'optimize="true"'))
+    p = subprocess.run([str(exe), bad.name], cwd=tmp_path, capture_output=True, text=True)
+    assert p.returncode == 1 and "Multi-T-RRT* is undefined!" in p.stdout
+    bad.write_text(cfg.read_text().replace('priorityBias="0"', 'priorityBias="0.5"'))
+    p = subprocess.run([str(exe), bad.name], cwd=tmp_path, capture_output=True, text=True)
+    assert p.returncode == 1 and "Multi-T-RRT with bias is undefined!" in p.stdout
