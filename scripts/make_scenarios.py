@@ -95,6 +95,10 @@ def main():
             tag = f"{name}_{solver}{'star' if optimize == 'true' else ''}"
             (out / f"{tag}.xml").write_text(CONFIG.format(solver=solver, optimize=optimize, name=tag, points=fmt(sc["points"]),
                                                           goal="", bias="0", **rest))
+        # the shipped configs carry priorityBias="0.95" (test_2D.xml:27, test_triang.xml:30): priority frontiers (forest.h:79-89)
+        tag = f"{name}_sffstar_bias"
+        (out / f"{tag}.xml").write_text(CONFIG.format(solver="sff", optimize="true", name=tag, points=fmt(sc["points"]), goal="",
+                                                      bias="0.95", **rest))
         # Multi-T-RRT: every root grows its own RRT, trees merge when they meet (src/rrt.h:219-317); the reference rejects
         # the optimal variant with several roots (src/main.cpp:286-287)
         tag = f"{name}_mtrrt"
@@ -102,6 +106,9 @@ def main():
                                                       bias="0", **rest))
         # single-query RRT / RRT*: first point = start, second point = goal, goal bias 0.05
         goal = '  <Goal coord="[%.17g; %.17g; %.17g]"/>\n' % tuple(sc["points"][1])
+        tag = f"{name}_sffstar_goal"   # single-query SFF*: one root + goal, goal-directed priority frontier (forest.h:91-109)
+        (out / f"{tag}.xml").write_text(CONFIG.format(solver="sff", optimize="true", name=tag, points=fmt(sc["points"][:1]),
+                                                      goal=goal, bias="0.95", **rest))
         for optimize in ("true", "false"):
             tag = f"{name}_rrt{'star' if optimize == 'true' else ''}_goal"
             (out / f"{tag}.xml").write_text(CONFIG.format(solver="rrt", optimize=optimize, name=tag, points=fmt(sc["points"][:1]),

@@ -203,9 +203,6 @@ inline Config load_config(const std::string &path) {
   if (c.solver == "rrt") {   // the reference's own validation, src/main.cpp:286-288, :327-329
     if (c.optimize && c.roots.size() > 1) die("Multi-T-RRT* is undefined!");
     if (!c.has_goal && c.priority_bias != 0) die("Multi-T-RRT with bias is undefined!");
-  } else {
-    if (c.has_goal) die("single-goal SFF is not covered by the batched host (use solver=\"rrt\" or the reference host with the shims)");
-    if (c.priority_bias != 0) die("priorityBias != 0 is not covered by the batched SFF host");
   }
   c.has_map = !c.obstacles.empty();
   return c;

@@ -16,13 +16,17 @@
 // Differences to the reference, all deliberate: neighbour search is exact with the intended metric (the reference's
 // FLANN setup is approximate and its functor assigns instead of accumulating); expansions of one round
 // do not see each other (a candidate that would interact with a node created in the same round is deferred to the
-// next round); stored angles are normalised into [-pi, pi); the RNG is seedable.  This file covers solver="sff" without a
-// goal and without priority bias; solver="rrt" (RRT / RRT* / Multi-T-RRT, with or without a goal) is in rrt_planner.h.
+// next round); stored angles are normalised into [-pi, pi); the RNG is seedable.  This file covers solver="sff" (SFF / SFF*,
+// plain or priority frontiers -- priorityBias, forest.h:79-89, :125-149 --, multi-goal or with a <Goal>, :91-109, :286-287);
+// solver="rrt" (RRT / RRT* / Multi-T-RRT, with or without a goal) is in rrt_planner.h.
 //
 //   sff_planner <config.xml> [run-id] [--seed S] [--batch B] [--paths file] [--quiet]
 //
 // Output: one line appended to the Params file in the reference's format (problemStruct.h:391-429):
 //   id,run,iterations,solved|unsolved,[connected tree ids],[pairwise path lengths],elapsed seconds
+#include <unordered_map>
+#include <unordered_set>
+
 #include "planner_common.h"
 #include "rrt_planner.h"
 
@@ -44,6 +48,66 @@ struct Border {
   int a, b;   // global node ids, a < b
 };
 
+// Heap<T,R> of the reference (src/heap.h:31-64) as the priority frontiers use it: a binary min-heap of node ids keyed by the
+// distance to a fixed target (cost function Distance, src/primitives.h:530-533), with removal at an arbitrary heap
+// position (pop(int), heap.h:203-227) and by node (the scan at forest.h:171-177).
+class TargetHeap {
+ public:
+  bool empty() const { return h_.empty(); }
+  int size() const { return (int)h_.size(); }
+  bool contains(int id) const { return where_.count(id) != 0; }
+  void push(int id, double key) {
+    if (contains(id)) return;
+    h_.push_back({key, id});
+    where_[id] = size() - 1;
+    up(size() - 1);
+  }
+  int pop_at(int pos) {
+    const int id = h_[pos].second;
+    where_.erase(id);
+    if (pos != size() - 1) {
+      h_[pos] = h_.back();
+      where_[h_[pos].second] = pos;
+      h_.pop_back();
+      up(pos);
+      down(pos);
+    } else {
+      h_.pop_back();
+    }
+    return id;
+  }
+  void remove(int id) {
+    auto it = where_.find(id);
+    if (it != where_.end()) pop_at(it->second);
+  }
+
+ private:
+  void swap_at(int a, int b) {
+    std::swap(h_[a], h_[b]);
+    where_[h_[a].second] = a;
+    where_[h_[b].second] = b;
+  }
+  void up(int i) {
+    while (i > 0 && h_[i] < h_[(i - 1) / 2]) {
+      swap_at(i, (i - 1) / 2);
+      i = (i - 1) / 2;
+    }
+  }
+  void down(int i) {
+    for (;;) {
+      int m = i;
+      const int l = 2 * i + 1, r = 2 * i + 2;
+      if (l < size() && h_[l] < h_[m]) m = l;
+      if (r < size() && h_[r] < h_[m]) m = r;
+      if (m == i) return;
+      swap_at(i, m);
+      i = m;
+    }
+  }
+  std::vector<std::pair<double, int>> h_;
+  std::unordered_map<int, int> where_;
+};
+
 struct Cand {
   int exp = -1;             // expanded node (global id)
   double p[6];
@@ -54,6 +118,7 @@ struct Cand {
   std::vector<int> nb;                      // radius neighbours in (d2, id) order
   std::vector<int> nb_edge;                 // edge index per neighbour or -1
   int border_nb = -1;                       // neighbour that recorded a border link when this attempt is replayed
+  bool reaches_goal = false;                // goal mode: the point sees the goal from within dtree (forest.h:286-287)
   // SFF* stage
   std::vector<int> knn;                     // same-tree neighbours, ascending distance
   std::vector<int> e_parent, e_rewire;      // edge index per knn entry or -1
@@ -65,6 +130,8 @@ class Planner {
   Planner(const Config &cfg, uint64_t seed, int batch, bool quiet) : cfg_(cfg), rng_(seed), batch_(batch), quiet_(quiet) {
     book_.pos = [this](int id) { return nodes_[id].p; };
     book_.origin = [this](int id) { return nodes_[id].tree; };
+    n_trees_ = (int)cfg_.roots.size() + (cfg_.has_goal ? 1 : 0);   // Problem::GetNumRoots, src/problemStruct.h:74-80
+    use_priority_ = cfg_.priority_bias != 0;                       // Solver::usePriority, src/problemStruct.h:150
   }
 
   void load() {
@@ -89,19 +156,35 @@ class Planner {
     if (cfg_.auto_range)
       for (int k = 0; k < 6; ++k) cfg_.range[k] = lim[k];
     check(sffg_env_create(obst.empty() ? nullptr : obst.data(), (int64_t)(obst.size() / 9), robot.data(), (int64_t)(robot.size() / 9), &env_));
-    const int T = (int)cfg_.roots.size();
+    const int T = n_trees_, R = (int)cfg_.roots.size();
     members_.resize(T);
     tree_idx_.resize(T, nullptr);
+    heaps_.resize(T);
     check(sffg_index_create(cfg_.dim, &global_idx_));
-    for (int t = 0; t < T; ++t) {
+    for (int t = 0; t < T; ++t) {   // one tree per root (forest.h:60-76); the goal is a tree of its own that is never expanded (:91-104)
       check(sffg_index_create(cfg_.dim, &tree_idx_[t]));
       Node nd{};
-      for (int k = 0; k < 3; ++k) nd.p[k] = cfg_.roots[t][k];
+      for (int k = 0; k < 3; ++k) nd.p[k] = t < R ? cfg_.roots[t][k] : cfg_.goal[k];
       nd.tree = t;
       nd.parent = -1;
       nd.d_parent = nd.d_root = 0;
       const int id = add_node(nd);
-      frontier_.push_back(id);
+      if (t < R) {
+        if (!use_priority_) frontier_.push_back(id);
+      } else {
+        goal_node_ = id;
+      }
+    }
+    if (use_priority_) {
+      // priority frontiers (forest.h:79-89, :105-109): without a goal every tree keeps one heap per OTHER root, ordered by
+      // the distance to that root; with a goal every tree keeps one heap ordered by the distance to the goal
+      for (int t = 0; t < R; ++t) {
+        for (int j = 0; j < R && !cfg_.has_goal; ++j)
+          if (j != t) heap_targets_[t].push_back(members_[j][0]);
+        if (cfg_.has_goal) heap_targets_[t].push_back(goal_node_);
+        heaps_[t].resize(heap_targets_[t].size());
+        push_to_heaps(members_[t][0]);
+      }
     }
     flush_index_appends();
   }
@@ -109,45 +192,66 @@ class Planner {
   void solve() {
     const auto t0 = std::chrono::steady_clock::now();
     bool solved = false;
-    const int T = (int)cfg_.roots.size();
+    const int T = n_trees_;
     while (!solved && iter_ < cfg_.max_iterations) {
-      const bool from_closed = frontier_.empty();
-      std::vector<int> &pool = from_closed ? closed_ : frontier_;
-      if (pool.empty()) break;
-      const int B = (int)std::min<size_t>((size_t)batch_, pool.size());
-      // B distinct pool positions (partial Fisher-Yates over a position array)
-      std::vector<int> pos(pool.size());
-      for (size_t i = 0; i < pos.size(); ++i) pos[i] = (int)i;
-      for (int i = 0; i < B; ++i) {
-        std::uniform_int_distribution<int> pick(i, (int)pos.size() - 1);
-        std::swap(pos[i], pos[pick(rng_)]);
+      const bool from_closed = use_priority_ ? heaps_empty() : frontier_.empty();   // emptyFrontier, forest.h:183-193
+      std::vector<int> chosen_nodes;
+      std::vector<int> chosen;             // plain frontier / closed list: pool positions
+      std::vector<TargetHeap *> prior;     // priority frontiers: the heap every node was popped from
+      if (use_priority_ && !from_closed) {
+        pick_by_priority(chosen_nodes, prior);
+      } else {
+        std::vector<int> &pool = from_closed ? closed_ : frontier_;
+        if (pool.empty()) break;
+        const int B = (int)std::min<size_t>((size_t)batch_, pool.size());
+        // B distinct pool positions (partial Fisher-Yates over a position array)
+        std::vector<int> pos(pool.size());
+        for (size_t i = 0; i < pos.size(); ++i) pos[i] = (int)i;
+        for (int i = 0; i < B; ++i) {
+          std::uniform_int_distribution<int> pick(i, (int)pos.size() - 1);
+          std::swap(pos[i], pos[pick(rng_)]);
+        }
+        chosen.assign(pos.begin(), pos.begin() + B);
+        for (int i = 0; i < B; ++i) chosen_nodes.push_back(pool[chosen[i]]);
       }
-      std::vector<int> chosen(pos.begin(), pos.begin() + B);
-      std::vector<int> chosen_nodes(B);
-      for (int i = 0; i < B; ++i) chosen_nodes[i] = pool[chosen[i]];
+      const int B = (int)chosen_nodes.size();
+      if (B == 0) break;
       std::vector<char> exhausted(B, 0);
       run_round(chosen_nodes, exhausted);
       if (!from_closed) {
-        // nodes whose every attempt failed leave the frontier for the closed list (forest.h:160-180)
+        // nodes whose every attempt failed leave the frontier for the closed list (forest.h:160-180); in priority mode the
+        // node was popped from one heap: it goes back there unless it is exhausted, in which case it leaves every heap
         std::vector<int> drop;
-        for (int i = 0; i < B; ++i)
+        for (int i = 0; i < B; ++i) {
+          const int id = chosen_nodes[i];
           if (exhausted[i]) {
-            nodes_[chosen_nodes[i]].force_children = true;
-            closed_.push_back(chosen_nodes[i]);
-            drop.push_back(chosen[i]);
+            nodes_[id].force_children = true;
+            closed_.push_back(id);
+            if (use_priority_) {
+              for (TargetHeap &h : heaps_[nodes_[id].tree]) h.remove(id);
+            } else {
+              drop.push_back(chosen[i]);
+            }
+          } else if (use_priority_) {
+            prior[i]->push(id, heap_key(id, prior[i]));
           }
+        }
         std::sort(drop.begin(), drop.end(), std::greater<int>());
         for (int d : drop) {
           frontier_[d] = frontier_.back();
           frontier_.pop_back();
         }
       }
-      const bool connected = max_connected() == T;
-      solved = frontier_.empty() && connected;   // (!hasGoal && emptyFrontier && connected), forest.h:199-201
+      if (goal_reached_) {
+        solved = true;   // forest.h:287: the solve loop ends as soon as a new node sees the goal
+      } else if (!cfg_.has_goal) {
+        const bool empty = use_priority_ ? heaps_empty() : frontier_.empty();
+        solved = empty && max_connected() == T;   // (!hasGoal && emptyFrontier && connected), forest.h:195-198
+      }
       ++rounds_;
     }
     elapsed_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (!solved) solved = max_connected() == T;   // forest.h:204-206
+    if (!solved && !cfg_.has_goal) solved = max_connected() == T;   // forest.h:204-206
     solved_ = solved;
     max_connected();
     build_paths();
@@ -175,6 +279,61 @@ class Planner {
   }
 
  private:
+  // ---- priority frontiers (forest.h:125-135, :142-149)
+  double heap_key(int id, const TargetHeap *h) const {
+    const int t = nodes_[id].tree;
+    const size_t j = (size_t)(h - heaps_[t].data());
+    return dist6(nodes_[id].p, nodes_[heap_targets_.at(t)[j]].p);
+  }
+  void push_to_heaps(int id) {   // forest.h:360-363
+    const int t = nodes_[id].tree;
+    for (size_t j = 0; j < heaps_[t].size(); ++j) heaps_[t][j].push(id, dist6(nodes_[id].p, nodes_[heap_targets_[t][j]].p));
+  }
+  bool heaps_empty() const {
+    for (const auto &hs : heaps_)
+      for (const TargetHeap &h : hs)
+        if (!h.empty()) return false;
+    return true;
+  }
+  // up to B distinct nodes: random tree with a non-empty heap, random non-empty heap of it, then the best node of that heap
+  // with probability priorityBias, else a random one
+  void pick_by_priority(std::vector<int> &out, std::vector<TargetHeap *> &prior) {
+    std::uniform_real_distribution<double> prob(0, 1);
+    std::unordered_set<int> taken;
+    // best-first search gains little from breadth: a round takes at most 4 nodes per live heap (a narrow beam), so that the
+    // iteration budget is not spent on nodes the sequential search would never have reached
+    int live_heaps = 0;
+    for (const auto &hs : heaps_)
+      for (const TargetHeap &h : hs) live_heaps += !h.empty();
+    const int beam = std::min(batch_, 4 * std::max(1, live_heaps));
+    for (int attempt = 0; attempt < 4 * beam && (int)out.size() < beam; ++attempt) {
+      std::vector<int> live;
+      for (int t = 0; t < n_trees_; ++t)
+        for (const TargetHeap &h : heaps_[t])
+          if (!h.empty()) {
+            live.push_back(t);
+            break;
+          }
+      if (live.empty()) break;
+      const int t = live[std::uniform_int_distribution<int>(0, (int)live.size() - 1)(rng_)];
+      std::vector<TargetHeap *> hs;
+      for (TargetHeap &h : heaps_[t])
+        if (!h.empty()) hs.push_back(&h);
+      TargetHeap *h = hs[std::uniform_int_distribution<int>(0, (int)hs.size() - 1)(rng_)];
+      const int pos = prob(rng_) <= cfg_.priority_bias ? 0 : std::uniform_int_distribution<int>(0, h->size() - 1)(rng_);
+      const int id = h->pop_at(pos);
+      if (taken.count(id)) {   // already picked through another heap of its tree in this round
+        deferred_push_.push_back({h, id});
+        continue;
+      }
+      taken.insert(id);
+      out.push_back(id);
+      prior.push_back(h);
+    }
+    for (auto &hp : deferred_push_) hp.first->push(hp.second, heap_key(hp.second, hp.first));
+    deferred_push_.clear();
+  }
+
   int add_node(const Node &nd) {
     const int id = (int)nodes_.size();
     nodes_.push_back(nd);
@@ -325,7 +484,9 @@ class Planner {
         const double real = dist6(nb.p, c.p);
         if (!ex.force_children && real < c.parent_dist - kTol && nb.tree == ex.tree) c.nb_edge[j] = eb.add(nb.p, c.p);
         if (nb.tree != ex.tree && real < cfg_.dtree - kTol) {
-          c.nb_edge[j] = eb.add(ex.p, nb.p);
+          if (!cfg_.has_goal) c.nb_edge[j] = eb.add(ex.p, nb.p);                       // forest.h:288
+          else if (c.nb[j] == goal_node_) c.nb_edge[j] = eb.add(c.p, nb.p);             // forest.h:286-287
+          else c.nb_edge[j] = -2;                                                       // goal mode: rejected untested
           c.nb.resize(j + 1);       // this neighbour always ends the scan
           c.nb_edge.resize(j + 1);
           break;
@@ -342,11 +503,15 @@ class Planner {
     for (int ci : alive) {
       Cand &c = cand[ci];
       const Node &ex = nodes_[c.exp];
-      for (size_t j = 0; j < c.nb.size() && !c.rejected; ++j) {
-        if (c.nb_edge[j] < 0) continue;
+      for (size_t j = 0; j < c.nb.size() && !c.rejected && !c.reaches_goal; ++j) {
+        if (c.nb_edge[j] == -1) continue;
         const Node &nb = nodes_[c.nb[j]];
         if (nb.tree == ex.tree) {
           if (eb.free_flag[c.nb_edge[j]]) c.rejected = true;             // a closer node of the same tree sees the point
+        } else if (cfg_.has_goal) {
+          // near another tree: only a free view of the goal keeps the point (it becomes the node that ends the search)
+          if (c.nb_edge[j] >= 0 && eb.free_flag[c.nb_edge[j]]) c.reaches_goal = true;
+          else c.rejected = true;
         } else {
           if (eb.free_flag[c.nb_edge[j]]) c.border_nb = c.nb[j];          // trees meet: remember the link
           c.rejected = true;
@@ -451,6 +616,14 @@ class Planner {
         }
         added.push_back(commit(c, eb2));
         success = true;
+        if (c.reaches_goal) {   // forest.h:369-372: link the new node to the goal; the solve loop ends
+          add_border(added.back(), goal_node_);
+          goal_reached_ = true;
+        }
+      }
+      if (goal_reached_) {
+        for (int r = b; r < B; ++r) exhausted[r] = 0;
+        break;
       }
       exhausted[b] = !success && !deferred;
     }
@@ -498,7 +671,8 @@ class Planner {
         }
       }
     }
-    frontier_.push_back(id);
+    if (use_priority_) push_to_heaps(id);
+    else frontier_.push_back(id);
     return id;
   }
 
@@ -514,7 +688,7 @@ class Planner {
 
   // SpaceForest::maxConnected, forest.h:378-418
   int max_connected() {
-    const int T = (int)cfg_.roots.size();
+    const int T = n_trees_;
     std::vector<char> seen(T, 0);
     int max_conn = 0, remaining = T, start = 0;
     while (max_conn < remaining) {
@@ -544,7 +718,7 @@ class Planner {
 
   // SpaceForest::getPaths (forest.h:420-463) + Solver::getAllPaths (problemStruct.h:183-253)
   void build_paths() {
-    const int T = (int)cfg_.roots.size();
+    const int T = n_trees_;
     for (int i = 0; i < T; ++i)
       for (int j = i + 1; j < T; ++j) {
         const std::vector<Border> &bs = borders(i, j);
@@ -566,6 +740,9 @@ class Planner {
         for (int n = best.n2; n >= 0; n = nodes_[n].parent) right.push_back(n);
         best.plan = left;
         best.plan.insert(best.plan.end(), right.begin(), right.end());
+        // the border is chosen on the stored costs as in the reference; the reported length is the true length of the plan
+        // (stored costs of a rewired node's descendants are stale -- never updated, forest.h:346-347 -- hence >= the truth)
+        best.distance = book_.plan_length(best.plan);
         book_.link(i, j) = best;
       }
     book_.compose(connected_);
@@ -585,6 +762,11 @@ class Planner {
   std::vector<int32_t> radius_ids_;
   std::vector<float> radius_d2_;
   std::vector<int> frontier_, closed_;
+  int n_trees_ = 0, goal_node_ = -1;
+  bool use_priority_ = false, goal_reached_ = false;
+  std::vector<std::vector<TargetHeap>> heaps_;          // Tree::frontiers, src/primitives.h:509
+  std::map<int, std::vector<int>> heap_targets_;        // per tree: target node of every heap
+  std::vector<std::pair<TargetHeap *, int>> deferred_push_;
   std::map<std::pair<int, int>, std::vector<Border>> borders_;
   PlanBook book_;
   std::vector<int> connected_;

@@ -68,6 +68,18 @@ def test_rrtstar_to_goal(exe, tmp_path, orc, meshes, scenario, mesh, robot, name
     PU.validate_plans(orc, meshes[mesh], meshes[robot], plans, roots_of(name, True))
 
 
+@pytest.mark.parametrize("scenario,n_plans,with_goal", [("triang_sffstar_bias", None, False), ("triang_sffstar_goal", 1, True),
+                                                         ("building_sffstar_goal", 1, True)])
+def test_sffstar_priority_and_goal_modes(exe, tmp_path, orc, meshes, scenario, n_plans, with_goal):
+    """priority frontiers (priorityBias 0.95 as test_triang.xml:23 sets it) and single-goal SFF* (forest.h:79-109, :286-287)"""
+    name = scenario.split("_")[0]
+    row, plans, out = PU.run_planner(exe, tmp_path, scenario, seed=6, max_iter=40000)
+    if with_goal:
+        assert ",solved,[0;1]," in row, row + out
+        assert len(plans) == n_plans
+    PU.validate_plans(orc, meshes[f"{name}_s10"], meshes["robot_small_s10"], plans, roots_of(name, with_goal))
+
+
 def test_multi_t_rrt_3d(exe, tmp_path, orc, meshes):
     """Multi-T-RRT: six trees merge into one (rrt.h:219-317); all 15 root pairs get a valid plan"""
     row, plans, _ = PU.run_planner(exe, tmp_path, "triang_mtrrt", seed=1)
@@ -80,7 +92,7 @@ def test_engine_and_double_agree_on_a_fixed_seed(exe, tmp_path):
     """same host, same seed: the engine (GPU) and the CPU double behind the same ABI must produce the same params row
     (iterations, solved flag, connected trees, path lengths) -- an end-to-end parity check of verdicts and neighbours"""
     dbl = PU.build_double_host()
-    for scenario in ("2d_mtrrt", "2d_rrtstar_goal", "2d_sffstar"):
+    for scenario in ("2d_mtrrt", "2d_rrtstar_goal", "2d_sffstar", "2d_sffstar_bias", "2d_sffstar_goal"):
         row_g, _, _ = PU.run_planner(exe, tmp_path, scenario, seed=9, run_id="g")
         row_c, _, _ = PU.run_planner(dbl, tmp_path, scenario, seed=9, run_id="c")
         assert row_g.split(",")[2:6] == row_c.split(",")[2:6], (scenario, row_g, row_c)

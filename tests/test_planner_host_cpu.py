@@ -43,6 +43,27 @@ def test_sffstar_2d(exe, tmp_path, orc, meshes):
     PU.validate_plans(orc, meshes["triangles_tri"], meshes["robot_small_s1"], plans, roots_of("2d"))
 
 
+def test_sffstar_priority_frontiers_2d(exe, tmp_path, orc, meshes):
+    """priorityBias = 0.95 as the shipped configs set it (test_2D.xml:17): per-tree heaps ordered by the distance to every
+    other root (forest.h:79-89), best-first node choice (:125-149)"""
+    row, plans, _ = PU.run_planner(exe, tmp_path, "2d_sffstar_bias", seed=2)
+    assert ",solved," in row, row
+    assert len(plans) == 6
+    PU.validate_plans(orc, meshes["triangles_tri"], meshes["robot_small_s1"], plans, roots_of("2d"))
+
+
+@pytest.mark.parametrize("scenario,mesh,robot,name", [("2d_sffstar_goal", "triangles_tri", "robot_small_s1", "2d"),
+                                                       ("triang_sffstar_goal", "triang_s10", "robot_small_s10", "triang")])
+def test_sffstar_single_goal(exe, tmp_path, orc, meshes, scenario, mesh, robot, name):
+    """one root + <Goal>: the goal is a tree that is never expanded; the search ends when a new node sees the goal from
+    within dtree (forest.h:91-109, :286-287, :369-372)"""
+    row, plans, _ = PU.run_planner(exe, tmp_path, scenario, seed=1)
+    assert ",solved,[0;1]," in row, row
+    assert len(plans) == 1
+    PU.validate_plans(orc, meshes[mesh], meshes[robot], plans, roots_of(name, True))
+    assert int(row.split(",")[2]) < 5000   # goal-directed: a narrow beam, not a breadth-first flood
+
+
 @pytest.mark.parametrize("scenario", ["2d_rrt_goal", "2d_rrtstar_goal"])
 def test_rrt_single_query_2d(exe, tmp_path, orc, meshes, scenario):
     """RRT / RRT* from one root to a goal (rrt.h:64-81, :130-134): solved at the first link to the goal tree"""
