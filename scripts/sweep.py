@@ -70,7 +70,7 @@ def main():
     for on, (rn, rng) in cases.items():
         env = S.Environment(m[on], m[rn])
         mo, mr = O.ObbModel(m[on]), O.ObbModel(m[rn])
-        ns = [10 ** 6, 10 ** 7] if a.quick else [10 ** 6, 10 ** 7, 10 ** 8]
+        ns = [10 ** 6, 10 ** 7] if a.quick else [10 ** 6, 10 ** 7, 10 ** 8] + ([10 ** 9] if on == "building_s10" else [])
         cpu_n = 1 << 21
         cp = O.gen_poses(SEED, 0, cpu_n, rng).astype(np.float64)
         t0 = time.perf_counter()
@@ -79,7 +79,7 @@ def main():
         for n in ns:
             poses = S.gen_poses_device(SEED, 0, n, rng)
             out = torch.empty(n, dtype=torch.uint8, device=dev)
-            sec = gpu_time(lambda: env.collide_device(poses, out=out))
+            sec = gpu_time(lambda: env.collide_device(poses, out=out), reps=5 if n < 10 ** 9 else 2)
             # parity on a random 200k subsample against the oracle
             idx = torch.randint(0, n, (200000,), device=dev, generator=torch.Generator(device=dev).manual_seed(1))
             sub = poses[idx].cpu().numpy()
@@ -145,7 +145,7 @@ def main():
         wi, wd = O.knn_linear(h_nodes, h_q[:nql], 16, threads=threads)
         cpu["exact_linear_knn16_queries_per_s"] = nql / (time.perf_counter() - t0)
         cpu["threads"] = threads
-        for k in (1, 16, 32):
+        for k in ((1, 16, 32) if a.quick else (1, 2, 4, 8, 16, 32)):
             ids = torch.empty((Q, k), dtype=torch.int32, device=dev)
             d2 = torch.empty((Q, k), dtype=torch.float32, device=dev)
             sec = gpu_time(lambda: idx.knn_device(q, k, ids, d2), reps=3)
@@ -156,19 +156,53 @@ def main():
             res["knn"].append(row)
             print(json.dumps(row), flush=True)
         if N <= 10 ** 6:
-            r2 = 169.0 if dim == 6 else 2500.0
-            nqr = 20000
-            t0 = time.perf_counter()
-            c, off, rid, rd = idx.radiusSearch(h_q[:nqr], r2)
-            sec = time.perf_counter() - t0
-            wc, _, wid, _ = O.radius_linear(h_nodes, h_q[:200], r2, threads=threads)
-            res["radius"].append({"dim": dim, "N": N, "Q": nqr, "r2": r2, "host_call_queries_per_s": nqr / sec, "mean_hits": float(c.mean()),
-                                  "parity_first_200": bool(np.array_equal(c[:200], wc) and np.array_equal(rid[:off[200]], wid))})
-            print(json.dumps(res["radius"][-1]), flush=True)
+            # the planner's radius (dtree + 2*circum)^2 and one tuned to ~32 expected hits: the 6-D ball volume
+            # pi^3/6 r^6 over the cloud's volume 140^3 (2 pi)^3 (2-D: pi r^2 over 1020*720)
+            tuned = (32.0 / N * 140.0 ** 3 * 8 * 6) ** (1.0 / 3.0) if dim == 6 else 32.0 / N * 1020 * 720 / np.pi
+            for r2 in ((169.0 if dim == 6 else 2500.0), float(tuned)):
+                nqr = 20000
+                idx.radiusSearch(h_q[:256], r2)
+                t0 = time.perf_counter()
+                c, off, rid, rd = idx.radiusSearch(h_q[:nqr], r2)
+                sec = time.perf_counter() - t0
+                wc, _, wid, _ = O.radius_linear(h_nodes, h_q[:200], r2, threads=threads)
+                res["radius"].append({"dim": dim, "N": N, "Q": nqr, "r2": r2, "host_call_queries_per_s": nqr / sec, "mean_hits": float(c.mean()),
+                                      "parity_first_200": bool(np.array_equal(c[:200], wc) and np.array_equal(rid[:off[200]], wid))})
+                print(json.dumps(res["radius"][-1]), flush=True)
         idx.close()
         del nodes, q
     Path(a.out).parent.mkdir(parents=True, exist_ok=True)
     Path(a.out).write_text(json.dumps(res, indent=1))
+    Path(a.out).with_suffix(".md").write_text(to_markdown(res))
+
+
+def to_markdown(res):
+    t = res["host_threads"]
+    L = [f"# sweep (SURVEY 8d), one B200, device-resident, CUDA events, median of reps; CPU = oracle / vendored FLANN on {t} host threads", "",
+         "## pose collision (robot_small, Philox stream; parity = mismatches vs oracle on a random 200k subsample)", "",
+         "| obstacle | N poses | GPU poses/s | hit frac | parity mismatches | CPU poses/s (OBB-tree, ALL_CONTACTS) | GPU/CPU |", "|---|---|---|---|---|---|---|"]
+    for r in res["collision"]:
+        L.append(f"| {r['obstacle']} | {r['n_poses']:.0e} | {r['gpu_poses_per_s']:.3e} | {r['hit_fraction']:.4f} | {r['parity_mismatches_of_200k']} | "
+                 f"{r['cpu_poses_per_s']:.3e} | {r['gpu_poses_per_s'] / r['cpu_poses_per_s']:.0f}x |")
+    L += ["", "## edges (isPathFree, length 4, 39 samples @0.1, building.obj)", "",
+          "| M edges | rot mode | GPU edges/s | free frac | parity mismatches (20k) | CPU edges/s | GPU/CPU |", "|---|---|---|---|---|---|---|"]
+    for r in res["edges"]:
+        L.append(f"| {r['n_edges']:.0e} | {r['rot_mode']} | {r['gpu_edges_per_s']:.3e} | {r['free_fraction']:.3f} | {r['parity_mismatches_of_20k']} | "
+                 f"{r['cpu_edges_per_s']:.3e} | {r['gpu_edges_per_s'] / r['cpu_edges_per_s']:.0f}x |")
+    L += ["", "## exact k-NN (Q = 1e5)", "",
+          "| dim | N | k | GPU queries/s | equivalent exhaustive pairs/s | FLANN as the planner uses it (approx., all threads / 1 core) | exact CPU linear scan | parity (ids, d2 bits) |",
+          "|---|---|---|---|---|---|---|---|"]
+    for r in res["knn"]:
+        c = r["cpu"]
+        fl = (f"{c['flann_planner_knn16_queries_per_s']:.3e} / {c['flann_planner_knn16_queries_per_s_1core']:.3e}"
+              if "flann_planner_knn16_queries_per_s" in c else "n/a")
+        par = [v for k, v in r.items() if k.startswith("parity")]
+        L.append(f"| {r['dim']} | {r['N']:.0e} | {r['k']} | {r['gpu_queries_per_s']:.3e} | {r['pairs_per_s']:.3e} | {fl} | "
+                 f"{c['exact_linear_knn16_queries_per_s']:.3e} | {'/'.join(str(p) for p in par) if par else ''} |")
+    L += ["", "## radius (host call incl. H2D/D2H and sorting, Q = 2e4)", "", "| dim | N | r2 | queries/s | mean hits/query | parity |", "|---|---|---|---|---|---|"]
+    for r in res["radius"]:
+        L.append(f"| {r['dim']} | {r['N']:.0e} | {r['r2']:.1f} | {r['host_call_queries_per_s']:.3e} | {r['mean_hits']:.1f} | {r['parity_first_200']} |")
+    return "\n".join(L) + "\n"
 
 
 if __name__ == "__main__":

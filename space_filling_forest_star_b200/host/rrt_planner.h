@@ -21,6 +21,7 @@
 #include <deque>
 
 #include "planner_common.h"
+#include "writers.h"
 
 namespace planner {
 
@@ -72,6 +73,12 @@ class RrtPlanner {
   }
 
   void solve() {
+    {
+      std::vector<int> roots;
+      for (size_t i = 0; i < nodes_.size(); ++i)
+        if (nodes_[i].parent < 0) roots.push_back((int)i);
+      save_goals(save_.goals, view(), roots);   // rrt.h:86-88
+    }
     const auto t0 = std::chrono::steady_clock::now();
     while (!solved_ && iter_ < cfg_.max_iterations) {
       run_round();
@@ -79,13 +86,33 @@ class RrtPlanner {
     }
     elapsed_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     connected_trees();
+    save_trees(save_.tree, view());
     build_paths();
-    if (cfg_.smoothing) book_.smooth(env_, cfg_.has_map, calls_, n_edges_);
+    save_paths(save_.raw_path, view(), book_);
+    if (cfg_.smoothing) {
+      book_.smooth(env_, cfg_.has_map, calls_, n_edges_);
+      save_paths(save_.smooth_path, view(), book_);
+    }
     book_.verify(env_, cfg_.has_map, calls_);
+    save_tsp(save_.tsp, cfg_, book_, connected_);
+  }
+
+  void set_save(const SaveOptions &so) { save_ = so; }
+  NodeView view() const {
+    NodeView v;
+    v.n_nodes = (int)nodes_.size();
+    v.n_trees = (int)trees_.size();
+    v.scale = cfg_.scale;
+    v.pos = [this](int i) { return nodes_[i].p; };
+    v.parent = [this](int i) { return nodes_[i].parent; };
+    v.tree = [this](int i) { return origin_of(i); };
+    v.age = [this](int i) { return nodes_[i].generation; };
+    v.is_root = [this](int i) { return nodes_[i].parent < 0; };
+    return v;
   }
 
   void save_params(const std::string &run_id) const { book_.save_params(cfg_, run_id, iter_, solved_, connected_, elapsed_); }
-  void save_paths(const std::string &file) const { book_.save_paths(file); }
+  void dump_plans(const std::string &file) const { book_.save_paths(file); }
 
   void report() const {
     if (quiet_) return;
@@ -111,6 +138,7 @@ class RrtPlanner {
     int parent;              // global id, -1 for a root (Closest)
     double d_parent, d_root;
     std::vector<int> children;
+    long generation = 0;
   };
   struct Tree {
     sffg_index *idx = nullptr;
@@ -432,6 +460,7 @@ class RrtPlanner {
       nd.d_parent = cfg_.circum;
       nd.d_root = nodes_[parent].d_root + cfg_.circum;
     }
+    nd.generation = iter_;
     const int id = add_node(nd);
     nodes_[parent].children.push_back(id);
     if (cfg_.optimize) {
@@ -524,6 +553,7 @@ class RrtPlanner {
 
   StageClock clk_;
   Config cfg_;
+  SaveOptions save_;
   std::mt19937_64 rng_;
   int batch_;
   bool quiet_;

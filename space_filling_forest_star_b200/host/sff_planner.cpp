@@ -28,6 +28,7 @@
 #include <unordered_set>
 
 #include "planner_common.h"
+#include "writers.h"
 #include "rrt_planner.h"
 
 using namespace planner;
@@ -190,6 +191,11 @@ class Planner {
   }
 
   void solve() {
+    {
+      std::vector<int> roots;
+      for (int t = 0; t < n_trees_; ++t) roots.push_back(members_[t][0]);
+      save_goals(save_.goals, view(), roots);   // forest.h:113-116
+    }
     const auto t0 = std::chrono::steady_clock::now();
     bool solved = false;
     const int T = n_trees_;
@@ -254,13 +260,33 @@ class Planner {
     if (!solved && !cfg_.has_goal) solved = max_connected() == T;   // forest.h:204-206
     solved_ = solved;
     max_connected();
+    save_trees(save_.tree, view());
     build_paths();
-    if (cfg_.smoothing) book_.smooth(env_, cfg_.has_map, calls_, n_edges_);
+    save_paths(save_.raw_path, view(), book_);
+    if (cfg_.smoothing) {
+      book_.smooth(env_, cfg_.has_map, calls_, n_edges_);
+      save_paths(save_.smooth_path, view(), book_);
+    }
     book_.verify(env_, cfg_.has_map, calls_);
+    save_tsp(save_.tsp, cfg_, book_, connected_);
+  }
+
+  void set_save(const SaveOptions &so) { save_ = so; }
+  NodeView view() const {
+    NodeView v;
+    v.n_nodes = (int)nodes_.size();
+    v.n_trees = n_trees_;
+    v.scale = cfg_.scale;
+    v.pos = [this](int i) { return nodes_[i].p; };
+    v.parent = [this](int i) { return nodes_[i].parent; };
+    v.tree = [this](int i) { return nodes_[i].tree; };
+    v.age = [this](int i) { return nodes_[i].generation; };
+    v.is_root = [this](int i) { return nodes_[i].parent < 0; };
+    return v;
   }
 
   void save_params(const std::string &run_id) const { book_.save_params(cfg_, run_id, iter_, solved_, connected_, elapsed_); }
-  void save_paths(const std::string &file) const { book_.save_paths(file); }
+  void dump_plans(const std::string &file) const { book_.save_paths(file); }
 
   void report() const {
     if (quiet_) return;
@@ -750,6 +776,7 @@ class Planner {
 
   StageClock clk_;
   Config cfg_;
+  SaveOptions save_;
   std::mt19937_64 rng_;
   int batch_;
   bool quiet_;
@@ -797,13 +824,21 @@ int main(int argc, char **argv) {
     else if (positional++ == 0) run_id = a;
   }
   Config cfg = load_config(argv[1]);
+  const auto t0 = std::chrono::steady_clock::now();
   check(sffg_init(-1));
+  const auto t1 = std::chrono::steady_clock::now();
+  const SaveOptions save = load_save_options(argv[1], run_id, cfg.smoothing);
   auto run = [&](auto &planner) {
+    planner.set_save(save);
     planner.load();
+    const auto t2 = std::chrono::steady_clock::now();
     planner.solve();
     planner.save_params(run_id);
-    if (!paths_file.empty()) planner.save_paths(paths_file);
+    if (!paths_file.empty()) planner.dump_plans(paths_file);
     planner.report();
+    if (!quiet)
+      std::cout << "start-up seconds: device init " << std::chrono::duration<double>(t1 - t0).count() << ", meshes + BVH + indices "
+                << std::chrono::duration<double>(t2 - t1).count() << "\n";
   };
   if (cfg.solver == "rrt") {
     RrtPlanner planner(cfg, seed, batch, quiet);

@@ -132,3 +132,45 @@ def test_reference_validation_rules(exe, tmp_path):
     bad.write_text(cfg.read_text().replace('priorityBias="0"', 'priorityBias="0.5"'))
     p = subprocess.run([str(exe), bad.name], cwd=tmp_path, capture_output=True, text=True)
     assert p.returncode == 1 and "Multi-T-RRT with bias is undefined!" in p.stdout
+
+
+SAVE = ('<Save>\n    <Goals file="output/goals.tri" is_obj="false"/>\n    <Tree file="output/tree.obj" is_obj="true"/>\n'
+        '    <RawPath file="output/raw.tri" is_obj="false"/>\n    <TSP file="output/tsp.tsp"/>')
+
+
+def _shape(path):
+    import re
+    return {re.sub(r"-?\d+(\.\d+)?(e[-+]?\d+)?", "N", l.rstrip("\n")) for l in open(path)}
+
+
+def test_output_files_follow_the_reference_formats(exe, tmp_path):
+    """Goals / Tree / RawPath / TSP files (Solver::saveCities, saveTrees, savePaths, saveTsp, src/problemStruct.h:263-341,
+    :431-527): self-consistent, "_<run>" suffix as getFile adds it (src/main.cpp:439-465) and -- where the reference host
+    was compiled (dev container) -- the same line grammar as the reference's own files"""
+    import subprocess
+    PU.run_planner(exe, tmp_path, "2d_sffstar", seed=1)
+    cfg = tmp_path / "2d_w.xml"
+    cfg.write_text((tmp_path / "2d_sffstar.xml").read_text().replace("<Save>", SAVE))
+    p = subprocess.run([str(exe), cfg.name, "3", "--seed", "1", "--quiet"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    out = tmp_path / "output"
+    row = (out / "params_2d_sffstar.csv").read_text().strip().splitlines()[-1]
+    trees = row.split("[")[1].split("]")[0].split(";")
+    dists = [float(x) for x in row.split("[")[2].split("]")[0].split(";")]
+    tsp = (out / "tsp_3.tsp").read_text().splitlines()
+    assert tsp[0] == "NAME: 2d_sffstar" and tsp[1] == "COMMENT: " + " ".join(trees) and tsp[3] == "DIMENSION: 4"
+    assert tsp[4:7] == ["EDGE_WEIGHT_TYPE : EXPLICIT", "EDGE_WEIGHT_FORMAT : LOWER_DIAG_ROW", "EDGE_WEIGHT_SECTION"]
+    lower = [float(x) for l in tsp[7:] for x in l.split()[:-1]]
+    assert all(l.split()[-1] == "0" for l in tsp[7:]) and lower == pytest.approx(dists, rel=1e-5)
+    assert (out / "goals_3.tri").read_text().splitlines()[0] == "60 60 0 0 0 0"
+    tree = (out / "tree_3.obj").read_text().splitlines()
+    n_v, n_l = sum(l.startswith("v ") for l in tree), sum(l.startswith("l ") for l in tree)
+    assert tree[0] == "o Trees" and n_l == n_v - 4   # every node but the 4 roots hangs on a parent
+    raw = [l.split() for l in (out / "raw_3.tri").read_text().split("\n\n")[0].splitlines()]
+    assert all(len(r) == 12 for r in raw) and all(raw[i][6:] == raw[i + 1][:6] for i in range(len(raw) - 1))
+    ref = PU.ROOT / "oracle" / "_ref" / "ref_main_cpu"
+    if ref.exists():
+        q = subprocess.run([str(ref), cfg.name, "4"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+        assert q.returncode == 0, q.stdout
+        for name in ("tsp_%d.tsp", "goals_%d.tri", "tree_%d.obj", "raw_%d.tri"):
+            assert _shape(out / (name % 3)) == _shape(out / (name % 4)), name
