@@ -189,14 +189,37 @@ def run_ours(args):
     verdict = torch.empty(P, dtype=torch.uint8, device=dev)
     gathered = torch.empty(world * P, dtype=torch.uint8, device=dev) if world > 1 else None
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # N > 1: the verdict all-gather is fused into the kernel's stores over NVLink peer memory (sharding.PeerGather);
+    # --gather nccl (or a box without CUDA IPC between the ranks) uses kernel + NCCL all_gather_into_tensor instead
+    pg, gather_mode, last_buf = None, "none", [0]
+    if world > 1:
+        gather_mode = "nccl"
+        ok = torch.zeros(1, device=dev)
+        if args.gather == "fused":
+            try:
+                from space_filling_forest_star_b200.sharding import PeerGather
+                pg = PeerGather(P)
+                ok += 1
+            except Exception as ex:   # no IPC between the ranks: every rank must agree on the fallback
+                print(f"[rank {rank}] peer gather unavailable ({ex!r}); falling back to NCCL all-gather", file=sys.stderr)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() > 0:
+            gather_mode = "fused"
+        else:
+            pg = None
 
     def step(i=None):
         if i is not None:
             k_ev[i][0].record()
-        env.collide_device(poses, out=verdict)
+        if pg is not None:
+            last_buf[0] = pg.collide(env, poses)
+        else:
+            env.collide_device(poses, out=verdict)
         if i is not None:
             k_ev[i][1].record()
-        if world > 1:
+        if pg is not None:
+            pg.barrier(env, dev)
+        elif world > 1:
             dist.all_gather_into_tensor(gathered, verdict)
 
     for _ in range(args.warmup):
@@ -226,6 +249,15 @@ def run_ours(args):
         dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     kernel_ms = float(kern_ms.item())
+    if pg is not None:
+        # every rank must hold every rank's verdicts: compare each gathered slice with the count its owner reports
+        full = pg.view(last_buf[0], dev)
+        verdict.copy_(full[rank, :P])
+        mine = torch.tensor([int(verdict.sum().item())], device=dev, dtype=torch.int64)
+        counts = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(counts, mine)
+        seen = [int(full[r, :P].sum().item()) for r in range(world)]
+        assert seen == [int(c.item()) for c in counts], ("peer gather mismatch", seen, counts)
     hits = int(verdict.sum().item())
 
     # ---- end-to-end leg: pinned host buffers through the host C-ABI call ----------------------------------------
@@ -258,7 +290,9 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "poses_per_gpu_per_step": P, "pose_seed": SEED, "obstacle_tris": int(len(obst)),
                        "robot_tris": int(len(robot)), "l2_policy": "inputs larger than L2 (402 MB of poses per step)",
-                       "parallelism": f"pose-shard x{world} + NCCL all-gather of verdict bytes" if world > 1 else "single GPU",
+                       "parallelism": (f"pose-shard x{world} + verdict all-gather fused into the kernel's stores over NVLink peer memory"
+                                       if gather_mode == "fused" else
+                                       f"pose-shard x{world} + NCCL all-gather of verdict bytes" if world > 1 else "single GPU"),
                        "hit_fraction": hits / P},
             "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": P * 24, "d2h_bytes_per_step": P,
                     "steps": e_steps, "api": "sffg_collide_poses_f32 on pinned host buffers"},
@@ -280,6 +314,8 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        if pg is not None:
+            pg.close()
         dist.destroy_process_group()
 
 
@@ -340,6 +376,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--poses-per-gpu", type=int, default=POSES_PER_GPU)
     ap.add_argument("--cpu-sample", type=int, default=1 << 22)
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()

@@ -635,7 +635,7 @@ __device__ __forceinline__ unsigned check_32_poses(const EnvDev &E, WarpScratch 
 
 template <int FMT, bool COUNT>
 __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) collide_poses_kernel(EnvDev E, const void *poses, long long n,
-                                                                                  uint8_t *out, int chunk) {
+                                                                                  OutSet outs, int chunk) {
   extern __shared__ __align__(16) unsigned char smem[];
   RobotTri *srob = reinterpret_cast<RobotTri *>(smem);
   stage_robot(E, srob);
@@ -658,7 +658,21 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) collide_poses_kerne
     else lp.clear();
     if (COUNT) nposes += mine ? 1 : 0;
     const unsigned hitmask = check_32_poses<FMT, COUNT>(E, ws, srob, mine, lp, lane, false, tally);
-    if (mine) out[i] = (uint8_t)((hitmask >> lane) & 1u);
+    if (outs.n == 1) {
+      if (mine) outs.p[0][i] = (uint8_t)((hitmask >> lane) & 1u);
+    } else if (chunk == 32 && (long long)c * 32 + 32 <= n) {
+      // peer-store gather: the 32 verdict bytes of this unit are 8 words; lane = 8 * destination + word, so one store
+      // instruction serves four destinations with one full 32-byte segment each (local HBM or a peer over NVLink)
+      const unsigned nib = (hitmask >> (4 * (lane & 7))) & 0xFu;
+      const unsigned word = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+      for (int r0 = 0; r0 < outs.n; r0 += 4) {
+        const int r = r0 + (lane >> 3);
+        if (r < outs.n) reinterpret_cast<unsigned *>(outs.p[r] + (long long)c * 32)[lane & 7] = word;
+      }
+    } else if (mine) {
+      const uint8_t v = (uint8_t)((hitmask >> lane) & 1u);
+      for (int r = 0; r < outs.n; ++r) outs.p[r][i] = v;
+    }
   }
   if (COUNT) {
 #pragma unroll
@@ -930,7 +944,7 @@ size_t collide_smem_bytes(int n_robot) {
 
 
 template <int FMT>
-static cudaError_t launch_poses_fmt(const EnvDev &env, const void *d_poses, int64_t n, uint8_t *d_verdict, cudaStream_t stream,
+static cudaError_t launch_poses_fmt(const EnvDev &env, const void *d_poses, int64_t n, const OutSet &d_verdict, cudaStream_t stream,
                                     const LaunchCfg &cfg, bool count, int chunk, int *grid_out) {
   const size_t smem = collide_smem_bytes(env.n_robot);
   const long long chunks = (n + chunk - 1) / chunk;
@@ -954,10 +968,48 @@ static cudaError_t launch_poses_fmt(const EnvDev &env, const void *d_poses, int6
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// cross-GPU completion barrier for the peer-store gather (one CTA of 32 threads, thread r talks to rank r)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void peer_barrier_kernel(FlagSet f, unsigned epoch, int *status) {
+  const int r = threadIdx.x;
+  if (r >= f.n) return;
+  __threadfence_system();   // everything this stream did before (the gather stores) is ordered before the signal
+  unsigned *theirs = f.p[r] + f.me;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+  const unsigned *mine = f.p[f.me] + r;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if ((int)(v - epoch) >= 0) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ull) {   // 2 s: a peer died or never launched -- flag it, never hang the GPU
+      if (status) atomicExch(status, 3);
+      break;
+    }
+    __nanosleep(200);
+  }
+}
+
+cudaError_t launch_peer_barrier(const FlagSet &flags, unsigned epoch, int *d_status, cudaStream_t stream) {
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(flags, epoch, d_status);
+  return cudaGetLastError();
+}
+
 // every warp of the grid leaves its loop through exactly one failing fetch, so a launch consumes
 // (units + grid * warps) values of the shared counter; the host advances the base instead of resetting the counter
 cudaError_t launch_collide_poses(const EnvDev &env_in, const void *d_poses, int pose_fmt, int64_t n, uint8_t *d_verdict,
                                  cudaStream_t stream, const LaunchCfg &cfg, bool count, unsigned *work_base_io) {
+  OutSet one;
+  one.n = 1;
+  one.p[0] = d_verdict;
+  return launch_collide_poses_gather(env_in, d_poses, pose_fmt, n, one, stream, cfg, count, work_base_io);
+}
+
+cudaError_t launch_collide_poses_gather(const EnvDev &env_in, const void *d_poses, int pose_fmt, int64_t n, const OutSet &d_verdict,
+                                        cudaStream_t stream, const LaunchCfg &cfg, bool count, unsigned *work_base_io) {
   if (n <= 0) return cudaSuccess;
   EnvDev env = env_in;
   env.work_base = *work_base_io;

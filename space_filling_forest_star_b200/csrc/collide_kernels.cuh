@@ -31,6 +31,19 @@ struct EnvDev {
   unsigned int work_base;
 };
 
+// destinations of a verdict: the local output plus (multi-GPU) the same offset in every peer's gathered buffer, mapped into
+// this process through CUDA IPC -- the kernel stores each verdict to all of them, so the result all-gather rides on the
+// kernel's own stores over NVLink instead of being a separate collective
+constexpr int kMaxPeers = 8;
+struct OutSet {
+  uint8_t *p[kMaxPeers];
+  int n;
+};
+struct FlagSet {
+  unsigned *p[kMaxPeers];   // p[r] = rank r's flag array (kMaxPeers words), p[me] is local
+  int n, me;
+};
+
 struct LaunchCfg {
   int sm_count;
   int blocks_per_sm;
@@ -41,6 +54,13 @@ struct LaunchCfg {
 cudaError_t launch_collide_poses(const EnvDev &env, const void *d_poses, int pose_fmt, int64_t n,
                                  uint8_t *d_verdict, cudaStream_t stream, const LaunchCfg &cfg, bool count,
                                  unsigned *work_base_io);
+// same, verdict i goes to outs.p[r][i] for every r < outs.n (peer-store gather)
+cudaError_t launch_collide_poses_gather(const EnvDev &env, const void *d_poses, int pose_fmt, int64_t n, const OutSet &outs,
+                                        cudaStream_t stream, const LaunchCfg &cfg, bool count, unsigned *work_base_io);
+// all ranks' stores of the kernels enqueued before this call are visible on every rank once the barrier kernel has run on
+// every rank: signal (st.release.sys into every peer's flag word) + wait (ld.acquire.sys on the own flag words), bounded
+// by a 2 s timeout that raises the env status instead of hanging the GPU
+cudaError_t launch_peer_barrier(const FlagSet &flags, unsigned epoch, int *d_status, cudaStream_t stream);
 
 cudaError_t launch_check_edges(const EnvDev &env, const double *d_starts, const double *d_ends, int64_t m,
                                double sample_dist, int rot_mode, uint8_t *d_free, int32_t *d_first_hit,

@@ -444,8 +444,10 @@ static EnvDev env_view(sffg_env *env, unsigned **base_io) {
 
 // call after the streams were synchronised
 static int check_status(sffg_env *env) {
-  if (*reinterpret_cast<volatile int *>(env->h_status) != 0) {
+  const int st = *reinterpret_cast<volatile int *>(env->h_status);
+  if (st != 0) {
     *env->h_status = 0;
+    if (st == 3) return fail(SFFG_ERR_INTERNAL, "peer barrier timed out: a rank of the gather group never signalled");
     return fail(SFFG_ERR_INTERNAL, "BVH traversal stack overflow: results of this call are invalid");
   }
   return SFFG_OK;
@@ -464,6 +466,71 @@ int sffg_collide_poses_device(sffg_env *env, const void *d_poses, int poses_are_
   EnvDev v = env_view(env, &base);
   SFFG_CUDA(launch_collide_poses(v, d_poses, poses_are_f64 ? 1 : 0, n, d_verdict_out, (cudaStream_t)stream, env->cfg,
                                  env->count, base));
+  return SFFG_OK;
+}
+
+// ---- multi-GPU: verdict all-gather fused into the kernel's stores -----------------------------------------
+int sffg_peer_buffer_create(int64_t bytes, void **d_ptr_out, uint8_t handle_out[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (bytes <= 0 || !d_ptr_out || !handle_out) return fail(SFFG_ERR_ARG, "sffg_peer_buffer_create: bad arguments");
+  void *p = nullptr;
+  SFFG_CUDA(cudaMalloc(&p, (size_t)bytes));
+  SFFG_CUDA(cudaMemset(p, 0, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    cudaGetLastError();
+    return fail(SFFG_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  std::memcpy(handle_out, &h, 64);
+  *d_ptr_out = p;
+  return SFFG_OK;
+}
+int sffg_peer_buffer_open(const uint8_t handle[64], void **d_ptr_out) {
+  if (!handle || !d_ptr_out) return fail(SFFG_ERR_ARG, "sffg_peer_buffer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  SFFG_CUDA(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return SFFG_OK;
+}
+int sffg_peer_buffer_close(void *d_ptr) {
+  if (d_ptr) SFFG_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return SFFG_OK;
+}
+int sffg_peer_buffer_destroy(void *d_ptr) {
+  if (d_ptr) SFFG_CUDA(cudaFree(d_ptr));
+  return SFFG_OK;
+}
+
+int sffg_collide_poses_gather_device(sffg_env *env, const void *d_poses, int poses_are_f64, int64_t n, uint8_t *const *d_outs,
+                                     int n_outs, void *stream) {
+  if (!env || n < 0 || n_outs < 1 || n_outs > kMaxPeers || !d_outs || (n > 0 && !d_poses))
+    return fail(SFFG_ERR_ARG, "sffg_collide_poses_gather_device: bad arguments");
+  OutSet outs;
+  outs.n = n_outs;
+  for (int r = 0; r < n_outs; ++r) {
+    if (!d_outs[r] || (reinterpret_cast<uintptr_t>(d_outs[r]) & 3u))
+      return fail(SFFG_ERR_ARG, "sffg_collide_poses_gather_device: every destination must be non-null and 4-byte aligned");
+    outs.p[r] = d_outs[r];
+  }
+  unsigned *base;
+  EnvDev v = env_view(env, &base);
+  SFFG_CUDA(launch_collide_poses_gather(v, d_poses, poses_are_f64 ? 1 : 0, n, outs, (cudaStream_t)stream, env->cfg, env->count, base));
+  return SFFG_OK;
+}
+
+int sffg_peer_barrier_device(sffg_env *env, uint32_t *const *d_flags, int n_ranks, int my_rank, uint32_t epoch, void *stream) {
+  if (!env || !d_flags || n_ranks < 1 || n_ranks > kMaxPeers || my_rank < 0 || my_rank >= n_ranks)
+    return fail(SFFG_ERR_ARG, "sffg_peer_barrier_device: bad arguments");
+  FlagSet f;
+  f.n = n_ranks;
+  f.me = my_rank;
+  for (int r = 0; r < n_ranks; ++r) {
+    if (!d_flags[r]) return fail(SFFG_ERR_ARG, "sffg_peer_barrier_device: null flag array");
+    f.p[r] = d_flags[r];
+  }
+  SFFG_CUDA(launch_peer_barrier(f, epoch, env->h_status, (cudaStream_t)stream));
   return SFFG_OK;
 }
 

@@ -73,3 +73,95 @@ def sharded_knn(index, queries: torch.Tensor, k: int, group=None) -> Tuple[torch
 
     packed = sharded_rows(nq, (k, 2), torch.int32, queries.device, compute, group)
     return packed[:, :, 0].contiguous(), packed[:, :, 1].contiguous().view(torch.float32)
+
+
+class PeerGather:
+    """Verdict all-gather fused into the collision kernel's stores (include/sffg.h "multi-GPU").
+
+    Every rank owns a gathered buffer of ``world * per_rank`` verdict bytes allocated by the engine (plain cudaMalloc, so
+    that it can be exported through CUDA IPC) and maps the buffers of all peers.  ``collide(env, poses)`` launches the
+    pose kernel with ``world`` destinations -- slice ``rank`` of every rank's buffer -- so the exchange rides on the
+    kernel's own 32-byte stores over NVLink while it computes; ``barrier()`` then enqueues the flag handshake after
+    which every rank's slice is visible locally.  Buffers are double-buffered: a rank that is one step ahead writes the
+    other buffer, so results of step k may be read until the barrier of step k+1 is enqueued.
+    torch.distributed is only the plumbing that ships the 64-byte IPC handles.
+    """
+
+    def __init__(self, per_rank: int, group=None):
+        import ctypes as C
+
+        from . import _lib
+        self._C, self._L, self._check = C, _lib.load(), _lib.check
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("PeerGather supports up to 8 ranks (one NVSwitch domain)")
+        self.per = (per_rank + 31) // 32 * 32          # slices start 32-byte aligned
+        self.bytes = self.world * self.per
+        self.own, handles = [], []
+        for _ in range(3):                              # two gathered buffers + the flag words
+            p = C.c_void_p()
+            h = (C.c_uint8 * 64)()
+            self._check(self._L.sffg_peer_buffer_create(self.bytes if len(self.own) < 2 else 256, C.byref(p), h))
+            self.own.append(p.value)
+            handles.append(bytes(h))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, handles, group=group)
+        self.ptrs = []                                  # ptrs[b][r] = buffer b of rank r, valid in this process
+        self._opened = []
+        for b in range(3):
+            row = []
+            for r in range(self.world):
+                if r == self.rank:
+                    row.append(self.own[b])
+                else:
+                    p = C.c_void_p()
+                    hb = (C.c_uint8 * 64).from_buffer_copy(everyone[r][b])
+                    self._check(self._L.sffg_peer_buffer_open(hb, C.byref(p)))
+                    self._opened.append(p.value)
+                    row.append(p.value)
+            self.ptrs.append(row)
+        self.step = 0
+        self.epoch = 0
+        dist.barrier(group=group)
+
+    def collide(self, env, poses: torch.Tensor) -> int:
+        """enqueue the pose kernel on the current stream; verdict i of this rank lands at offset rank*per + i of the current
+        gathered buffer of EVERY rank.  Returns the buffer number to pass to :meth:`view`."""
+        n = poses.shape[0]
+        assert n <= self.per and poses.is_cuda and poses.is_contiguous()
+        b = self.step & 1
+        self.step += 1
+        dests = (self._C.c_void_p * self.world)(*[self.ptrs[b][r] + self.rank * self.per for r in range(self.world)])
+        st = torch.cuda.current_stream(poses.device).cuda_stream
+        self._check(self._L.sffg_collide_poses_gather_device(env._h, poses.data_ptr(), int(poses.dtype == torch.float64), n, dests,
+                                                             self.world, st))
+        return b
+
+    def barrier(self, env, device=None) -> None:
+        """enqueue the cross-GPU completion handshake on the current stream"""
+        self.epoch += 1
+        flags = (self._C.c_void_p * self.world)(*self.ptrs[2])
+        st = torch.cuda.current_stream(device).cuda_stream
+        self._check(self._L.sffg_peer_barrier_device(env._h, flags, self.world, self.rank, self.epoch, st))
+
+    def view(self, b: int, device) -> torch.Tensor:
+        """the gathered buffer ``b`` of this rank as a torch uint8 tensor [world, per] (no copy)"""
+        iface = {"shape": (self.world, self.per), "typestr": "|u1", "data": (self.own[b], False), "version": 2}
+        holder = type("_Dev", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device=device)
+
+    def close(self) -> None:
+        for p in self._opened:
+            self._L.sffg_peer_buffer_close(p)
+        self._opened = []
+        for p in self.own:
+            self._L.sffg_peer_buffer_destroy(p)
+        self.own = []
+
+
+def gathered_collide(env, pg: "PeerGather", poses_local: torch.Tensor) -> torch.Tensor:
+    """one fused step: local slice -> every rank's gathered buffer, then the completion barrier; returns [world, per]"""
+    b = pg.collide(env, poses_local)
+    pg.barrier(env, poses_local.device)
+    return pg.view(b, poses_local.device)

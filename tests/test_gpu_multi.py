@@ -39,6 +39,26 @@ idx = S.Index(nodes)
 ids, d2 = sharded_knn(idx, torch.from_numpy(q).cuda(), 16)
 wi, wd = O.knn_linear(nodes, q, 16)
 assert np.array_equal(ids.cpu().numpy(), wi) and np.array_equal(d2.cpu().numpy().view(np.uint32), wd.view(np.uint32)), "sharded knn mismatch"
+# verdict all-gather fused into the kernel's stores (peer memory over NVLink) == oracle, on every rank, over several steps
+from space_filling_forest_star_b200.sharding import PeerGather, shard_bounds, gathered_collide
+world = dist.get_world_size()
+# 1 400 011 poses: full 32-pose units take the packed-word store path, the ragged tail and the small batches the byte path
+big = O.gen_poses(11, 0, 1400011, [-60, 60, -60, 60, 0, 100])
+want_big, _ = O.collide_obbtree(O.ObbModel(obst), O.ObbModel(robot), big.astype(np.float64))
+for n_g in (100003, 64, 1400011):
+    src, want = (big, want_big) if n_g > len(poses) else (poses, want)
+    b, e, per = shard_bounds(n_g, rank, world)
+    pg = PeerGather(per)
+    for rep in range(3):
+        mine = torch.from_numpy(src[:n_g][b:e]).cuda().contiguous()
+        full = gathered_collide(env, pg, mine)
+        torch.cuda.synchronize()
+        env.sync_check()
+        for r in range(world):
+            rb, re_, _ = shard_bounds(n_g, r, world)
+            assert np.array_equal(full[r, : re_ - rb].cpu().numpy(), want[rb:re_]), ("peer gather mismatch", n_g, rep, r)
+    dist.barrier()
+    pg.close()
 dist.barrier()
 if rank == 0:
     print("SHARDED_OK")
