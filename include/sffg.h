@@ -69,6 +69,20 @@ SFFG_API int sffg_env_create(const double *obst_tris, int64_t n_obst, const doub
                     sffg_env **out);
 SFFG_API int sffg_env_destroy(sffg_env *env);
 
+/* where the obstacle hierarchy is built (RAPID builds its OBB tree on the host at EndModel(), src/environment.h:114):
+ * HOST = binned-SAH builder on the CPU (best traversal, ~1 us per triangle); DEVICE = Morton-ordered builder on the GPU
+ * (a few ms for millions of triangles: large maps, obstacles that move every frame); AUTO = HOST below 2^18 triangles.
+ * Verdicts do not depend on the builder -- both hierarchies are conservative and every surviving pair is tested exactly. */
+#define SFFG_BUILD_AUTO 0
+#define SFFG_BUILD_HOST 1
+#define SFFG_BUILD_DEVICE 2
+SFFG_API int sffg_env_create_ex(const double *obst_tris, int64_t n_obst, const double *robot_tris, int64_t n_robot,
+                       int build_mode, sffg_env **out);
+/* replaces the obstacle soup of an existing environment (moving / re-scanned obstacles; the reference would have to
+ * delete and re-create its Obstacle objects, src/main.cpp:254): rebuilds hierarchy, triangle arrays and clearance grid,
+ * keeps robot, streams, staging buffers and counters.  Blocks until the device is idle, then until the rebuild is done. */
+SFFG_API int sffg_env_set_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obst, int build_mode);
+
 typedef struct {
   int64_t n_obst_tris, n_robot_tris;
   int64_t n_nodes;          /* 8-wide BVH nodes                                                               */
@@ -77,6 +91,7 @@ typedef struct {
   double build_ms;          /* host BVH build + upload + clearance grid                                       */
   int64_t grid_cells;       /* cells of the free-space (clearance) grid, 0 when disabled                      */
   double grid_cell_size;
+  int32_t built_on_device;  /* 1 if the hierarchy came from the GPU builder                                   */
 } sffg_env_info_t;
 SFFG_API int sffg_env_info(const sffg_env *env, sffg_env_info_t *out);
 

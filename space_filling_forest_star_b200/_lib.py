@@ -13,6 +13,7 @@ from . import build as _build
 SFFG_OK = 0
 ERR_NAMES = {1: "NO_DEVICE", 2: "CUDA", 3: "ARG", 4: "IO", 5: "CAPACITY", 6: "DOMAIN", 7: "INTERNAL"}
 ROT_REFERENCE, ROT_INTERPOLATE = 0, 1
+BUILD_AUTO, BUILD_HOST, BUILD_DEVICE = 0, 1, 2
 MAX_K = 128
 
 
@@ -24,7 +25,8 @@ class SffgError(RuntimeError):
 
 class EnvInfo(C.Structure):
     _fields_ = [("n_obst_tris", C.c_int64), ("n_robot_tris", C.c_int64), ("n_nodes", C.c_int64), ("depth", C.c_int32),
-                ("device_bytes", C.c_int64), ("build_ms", C.c_double), ("grid_cells", C.c_int64), ("grid_cell_size", C.c_double)]
+                ("device_bytes", C.c_int64), ("build_ms", C.c_double), ("grid_cells", C.c_int64), ("grid_cell_size", C.c_double),
+                ("built_on_device", C.c_int32)]
 
 
 class Counters(C.Structure):
@@ -44,6 +46,8 @@ SIGNATURES = {
     "sffg_free": (None, [_p]),
     "sffg_env_create": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.POINTER(_p)]),
     "sffg_env_destroy": (C.c_int, [_p]),
+    "sffg_env_create_ex": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.c_int, C.POINTER(_p)]),
+    "sffg_env_set_obstacles": (C.c_int, [_p, _p, C.c_int64, C.c_int]),
     "sffg_env_info": (C.c_int, [_p, C.POINTER(EnvInfo)]),
     "sffg_collide_poses_f32": (C.c_int, [_p, _p, C.c_int64, _p]),
     "sffg_collide_poses_f64": (C.c_int, [_p, _p, C.c_int64, _p]),

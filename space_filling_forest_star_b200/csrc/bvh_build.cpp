@@ -237,6 +237,7 @@ void top_cut(const HostBvh &bvh, std::vector<ChildSlot> *out) {
     for (int i = 0; i < (int)out->size(); ++i) {
       const ChildSlot &s = (*out)[i];
       if (s.child < 0) continue;
+      if (((size_t)s.child + 1) * kWide > bvh.slots.size()) continue;   // only the head of a device-built hierarchy is on the host
       int kids = 0;
       for (int c = 0; c < kWide; ++c) kids += bvh.slots[(size_t)s.child * kWide + c].child != kEmptyChild;
       if ((int)out->size() - 1 + kids > 32) continue;

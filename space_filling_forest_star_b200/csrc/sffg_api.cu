@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "bvh_device.cuh"
 #include "collide_kernels.cuh"
 #include "common.h"
 #include "knn_kernels.cuh"
@@ -98,6 +99,7 @@ struct sffg_env {
   cudaStream_t streams[2] = {nullptr, nullptr};
   DevBuf in[2], out[2], aux[2], fh;   // fh: per-edge first-hit scratch of small edge batches
   bool count = false;
+  int64_t robot_bytes = 0;
   sffg_env_info_t info{};
   LaunchCfg cfg{};
 };
@@ -248,8 +250,154 @@ int sffg_env_destroy(sffg_env *env) {
   return SFFG_OK;
 }
 
-int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot_tris, int64_t n_robot, sffg_env **out) {
-  if (!out || n_obst < 0 || n_robot <= 0 || !robot_tris || (n_obst > 0 && !obst_tris))
+// (re)builds everything that depends on the obstacle soup: hierarchy, triangle arrays, root box, clearance grid.
+// The robot side of `env` must already be in place (the grid is dilated by the robot's bounding radius).
+constexpr int64_t kDeviceBuildMin = 1 << 18;   // SFFG_BUILD_AUTO: triangle count from which the hierarchy is built on the GPU
+
+static int set_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obst, int build_mode) {
+  const bool on_device = n_obst > 0 && (build_mode == SFFG_BUILD_DEVICE || (build_mode == SFFG_BUILD_AUTO && n_obst >= kDeviceBuildMin));
+  void **olds[] = {&env->d_slots, &env->d_top, &env->d_clear, &env->d_tris32, &env->d_tris64};
+  for (void **p : olds) {
+    cudaFree(*p);
+    *p = nullptr;
+  }
+  EnvDev &d = env->dev;
+  size_t bytes = 0;
+  auto upload = [&](void **dst, const void *src, size_t n) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, std::max<size_t>(n, 16));
+    if (e != cudaSuccess) return e;
+    bytes += n;
+    if (n) e = cudaMemcpy(*dst, src, n, cudaMemcpyHostToDevice);
+    return e;
+  };
+  double root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
+  std::vector<ChildSlot> top;
+  int64_t n_nodes = 0;
+  int depth = 0;
+  if (!on_device) {
+    // ---- host: binned-SAH hierarchy + FP32 / FP64 triangle arrays in leaf order
+    HostBvh bvh;
+    build_wide_bvh(obst_tris, n_obst, &bvh);
+    std::vector<TriF32> t32((size_t)n_obst);
+    std::vector<double> t64(9 * (size_t)n_obst);
+    for (int64_t i = 0; i < n_obst; ++i) {
+      const double *src = obst_tris + 9 * (size_t)bvh.tri_order[(size_t)i];
+      std::memcpy(&t64[9 * (size_t)i], src, 9 * sizeof(double));
+      double err = 0;
+      for (int v = 0; v < 3; ++v) {
+        for (int k = 0; k < 3; ++k) {
+          float f = (float)src[3 * v + k];
+          t32[(size_t)i].p[v][k] = f;
+          err = std::max(err, std::fabs(src[3 * v + k] - (double)f));
+        }
+        t32[(size_t)i].p[v][3] = 0.f;
+      }
+      t32[(size_t)i].p[0][3] = round_up_f32(err * 1.0000001);
+    }
+    SFFG_CUDA(upload(&env->d_slots, bvh.slots.data(), bvh.slots.size() * sizeof(ChildSlot)));
+    SFFG_CUDA(upload(&env->d_tris32, t32.data(), t32.size() * sizeof(TriF32)));
+    SFFG_CUDA(upload(&env->d_tris64, t64.data(), t64.size() * sizeof(double)));
+    top_cut(bvh, &top);
+    n_nodes = (int64_t)(bvh.slots.size() / kWide);
+    depth = bvh.depth;
+    for (int k = 0; k < 3; ++k) {
+      root_lo[k] = bvh.root_lo[k];
+      root_hi[k] = bvh.root_hi[k];
+    }
+  } else {
+    // ---- device: Morton-ordered 8-wide hierarchy built by bvh_device.cu from the uploaded soup
+    void *d_soup = nullptr;
+    size_t dummy = 0;
+    (void)dummy;
+    SFFG_CUDA(cudaMalloc(&d_soup, 9 * (size_t)n_obst * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d_soup, obst_tris, 9 * (size_t)n_obst * sizeof(double), cudaMemcpyHostToDevice, env->streams[0]);
+    DeviceBvh db;
+    if (e == cudaSuccess) e = build_bvh_device((const double *)d_soup, (int)n_obst, env->streams[0], &db);
+    cudaFree(d_soup);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(SFFG_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString(e));
+    }
+    env->d_slots = db.d_slots;
+    env->d_tris32 = db.d_tris32;
+    env->d_tris64 = db.d_tris64;
+    cudaFree(db.d_order);
+    bytes += (size_t)db.n_nodes * kWide * sizeof(ChildSlot) + (size_t)n_obst * (sizeof(TriF32) + 9 * sizeof(double));
+    // the cut through the top of the hierarchy is chosen on the host from the first levels (nodes are stored level by level)
+    HostBvh head;
+    head.slots.resize((size_t)std::min<int64_t>(db.n_nodes, 1 + 8 + 64) * kWide);
+    SFFG_CUDA(cudaMemcpy(head.slots.data(), env->d_slots, head.slots.size() * sizeof(ChildSlot), cudaMemcpyDeviceToHost));
+    top_cut(head, &top);
+    n_nodes = db.n_nodes;
+    depth = db.depth;
+    for (int k = 0; k < 3; ++k) {
+      root_lo[k] = db.root_lo[k];
+      root_hi[k] = db.root_hi[k];
+    }
+  }
+  SFFG_CUDA(upload(&env->d_top, top.data(), top.size() * sizeof(ChildSlot)));
+  d.n_obst = (int)n_obst;
+  for (int k = 0; k < 3; ++k) {
+    const double oc = 0.5 * (root_lo[k] + root_hi[k]);
+    d.root_c[k] = (float)oc;
+    d.root_h[k] = n_obst ? round_up_f32(std::max(root_hi[k] - (double)d.root_c[k], (double)d.root_c[k] - root_lo[k]) * 1.0000001) : 0.f;
+  }
+  // ---- clearance grid (free-space bitmap) over the obstacle AABB dilated by the robot's reach
+  d.clear_bits = nullptr;
+  d.grid_n[0] = d.grid_n[1] = d.grid_n[2] = 0;
+  d.grid_inv_h = 0.f;
+  d.grid_o[0] = d.grid_o[1] = d.grid_o[2] = 0.f;
+  const char *grid_env = std::getenv("SFFG_CLEARANCE_GRID");
+  if (n_obst > 0 && !(grid_env && grid_env[0] == '0')) {
+    const double rho = d.rob_radius;
+    double h = rho / 4.0;
+    double ext[3], maxc = 0;
+    for (int k = 0; k < 3; ++k) {
+      ext[k] = (root_hi[k] - root_lo[k]) + 2.0 * rho;
+      maxc = std::max({maxc, std::fabs(root_lo[k]) + rho, std::fabs(root_hi[k]) + rho});
+    }
+    // cap the grid at 2^24 cells (2 MB of bits, L2-resident)
+    while ((ext[0] / h + 1) * (ext[1] / h + 1) * (ext[2] / h + 1) > double(1 << 24)) h *= 1.25;
+    int gn[3];
+    float go[3];
+    for (int k = 0; k < 3; ++k) {
+      go[k] = (float)(root_lo[k] - rho);
+      gn[k] = std::max(1, (int)std::ceil(ext[k] / h));
+    }
+    // reach = bounding radius + half cell diagonal + margins for float rounding of vertices, cell lookup and distances
+    const double reach = (rho + 0.8661 * h) * 1.002 + 1e-3 * h + maxc * 3.9e-6;
+    const size_t words = ((size_t)gn[0] * gn[1] * gn[2] + 31) / 32;
+    SFFG_CUDA(cudaMalloc(&env->d_clear, words * sizeof(unsigned)));
+    SFFG_CUDA(cudaMemset(env->d_clear, 0, words * sizeof(unsigned)));
+    SFFG_CUDA(launch_build_clearance(reinterpret_cast<const float4 *>(env->d_tris32), (int)n_obst, go, (float)h, gn, (float)reach,
+                                         (unsigned *)env->d_clear, env->streams[0]));
+    SFFG_CUDA(cudaStreamSynchronize(env->streams[0]));
+    bytes += words * sizeof(unsigned);
+    d.clear_bits = reinterpret_cast<const unsigned *>(env->d_clear);
+    for (int k = 0; k < 3; ++k) {
+      d.grid_o[k] = go[k];
+      d.grid_n[k] = gn[k];
+    }
+    d.grid_inv_h = (float)(1.0 / h);
+    env->info.grid_cells = (int64_t)gn[0] * gn[1] * gn[2];
+    env->info.grid_cell_size = h;
+  }
+  d.slots = reinterpret_cast<const float4 *>(env->d_slots);
+  d.top = reinterpret_cast<const float4 *>(env->d_top);
+  d.n_top = (int)top.size();
+  d.tris32 = reinterpret_cast<const float4 *>(env->d_tris32);
+  d.tris64 = reinterpret_cast<const double *>(env->d_tris64);
+  env->info.n_obst_tris = n_obst;
+  env->info.n_nodes = n_nodes;
+  env->info.depth = depth;
+  env->info.device_bytes = env->robot_bytes + (int64_t)bytes;
+  env->info.built_on_device = on_device ? 1 : 0;
+  return SFFG_OK;
+}
+
+int sffg_env_create_ex(const double *obst_tris, int64_t n_obst, const double *robot_tris, int64_t n_robot, int build_mode,
+                       sffg_env **out) {
+  if (!out || n_obst < 0 || n_robot <= 0 || !robot_tris || (n_obst > 0 && !obst_tris) || build_mode < 0 || build_mode > 2)
     return fail(SFFG_ERR_ARG, "sffg_env_create: bad arguments");
   if (n_obst > 0x3fffffff || n_robot > 4096) return fail(SFFG_ERR_ARG, "sffg_env_create: mesh too large");
   int rc = ensure_runtime();
@@ -267,25 +415,6 @@ int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot
     if (e_ != cudaSuccess) return bail(fail(SFFG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)));   \
   } while (0)
 
-  // ---- obstacle: BVH + FP32 / FP64 triangle arrays in leaf order
-  HostBvh bvh;
-  build_wide_bvh(obst_tris, n_obst, &bvh);
-  std::vector<TriF32> t32((size_t)n_obst);
-  std::vector<double> t64(9 * (size_t)n_obst);
-  for (int64_t i = 0; i < n_obst; ++i) {
-    const double *src = obst_tris + 9 * (size_t)bvh.tri_order[(size_t)i];
-    std::memcpy(&t64[9 * (size_t)i], src, 9 * sizeof(double));
-    double err = 0;
-    for (int v = 0; v < 3; ++v) {
-      for (int k = 0; k < 3; ++k) {
-        float f = (float)src[3 * v + k];
-        t32[(size_t)i].p[v][k] = f;
-        err = std::max(err, std::fabs(src[3 * v + k] - (double)f));
-      }
-      t32[(size_t)i].p[v][3] = 0.f;
-    }
-    t32[(size_t)i].p[0][3] = round_up_f32(err * 1.0000001);
-  }
   // ---- robot
   std::vector<RobotTri> rob((size_t)n_robot);
   double rlo[3] = {1e300, 1e300, 1e300}, rhi[3] = {-1e300, -1e300, -1e300}, rad2 = 0;
@@ -307,9 +436,6 @@ int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot
     const double c = 0.5 * (rlo[k] + rhi[k]);
     d.rob_c[k] = (float)c;
     d.rob_h[k] = round_up_f32(std::max(rhi[k] - (double)d.rob_c[k], (double)d.rob_c[k] - rlo[k]) * 1.0000001);
-    const double oc = 0.5 * (bvh.root_lo[k] + bvh.root_hi[k]);
-    d.root_c[k] = (float)oc;
-    d.root_h[k] = n_obst ? round_up_f32(std::max(bvh.root_hi[k] - (double)d.root_c[k], (double)d.root_c[k] - bvh.root_lo[k]) * 1.0000001) : 0.f;
   }
   d.rob_radius = round_up_f32(std::sqrt(rad2) * 1.000001);
 
@@ -321,12 +447,6 @@ int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot
     if (n) e = cudaMemcpy(*dst, src, n, cudaMemcpyHostToDevice);
     return e;
   };
-  SFFG_ENV_CUDA(upload(&env->d_slots, bvh.slots.data(), bvh.slots.size() * sizeof(ChildSlot)));
-  std::vector<ChildSlot> top;
-  top_cut(bvh, &top);
-  SFFG_ENV_CUDA(upload(&env->d_top, top.data(), top.size() * sizeof(ChildSlot)));
-  SFFG_ENV_CUDA(upload(&env->d_tris32, t32.data(), t32.size() * sizeof(TriF32)));
-  SFFG_ENV_CUDA(upload(&env->d_tris64, t64.data(), t64.size() * sizeof(double)));
   SFFG_ENV_CUDA(upload(&env->d_robot, rob.data(), rob.size() * sizeof(RobotTri)));
   SFFG_ENV_CUDA(upload(&env->d_robot64, robot_tris, 9 * (size_t)n_robot * sizeof(double)));
   SFFG_ENV_CUDA(cudaMalloc((void **)&env->d_counters, 10 * sizeof(unsigned long long)));
@@ -337,51 +457,6 @@ int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot
   SFFG_ENV_CUDA(cudaMalloc((void **)&env->d_work, 8 * sizeof(unsigned)));
   SFFG_ENV_CUDA(cudaMemset(env->d_work, 0, 8 * sizeof(unsigned)));
   for (int s = 0; s < 2; ++s) SFFG_ENV_CUDA(cudaStreamCreateWithFlags(&env->streams[s], cudaStreamNonBlocking));
-  // ---- clearance grid (free-space bitmap) over the obstacle AABB dilated by the robot's reach
-  d.clear_bits = nullptr;
-  d.grid_n[0] = d.grid_n[1] = d.grid_n[2] = 0;
-  d.grid_inv_h = 0.f;
-  d.grid_o[0] = d.grid_o[1] = d.grid_o[2] = 0.f;
-  const char *grid_env = std::getenv("SFFG_CLEARANCE_GRID");
-  if (n_obst > 0 && !(grid_env && grid_env[0] == '0')) {
-    const double rho = d.rob_radius;
-    double h = rho / 4.0;
-    double ext[3], maxc = 0;
-    for (int k = 0; k < 3; ++k) {
-      ext[k] = (bvh.root_hi[k] - bvh.root_lo[k]) + 2.0 * rho;
-      maxc = std::max({maxc, std::fabs(bvh.root_lo[k]) + rho, std::fabs(bvh.root_hi[k]) + rho});
-    }
-    // cap the grid at 2^24 cells (2 MB of bits, L2-resident)
-    while ((ext[0] / h + 1) * (ext[1] / h + 1) * (ext[2] / h + 1) > double(1 << 24)) h *= 1.25;
-    int gn[3];
-    float go[3];
-    for (int k = 0; k < 3; ++k) {
-      go[k] = (float)(bvh.root_lo[k] - rho);
-      gn[k] = std::max(1, (int)std::ceil(ext[k] / h));
-    }
-    // reach = bounding radius + half cell diagonal + margins for float rounding of vertices, cell lookup and distances
-    const double reach = (rho + 0.8661 * h) * 1.002 + 1e-3 * h + maxc * 3.9e-6;
-    const size_t words = ((size_t)gn[0] * gn[1] * gn[2] + 31) / 32;
-    SFFG_ENV_CUDA(cudaMalloc(&env->d_clear, words * sizeof(unsigned)));
-    SFFG_ENV_CUDA(cudaMemset(env->d_clear, 0, words * sizeof(unsigned)));
-    SFFG_ENV_CUDA(launch_build_clearance(reinterpret_cast<const float4 *>(env->d_tris32), (int)n_obst, go, (float)h, gn, (float)reach,
-                                         (unsigned *)env->d_clear, env->streams[0]));
-    SFFG_ENV_CUDA(cudaStreamSynchronize(env->streams[0]));
-    bytes += words * sizeof(unsigned);
-    d.clear_bits = reinterpret_cast<const unsigned *>(env->d_clear);
-    for (int k = 0; k < 3; ++k) {
-      d.grid_o[k] = go[k];
-      d.grid_n[k] = gn[k];
-    }
-    d.grid_inv_h = (float)(1.0 / h);
-    env->info.grid_cells = (int64_t)gn[0] * gn[1] * gn[2];
-    env->info.grid_cell_size = h;
-  }
-  d.slots = reinterpret_cast<const float4 *>(env->d_slots);
-  d.top = reinterpret_cast<const float4 *>(env->d_top);
-  d.n_top = (int)top.size();
-  d.tris32 = reinterpret_cast<const float4 *>(env->d_tris32);
-  d.tris64 = reinterpret_cast<const double *>(env->d_tris64);
   d.robot = reinterpret_cast<const RobotTri *>(env->d_robot);
   d.robot64 = reinterpret_cast<const double *>(env->d_robot64);
   d.counters = nullptr;
@@ -390,15 +465,28 @@ int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot
   env->cfg.sm_count = g_rt.sm_count;
   env->cfg.blocks_per_sm = 0;
 
-  env->info.n_obst_tris = n_obst;
   env->info.n_robot_tris = n_robot;
-  env->info.n_nodes = (int64_t)(bvh.slots.size() / kWide);
-  env->info.depth = bvh.depth;
-  env->info.device_bytes = (int64_t)bytes;
+  env->robot_bytes = (int64_t)bytes;
+  rc = set_obstacles(env, obst_tris, n_obst, build_mode);
+  if (rc != SFFG_OK) return bail(rc);
   env->info.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   *out = env;
   return SFFG_OK;
 #undef SFFG_ENV_CUDA
+}
+
+int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot_tris, int64_t n_robot, sffg_env **out) {
+  return sffg_env_create_ex(obst_tris, n_obst, robot_tris, n_robot, SFFG_BUILD_AUTO, out);
+}
+
+int sffg_env_set_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obst, int build_mode) {
+  if (!env || n_obst < 0 || (n_obst > 0 && !obst_tris) || n_obst > 0x3fffffff || build_mode < 0 || build_mode > 2)
+    return fail(SFFG_ERR_ARG, "sffg_env_set_obstacles: bad arguments");
+  SFFG_CUDA(cudaDeviceSynchronize());   // nothing may still be traversing the old hierarchy
+  const auto t0 = std::chrono::steady_clock::now();
+  int rc = set_obstacles(env, obst_tris, n_obst, build_mode);
+  env->info.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
 }
 
 int sffg_env_info(const sffg_env *env, sffg_env_info_t *out) {

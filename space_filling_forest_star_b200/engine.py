@@ -19,7 +19,7 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import ROT_INTERPOLATE, ROT_REFERENCE, SffgError, check  # noqa: F401
+from ._lib import BUILD_AUTO, BUILD_DEVICE, BUILD_HOST, ROT_INTERPOLATE, ROT_REFERENCE, SffgError, check  # noqa: F401
 
 COLLISION_SAMPLE_SIZE = 0.1   # Solver::collisionSampleSize, src/problemStruct.h:121
 
@@ -57,12 +57,18 @@ def load_mesh(path: str, is_obj: bool, position: Sequence[float] = (0.0, 0.0, 0.
 class Environment:
     """Obstacle BVH + robot mesh resident on one GPU."""
 
-    def __init__(self, obstacle_tris, robot_tris):
+    def __init__(self, obstacle_tris, robot_tris, build: int = BUILD_AUTO):
+        """``build``: where the obstacle hierarchy is built (BUILD_AUTO / BUILD_HOST / BUILD_DEVICE, include/sffg.h)"""
         self._L = _lib.load()
         self._h = C.c_void_p()
         o = np.ascontiguousarray(np.asarray(obstacle_tris, dtype=np.float64).reshape(-1, 9))
         r = np.ascontiguousarray(np.asarray(robot_tris, dtype=np.float64).reshape(-1, 9))
-        check(self._L.sffg_env_create(_ptr(o) if len(o) else None, len(o), _ptr(r), len(r), C.byref(self._h)))
+        check(self._L.sffg_env_create_ex(_ptr(o) if len(o) else None, len(o), _ptr(r), len(r), int(build), C.byref(self._h)))
+
+    def set_obstacles(self, obstacle_tris, build: int = BUILD_AUTO) -> None:
+        """replace the obstacle soup in place (moving obstacles): hierarchy, triangle arrays and clearance grid are rebuilt"""
+        o = np.ascontiguousarray(np.asarray(obstacle_tris, dtype=np.float64).reshape(-1, 9))
+        check(self._L.sffg_env_set_obstacles(self._h, _ptr(o) if len(o) else None, len(o), int(build)))
 
     @classmethod
     def from_files(cls, robot_file: str, robot_is_obj: bool, obstacles: Sequence[Tuple[str, bool, Sequence[float]]],
