@@ -58,6 +58,11 @@ SFFG_API int sffg_device_count(void);
  * used, 'o' never changes the index offset); is_obj == 0: 2-D ".tri" map (x1 y1 x2 y2 x3 y3, z = 0).
  * vertex = (file value + position[i]) * scale.  *tris_out is malloc'ed by the library: free with sffg_free.
  * bbox_out (optional) = minX maxX minY maxY minZ maxZ over all parsed vertices (Obstacle::localRange).       */
+#define SFFG_MESH_TRI 0        /* 2-D ".tri" map                                                                     */
+#define SFFG_MESH_OBJ 1        /* OBJ exactly as the reference reads it (parity mode)                                 */
+#define SFFG_MESH_OBJ_FIXED 2  /* opt-in: only "v" lines are vertices, polygons are fan-triangulated (a quad gives two
+                                * triangles), negative indices are relative -- what the files mean, not what the
+                                * reference loads; leaves parity with the reference's triangle soup                   */
 SFFG_API int sffg_mesh_load(const char *path, int is_obj, const double position[3], double scale,
                    double **tris_out, int64_t *n_tris_out, double bbox_out[6]);
 SFFG_API void sffg_free(void *p);

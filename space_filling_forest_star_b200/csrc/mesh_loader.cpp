@@ -97,9 +97,11 @@ int load_mesh(const char *path, int is_obj, const double position[3], double sca
   while (std::getline(in, line)) {
     ++lineno;
     if (is_obj) {
+      const bool fixed = is_obj == SFFG_MESH_OBJ_FIXED;
+      if (fixed) line = trim_ws(line);
       next_token(line, &tok, &rest);
       if (tok.empty()) continue;
-      if (tok[0] == 'v') {
+      if (fixed ? tok == "v" : tok[0] == 'v') {
         double c[3];
         for (int i = 0; i < 3; ++i) {
           std::string cur = rest;
@@ -110,7 +112,27 @@ int load_mesh(const char *path, int is_obj, const double position[3], double sca
           c[i] = d + position[i];
         }
         soup.add_point(c);
-      } else if (tok[0] == 'f') {
+      } else if (fixed && tok == "f") {
+        // opt-in repair of the reference loader: every polygon is fan-triangulated (a quad gives two triangles, not one)
+        // and relative (negative) indices are resolved against the vertices read so far
+        std::vector<long> poly;
+        while (!rest.empty()) {
+          std::string cur = rest;
+          next_token(cur, &tok, &rest);
+          if (tok.empty()) continue;
+          long v;
+          if (!parse_int(tok, &v))
+            return fail(SFFG_ERR_IO, std::string(path) + ":" + std::to_string(lineno) + ": bad face index");
+          if (v < 0) v = (long)(soup.pts.size() / 3) + 1 + v;
+          poly.push_back(v);
+        }
+        if (poly.size() < 3) return fail(SFFG_ERR_IO, std::string(path) + ":" + std::to_string(lineno) + ": face with fewer than 3 vertices");
+        for (size_t k = 1; k + 1 < poly.size(); ++k) {
+          const long idx[3] = {poly[0], poly[k], poly[k + 1]};
+          if (!soup.add_facet(idx))
+            return fail(SFFG_ERR_IO, std::string(path) + ":" + std::to_string(lineno) + ": face index out of range");
+        }
+      } else if (!fixed && tok[0] == 'f') {
         long idx[3];
         for (int i = 0; i < 3; ++i) {
           std::string cur = rest;

@@ -37,15 +37,17 @@ def device_count() -> int:
     return _lib.load().sffg_device_count()
 
 
-def load_mesh(path: str, is_obj: bool, position: Sequence[float] = (0.0, 0.0, 0.0), scale: float = 1.0
+def load_mesh(path: str, is_obj, position: Sequence[float] = (0.0, 0.0, 0.0), scale: float = 1.0
               ) -> Tuple[np.ndarray, np.ndarray]:
-    """-> (triangles float64 [n][3][3], bbox float64[6] = minX maxX minY maxY minZ maxZ)."""
+    """-> (triangles float64 [n][3][3], bbox float64[6] = minX maxX minY maxY minZ maxZ).
+
+    ``is_obj``: False/0 = 2-D .tri map, True/1 = OBJ as the reference reads it, 2 = repaired OBJ reading (opt-in)."""
     L = _lib.load()
     pos = np.asarray(position, dtype=np.float64)
     out = C.c_void_p()
     n = C.c_int64()
     bbox = np.zeros(6, dtype=np.float64)
-    check(L.sffg_mesh_load(str(path).encode(), int(bool(is_obj)), _ptr(pos), float(scale), C.byref(out), C.byref(n), _ptr(bbox)))
+    check(L.sffg_mesh_load(str(path).encode(), int(is_obj), _ptr(pos), float(scale), C.byref(out), C.byref(n), _ptr(bbox)))
     try:
         buf = (C.c_double * (9 * n.value)).from_address(out.value) if n.value else []
         tris = np.array(buf, dtype=np.float64).reshape(-1, 3, 3)

@@ -96,7 +96,7 @@ inline bool parse_point(const std::string &s, double scale, double out[3]) {
 
 struct MeshRef {
   std::string file;
-  bool is_obj = false;
+  int is_obj = 0;   // SFFG_MESH_TRI / SFFG_MESH_OBJ / SFFG_MESH_OBJ_FIXED (extension attribute fix_mesh="true")
   double pos[3] = {0, 0, 0};
 };
 
@@ -149,10 +149,12 @@ inline Config load_config(const std::string &path) {
       seen_robot = true;
       if (auto v = get("file")) c.robot.file = *v; else die("invalid file node in Robot node!");
       if (auto v = get("is_obj")) c.robot.is_obj = *v == "true";
+      if (auto v = get("fix_mesh")) if (*v == "true" && c.robot.is_obj) c.robot.is_obj = SFFG_MESH_OBJ_FIXED;
     } else if (t.name == "Obstacle") {
       MeshRef m;
       if (auto v = get("file")) m.file = *v; else die("invalid file attribute in Obstacle node!");
       if (auto v = get("is_obj")) m.is_obj = *v == "true";
+      if (auto v = get("fix_mesh")) if (*v == "true" && m.is_obj) m.is_obj = SFFG_MESH_OBJ_FIXED;
       if (auto v = get("position")) if (!parse_point(*v, 1.0, m.pos)) die("Unknown format of point");
       c.obstacles.push_back(m);
     } else if (t.name == "Point") {

@@ -100,6 +100,24 @@ def test_mesh_loader_obj_quirks(tmp_path, orc):
     assert bbox[1] == (9 + 1.0) * 10.0   # the bbox covers every parsed 'v*' line, like Obstacle::localRange
 
 
+def test_mesh_loader_fixed_mode_is_opt_in(tmp_path):
+    """SFFG_MESH_OBJ_FIXED (include/sffg.h): only 'v' lines are vertices, polygons are fan-triangulated, negative indices
+    are relative -- the repaired reading of the file, never the default (the default keeps parity with the reference)"""
+    import space_filling_forest_star_b200 as S
+    p = tmp_path / "q.obj"
+    body = "o quad\nv 0 0 0\nvn 0 0 1\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1//1 2//1 3//1 4//1\n"
+    p.write_text(body)
+    ref, _ = S.load_mesh(str(p), True)
+    p.write_text(body + "f -4 -3 -2\n")
+    fixed, bbox = S.load_mesh(str(p), 2)
+    assert ref.shape == (1, 3, 3) and fixed.shape == (3, 3, 3)
+    np.testing.assert_array_equal(ref[0][1], [0, 0, 1])                      # the reference takes the vn line for vertex 2
+    np.testing.assert_array_equal(fixed[0], [[0, 0, 0], [1, 0, 0], [1, 1, 0]])
+    np.testing.assert_array_equal(fixed[1], [[0, 0, 0], [1, 1, 0], [0, 1, 0]])   # second half of the quad
+    np.testing.assert_array_equal(fixed[2], [[0, 0, 0], [1, 0, 0], [1, 1, 0]])   # relative indices
+    assert list(bbox) == [0, 1, 0, 1, 0, 0]
+
+
 def test_mesh_loader_tri_map(tmp_path, orc):
     import space_filling_forest_star_b200 as S
     p = tmp_path / "m.tri"
