@@ -143,6 +143,11 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_extra:
+        try:
+            line["extra"] = {"sffstar_solve": planner_solves("reference", 1)}
+        except Exception as ex:
+            line["extra"] = {"sffstar_solve": {"error": repr(ex)}}
     print(json.dumps(line), flush=True)
 
 
@@ -319,6 +324,51 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+PLANNER_SCENARIOS = ["2d_sffstar", "triang_sffstar", "building_sffstar"]   # BASELINE.json configs[0..2] as solver="sff" variants
+
+
+def planner_solves(impl: str, runs: int):
+    """SFF* solve wall time (BASELINE.json metric, third part): the batched host on the engine (`ours`) or the UNMODIFIED
+    reference host on its own FLANN + the CPU RAPID stand-in (`reference`, oracle/_ref/ref_main_cpu, built in the dev
+    container from /root/reference where it lies; absent -> reported as unavailable).  Solve seconds are the ones both
+    programs write to params.csv (src/problemStruct.h:425); scenarios come from scripts/make_scenarios.py."""
+    import re
+    import subprocess
+    import tempfile
+    exe = (ROOT / "space_filling_forest_star_b200" / "host" / "sff_planner") if impl == "ours" else (ROOT / "oracle" / "_ref" / "ref_main_cpu")
+    if not exe.exists():
+        return {"unavailable": f"{exe.relative_to(ROOT)} not built"}
+    work = Path(tempfile.mkdtemp(prefix="sff_bench_"))
+    subprocess.run([sys.executable, str(ROOT / "scripts" / "make_scenarios.py"), str(work)], check=True, capture_output=True)
+    out = {}
+    for sc in PLANNER_SCENARIOS:
+        secs, lens, solved, iters = [], [], 0, []
+        for r in range(runs):
+            cmd = [str(exe), f"{sc}.xml", str(r)] + (["--seed", str(100 + r), "--quiet"] if impl == "ours" else [])
+            try:
+                p = subprocess.run(cmd, cwd=work, capture_output=True, text=True, timeout=300)
+            except subprocess.TimeoutExpired:
+                break
+            if p.returncode != 0:
+                break
+            row = (work / "output" / f"params_{sc}.csv").read_text().strip().splitlines()[-1]
+            m = re.match(r"[^,]*,[^,]*,(\d+),(solved|unsolved),\[[^\]]*\],\[([^\]]*)\],([-+.\deE]+)", row)
+            if not m:
+                break
+            iters.append(int(m.group(1)))
+            solved += m.group(2) == "solved"
+            d = [float(x) for x in m.group(3).split(";") if x and float(x) < 1e300]
+            if d:
+                lens.append(sum(d) / len(d))
+            secs.append(float(m.group(4)))
+        if secs:
+            out[sc] = {"solve_s_mean": sum(secs) / len(secs), "runs": len(secs), "solved": solved, "iterations_mean": sum(iters) / len(iters),
+                       "mean_path_length": (sum(lens) / len(lens)) if lens else None}
+        else:
+            out[sc] = {"error": "no result"}
+    return out
+
+
 def extra_metrics(S, env, torch):
     """secondary numbers of the same hot path (not the headline): edges/s and exact k-NN queries/s"""
     out = {}
@@ -365,6 +415,11 @@ def extra_metrics(S, env, torch):
         out["knn_pair_rate_per_s"] = nq * n / sec
     except Exception as ex:   # secondary numbers must never break the headline line
         out["error"] = repr(ex)
+    try:
+        env.sync_check()
+        out["sffstar_solve"] = planner_solves("ours", 3)
+    except Exception as ex:
+        out["sffstar_solve"] = {"error": repr(ex)}
     return out
 
 
