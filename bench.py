@@ -285,6 +285,9 @@ def run_ours(args):
     e2e_hits = int(h_out.sum().item())
     assert e2e_hits == hits, (e2e_hits, hits)
 
+    knn_multi = None
+    if world > 1 and not args.no_extra:
+        knn_multi = sharded_knn_rate(S, torch, dist, dev, rank, world)
     if rank == 0:
         peak, which = measured_peak_hbm()
         achieved = ALGO_BYTES_PER_POSE * P / (kernel_ms * 1e-3) / 1e9
@@ -316,6 +319,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
         if world == 1 and not args.no_extra:
             line["extra"] = extra_metrics(S, env, torch)
+        if knn_multi is not None:
+            line["extra"] = knn_multi
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -367,6 +372,39 @@ def planner_solves(impl: str, runs: int):
         else:
             out[sc] = {"error": "no result"}
     return out
+
+
+def sharded_knn_rate(S, torch, dist, dev, rank, world):
+    """N > 1: exact k-NN with the node set replicated and the query rows split over the ranks; every rank ends up with all
+    rows (packed (id, d2) pairs, one NCCL all-gather).  Same shape per rank as the N = 1 `extra` block (weak scaling)."""
+    try:
+        from space_filling_forest_star_b200.sharding import sharded_knn
+        n, nq, k = 1_000_000, 1 << 15, 16
+        lo = torch.tensor([-70, -70, 0, -3.14159, -3.14159, -3.14159], device=dev)
+        hi = torch.tensor([70, 70, 140, 3.14159, 3.14159, 3.14159], device=dev)
+        g = torch.Generator(device=dev).manual_seed(2)           # the same node set on every rank
+        nodes = (lo + (hi - lo) * torch.rand((n, 6), device=dev, generator=g)).float().contiguous()
+        gq = torch.Generator(device=dev).manual_seed(3)
+        q = (lo + (hi - lo) * torch.rand((world * nq, 6), device=dev, generator=gq)).float().contiguous()
+        idx = S.Index(dim=6)
+        idx.add_device(nodes)
+        for _ in range(2):
+            sharded_knn(idx, q, k)
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            ids, d2 = sharded_knn(idx, q, k)
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b) / 5], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        idx.close()
+        return {"knn_queries_per_s": world * nq / (float(ms.item()) * 1e-3),
+                "knn_config": f"N={n} 6-D nodes replicated, Q={nq} per GPU, k={k}, exact, rows all-gathered over NCCL"}
+    except Exception as ex:
+        return {"error": repr(ex)}
 
 
 def extra_metrics(S, env, torch):
