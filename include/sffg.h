@@ -169,6 +169,9 @@ SFFG_API int sffg_index_create(int dim /* 2 or 6 */, sffg_index **out);
 SFFG_API int sffg_index_destroy(sffg_index *idx);
 SFFG_API int sffg_index_add(sffg_index *idx, const float *pts /* [n][dim] */, int64_t n);   /* copies; ids continue */
 SFFG_API int sffg_index_add_device(sffg_index *idx, const float *d_pts, int64_t n, void *stream);
+/* appends to several indices in one call (one upload, one synchronisation): pts holds n_per[0] rows for idx[0], then
+ * n_per[1] rows for idx[1], ... -- the planner appends every new node to its tree's index (src/forest.h:367)        */
+SFFG_API int sffg_index_add_multi(sffg_index *const *idx, const int64_t *n_per, int n_idx, const float *pts);
 SFFG_API int64_t sffg_index_size(const sffg_index *idx);
 
 /* k nearest, ascending (d2,id); rows shorter than k (index smaller than k) are padded with id -1, d2 +inf */
@@ -177,7 +180,8 @@ SFFG_API int sffg_knn_device(sffg_index *idx, const float *d_queries, int64_t nq
                     void *stream);
 
 /* several indices in one call (the planner keeps one index per tree, src/forest.h:72): queries are concatenated in index
- * order, nq_per[i] rows for idx[i]; one upload, one kernel per index on one stream, one download, one synchronisation. */
+ * order, nq_per[i] rows for idx[i]; one upload, the per-index searches run concurrently on the indices' own streams, one
+ * download, one synchronisation. */
 SFFG_API int sffg_knn_multi(sffg_index *const *idx, const int64_t *nq_per, int n_idx, const float *queries, int k,
                             int32_t *ids_out, float *d2_out);
 

@@ -69,6 +69,7 @@ SIGNATURES = {
     "sffg_index_destroy": (C.c_int, [_p]),
     "sffg_index_add": (C.c_int, [_p, _p, C.c_int64]),
     "sffg_index_add_device": (C.c_int, [_p, _p, C.c_int64, _p]),
+    "sffg_index_add_multi": (C.c_int, [_p, _p, C.c_int, _p]),
     "sffg_index_size": (C.c_int64, [_p]),
     "sffg_knn": (C.c_int, [_p, _p, C.c_int64, C.c_int, _p, _p]),
     "sffg_knn_device": (C.c_int, [_p, _p, C.c_int64, C.c_int, _p, _p, _p]),

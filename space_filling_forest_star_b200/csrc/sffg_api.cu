@@ -109,6 +109,7 @@ struct sffg_index {
   float *d_coords = nullptr;
   int64_t cap = 0, n = 0;
   cudaStream_t stream = nullptr;
+  cudaEvent_t ev = nullptr;   // fork / join of multi-index calls
   DevBuf q, ids, d2, scratch, counts, offsets, cursor, keys, stage;
   unsigned char *h_small = nullptr;   // pinned + device-mapped staging for planner-sized queries
   // spatially sorted view (knn_pruned.cu): covers nodes [0, n_sorted); rebuilt when the unsorted tail grows too long
@@ -756,6 +757,7 @@ int sffg_index_create(int dim, sffg_index **out) {
   const char *pr = std::getenv("SFFG_KNN_PRUNING");
   idx->pruning = !(pr && pr[0] == '0');
   cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->ev, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaHostAlloc((void **)&idx->h_small, kSmallBytes, cudaHostAllocMapped);
   if (e == cudaSuccess) {   // storage exists from the start: the scan kernels may touch the first block of an empty index
     idx->cap = 4096 + 128;
@@ -764,6 +766,7 @@ int sffg_index_create(int dim, sffg_index **out) {
   }
   if (e != cudaSuccess) {
     if (idx->stream) cudaStreamDestroy(idx->stream);
+    if (idx->ev) cudaEventDestroy(idx->ev);
     if (idx->h_small) cudaFreeHost(idx->h_small);
     delete idx;
     return fail(SFFG_ERR_CUDA, cudaGetErrorString(e));
@@ -780,6 +783,7 @@ int sffg_index_destroy(sffg_index *idx) {
                     &idx->s_coords, &idx->s_ids, &idx->s_bb, &idx->s_keys, &idx->s_vals, &idx->s_temp, &idx->s_bounds};
   for (DevBuf *b : bufs) b->release();
   if (idx->h_small) cudaFreeHost(idx->h_small);
+  if (idx->ev) cudaEventDestroy(idx->ev);
   if (idx->stream) cudaStreamDestroy(idx->stream);
   delete idx;
   return SFFG_OK;
@@ -836,6 +840,40 @@ int sffg_index_add(sffg_index *idx, const float *pts, int64_t n) {
   rc = sffg_index_add_device(idx, (const float *)idx->stage.p, n, idx->stream);
   if (rc != SFFG_OK) return rc;
   SFFG_CUDA(cudaStreamSynchronize(idx->stream));
+  return SFFG_OK;
+}
+
+int sffg_index_add_multi(sffg_index *const *idx, const int64_t *n_per, int n_idx, const float *pts) {
+  if (!idx || !n_per || n_idx < 1) return fail(SFFG_ERR_ARG, "sffg_index_add_multi: bad arguments");
+  int64_t total = 0;
+  const int dim = idx[0] ? idx[0]->dim : 0;
+  for (int i = 0; i < n_idx; ++i) {
+    if (!idx[i] || idx[i]->dim != dim || n_per[i] < 0) return fail(SFFG_ERR_ARG, "sffg_index_add_multi: bad index / count");
+    total += n_per[i];
+  }
+  if (total == 0) return SFFG_OK;
+  if (!pts) return fail(SFFG_ERR_ARG, "sffg_index_add_multi: null points");
+  int rc = check_angles(pts, total, dim);
+  if (rc != SFFG_OK) return rc;
+  sffg_index *lead = idx[0];   // one staging buffer, one upload, one synchronisation for all indices
+  cudaStream_t st = lead->stream;
+  const size_t bytes = (size_t)total * dim * sizeof(float);
+  rc = lead->stage.reserve(bytes);
+  if (rc != SFFG_OK) return rc;
+  if (bytes <= kSmallBytes) {
+    std::memcpy(lead->h_small, pts, bytes);
+    SFFG_CUDA(cudaMemcpyAsync(lead->stage.p, lead->h_small, bytes, cudaMemcpyHostToDevice, st));
+  } else {
+    SFFG_CUDA(cudaMemcpyAsync(lead->stage.p, pts, bytes, cudaMemcpyHostToDevice, st));
+  }
+  int64_t off = 0;
+  for (int i = 0; i < n_idx; ++i) {
+    if (n_per[i] == 0) continue;
+    rc = sffg_index_add_device(idx[i], (const float *)lead->stage.p + off * dim, n_per[i], st);
+    if (rc != SFFG_OK) return rc;
+    off += n_per[i];
+  }
+  SFFG_CUDA(cudaStreamSynchronize(st));
   return SFFG_OK;
 }
 
@@ -983,12 +1021,20 @@ int sffg_knn_multi(sffg_index *const *idx, const int64_t *nq_per, int n_idx, con
   } else {
     SFFG_CUDA(cudaMemcpyAsync(lead->q.p, queries, qbytes, cudaMemcpyHostToDevice, st));
   }
+  // fork: every index searches on its own stream once the queries have arrived; join: the lead stream waits for all
+  SFFG_CUDA(cudaEventRecord(lead->ev, st));
   int64_t off = 0;
   for (int i = 0; i < n_idx; ++i) {
     if (nq_per[i] == 0) continue;
+    cudaStream_t si = idx[i] == lead ? st : idx[i]->stream;
+    if (si != st) SFFG_CUDA(cudaStreamWaitEvent(si, lead->ev, 0));
     rc = sffg_knn_device(idx[i], (const float *)lead->q.p + off * dim, nq_per[i], k, (int32_t *)lead->ids.p + off * k,
-                         (float *)lead->d2.p + off * k, st);
+                         (float *)lead->d2.p + off * k, si);
     if (rc != SFFG_OK) return rc;
+    if (si != st) {
+      SFFG_CUDA(cudaEventRecord(idx[i]->ev, si));
+      SFFG_CUDA(cudaStreamWaitEvent(st, idx[i]->ev, 0));
+    }
     off += nq_per[i];
   }
   if (small) {

@@ -184,15 +184,24 @@ class RrtPlanner {
   void flush_index_appends() {
     if (pending_.empty()) return;
     const int dim = cfg_.dim;
+    std::vector<sffg_index *> idx;
+    std::vector<int64_t> per;
+    std::vector<float> rows;
     for (size_t t = 0; t < trees_.size(); ++t) {
-      std::vector<float> rows;
+      int64_t cnt = 0;
       for (int id : pending_)
-        if (nodes_[id].tree == (int)t)
+        if (nodes_[id].tree == (int)t) {
           for (int c = 0; c < dim; ++c) rows.push_back((float)nodes_[id].p[c]);   // double -> float, rrt.h:206-209
-      if (!rows.empty()) {
-        check(sffg_index_add(trees_[t].idx, rows.data(), (int64_t)(rows.size() / dim)));
-        ++calls_;
+          ++cnt;
+        }
+      if (cnt) {
+        idx.push_back(trees_[t].idx);
+        per.push_back(cnt);
       }
+    }
+    if (!idx.empty()) {
+      check(sffg_index_add_multi(idx.data(), per.data(), (int)idx.size(), rows.data()));
+      ++calls_;
     }
     pending_.clear();
   }

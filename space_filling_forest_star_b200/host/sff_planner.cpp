@@ -372,18 +372,29 @@ class Planner {
   void flush_index_appends() {
     if (pending_.empty()) return;
     const int dim = cfg_.dim;
-    std::vector<float> rows(pending_.size() * (size_t)dim);
+    // one engine call: the global index first, then every tree index that got nodes (sffg_index_add_multi)
+    std::vector<sffg_index *> idx{global_idx_};
+    std::vector<int64_t> per{(int64_t)pending_.size()};
+    std::vector<float> base(pending_.size() * (size_t)dim);
     for (size_t i = 0; i < pending_.size(); ++i)
-      for (int c = 0; c < dim; ++c) rows[i * dim + c] = (float)nodes_[pending_[i]].p[c];   // double -> float, forest.h:258-260
-    check(sffg_index_add(global_idx_, rows.data(), (int64_t)pending_.size()));
+      for (int c = 0; c < dim; ++c) base[i * dim + c] = (float)nodes_[pending_[i]].p[c];   // double -> float, forest.h:258-260
+    std::vector<float> rows(base);
+    rows.reserve(2 * base.size());
     const int T = (int)tree_idx_.size();
     for (int t = 0; t < T; ++t) {
-      std::vector<float> tr;
+      int64_t cnt = 0;
       for (size_t i = 0; i < pending_.size(); ++i)
-        if (nodes_[pending_[i]].tree == t) tr.insert(tr.end(), rows.begin() + i * dim, rows.begin() + (i + 1) * dim);
-      if (!tr.empty()) check(sffg_index_add(tree_idx_[t], tr.data(), (int64_t)(tr.size() / dim)));
+        if (nodes_[pending_[i]].tree == t) {
+          rows.insert(rows.end(), base.begin() + i * dim, base.begin() + (i + 1) * dim);
+          ++cnt;
+        }
+      if (cnt) {
+        idx.push_back(tree_idx_[t]);
+        per.push_back(cnt);
+      }
     }
-    calls_ += 1 + T;
+    check(sffg_index_add_multi(idx.data(), per.data(), (int)idx.size(), rows.data()));
+    ++calls_;
     pending_.clear();
   }
 

@@ -123,6 +123,14 @@ SFFG_API int sffg_index_add(sffg_index *idx, const float *pts, int64_t n) {
   idx->rows.insert(idx->rows.end(), pts, pts + n * idx->dim);
   return SFFG_OK;
 }
+SFFG_API int sffg_index_add_multi(sffg_index *const *idx, const int64_t *n_per, int n_idx, const float *pts) {
+  int64_t off = 0;
+  for (int i = 0; i < n_idx; ++i) {
+    sffg_index_add(idx[i], pts + off * idx[i]->dim, n_per[i]);
+    off += n_per[i];
+  }
+  return SFFG_OK;
+}
 SFFG_API int64_t sffg_index_size(const sffg_index *idx) { return (int64_t)(idx->rows.size() / idx->dim); }
 
 SFFG_API int sffg_knn(sffg_index *idx, const float *queries, int64_t nq, int k, int32_t *ids_out, float *d2_out) {
