@@ -68,6 +68,24 @@ def measured_peak_hbm():
     return 6650.0, "fallback"
 
 
+def bind_to_gpu_numa_node(index: int):
+    """N > 1: pin this rank to the CPUs next to its GPU (NVML's ideal affinity) before any pinned host buffer is allocated,
+    so that the e2e leg's H2D stream reads from the local NUMA node instead of crossing the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """samples SM clock + throttle reasons of one GPU during the timed region (nvidia_ml_py)"""
 
@@ -180,6 +198,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import space_filling_forest_star_b200 as S
@@ -301,7 +320,7 @@ def run_ours(args):
                        "parallelism": (f"pose-shard x{world} + verdict all-gather fused into the kernel's stores over NVLink peer memory"
                                        if gather_mode == "fused" else
                                        f"pose-shard x{world} + NCCL all-gather of verdict bytes" if world > 1 else "single GPU"),
-                       "hit_fraction": hits / P},
+                       "hit_fraction": hits / P, "cpus_bound_per_rank": numa},
             "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": P * 24, "d2h_bytes_per_step": P,
                     "steps": e_steps, "api": "sffg_collide_poses_f32 on pinned host buffers"},
             "gpu_launches": args.steps,
