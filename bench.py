@@ -323,7 +323,8 @@ def run_ours(args):
                        "hit_fraction": hits / P, "cpus_bound_per_rank": numa},
             "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": P * 24, "d2h_bytes_per_step": P,
                     "steps": e_steps, "api": "sffg_collide_poses_f32 on pinned host buffers"},
-            "gpu_launches": args.steps,
+            # collide_poses_kernel per step (+ peer_barrier_kernel when the gather is fused into it)
+            "gpu_launches": args.steps * (2 if gather_mode == "fused" else 1),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": which, "kernel": "collide_poses_kernel<f32>",
