@@ -96,3 +96,21 @@ def test_engine_and_double_agree_on_a_fixed_seed(exe, tmp_path):
         row_g, _, _ = PU.run_planner(exe, tmp_path, scenario, seed=9, run_id="g")
         row_c, _, _ = PU.run_planner(dbl, tmp_path, scenario, seed=9, run_id="c")
         assert row_g.split(",")[2:6] == row_c.split(",")[2:6], (scenario, row_g, row_c)
+
+
+# mean path lengths of the UNMODIFIED reference host (its own FLANN + the CPU RAPID stand-in) over 10 clock-seeded runs,
+# recorded in profiles/r01_e2e_sffstar.json and profiles/r01_e2e_rrt.json (scripts/e2e_compare.py on the GPU box)
+REFERENCE_MEAN_LENGTH = {"2d_sffstar": 1326.77, "2d_rrtstar_goal": 1128.73, "2d_mtrrt": 1349.09}
+TOLERANCE = 0.10   # north_star: end-to-end path costs within a stated tolerance of the reference
+
+
+@pytest.mark.parametrize("scenario", sorted(REFERENCE_MEAN_LENGTH))
+def test_path_cost_within_tolerance_of_the_reference(exe, tmp_path, scenario):
+    """the reference seeds from the clock, so the comparison is statistical: over 10 seeds every run solves and the mean path
+    length (mean over the root pairs, as params.csv lists them) is at most 10 % above the reference's recorded mean"""
+    means = []
+    for seed in range(10):
+        row, plans, _ = PU.run_planner(exe, tmp_path, scenario, seed=500 + seed, run_id=str(seed))
+        assert ",solved," in row, row
+        means.append(np.mean([d for _, _, d, _ in plans]))
+    assert np.mean(means) <= (1.0 + TOLERANCE) * REFERENCE_MEAN_LENGTH[scenario], (np.mean(means), REFERENCE_MEAN_LENGTH[scenario])
