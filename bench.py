@@ -213,7 +213,8 @@ def run_ours(args):
     verdict = torch.empty(P, dtype=torch.uint8, device=dev)
     gathered = torch.empty(world * P, dtype=torch.uint8, device=dev) if world > 1 else None
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    # N > 1: the verdict all-gather is fused into the kernel's stores over NVLink peer memory (sharding.PeerGather);
+    # N > 1: the verdict all-gather and its completion handshake are fused into the kernel (sharding.PeerGather): stores go
+    # to every rank's buffer over NVLink peer memory, the last CTA publishes the step's epoch, no barrier between steps;
     # --gather nccl (or a box without CUDA IPC between the ranks) uses kernel + NCCL all_gather_into_tensor instead
     pg, gather_mode, last_buf = None, "none", [0]
     if world > 1:
@@ -241,13 +242,13 @@ def run_ours(args):
             env.collide_device(poses, out=verdict)
         if i is not None:
             k_ev[i][1].record()
-        if pg is not None:
-            pg.barrier(env, dev)
-        elif world > 1:
+        if pg is None and world > 1:
             dist.all_gather_into_tensor(gathered, verdict)
 
     for _ in range(args.warmup):
         step()
+    if pg is not None:
+        pg.wait(env, last_buf[0], dev)
     torch.cuda.synchronize()
     env.sync_check()
     if world > 1:
@@ -259,6 +260,8 @@ def run_ours(args):
     t_beg.record()
     for i in range(args.steps):
         step(i)
+    if pg is not None:
+        pg.wait(env, last_buf[0], dev)   # every rank holds every rank's verdicts of the last step when the clock stops
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -323,8 +326,8 @@ def run_ours(args):
                        "hit_fraction": hits / P, "cpus_bound_per_rank": numa},
             "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": P * 24, "d2h_bytes_per_step": P,
                     "steps": e_steps, "api": "sffg_collide_poses_f32 on pinned host buffers"},
-            # collide_poses_kernel per step (+ peer_barrier_kernel when the gather is fused into it)
-            "gpu_launches": args.steps * (2 if gather_mode == "fused" else 1),
+            # collide_poses_kernel per step (gather and completion signal are inside it) + one final wait kernel
+            "gpu_launches": args.steps + (1 if gather_mode == "fused" else 0),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": which, "kernel": "collide_poses_kernel<f32>",

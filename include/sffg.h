@@ -113,21 +113,36 @@ SFFG_API int sffg_collide_poses_device(sffg_env *env, const void *d_poses, int p
 /* ---- multi-GPU: pose batches are split over ranks, every rank needs all verdicts.  Instead of a separate
  * all-gather, the kernel stores verdict i to d_outs[r][i] for EVERY destination r: the local result buffer and the same
  * slice of every peer's buffer, mapped into this process through CUDA IPC -- the exchange rides on the kernel's own stores
- * over NVLink while it computes.  One process per GPU:
+ * over NVLink while it computes -- and the last CTA to finish publishes a completion epoch to every rank.  One process per
+ * GPU:
  *   sffg_peer_buffer_create   cudaMalloc'ed (zeroed) buffer + its 64-byte IPC handle (ship it to the peers, e.g. with
  *                             torch.distributed.all_gather_object)
  *   sffg_peer_buffer_open     map a peer's buffer into this process; _close unmaps; _destroy frees an own buffer
- *   sffg_collide_poses_gather_device   as sffg_collide_poses_device with n_outs (1..8) destinations, each 4-byte aligned
- *   sffg_peer_barrier_device  enqueues signal + wait on per-rank flag words (d_flags[r] = rank r's array of 8 uint32 in a
- *                             peer buffer; epoch must grow by 1 per call): after it has run, the stores of every rank's
- *                             earlier kernels are visible locally.  A rank that never arrives raises SFFG_ERR_INTERNAL
- *                             at the next sffg_env_sync_check after 2 s instead of hanging the GPU.                      */
+ *   sffg_collide_poses_gather_device        as sffg_collide_poses_device with n_outs (1..8) destinations, 4-byte aligned
+ *   sffg_collide_poses_gather_sync_device   the same with the handshake fused in.  d_flags[r] = rank r's array of 8 uint32 in a
+ *                             peer buffer, d_done_counter = a zeroed local uint32.  Before touching the destinations the
+ *                             kernel waits until every rank has published an epoch >= wait_epoch (0 = do not wait); when
+ *                             its last CTA finishes it publishes signal_epoch (> 0, growing by 1 per call) to every rank.
+ *                             With B result buffers used round-robin, call j (1-based epoch j) may pass wait_epoch =
+ *                             j - B + 2 provided every rank reads the results of call s before it enqueues call s + 2:
+ *                             B = 4 lets a rank run a full kernel ahead of the slowest one instead of meeting it at a
+ *                             barrier after every call.
+ *   sffg_peer_wait_device     enqueue "wait until every rank has published >= epoch": what a consumer of call `epoch`'s
+ *                             gathered results puts in front of its work
+ *   sffg_peer_barrier_device  signal + wait in one call (stand-alone barrier on the same flag words)
+ * A rank that never arrives raises SFFG_ERR_INTERNAL at the next sffg_env_sync_check after 10 s instead of hanging the GPU. */
 SFFG_API int sffg_peer_buffer_create(int64_t bytes, void **d_ptr_out, uint8_t handle_out[64]);
 SFFG_API int sffg_peer_buffer_open(const uint8_t handle[64], void **d_ptr_out);
 SFFG_API int sffg_peer_buffer_close(void *d_ptr);
 SFFG_API int sffg_peer_buffer_destroy(void *d_ptr);
 SFFG_API int sffg_collide_poses_gather_device(sffg_env *env, const void *d_poses, int poses_are_f64, int64_t n,
                                      uint8_t *const *d_outs, int n_outs, void *stream);
+SFFG_API int sffg_collide_poses_gather_sync_device(sffg_env *env, const void *d_poses, int poses_are_f64, int64_t n,
+                                          uint8_t *const *d_outs, uint32_t *const *d_flags, int n_ranks, int my_rank,
+                                          uint32_t signal_epoch, uint32_t wait_epoch, uint32_t *d_done_counter,
+                                          void *stream);
+SFFG_API int sffg_peer_wait_device(sffg_env *env, uint32_t *const *d_flags, int n_ranks, int my_rank, uint32_t epoch,
+                          void *stream);
 SFFG_API int sffg_peer_barrier_device(sffg_env *env, uint32_t *const *d_flags, int n_ranks, int my_rank, uint32_t epoch,
                              void *stream);
 

@@ -58,6 +58,9 @@ SIGNATURES = {
     "sffg_peer_buffer_close": (C.c_int, [_p]),
     "sffg_peer_buffer_destroy": (C.c_int, [_p]),
     "sffg_collide_poses_gather_device": (C.c_int, [_p, _p, C.c_int, C.c_int64, _p, C.c_int, _p]),
+    "sffg_collide_poses_gather_sync_device": (C.c_int, [_p, _p, C.c_int, C.c_int64, _p, _p, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
+                                                       _p, _p]),
+    "sffg_peer_wait_device": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_uint32, _p]),
     "sffg_peer_barrier_device": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_uint32, _p]),
     "sffg_check_edges": (C.c_int, [_p, _p, _p, C.c_int64, C.c_double, C.c_int, _p, _p]),
     "sffg_check_edges_device": (C.c_int, [_p, _p, _p, C.c_int64, C.c_double, C.c_int, _p, _p, _p]),

@@ -633,12 +633,33 @@ __device__ __forceinline__ unsigned check_32_poses(const EnvDev &E, WarpScratch 
   return hitmask;
 }
 
+// spins (one thread) until every rank has published an epoch >= `epoch` in the local flag words; bounded by a 10 s timeout
+__device__ __forceinline__ void wait_flags(const FlagSet &f, unsigned epoch, int *status) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int r = 0; r < f.n; ++r) {
+    const unsigned *mine = f.p[f.me] + r;
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 10000000000ull) {   // a peer died or never launched -- flag it, never hang the GPU
+        if (status) atomicExch(status, 3);
+        return;
+      }
+      __nanosleep(100);
+    }
+  }
+}
+
 template <int FMT, bool COUNT>
 __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) collide_poses_kernel(EnvDev E, const void *poses, long long n,
-                                                                                  OutSet outs, int chunk) {
+                                                                                  OutSet outs, GatherSync gs, int chunk) {
   extern __shared__ __align__(16) unsigned char smem[];
   RobotTri *srob = reinterpret_cast<RobotTri *>(smem);
-  stage_robot(E, srob);
+  if (gs.flags.n > 0 && gs.wait_epoch != 0 && threadIdx.x == 0) wait_flags(gs.flags, gs.wait_epoch, E.status);
+  stage_robot(E, srob);   // (its __syncthreads also releases the CTA from the wait above)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + (size_t)E.n_robot * sizeof(RobotTri))[warp];
   // a work unit is `chunk` (1..32) consecutive poses: 32 for large batches (full lanes in phase A), fewer when the
@@ -678,6 +699,19 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) collide_poses_kerne
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) nposes += __shfl_xor_sync(kFull, nposes, s);
     flush_tally(E, tally, nposes, lane);
+  }
+  if (gs.flags.n > 0) {
+    // completion signal of the fused gather: the last CTA to get here publishes the epoch to every rank
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      if (atomicAdd(gs.done_counter, 1u) == gridDim.x - 1) {
+        *gs.done_counter = 0;
+        __threadfence_system();
+        for (int r = 0; r < gs.flags.n; ++r)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(gs.flags.p[r] + gs.flags.me), "r"(gs.signal_epoch) : "memory");
+      }
+    }
   }
 }
 
@@ -944,8 +978,8 @@ size_t collide_smem_bytes(int n_robot) {
 
 
 template <int FMT>
-static cudaError_t launch_poses_fmt(const EnvDev &env, const void *d_poses, int64_t n, const OutSet &d_verdict, cudaStream_t stream,
-                                    const LaunchCfg &cfg, bool count, int chunk, int *grid_out) {
+static cudaError_t launch_poses_fmt(const EnvDev &env, const void *d_poses, int64_t n, const OutSet &d_verdict, const GatherSync &gs,
+                                    cudaStream_t stream, const LaunchCfg &cfg, bool count, int chunk, int *grid_out) {
   const size_t smem = collide_smem_bytes(env.n_robot);
   const long long chunks = (n + chunk - 1) / chunk;
   const long long want = (chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -956,14 +990,14 @@ static cudaError_t launch_poses_fmt(const EnvDev &env, const void *d_poses, int6
     int grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;
     *grid_out = grid;
-    collide_poses_kernel<FMT, true><<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict, chunk);
+    collide_poses_kernel<FMT, true><<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict, gs, chunk);
   } else {
     const KernelCfg &kc = kernel_cfg<collide_poses_kernel<FMT, false>>(smem);
     if ((e = kc.err) != cudaSuccess) return e;
     int grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;
     *grid_out = grid;
-    collide_poses_kernel<FMT, false><<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict, chunk);
+    collide_poses_kernel<FMT, false><<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict, gs, chunk);
   }
   return cudaGetLastError();
 }
@@ -971,30 +1005,21 @@ static cudaError_t launch_poses_fmt(const EnvDev &env, const void *d_poses, int6
 // ---------------------------------------------------------------------------------------------------------
 // cross-GPU completion barrier for the peer-store gather (one CTA of 32 threads, thread r talks to rank r)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void peer_barrier_kernel(FlagSet f, unsigned epoch, int *status) {
-  const int r = threadIdx.x;
-  if (r >= f.n) return;
-  __threadfence_system();   // everything this stream did before (the gather stores) is ordered before the signal
-  unsigned *theirs = f.p[r] + f.me;
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
-  const unsigned *mine = f.p[f.me] + r;
-  unsigned long long t0, t1;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  for (;;) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-    if ((int)(v - epoch) >= 0) break;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 2000000000ull) {   // 2 s: a peer died or never launched -- flag it, never hang the GPU
-      if (status) atomicExch(status, 3);
-      break;
-    }
-    __nanosleep(200);
+// signal == true : publish `epoch` to every rank (no wait)      -- what an empty shard owes its peers
+// signal == false: wait until every rank has published >= epoch -- what a consumer of the gathered results enqueues
+__global__ void peer_barrier_kernel(FlagSet f, unsigned epoch, bool signal, int *status) {
+  if (signal) {
+    const int r = threadIdx.x;
+    if (r >= f.n) return;
+    __threadfence_system();   // everything this stream did before is ordered before the signal
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.p[r] + f.me), "r"(epoch) : "memory");
+  } else if (threadIdx.x == 0) {
+    wait_flags(f, epoch, status);
   }
 }
 
-cudaError_t launch_peer_barrier(const FlagSet &flags, unsigned epoch, int *d_status, cudaStream_t stream) {
-  peer_barrier_kernel<<<1, 32, 0, stream>>>(flags, epoch, d_status);
+cudaError_t launch_peer_barrier(const FlagSet &flags, unsigned epoch, bool signal, int *d_status, cudaStream_t stream) {
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(flags, epoch, signal, d_status);
   return cudaGetLastError();
 }
 
@@ -1005,12 +1030,23 @@ cudaError_t launch_collide_poses(const EnvDev &env_in, const void *d_poses, int 
   OutSet one;
   one.n = 1;
   one.p[0] = d_verdict;
-  return launch_collide_poses_gather(env_in, d_poses, pose_fmt, n, one, stream, cfg, count, work_base_io);
+  GatherSync none{};
+  return launch_collide_poses_gather(env_in, d_poses, pose_fmt, n, one, none, stream, cfg, count, work_base_io);
 }
 
 cudaError_t launch_collide_poses_gather(const EnvDev &env_in, const void *d_poses, int pose_fmt, int64_t n, const OutSet &d_verdict,
-                                        cudaStream_t stream, const LaunchCfg &cfg, bool count, unsigned *work_base_io) {
-  if (n <= 0) return cudaSuccess;
+                                        const GatherSync &gs, cudaStream_t stream, const LaunchCfg &cfg, bool count,
+                                        unsigned *work_base_io) {
+  if (n <= 0) {
+    // an empty shard still owes its peers the completion signal (after waiting like a real launch would)
+    if (gs.flags.n > 0) {
+      cudaError_t e = cudaSuccess;
+      if (gs.wait_epoch != 0) e = launch_peer_barrier(gs.flags, gs.wait_epoch, false, env_in.status, stream);
+      if (e == cudaSuccess) e = launch_peer_barrier(gs.flags, gs.signal_epoch, true, nullptr, stream);
+      return e;
+    }
+    return cudaSuccess;
+  }
   EnvDev env = env_in;
   env.work_base = *work_base_io;
   int grid = 0;
@@ -1020,9 +1056,9 @@ cudaError_t launch_collide_poses_gather(const EnvDev &env_in, const void *d_pose
   while (chunk > 1 && (n + chunk - 1) / chunk < warps) chunk >>= 1;
   cudaError_t e = cudaErrorInvalidValue;
   switch (pose_fmt) {
-    case 0: e = launch_poses_fmt<kFmtEulerF32>(env, d_poses, n, d_verdict, stream, cfg, count, chunk, &grid); break;
-    case 1: e = launch_poses_fmt<kFmtEulerF64>(env, d_poses, n, d_verdict, stream, cfg, count, chunk, &grid); break;
-    case 2: e = launch_poses_fmt<kFmtMatrixF64>(env, d_poses, n, d_verdict, stream, cfg, count, chunk, &grid); break;
+    case 0: e = launch_poses_fmt<kFmtEulerF32>(env, d_poses, n, d_verdict, gs, stream, cfg, count, chunk, &grid); break;
+    case 1: e = launch_poses_fmt<kFmtEulerF64>(env, d_poses, n, d_verdict, gs, stream, cfg, count, chunk, &grid); break;
+    case 2: e = launch_poses_fmt<kFmtMatrixF64>(env, d_poses, n, d_verdict, gs, stream, cfg, count, chunk, &grid); break;
   }
   if (e == cudaSuccess) *work_base_io += (unsigned)((n + chunk - 1) / chunk) + (unsigned)grid * kWarpsPerBlock;
   return e;

@@ -43,6 +43,14 @@ struct FlagSet {
   unsigned *p[kMaxPeers];   // p[r] = rank r's flag array (kMaxPeers words), p[me] is local
   int n, me;
 };
+// completion signalling fused into the gather kernel: before touching the destinations every CTA waits until all ranks
+// have published an epoch >= wait_epoch (their earlier results have been consumed, see sffg.h); the last CTA to finish
+// publishes signal_epoch to every rank.  flags.n == 0 disables both.
+struct GatherSync {
+  FlagSet flags;
+  unsigned signal_epoch, wait_epoch;
+  unsigned *done_counter;   // local word, zero between launches
+};
 
 struct LaunchCfg {
   int sm_count;
@@ -56,11 +64,12 @@ cudaError_t launch_collide_poses(const EnvDev &env, const void *d_poses, int pos
                                  unsigned *work_base_io);
 // same, verdict i goes to outs.p[r][i] for every r < outs.n (peer-store gather)
 cudaError_t launch_collide_poses_gather(const EnvDev &env, const void *d_poses, int pose_fmt, int64_t n, const OutSet &outs,
-                                        cudaStream_t stream, const LaunchCfg &cfg, bool count, unsigned *work_base_io);
+                                        const GatherSync &sync, cudaStream_t stream, const LaunchCfg &cfg, bool count,
+                                        unsigned *work_base_io);
 // all ranks' stores of the kernels enqueued before this call are visible on every rank once the barrier kernel has run on
 // every rank: signal (st.release.sys into every peer's flag word) + wait (ld.acquire.sys on the own flag words), bounded
-// by a 2 s timeout that raises the env status instead of hanging the GPU
-cudaError_t launch_peer_barrier(const FlagSet &flags, unsigned epoch, int *d_status, cudaStream_t stream);
+// by a 10 s timeout that raises the env status instead of hanging the GPU
+cudaError_t launch_peer_barrier(const FlagSet &flags, unsigned epoch, bool signal, int *d_status, cudaStream_t stream);
 
 cudaError_t launch_check_edges(const EnvDev &env, const double *d_starts, const double *d_ends, int64_t m,
                                double sample_dist, int rot_mode, uint8_t *d_free, int32_t *d_first_hit,

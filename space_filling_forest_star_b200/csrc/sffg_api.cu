@@ -592,34 +592,77 @@ int sffg_peer_buffer_destroy(void *d_ptr) {
   return SFFG_OK;
 }
 
-int sffg_collide_poses_gather_device(sffg_env *env, const void *d_poses, int poses_are_f64, int64_t n, uint8_t *const *d_outs,
-                                     int n_outs, void *stream) {
-  if (!env || n < 0 || n_outs < 1 || n_outs > kMaxPeers || !d_outs || (n > 0 && !d_poses))
-    return fail(SFFG_ERR_ARG, "sffg_collide_poses_gather_device: bad arguments");
-  OutSet outs;
-  outs.n = n_outs;
+static int fill_flags(FlagSet *f, uint32_t *const *d_flags, int n_ranks, int my_rank, const char *who) {
+  if (!d_flags || n_ranks < 1 || n_ranks > kMaxPeers || my_rank < 0 || my_rank >= n_ranks)
+    return fail(SFFG_ERR_ARG, std::string(who) + ": bad rank arguments");
+  f->n = n_ranks;
+  f->me = my_rank;
+  for (int r = 0; r < n_ranks; ++r) {
+    if (!d_flags[r]) return fail(SFFG_ERR_ARG, std::string(who) + ": null flag array");
+    f->p[r] = d_flags[r];
+  }
+  return SFFG_OK;
+}
+
+static int fill_outs(OutSet *outs, uint8_t *const *d_outs, int n_outs, const char *who) {
+  if (!d_outs || n_outs < 1 || n_outs > kMaxPeers) return fail(SFFG_ERR_ARG, std::string(who) + ": bad destination list");
+  outs->n = n_outs;
   for (int r = 0; r < n_outs; ++r) {
     if (!d_outs[r] || (reinterpret_cast<uintptr_t>(d_outs[r]) & 3u))
-      return fail(SFFG_ERR_ARG, "sffg_collide_poses_gather_device: every destination must be non-null and 4-byte aligned");
-    outs.p[r] = d_outs[r];
+      return fail(SFFG_ERR_ARG, std::string(who) + ": every destination must be non-null and 4-byte aligned");
+    outs->p[r] = d_outs[r];
   }
+  return SFFG_OK;
+}
+
+int sffg_collide_poses_gather_device(sffg_env *env, const void *d_poses, int poses_are_f64, int64_t n, uint8_t *const *d_outs,
+                                     int n_outs, void *stream) {
+  if (!env || n < 0 || (n > 0 && !d_poses)) return fail(SFFG_ERR_ARG, "sffg_collide_poses_gather_device: bad arguments");
+  OutSet outs;
+  int rc = fill_outs(&outs, d_outs, n_outs, "sffg_collide_poses_gather_device");
+  if (rc != SFFG_OK) return rc;
+  GatherSync none{};
   unsigned *base;
   EnvDev v = env_view(env, &base);
-  SFFG_CUDA(launch_collide_poses_gather(v, d_poses, poses_are_f64 ? 1 : 0, n, outs, (cudaStream_t)stream, env->cfg, env->count, base));
+  SFFG_CUDA(launch_collide_poses_gather(v, d_poses, poses_are_f64 ? 1 : 0, n, outs, none, (cudaStream_t)stream, env->cfg, env->count, base));
+  return SFFG_OK;
+}
+
+int sffg_collide_poses_gather_sync_device(sffg_env *env, const void *d_poses, int poses_are_f64, int64_t n, uint8_t *const *d_outs,
+                                          uint32_t *const *d_flags, int n_ranks, int my_rank, uint32_t signal_epoch,
+                                          uint32_t wait_epoch, uint32_t *d_done_counter, void *stream) {
+  if (!env || n < 0 || (n > 0 && !d_poses) || !d_done_counter || signal_epoch == 0)
+    return fail(SFFG_ERR_ARG, "sffg_collide_poses_gather_sync_device: bad arguments");
+  OutSet outs;
+  GatherSync gs{};
+  int rc = fill_outs(&outs, d_outs, n_ranks, "sffg_collide_poses_gather_sync_device");
+  if (rc == SFFG_OK) rc = fill_flags(&gs.flags, d_flags, n_ranks, my_rank, "sffg_collide_poses_gather_sync_device");
+  if (rc != SFFG_OK) return rc;
+  gs.signal_epoch = signal_epoch;
+  gs.wait_epoch = wait_epoch;
+  gs.done_counter = d_done_counter;
+  unsigned *base;
+  EnvDev v = env_view(env, &base);
+  SFFG_CUDA(launch_collide_poses_gather(v, d_poses, poses_are_f64 ? 1 : 0, n, outs, gs, (cudaStream_t)stream, env->cfg, env->count, base));
+  return SFFG_OK;
+}
+
+int sffg_peer_wait_device(sffg_env *env, uint32_t *const *d_flags, int n_ranks, int my_rank, uint32_t epoch, void *stream) {
+  if (!env) return fail(SFFG_ERR_ARG, "sffg_peer_wait_device: null env");
+  FlagSet f;
+  int rc = fill_flags(&f, d_flags, n_ranks, my_rank, "sffg_peer_wait_device");
+  if (rc != SFFG_OK) return rc;
+  SFFG_CUDA(launch_peer_barrier(f, epoch, false, env->h_status, (cudaStream_t)stream));
   return SFFG_OK;
 }
 
 int sffg_peer_barrier_device(sffg_env *env, uint32_t *const *d_flags, int n_ranks, int my_rank, uint32_t epoch, void *stream) {
-  if (!env || !d_flags || n_ranks < 1 || n_ranks > kMaxPeers || my_rank < 0 || my_rank >= n_ranks)
-    return fail(SFFG_ERR_ARG, "sffg_peer_barrier_device: bad arguments");
+  if (!env) return fail(SFFG_ERR_ARG, "sffg_peer_barrier_device: null env");
   FlagSet f;
-  f.n = n_ranks;
-  f.me = my_rank;
-  for (int r = 0; r < n_ranks; ++r) {
-    if (!d_flags[r]) return fail(SFFG_ERR_ARG, "sffg_peer_barrier_device: null flag array");
-    f.p[r] = d_flags[r];
-  }
-  SFFG_CUDA(launch_peer_barrier(f, epoch, env->h_status, (cudaStream_t)stream));
+  int rc = fill_flags(&f, d_flags, n_ranks, my_rank, "sffg_peer_barrier_device");
+  if (rc != SFFG_OK) return rc;
+  SFFG_CUDA(launch_peer_barrier(f, epoch, true, nullptr, (cudaStream_t)stream));
+  SFFG_CUDA(launch_peer_barrier(f, epoch, false, env->h_status, (cudaStream_t)stream));
   return SFFG_OK;
 }
 

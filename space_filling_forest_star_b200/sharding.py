@@ -76,16 +76,21 @@ def sharded_knn(index, queries: torch.Tensor, k: int, group=None) -> Tuple[torch
 
 
 class PeerGather:
-    """Verdict all-gather fused into the collision kernel's stores (include/sffg.h "multi-GPU").
+    """Verdict all-gather fused into the collision kernel (include/sffg.h "multi-GPU").
 
-    Every rank owns a gathered buffer of ``world * per_rank`` verdict bytes allocated by the engine (plain cudaMalloc, so
-    that it can be exported through CUDA IPC) and maps the buffers of all peers.  ``collide(env, poses)`` launches the
-    pose kernel with ``world`` destinations -- slice ``rank`` of every rank's buffer -- so the exchange rides on the
-    kernel's own 32-byte stores over NVLink while it computes; ``barrier()`` then enqueues the flag handshake after
-    which every rank's slice is visible locally.  Buffers are double-buffered: a rank that is one step ahead writes the
-    other buffer, so results of step k may be read until the barrier of step k+1 is enqueued.
+    Every rank owns ``NBUF`` gathered buffers of ``world * per_rank`` verdict bytes plus a few flag words, allocated by the
+    engine (plain cudaMalloc, so that they can be exported through CUDA IPC), and maps those of all peers.
+    ``collide(env, poses)`` launches the pose kernel with ``world`` destinations -- slice ``rank`` of the current buffer of
+    every rank -- so the exchange rides on the kernel's own 32-byte stores over NVLink while it computes; the last CTA to
+    finish publishes the call's epoch to every rank, and before touching its destinations a kernel waits until every rank
+    has published epoch ``j - NBUF + 2`` (the buffer it is about to overwrite has been consumed everywhere).  With
+    NBUF = 4 a rank may run a full kernel ahead of the slowest one: there is no barrier between consecutive calls.
+    ``wait(env, step)`` enqueues the wait a consumer of that call's results needs; the contract is that the results of call
+    ``s`` are read (enqueued on the same stream) before call ``s + 2`` is enqueued.
     torch.distributed is only the plumbing that ships the 64-byte IPC handles.
     """
+
+    NBUF = 4
 
     def __init__(self, per_rank: int, group=None):
         import ctypes as C
@@ -99,17 +104,17 @@ class PeerGather:
         self.per = (per_rank + 31) // 32 * 32          # slices start 32-byte aligned
         self.bytes = self.world * self.per
         self.own, handles = [], []
-        for _ in range(3):                              # two gathered buffers + the flag words
+        for b in range(self.NBUF + 1):                  # gathered buffers + one block of flag words
             p = C.c_void_p()
             h = (C.c_uint8 * 64)()
-            self._check(self._L.sffg_peer_buffer_create(self.bytes if len(self.own) < 2 else 256, C.byref(p), h))
+            self._check(self._L.sffg_peer_buffer_create(self.bytes if b < self.NBUF else 256, C.byref(p), h))
             self.own.append(p.value)
             handles.append(bytes(h))
         everyone = [None] * self.world
         dist.all_gather_object(everyone, handles, group=group)
         self.ptrs = []                                  # ptrs[b][r] = buffer b of rank r, valid in this process
         self._opened = []
-        for b in range(3):
+        for b in range(self.NBUF + 1):
             row = []
             for r in range(self.world):
                 if r == self.rank:
@@ -121,33 +126,36 @@ class PeerGather:
                     self._opened.append(p.value)
                     row.append(p.value)
             self.ptrs.append(row)
+        self._flags = (C.c_void_p * self.world)(*self.ptrs[self.NBUF])      # flag words: [0..7] epochs, [16] CTA counter
+        self._done_counter = self.own[self.NBUF] + 64
         self.step = 0
-        self.epoch = 0
         dist.barrier(group=group)
 
     def collide(self, env, poses: torch.Tensor) -> int:
         """enqueue the pose kernel on the current stream; verdict i of this rank lands at offset rank*per + i of the current
-        gathered buffer of EVERY rank.  Returns the buffer number to pass to :meth:`view`."""
+        gathered buffer of EVERY rank.  Returns the step number to pass to :meth:`wait` / :meth:`view`."""
         n = poses.shape[0]
         assert n <= self.per and poses.is_cuda and poses.is_contiguous()
-        b = self.step & 1
+        j = self.step
         self.step += 1
+        b = j % self.NBUF
         dests = (self._C.c_void_p * self.world)(*[self.ptrs[b][r] + self.rank * self.per for r in range(self.world)])
         st = torch.cuda.current_stream(poses.device).cuda_stream
-        self._check(self._L.sffg_collide_poses_gather_device(env._h, poses.data_ptr(), int(poses.dtype == torch.float64), n, dests,
-                                                             self.world, st))
-        return b
+        epoch = j + 1
+        wait = max(0, epoch - self.NBUF + 2)
+        self._check(self._L.sffg_collide_poses_gather_sync_device(env._h, poses.data_ptr(), int(poses.dtype == torch.float64), n, dests,
+                                                                  self._flags, self.world, self.rank, epoch, wait, self._done_counter, st))
+        return j
 
-    def barrier(self, env, device=None) -> None:
-        """enqueue the cross-GPU completion handshake on the current stream"""
-        self.epoch += 1
-        flags = (self._C.c_void_p * self.world)(*self.ptrs[2])
+    def wait(self, env, step: int, device=None) -> None:
+        """enqueue, on the current stream, the wait for every rank's results of call ``step``"""
         st = torch.cuda.current_stream(device).cuda_stream
-        self._check(self._L.sffg_peer_barrier_device(env._h, flags, self.world, self.rank, self.epoch, st))
+        self._check(self._L.sffg_peer_wait_device(env._h, self._flags, self.world, self.rank, step + 1, st))
 
-    def view(self, b: int, device) -> torch.Tensor:
-        """the gathered buffer ``b`` of this rank as a torch uint8 tensor [world, per] (no copy)"""
-        iface = {"shape": (self.world, self.per), "typestr": "|u1", "data": (self.own[b], False), "version": 2}
+    def view(self, step: int, device) -> torch.Tensor:
+        """the gathered buffer of call ``step`` on this rank as a torch uint8 tensor [world, per] (no copy)"""
+        ptr = self.own[step % self.NBUF]
+        iface = {"shape": (self.world, self.per), "typestr": "|u1", "data": (ptr, False), "version": 2}
         holder = type("_Dev", (), {"__cuda_array_interface__": iface})()
         return torch.as_tensor(holder, device=device)
 
@@ -161,7 +169,7 @@ class PeerGather:
 
 
 def gathered_collide(env, pg: "PeerGather", poses_local: torch.Tensor) -> torch.Tensor:
-    """one fused step: local slice -> every rank's gathered buffer, then the completion barrier; returns [world, per]"""
-    b = pg.collide(env, poses_local)
-    pg.barrier(env, poses_local.device)
-    return pg.view(b, poses_local.device)
+    """one fused step: local slice -> every rank's gathered buffer, then wait for everyone's slice; returns [world, per]"""
+    j = pg.collide(env, poses_local)
+    pg.wait(env, j, poses_local.device)
+    return pg.view(j, poses_local.device)
