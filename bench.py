@@ -251,12 +251,16 @@ def run_ours(args):
         pg.wait(env, last_buf[0], dev)
     torch.cuda.synchronize()
     env.sync_check()
+    sampler = ClockSampler(local)   # (NVML initialisation happens before the barrier, not inside the timed region)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
     sampler.start()
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        # the host-side barrier above lets the ranks' Python threads drift apart by milliseconds again; a stream-ordered
+        # all-reduce right in front of the start event makes every rank's clock start at the same point on the device
+        dist.all_reduce(torch.zeros(1, device=dev))
     t_beg.record()
     for i in range(args.steps):
         step(i)
