@@ -637,8 +637,11 @@ class Planner {
           const Node &ex = nodes_[c.exp];
           for (int id : added) {
             const Node &o = nodes_[id];
-            const double d = dist6(o.p, c.p);
-            if ((o.tree == ex.tree && d < c.parent_dist - kTol) || (o.tree != ex.tree && d < cfg_.dtree - kTol)) {
+            const double thr = o.tree == ex.tree ? c.parent_dist - kTol : cfg_.dtree - kTol;
+            // the translational part is a lower bound of the 6-D distance: most pairs are settled without wraps and sqrt
+            const double dx = o.p[0] - c.p[0], dy = o.p[1] - c.p[1], dz = o.p[2] - c.p[2];
+            if (dx * dx + dy * dy + dz * dz >= thr * thr) continue;
+            if (dist6(o.p, c.p) < thr) {
               deferred = true;
               break;
             }
