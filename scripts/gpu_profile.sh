@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TAG=${1:-r01}
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
+    python bench.py --steps 5 --warmup 3 --no-cpu --no-extra > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
 echo "launch list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:collide_poses_kernel -s 3 -c 1 -f -o gpurun_out/${TAG}_collide \
     python bench.py --steps 1 --warmup 3 --no-cpu --no-extra > gpurun_out/${TAG}_ncu_collide.log 2>&1
