@@ -99,7 +99,7 @@ def test_engine_and_double_agree_on_a_fixed_seed(exe, tmp_path):
 
 
 # mean path lengths of the UNMODIFIED reference host (its own FLANN + the CPU RAPID stand-in) over 10 clock-seeded runs,
-# recorded in profiles/r01_e2e_sffstar.json and profiles/r01_e2e_rrt.json (scripts/e2e_compare.py on the GPU box)
+# recorded in profiles/r01_e2e_sffstar.json (r01f: 1314.2) and profiles/r01_e2e_rrt.json (tests/tools/e2e_compare.py on the GPU box)
 REFERENCE_MEAN_LENGTH = {"2d_sffstar": 1326.77, "2d_rrtstar_goal": 1128.73, "2d_mtrrt": 1349.09}
 TOLERANCE = 0.10   # north_star: end-to-end path costs within a stated tolerance of the reference
 

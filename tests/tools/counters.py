@@ -3,11 +3,11 @@
 import json, sys
 from pathlib import Path
 import numpy as np
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import space_filling_forest_star_b200 as S
 import oracle as O
 S.init(0)
-m = np.load(Path(__file__).resolve().parents[1] / "tests" / "golden" / "meshes.npz")
+m = np.load(Path(__file__).resolve().parents[2] / "tests" / "golden" / "meshes.npz")
 for on, rn, rng in (("building_s10", "robot_small_s10", [-70, 70, -70, 70, 0, 140]), ("dense3d_s1", "robot_small_s1", [-60, 2060, -60, 2110, 0, 1000]),
                     ("triang_s10", "robot_cyl_small_s10", [-100, 100, -100, 100, 0, 100])):
     env = S.Environment(m[on], m[rn])

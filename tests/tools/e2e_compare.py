@@ -9,7 +9,7 @@
 Same XML + same mesh files for all three; runs differ by seed (the reference seeds from the clock), so the comparison
 is statistical: solved rate, pairwise path lengths (params.csv), wall time per run.
 
-    python scripts/e2e_compare.py [--runs R] [--scenarios building_sffstar,2d_sffstar,...] [--out gpurun_out/e2e.json]
+    python tests/tools/e2e_compare.py [--runs R] [--scenarios building_sffstar,2d_sffstar,...] [--out gpurun_out/e2e.json]
 """
 import argparse
 import json
@@ -23,7 +23,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 BINS = {
     "ref_cpu": ROOT / "oracle" / "_ref" / "ref_main_cpu",

@@ -2,7 +2,7 @@
 """SURVEY 8d sweeps on one B200 (device-resident, CUDA-event timed, median of reps), with the CPU reference path timed on
 bounded samples beside every line.  GPU box only.
 
-    python scripts/sweep.py [--quick] [--out gpurun_out/sweep.json]
+    python tests/tools/sweep.py [--quick] [--out gpurun_out/sweep.json]
 
   collision : obstacle in {building.obj s10, dense_3D.obj s1}, robot_small, N in {1e6, 1e7, 1e8} Philox poses
   edges     : M in {1e5, 1e6} edges of length 4 (39 samples) in building.obj, both rotation modes; 2-D long edges
@@ -19,7 +19,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 import oracle as O  # noqa: E402  (CPU baselines only)
 import space_filling_forest_star_b200 as S  # noqa: E402
