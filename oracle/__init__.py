@@ -257,6 +257,13 @@ def edges_free(obst, robot, starts, ends, sample: float = 0.1, rot_mode: int = 0
     return free, first, int(tested[0])
 
 
+def d6_float(a, b) -> float:
+    """the intended D6Distance in float (squared), a = stored point, b = query (orc_d6_float)"""
+    x = np.ascontiguousarray(a, dtype=np.float32)
+    y = np.ascontiguousarray(b, dtype=np.float32)
+    return float(lib().orc_d6_float(x, y, len(x)))
+
+
 def knn_linear(nodes, queries, k: int, threads: int = 0):
     n = np.ascontiguousarray(nodes, dtype=np.float32)
     q = np.ascontiguousarray(queries, dtype=np.float32)
