@@ -339,9 +339,17 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POSE * P,
                          "ncu": ({"warp_instructions_per_pose": tinfo["warp_instructions"] / tinfo["poses_per_launch"],
                                   "issue_slots_active_pct": tinfo["issue_active_pct"], "source": tinfo["source"]} if tinfo else None),
+                         # the roofline that does bound this kernel: warp-instruction issue.  achieved = committed ncu count of
+                         # executed warp instructions per launch / the kernel time measured live here; peak = SMs x 4 schedulers
+                         # x the SM clock sampled during the timed region (one warp instruction per scheduler per cycle)
+                         "issue": ({"achieved": tinfo["warp_instructions"] / (kernel_ms * 1e-3) / 1e9,
+                                    "peak": torch.cuda.get_device_properties(dev).multi_processor_count * 4 * (clocks["sm_mhz"] or 1965) * 1e6 / 1e9,
+                                    "unit": "G warp-instructions/s"} if tinfo else None),
                          "note": "the path is instruction-issue / L2-latency bound, not HBM bound (SURVEY 8d): the informative "
                                  "fraction is issue_slots_active_pct; see DESIGN.md 4.1"},
         }
+        if line["roofline"].get("issue"):
+            line["roofline"]["issue"]["frac"] = line["roofline"]["issue"]["achieved"] / line["roofline"]["issue"]["peak"]
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
         if world == 1 and not args.no_extra:
