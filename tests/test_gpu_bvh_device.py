@@ -66,3 +66,59 @@ def test_set_obstacles_replaces_the_map_in_place(sff, orc, meshes):
     env.set_obstacles(np.zeros((0, 3, 3)))            # HasMap == false: nothing collides (src/environment.h:307-309)
     assert env.Collide(poses).sum() == 0
     env.close()
+
+
+def test_multi_destination_stores_on_one_gpu(sff, orc, meshes):
+    """the peer-store gather of the multi-GPU path, exercised on a single GPU: two local destination buffers stand in for
+    two ranks' buffers; both must hold the plain kernel's verdicts for full 32-pose units (packed-word stores), ragged
+    tails and planner-sized batches (byte stores); then the fused handshake with a world of one rank"""
+    import ctypes as C
+
+    import torch
+
+    from space_filling_forest_star_b200 import _lib
+    L = _lib.load()
+    on, rn, rng = CASES["B"]
+    env = sff.Environment(meshes[on], meshes[rn])
+    st = torch.cuda.current_stream().cuda_stream
+    for n in (1 << 20, (1 << 20) + 13, 777, 31):
+        poses = sff.gen_poses_device(SEED + 9, 0, n, rng)
+        want = env.collide_device(poses)
+        a = torch.full((n + 64,), 7, dtype=torch.uint8, device="cuda")
+        b = torch.full((n + 64,), 7, dtype=torch.uint8, device="cuda")
+        dests = (C.c_void_p * 2)(a.data_ptr(), b.data_ptr())
+        _lib.check(L.sffg_collide_poses_gather_device(env._h, poses.data_ptr(), 0, n, dests, 2, st))
+        torch.cuda.synchronize()
+        env.sync_check()
+        assert torch.equal(a[:n], want) and torch.equal(b[:n], want), n
+        assert int(a[n:].min()) == 7 and int(b[n:].max()) == 7           # nothing written past the batch
+    # misaligned destination -> argument error, not a misaligned store
+    bad = (C.c_void_p * 2)(a.data_ptr() + 1, b.data_ptr())
+    assert L.sffg_collide_poses_gather_device(env._h, poses.data_ptr(), 0, 31, bad, 2, st) == 3   # SFFG_ERR_ARG
+    # fused handshake, world of one: epochs 1..6 over four round-robin buffers, wait kernel in front of the reader
+    n = 1 << 18
+    poses = sff.gen_poses_device(SEED + 10, 0, n, rng)
+    want = env.collide_device(poses)
+    flags = torch.zeros(64, dtype=torch.int32, device="cuda")
+    bufs = [torch.zeros(n, dtype=torch.uint8, device="cuda") for _ in range(4)]
+    fl = (C.c_void_p * 1)(flags.data_ptr())
+    for j in range(6):
+        d = (C.c_void_p * 1)(bufs[j % 4].data_ptr())
+        _lib.check(L.sffg_collide_poses_gather_sync_device(env._h, poses.data_ptr(), 0, n, d, fl, 1, 0, j + 1, max(0, j - 1),
+                                                          flags.data_ptr() + 64, st))
+        _lib.check(L.sffg_peer_wait_device(env._h, fl, 1, 0, j + 1, st))
+        assert torch.equal(bufs[j % 4], want)
+    torch.cuda.synchronize()
+    env.sync_check()
+    assert int(flags[0]) == 6 and int(flags[16]) == 0                     # epoch published, CTA counter back to zero
+    env.close()
+
+
+def test_build_mode_and_null_arguments_are_rejected(sff, meshes):
+    on, rn, _ = CASES["T"]
+    with pytest.raises(sff.SffgError):
+        sff.Environment(meshes[on], meshes[rn], build=7)
+    env = sff.Environment(meshes[on], meshes[rn])
+    with pytest.raises(sff.SffgError):
+        env.set_obstacles(meshes[on], build=-1)
+    env.close()
