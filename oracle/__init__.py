@@ -257,6 +257,14 @@ def edges_free(obst, robot, starts, ends, sample: float = 0.1, rot_mode: int = 0
     return free, first, int(tested[0])
 
 
+def tri_contact(P, Q) -> int:
+    """17-axis triangle-pair test (orc_tri_contact): P, Q = [3][3] vertices in one common frame -> 1 when in contact"""
+    p = np.ascontiguousarray(P, dtype=np.float64).reshape(3, 3)
+    q = np.ascontiguousarray(Q, dtype=np.float64).reshape(3, 3)
+    return int(lib().orc_tri_contact(np.ascontiguousarray(p[0]), np.ascontiguousarray(p[1]), np.ascontiguousarray(p[2]),
+                                     np.ascontiguousarray(q[0]), np.ascontiguousarray(q[1]), np.ascontiguousarray(q[2])))
+
+
 def d6_float(a, b) -> float:
     """the intended D6Distance in float (squared), a = stored point, b = query (orc_d6_float)"""
     x = np.ascontiguousarray(a, dtype=np.float32)
