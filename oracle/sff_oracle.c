@@ -10,7 +10,10 @@
  *                (UNC GAMMA group), which is NOT vendored (lib/rapid-2.01/ holds only a README) and the
  *                reference ships no golden verdicts.  This file restates RAPID's published algorithm
  *                (Gottschalk/Lin/Manocha, "OBBTree", SIGGRAPH'96) behind the reference's own call
- *                contract (src/environment.h:269-276, src/primitives.h:252-262).
+ *                contract (src/environment.h:269-276, src/primitives.h:252-262).  What IS pinned,
+ *                independently of any restatement, is the meaning of the verdict: on integer-coordinate
+ *                triangles (all quantities exact) orc_tri_contact equals exact closed-triangle
+ *                intersection computed by a different algorithm (tests/test_oracle_exact_geometry.py).
  *   k-NN/radius: pinned against vendored FLANN 1.9.1 LinearIndex compiled from /root/reference
  *                (oracle/_ref, see oracle/Makefile + oracle/ref_flann.cpp) by tests/test_oracle_knn.py.
  *
