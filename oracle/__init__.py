@@ -257,6 +257,16 @@ def edges_free(obst, robot, starts, ends, sample: float = 0.1, rot_mode: int = 0
     return free, first, int(tested[0])
 
 
+def collide_obbtree_rt(mo: "ObbModel", mr: "ObbModel", R, T) -> int:
+    """RAPID_Collide's own argument form (robot at rotation R row-major, translation T): orc_collide_obbtree_rt"""
+    L = lib()
+    L.orc_collide_obbtree_rt.argtypes = [C.c_void_p, C.c_void_p, _f64p, _f64p, C.c_int, C.c_void_p]
+    L.orc_collide_obbtree_rt.restype = C.c_int
+    r = np.ascontiguousarray(R, dtype=np.float64).reshape(9)
+    t = np.ascontiguousarray(T, dtype=np.float64).reshape(3)
+    return int(L.orc_collide_obbtree_rt(mo.handle, mr.handle, r, t, 1, None))
+
+
 def tri_contact(P, Q) -> int:
     """17-axis triangle-pair test (orc_tri_contact): P, Q = [3][3] vertices in one common frame -> 1 when in contact"""
     p = np.ascontiguousarray(P, dtype=np.float64).reshape(3, 3)

@@ -165,3 +165,52 @@ def test_engine_verdicts_equal_exact_geometry_for_integer_scenes(sff, orc):
             np.testing.assert_array_equal(env.Collide(poses), want)
             np.testing.assert_array_equal(env.Collide(poses.astype(np.float32)), want)
             env.close()
+
+
+def cube_rotations():
+    """the 24 proper rotations of the cube: signed permutation matrices with determinant +1 (exact in any arithmetic)"""
+    out = []
+    for perm in itertools.permutations(range(3)):
+        for signs in itertools.product((1, -1), repeat=3):
+            m = [[signs[r] if perm[r] == c else 0 for c in range(3)] for r in range(3)]
+            det = (m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0])
+                   + m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]))
+            if det == 1:
+                out.append(m)
+    return out
+
+
+def rotated_scene(seed, n_per_rot=12):
+    """integer scene + every cube rotation at a few integer translations; world point of a robot vertex = R q + T
+    (A.1: RAPID places model 2 at (R2, T2)), evaluated in integers"""
+    rng = np.random.default_rng(seed)
+    obst = [a for a, _ in random_pairs(rng, 40, 10)]
+    robot = [a for a, _ in random_pairs(rng, 3, 4)]
+    Rs, Ts, want = [], [], []
+    for R in cube_rotations():
+        for t in rng.integers(-12, 13, size=(n_per_rot, 3)).tolist():
+            placed = [[tuple(sum(R[r][c] * q[c] for c in range(3)) + t[r] for r in range(3)) for q in tri] for tri in robot]
+            Rs.append(R)
+            Ts.append(t)
+            want.append(any(triangles_meet(o, p) for o in obst for p in placed))
+    return (np.array(obst, dtype=np.float64), np.array(robot, dtype=np.float64), np.array(Rs, dtype=np.float64),
+            np.array(Ts, dtype=np.float64), np.array(want, dtype=np.uint8))
+
+
+def test_rotation_convention_is_exact_for_cube_rotations(orc):
+    """pins the transform convention (robot at R2, T2; obstacle vertices taken into the robot frame as R2^T (p - T2)) with
+    the 24 exact rotations: a transposed or inverted convention fails on the non-symmetric ones"""
+    obst, robot, Rs, Ts, want = rotated_scene(21)
+    assert 30 < want.sum() < len(want) - 30
+    mo, mr = orc.ObbModel(obst), orc.ObbModel(robot)
+    got = np.array([orc.collide_obbtree_rt(mo, mr, R, T) for R, T in zip(Rs, Ts)], dtype=np.uint8)
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_engine_rotation_convention_is_exact_for_cube_rotations(sff):
+    """sffg_collide_transforms_f64 (RAPID_Collide's argument form, what the RAPID.H shim forwards) against exact geometry"""
+    obst, robot, Rs, Ts, want = rotated_scene(21)
+    env = sff.Environment(obst, robot)
+    np.testing.assert_array_equal(env.CollideTransforms(Rs, Ts), want)
+    env.close()
