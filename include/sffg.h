@@ -157,6 +157,13 @@ SFFG_API int sffg_check_edges_device(sffg_env *env, const double *d_starts, cons
                             double sample_dist, int rot_mode, uint8_t *d_free_out, int32_t *d_first_hit_out,
                             void *stream);
 
+/* a move start -> end as every expansion step of the reference validates it: the end pose must be collision free AND the
+ * segment must pass the local planner -- `env.Collide(newPoint) || !isPathFree(node, newPoint)` rejects
+ * (src/forest.h:246, src/rrt.h:149, src/lazy.h:197).  ok_out[i] = 1 when move i is valid.  One call, one upload, both
+ * kernels on one stream, one synchronisation.                                                                          */
+SFFG_API int sffg_check_moves(sffg_env *env, const double *starts, const double *ends, int64_t m, double sample_dist,
+                     int rot_mode, uint8_t *ok_out);
+
 /* work counters of the last call on this env (debug/roofline): poses past the root cull, BVH child-box tests,
  * triangle-pair FP32 SAT tests, FP64 exact re-tests                                                          */
 typedef struct {

@@ -63,6 +63,7 @@ SIGNATURES = {
     "sffg_peer_wait_device": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_uint32, _p]),
     "sffg_peer_barrier_device": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_uint32, _p]),
     "sffg_check_edges": (C.c_int, [_p, _p, _p, C.c_int64, C.c_double, C.c_int, _p, _p]),
+    "sffg_check_moves": (C.c_int, [_p, _p, _p, C.c_int64, C.c_double, C.c_int, _p]),
     "sffg_check_edges_device": (C.c_int, [_p, _p, _p, C.c_int64, C.c_double, C.c_int, _p, _p, _p]),
     "sffg_env_enable_counters": (C.c_int, [_p, C.c_int]),
     "sffg_env_sync_check": (C.c_int, [_p]),

@@ -781,6 +781,42 @@ int sffg_check_edges(sffg_env *env, const double *starts, const double *ends, in
   return check_status(env);
 }
 
+int sffg_check_moves(sffg_env *env, const double *starts, const double *ends, int64_t m, double sample_dist, int rot_mode,
+                     uint8_t *ok_out) {
+  if (!env || m < 0 || (m > 0 && (!starts || !ends || !ok_out)) || !(sample_dist > 0) ||
+      (rot_mode != SFFG_ROT_REFERENCE && rot_mode != SFFG_ROT_INTERPOLATE))
+    return fail(SFFG_ERR_ARG, "sffg_check_moves: bad arguments");
+  if (m == 0) return SFFG_OK;
+  unsigned *base;
+  if ((size_t)m * 96 <= kSmallIn && (size_t)m * 6 <= kSmallBytes - kSmallIn) {
+    // planner-sized call: one upload, the pose kernel on the end points and the edge kernel on the segments back to back
+    // on one stream, results straight into pinned mapped memory, one synchronisation
+    cudaStream_t st = env->streams[0];
+    int rc = env->in[0].reserve((size_t)m * 96);
+    if (rc == SFFG_OK) rc = env->fh.reserve((size_t)m * sizeof(int));
+    if (rc != SFFG_OK) return rc;
+    std::memcpy(env->h_small, starts, (size_t)m * 48);
+    std::memcpy(env->h_small + (size_t)m * 48, ends, (size_t)m * 48);
+    double *ds = (double *)env->in[0].p, *de = ds + 6 * m;
+    SFFG_CUDA(cudaMemcpyAsync(ds, env->h_small, (size_t)m * 96, cudaMemcpyHostToDevice, st));
+    uint8_t *h_free = env->h_small + kSmallIn, *h_hit = h_free + (size_t)m;
+    EnvDev v = env_view(env, &base);
+    SFFG_CUDA(launch_collide_poses(v, de, 1, m, h_hit, st, env->cfg, env->count, base));
+    EnvDev w = env_view(env, &base);
+    SFFG_CUDA(launch_check_edges(w, ds, de, m, sample_dist, rot_mode, h_free, nullptr, st, env->cfg, env->count, base,
+                                 (int *)env->fh.p));
+    SFFG_CUDA(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < m; ++i) ok_out[i] = (uint8_t)(h_free[i] && !h_hit[i]);
+    return check_status(env);
+  }
+  std::vector<uint8_t> hit((size_t)m);
+  int rc = sffg_collide_poses_f64(env, ends, m, hit.data());
+  if (rc == SFFG_OK) rc = sffg_check_edges(env, starts, ends, m, sample_dist, rot_mode, ok_out, nullptr);
+  if (rc != SFFG_OK) return rc;
+  for (int64_t i = 0; i < m; ++i) ok_out[i] = (uint8_t)(ok_out[i] && !hit[(size_t)i]);
+  return SFFG_OK;
+}
+
 int sffg_gen_poses_device(uint64_t seed, uint64_t first_index, int64_t n, const float range[6], float *d_poses_out,
                           void *stream) {
   if (n < 0 || !range || (n > 0 && !d_poses_out)) return fail(SFFG_ERR_ARG, "sffg_gen_poses_device: bad arguments");

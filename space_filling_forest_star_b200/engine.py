@@ -148,6 +148,18 @@ class Environment:
                                        _ptr(free) if m else None, _ptr(first) if (want_first_hit and m) else None))
         return (free, first) if want_first_hit else free
 
+    def checkMoves(self, starts, ends, sample_dist: float = COLLISION_SAMPLE_SIZE, rot_mode: int = ROT_REFERENCE) -> np.ndarray:
+        """``!env.Collide(end) && isPathFree(start, end)`` per row: the validity test of an expansion step
+        (src/forest.h:246, src/rrt.h:149) in one engine call -> uint8[m], 1 = valid"""
+        s = np.ascontiguousarray(np.asarray(starts, dtype=np.float64).reshape(-1, 6))
+        e = np.ascontiguousarray(np.asarray(ends, dtype=np.float64).reshape(-1, 6))
+        assert len(s) == len(e)
+        ok = np.empty(len(s), dtype=np.uint8)
+        m = len(s)
+        check(self._L.sffg_check_moves(self._h, _ptr(s) if m else None, _ptr(e) if m else None, m, float(sample_dist), rot_mode,
+                                       _ptr(ok) if m else None))
+        return ok
+
     def edges_device(self, starts, ends, sample_dist: float = COLLISION_SAMPLE_SIZE, rot_mode: int = ROT_REFERENCE,
                      free_out=None, first_hit_out=None, stream: Optional[int] = None):
         import torch

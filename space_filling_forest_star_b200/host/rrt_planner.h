@@ -310,30 +310,26 @@ class RrtPlanner {
     }
     clk_.lap(0);
     // ---- 3. steer, pose + first-edge verdicts
-    std::vector<double> poses;
     std::vector<int> pose_of;
     EdgeBatch eb;
     for (size_t i = 0; i < cand.size(); ++i) {
       Cand &c = cand[i];
       if (!steer(nodes_[c.nearest].p, c.s.rnd, cfg_.circum, c.p)) continue;
-      poses.insert(poses.end(), c.p, c.p + 6);
       pose_of.push_back((int)i);
       c.e_first = eb.add(nodes_[c.nearest].p, c.p);
     }
-    std::vector<uint8_t> hit(pose_of.size(), 0);
+    // one engine call validates every step: end pose free AND segment free (rrt.h:149, sffg_check_moves)
+    std::vector<uint8_t> ok(pose_of.size(), 1);
     if (!pose_of.empty() && cfg_.has_map) {
-      check(sffg_collide_poses_f64(env_, poses.data(), (int64_t)pose_of.size(), hit.data()));
-      eb.run(env_);
-      calls_ += 2;
-    } else {
-      eb.free_flag.assign(pose_of.size(), 1);
+      check(sffg_check_moves(env_, eb.s.data(), eb.e.data(), (int64_t)pose_of.size(), kSample, SFFG_ROT_REFERENCE, ok.data()));
+      ++calls_;
     }
     n_poses_ += (long)pose_of.size();
     n_edges_ += (long)pose_of.size();
     std::vector<int> alive;
     for (size_t i = 0; i < pose_of.size(); ++i) {
       Cand &c = cand[pose_of[i]];
-      c.alive = !hit[i] && eb.free_flag[c.e_first];
+      c.alive = ok[i] != 0;
       if (c.alive) {
         c.step = dist6(nodes_[c.nearest].p, c.p);
         alive.push_back(pose_of[i]);

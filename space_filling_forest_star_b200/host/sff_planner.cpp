@@ -437,7 +437,6 @@ class Planner {
     std::vector<Cand> cand((size_t)B * A);
     clk_.start();
     // ---- stage 1: candidate points, pose + first-edge verdicts
-    std::vector<double> poses;
     std::vector<int> pose_of;
     EdgeBatch eb;
     for (int b = 0; b < B; ++b)
@@ -446,25 +445,22 @@ class Planner {
         c.exp = chosen[b];
         c.in_limits = sample_around(nodes_[c.exp].p, c.p);
         if (!c.in_limits) continue;
-        poses.insert(poses.end(), c.p, c.p + 6);
         pose_of.push_back(b * A + a);
         c.e_first = eb.add(nodes_[c.exp].p, c.p);
       }
     clk_.lap(0);
-    std::vector<uint8_t> hit(pose_of.size(), 0);
+    // one engine call validates every candidate: end pose free AND segment free (forest.h:246, sffg_check_moves)
+    std::vector<uint8_t> ok(pose_of.size(), 1);
     if (!pose_of.empty() && cfg_.has_map) {
-      check(sffg_collide_poses_f64(env_, poses.data(), (int64_t)pose_of.size(), hit.data()));
-      eb.run(env_);
-      calls_ += 2;
+      check(sffg_check_moves(env_, eb.s.data(), eb.e.data(), (int64_t)pose_of.size(), kSample, SFFG_ROT_REFERENCE, ok.data()));
+      ++calls_;
       n_poses_ += (long)pose_of.size();
       n_edges_ += (long)pose_of.size();
-    } else {
-      eb.free_flag.assign(pose_of.size(), 1);
     }
     std::vector<int> alive;
     for (size_t i = 0; i < pose_of.size(); ++i) {
       Cand &c = cand[pose_of[i]];
-      c.alive = !hit[i] && eb.free_flag[c.e_first];
+      c.alive = ok[i] != 0;
       if (c.alive) {
         c.parent_dist = dist6(nodes_[c.exp].p, c.p);
         alive.push_back(pose_of[i]);

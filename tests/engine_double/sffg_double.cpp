@@ -110,6 +110,15 @@ SFFG_API int sffg_check_edges(sffg_env *e, const double *starts, const double *e
   return SFFG_OK;
 }
 
+SFFG_API int sffg_check_moves(sffg_env *e, const double *starts, const double *ends, int64_t m, double sample_dist, int rot_mode,
+                              uint8_t *ok_out) {
+  std::vector<uint8_t> hit((size_t)m);
+  sffg_collide_poses_f64(e, ends, m, hit.data());
+  sffg_check_edges(e, starts, ends, m, sample_dist, rot_mode, ok_out, nullptr);
+  for (int64_t i = 0; i < m; ++i) ok_out[i] = (uint8_t)(ok_out[i] && !hit[(size_t)i]);
+  return SFFG_OK;
+}
+
 SFFG_API int sffg_index_create(int dim, sffg_index **out) {
   if (dim != 2 && dim != 6) return sffg::fail(SFFG_ERR_ARG, "dim must be 2 or 6");
   *out = new sffg_index{dim, {}};

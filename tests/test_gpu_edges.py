@@ -60,3 +60,23 @@ def test_edge_sample_counts_match_reference_loop(sff, orc, meshes):
     wf, wh, _ = orc.edges_free(wall, rob, s, e, 0.1, 0)
     np.testing.assert_array_equal(free, wf)
     np.testing.assert_array_equal(first, wh)
+
+
+def test_check_moves_is_collide_or_not_path_free(sff, orc, meshes):
+    """sffg_check_moves: `env.Collide(newPoint) || !isPathFree(node, newPoint)` rejects (src/forest.h:246, src/rrt.h:149):
+    planner-sized and large batches against the oracle, and against the two separate engine calls"""
+    on, rn, rng = CASES["B"]
+    env = sff.Environment(meshes[on], meshes[rn])
+    mo, mr = orc.ObbModel(meshes[on]), orc.ObbModel(meshes[rn])
+    for m in (1, 640, 70000):
+        s = orc.gen_poses(SEED + 21, 0, m, [-45, 45, -45, 45, 0, 125]).astype(np.float64)
+        d = np.random.RandomState(m).randn(m, 3)
+        e = orc.gen_poses(SEED + 22, 0, m, rng).astype(np.float64)
+        e[:, :3] = s[:, :3] + 4.0 * d / np.linalg.norm(d, axis=1, keepdims=True)
+        ok = env.checkMoves(s, e)
+        hit, _ = orc.collide_obbtree(mo, mr, e)
+        free, _, _ = orc.edges_free(meshes[on], meshes[rn], s, e, 0.1, 0, models=(mo, mr))
+        np.testing.assert_array_equal(ok, (free.astype(bool) & ~hit.astype(bool)).astype(np.uint8))
+        np.testing.assert_array_equal(ok, (env.isPathFree(s, e).astype(bool) & ~env.Collide(e).astype(bool)).astype(np.uint8))
+    assert len(env.checkMoves(np.zeros((0, 6)), np.zeros((0, 6)))) == 0
+    env.close()
