@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import SEED
+from conftest import CASES, SEED
 
 pytestmark = pytest.mark.gpu
 
