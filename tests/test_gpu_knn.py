@@ -162,3 +162,46 @@ def test_pruning_can_be_disabled(sff, orc, monkeypatch):
     ids, d2 = idx.knnSearch(q, 8)
     wi, wd = orc.knn_linear(nodes, q, 8)
     np.testing.assert_array_equal(ids, wi)
+
+
+def forest_like(n, dim, seed):
+    """clustered node set shaped like a grown forest: random-walk branches of step 4 from a few roots (dense strands with
+    near-duplicates and large empty regions) plus runs of exact duplicates -- the opposite of a uniform cloud for a
+    Morton-block pruned search"""
+    r = np.random.RandomState(seed)
+    pts = np.zeros((n, 6), dtype=np.float64)
+    roots = 6
+    pts[:roots, :3] = r.uniform([-60, -60, 10], [60, 60, 130], (roots, 3))
+    for i in range(roots, n):
+        parent = r.randint(max(0, i - 400), i)
+        step = r.randn(3)
+        pts[i, :3] = np.clip(pts[parent, :3] + 4.0 * step / np.linalg.norm(step), [-70, -70, 0], [70, 70, 140])
+        pts[i, 3:] = r.uniform(-np.pi, np.pi, 3)
+    dup = r.randint(0, n, n // 50)
+    pts[r.randint(0, n, n // 50)] = pts[dup]          # exact duplicates: ties that only the id can break
+    out = pts.astype(np.float32)
+    return out if dim == 6 else np.ascontiguousarray(out[:, :2])
+
+
+@pytest.mark.parametrize("dim", [6, 2])
+def test_forest_like_clustered_nodes(sff, orc, dim):
+    """pruned k-NN / radius on clustered data with duplicate runs ('forest-like' node set): bit-exact ids and
+    distances against the exhaustive oracle, queries on the strands, off the strands and exactly on duplicated nodes"""
+    n = 60000
+    nodes = forest_like(n, dim, 41)
+    r = np.random.RandomState(42)
+    q = np.concatenate([nodes[r.randint(0, n, 200)] + np.float32(0.01), cloud(200, dim, 43)[:, :dim], nodes[r.randint(0, n, 100)]])
+    if dim == 2:
+        q = np.concatenate([q[:300], cloud(100, 2, 44) * np.float32(0.1)])
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    idx = sff.Index(nodes)
+    for k in (1, 16, 33, 128):
+        ids, d2 = idx.knnSearch(q, k)
+        wi, wd = orc.knn_linear(nodes, q, k)
+        assert np.array_equal(ids, wi), k
+        assert np.array_equal(d2.view(np.uint32), wd.view(np.uint32)), k
+    for r2 in (4.0, 169.0):
+        c, off, rid, rd = idx.radiusSearch(q, r2)
+        wc, woff, wid, wd2 = orc.radius_linear(nodes, q, r2)
+        assert np.array_equal(c, wc) and np.array_equal(rid, wid), r2
+        assert np.array_equal(rd.view(np.uint32), wd2.view(np.uint32)), r2
