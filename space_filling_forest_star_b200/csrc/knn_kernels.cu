@@ -189,7 +189,7 @@ template <int DIM, int QW, bool FILL>
 __global__ void __launch_bounds__(kThreads) radius_scan_kernel(IndexDev idx, const float *__restrict__ queries, long long nq,
                                                                float r2, int slices, long long slice_len, int *counts,
                                                                const long long *offsets, int *cursor,
-                                                               unsigned long long *keys, long long first, long long cap) {
+                                                               unsigned long long *keys, long long first) {
   const int lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   const long long group = item / slices;
@@ -226,9 +226,9 @@ __global__ void __launch_bounds__(kThreads) radius_scan_kernel(IndexDev idx, con
           int at = 0;
           if (lane == 0) at = atomicAdd(cursor + qi, __popc(mask));
           at = __shfl_sync(kFull, at, 0);
-          const long long pos = offsets[qi] + at + __popc(mask & lt);
-          if (in && pos < cap)   // cap: size of the key buffer when the offsets were computed on the device (optimistic call)
-            keys[pos] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)i;
+          if (in)
+            keys[offsets[qi] + at + __popc(mask & lt)] =
+                ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)i;
         }
       } else {
         cnt[w] += __popc(mask);
@@ -252,11 +252,11 @@ __device__ __forceinline__ void cmpswap(unsigned long long *a, long long i, long
   if (x > y) { a[i] = y; a[l] = x; }
 }
 __global__ void __launch_bounds__(kThreads) radius_sort_kernel(unsigned long long *keys, const long long *offsets,
-                                                               const int *counts, int *ids, float *d2, long long cap) {
+                                                               const int *counts, int *ids, float *d2) {
   __shared__ unsigned long long sk[kSortSmem];
   const long long row = blockIdx.x;
   const long long len = counts[row];
-  if (len == 0 || offsets[row] + len > cap) return;   // rows past the buffer were never written (the call reports CAPACITY)
+  if (len == 0) return;
   unsigned long long *g = keys + offsets[row];
   unsigned long long *a = g;
   const bool in_smem = len <= kSortSmem;
@@ -382,7 +382,7 @@ cudaError_t launch_knn(const IndexDev &idx, const float *d_queries, int64_t nq, 
 template <bool FILL>
 static cudaError_t launch_radius_any(const IndexDev &idx, const float *q, int64_t nq, float r2, int *counts,
                                      const long long *offsets, int *cursor, unsigned long long *keys, const KnnPlan &plan_in,
-                                     cudaStream_t st, long long first, long long cap) {
+                                     cudaStream_t st, long long first) {
   if (nq <= 0) return cudaSuccess;
   KnnPlan plan = plan_in;
   if (plan.qw == 8) {   // the radius kernels are instantiated for 1 and 4 queries per warp
@@ -392,75 +392,32 @@ static cudaError_t launch_radius_any(const IndexDev &idx, const float *q, int64_
   const int64_t items = plan.groups * plan.slices;
   const unsigned grid = (unsigned)((items + kWarps - 1) / kWarps);
   if (idx.dim == 6) {
-    if (plan.qw == 4) radius_scan_kernel<6, 4, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys, first, cap);
-    else radius_scan_kernel<6, 1, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys, first, cap);
+    if (plan.qw == 4) radius_scan_kernel<6, 4, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys, first);
+    else radius_scan_kernel<6, 1, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys, first);
   } else {
-    if (plan.qw == 4) radius_scan_kernel<2, 4, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys, first, cap);
-    else radius_scan_kernel<2, 1, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys, first, cap);
+    if (plan.qw == 4) radius_scan_kernel<2, 4, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys, first);
+    else radius_scan_kernel<2, 1, FILL><<<grid, kThreads, 0, st>>>(idx, q, nq, r2, plan.slices, plan.slice_len, counts, offsets, cursor, keys, first);
   }
   return cudaGetLastError();
 }
 
 cudaError_t launch_radius_count(const IndexDev &idx, const float *d_queries, int64_t nq, float r2, int32_t *d_counts,
                                 const KnnPlan &plan, cudaStream_t stream, int64_t first) {
-  return launch_radius_any<false>(idx, d_queries, nq, r2, d_counts, nullptr, nullptr, nullptr, plan, stream, first, 0);
+  return launch_radius_any<false>(idx, d_queries, nq, r2, d_counts, nullptr, nullptr, nullptr, plan, stream, first);
 }
 
 cudaError_t launch_radius_fill(const IndexDev &idx, const float *d_queries, int64_t nq, float r2, const int64_t *d_offsets,
                                int32_t *d_cursor, unsigned long long *d_keys, const KnnPlan &plan, cudaStream_t stream,
-                               int64_t first, int64_t cap) {
+                               int64_t first) {
   return launch_radius_any<true>(idx, d_queries, nq, r2, nullptr, reinterpret_cast<const long long *>(d_offsets), d_cursor,
-                                 d_keys, plan, stream, first, cap);
+                                 d_keys, plan, stream, first);
 }
 
 cudaError_t launch_radius_sort(unsigned long long *d_keys, const int64_t *d_offsets, const int32_t *d_counts, int64_t nq,
-                               int32_t *d_ids, float *d_d2, cudaStream_t stream, int64_t cap) {
+                               int32_t *d_ids, float *d_d2, cudaStream_t stream) {
   if (nq <= 0) return cudaSuccess;
   radius_sort_kernel<<<(unsigned)nq, kThreads, 0, stream>>>(d_keys, reinterpret_cast<const long long *>(d_offsets), d_counts,
-                                                            d_ids, d_d2, cap);
-  return cudaGetLastError();
-}
-
-// offsets[0..nq] = exclusive scan of counts (offsets[nq] = total), one block: what lets a radius call size and fill its
-// result in one go without a host round trip
-__global__ void __launch_bounds__(1024) radius_offsets_kernel(const int *__restrict__ counts, long long nq, long long *offsets) {
-  __shared__ long long warp_sum[32];
-  __shared__ long long carry;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (long long base = 0; base < nq; base += 1024) {
-    const long long i = base + threadIdx.x;
-    const long long v = i < nq ? counts[i] : 0;
-    long long x = v;
-#pragma unroll
-    for (int s = 1; s < 32; s <<= 1) {
-      const long long y = __shfl_up_sync(0xffffffffu, x, s);
-      if (lane >= s) x += y;
-    }
-    if (lane == 31) warp_sum[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      long long w = warp_sum[lane];
-#pragma unroll
-      for (int s = 1; s < 32; s <<= 1) {
-        const long long y = __shfl_up_sync(0xffffffffu, w, s);
-        if (lane >= s) w += y;
-      }
-      warp_sum[lane] = w;
-    }
-    __syncthreads();
-    const long long before = carry + (warp ? warp_sum[warp - 1] : 0) + x - v;
-    if (i < nq) offsets[i] = before;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = before + v;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) offsets[nq] = carry;
-}
-
-cudaError_t launch_radius_offsets(const int32_t *d_counts, int64_t nq, int64_t *d_offsets, cudaStream_t stream) {
-  radius_offsets_kernel<<<1, 1024, 0, stream>>>(d_counts, (long long)nq, reinterpret_cast<long long *>(d_offsets));
+                                                            d_ids, d_d2);
   return cudaGetLastError();
 }
 

@@ -41,14 +41,11 @@ cudaError_t launch_radius_count(const IndexDev &idx, const float *d_queries, int
 // d_cursor must be zeroed [nq]; d_offsets = exclusive scan of counts [nq]; d_keys receives (d2 bits << 32 | id)
 cudaError_t launch_radius_fill(const IndexDev &idx, const float *d_queries, int64_t nq, float r2, const int64_t *d_offsets,
                                int32_t *d_cursor, unsigned long long *d_keys, const KnnPlan &plan, cudaStream_t stream,
-                               int64_t first = 0, int64_t cap = INT64_MAX);
+                               int64_t first = 0);
 
 // sorts every row of d_keys ascending and unpacks it into ids / d2
 cudaError_t launch_radius_sort(unsigned long long *d_keys, const int64_t *d_offsets, const int32_t *d_counts, int64_t nq,
-                               int32_t *d_ids, float *d_d2, cudaStream_t stream, int64_t cap = INT64_MAX);
-
-// d_offsets[0..nq] = exclusive scan of d_counts on the device (d_offsets[nq] = total)
-cudaError_t launch_radius_offsets(const int32_t *d_counts, int64_t nq, int64_t *d_offsets, cudaStream_t stream);
+                               int32_t *d_ids, float *d_d2, cudaStream_t stream);
 
 // AoS [n][dim] -> SoA append at position `at`
 cudaError_t launch_index_append(float *d_coords, int64_t capacity, int dim, int64_t at, const float *d_pts, int64_t n,

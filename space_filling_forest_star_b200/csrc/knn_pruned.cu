@@ -304,8 +304,7 @@ __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, cons
 template <int DIM, int QW, bool FILL>
 __global__ void __launch_bounds__(kThreads) radius_pruned_kernel(SortedDev sv, const float *__restrict__ queries, long long nq,
                                                                  float r2, int slices, int sb_per_slice, int *counts,
-                                                                 const long long *offsets, int *cursor, unsigned long long *keys,
-                                                                 long long cap) {
+                                                                 const long long *offsets, int *cursor, unsigned long long *keys) {
   constexpr int LIN = DIM == 6 ? 3 : 2;
   const int lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
@@ -360,8 +359,7 @@ __global__ void __launch_bounds__(kThreads) radius_pruned_kernel(SortedDev sv, c
             int at = 0;
             if (lane == 0) at = atomicAdd(cursor + qi, __popc(mask));
             at = __shfl_sync(kFull, at, 0);
-            const long long pos = offsets[qi] + at + __popc(mask & lt);
-            if (in && pos < cap) keys[pos] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)id;
+            if (in) keys[offsets[qi] + at + __popc(mask & lt)] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)id;
           }
         } else {
           cnt[w] += __popc(mask);
@@ -483,7 +481,7 @@ cudaError_t launch_knn_pruned(const IndexDev &idx, const SortedDev &sv, const fl
 template <bool FILL>
 static cudaError_t launch_radius_pruned_any(const IndexDev &idx, const SortedDev &sv, const float *q, int64_t nq, float r2, int *counts,
                                             const long long *offsets, int *cursor, unsigned long long *keys, int sm_count,
-                                            cudaStream_t st, long long cap) {
+                                            cudaStream_t st) {
   if (nq <= 0) return cudaSuccess;
   // sorted part
   const int qw = nq >= 1024 ? 4 : 1;
@@ -496,11 +494,11 @@ static cudaError_t launch_radius_pruned_any(const IndexDev &idx, const SortedDev
   slices = (nsb + sb_per_slice - 1) / std::max(1, sb_per_slice);
   const unsigned grid = (unsigned)((groups * slices + kWarps - 1) / kWarps);
   if (idx.dim == 6) {
-    if (qw == 4) radius_pruned_kernel<6, 4, FILL><<<grid, kThreads, 0, st>>>(sv, q, nq, r2, slices, sb_per_slice, counts, offsets, cursor, keys, cap);
-    else radius_pruned_kernel<6, 1, FILL><<<grid, kThreads, 0, st>>>(sv, q, nq, r2, slices, sb_per_slice, counts, offsets, cursor, keys, cap);
+    if (qw == 4) radius_pruned_kernel<6, 4, FILL><<<grid, kThreads, 0, st>>>(sv, q, nq, r2, slices, sb_per_slice, counts, offsets, cursor, keys);
+    else radius_pruned_kernel<6, 1, FILL><<<grid, kThreads, 0, st>>>(sv, q, nq, r2, slices, sb_per_slice, counts, offsets, cursor, keys);
   } else {
-    if (qw == 4) radius_pruned_kernel<2, 4, FILL><<<grid, kThreads, 0, st>>>(sv, q, nq, r2, slices, sb_per_slice, counts, offsets, cursor, keys, cap);
-    else radius_pruned_kernel<2, 1, FILL><<<grid, kThreads, 0, st>>>(sv, q, nq, r2, slices, sb_per_slice, counts, offsets, cursor, keys, cap);
+    if (qw == 4) radius_pruned_kernel<2, 4, FILL><<<grid, kThreads, 0, st>>>(sv, q, nq, r2, slices, sb_per_slice, counts, offsets, cursor, keys);
+    else radius_pruned_kernel<2, 1, FILL><<<grid, kThreads, 0, st>>>(sv, q, nq, r2, slices, sb_per_slice, counts, offsets, cursor, keys);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -508,7 +506,7 @@ static cudaError_t launch_radius_pruned_any(const IndexDev &idx, const SortedDev
   const int64_t tail = idx.n - sv.n_sorted;
   if (tail > 0) {
     KnnPlan tp = plan_knn(nq, tail, sm_count);
-    if (FILL) e = launch_radius_fill(idx, q, nq, r2, reinterpret_cast<const int64_t *>(offsets), cursor, keys, tp, st, sv.n_sorted, cap);
+    if (FILL) e = launch_radius_fill(idx, q, nq, r2, reinterpret_cast<const int64_t *>(offsets), cursor, keys, tp, st, sv.n_sorted);
     else e = launch_radius_count(idx, q, nq, r2, counts, tp, st, sv.n_sorted);
   }
   return e;
@@ -516,14 +514,14 @@ static cudaError_t launch_radius_pruned_any(const IndexDev &idx, const SortedDev
 
 cudaError_t launch_radius_count_pruned(const IndexDev &idx, const SortedDev &sv, const float *d_queries, int64_t nq, float r2,
                                        int32_t *d_counts, int sm_count, cudaStream_t st) {
-  return launch_radius_pruned_any<false>(idx, sv, d_queries, nq, r2, d_counts, nullptr, nullptr, nullptr, sm_count, st, 0);
+  return launch_radius_pruned_any<false>(idx, sv, d_queries, nq, r2, d_counts, nullptr, nullptr, nullptr, sm_count, st);
 }
 
 cudaError_t launch_radius_fill_pruned(const IndexDev &idx, const SortedDev &sv, const float *d_queries, int64_t nq, float r2,
                                       const int64_t *d_offsets, int32_t *d_cursor, unsigned long long *d_keys, int sm_count,
-                                      cudaStream_t st, int64_t cap) {
+                                      cudaStream_t st) {
   return launch_radius_pruned_any<true>(idx, sv, d_queries, nq, r2, nullptr, reinterpret_cast<const long long *>(d_offsets), d_cursor,
-                                        d_keys, sm_count, st, cap);
+                                        d_keys, sm_count, st);
 }
 
 }  // namespace sffg

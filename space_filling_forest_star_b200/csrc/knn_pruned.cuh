@@ -52,6 +52,6 @@ cudaError_t launch_radius_count_pruned(const IndexDev &idx, const SortedDev &sv,
                                        int32_t *d_counts, int sm_count, cudaStream_t st);
 cudaError_t launch_radius_fill_pruned(const IndexDev &idx, const SortedDev &sv, const float *d_queries, int64_t nq, float r2,
                                       const int64_t *d_offsets, int32_t *d_cursor, unsigned long long *d_keys, int sm_count,
-                                      cudaStream_t st, int64_t cap = INT64_MAX);
+                                      cudaStream_t st);
 
 }  // namespace sffg

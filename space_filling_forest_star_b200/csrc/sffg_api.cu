@@ -1161,45 +1161,6 @@ int sffg_radius(sffg_index *idx, const float *queries, int64_t nq, float r2, int
   if (rc != SFFG_OK) return rc;
   const bool pruned = idx->n_sorted > 0;
   const SortedDev sv = sorted_view(idx);
-  constexpr int64_t kOptimisticCap = 32768;
-  if (small && ids_out && capacity > 0 && capacity <= kOptimisticCap && (size_t)capacity * 8 <= hr_bytes) {
-    // planner-sized call with a caller-sized result buffer: offsets are scanned on the device and the rows are filled,
-    // sorted and downloaded without the host ever looking at the counts -- one synchronisation.  Writes are bounded by
-    // `capacity`; when the result does not fit the call reports SFFG_ERR_CAPACITY with the needed size, as always.
-    rc = idx->offsets.reserve((size_t)(nq + 1) * 8);
-    if (rc == SFFG_OK) rc = idx->cursor.reserve(cbytes);
-    if (rc == SFFG_OK) rc = idx->keys.reserve((size_t)capacity * 8);
-    if (rc == SFFG_OK) rc = idx->ids.reserve((size_t)capacity * 4);
-    if (rc == SFFG_OK) rc = idx->d2.reserve((size_t)capacity * 4);
-    if (rc != SFFG_OK) return rc;
-    if (pruned) SFFG_CUDA(launch_radius_count_pruned(v, sv, (const float *)idx->q.p, nq, r2, (int32_t *)idx->counts.p, g_rt.sm_count, st));
-    else SFFG_CUDA(launch_radius_count(v, (const float *)idx->q.p, nq, r2, (int32_t *)idx->counts.p, plan, st));
-    SFFG_CUDA(launch_radius_offsets((const int32_t *)idx->counts.p, nq, (int64_t *)idx->offsets.p, st));
-    SFFG_CUDA(cudaMemsetAsync(idx->cursor.p, 0, cbytes, st));
-    if (pruned)
-      SFFG_CUDA(launch_radius_fill_pruned(v, sv, (const float *)idx->q.p, nq, r2, (const int64_t *)idx->offsets.p, (int32_t *)idx->cursor.p,
-                                          (unsigned long long *)idx->keys.p, g_rt.sm_count, st, capacity));
-    else
-      SFFG_CUDA(launch_radius_fill(v, (const float *)idx->q.p, nq, r2, (const int64_t *)idx->offsets.p, (int32_t *)idx->cursor.p,
-                                   (unsigned long long *)idx->keys.p, plan, st, 0, capacity));
-    SFFG_CUDA(launch_radius_sort((unsigned long long *)idx->keys.p, (const int64_t *)idx->offsets.p, (const int32_t *)idx->counts.p,
-                                 nq, (int32_t *)idx->ids.p, (float *)idx->d2.p, st, capacity));
-    SFFG_CUDA(cudaMemcpyAsync(hc, idx->counts.p, cbytes, cudaMemcpyDeviceToHost, st));
-    SFFG_CUDA(cudaMemcpyAsync(hq, (const int64_t *)idx->offsets.p + nq, 8, cudaMemcpyDeviceToHost, st));   // queries are on the device by now
-    SFFG_CUDA(cudaMemcpyAsync(hr, idx->ids.p, (size_t)capacity * 4, cudaMemcpyDeviceToHost, st));
-    SFFG_CUDA(cudaMemcpyAsync(hr + (size_t)capacity * 4, idx->d2.p, (size_t)capacity * 4, cudaMemcpyDeviceToHost, st));
-    SFFG_CUDA(cudaStreamSynchronize(st));
-    std::memcpy(counts_out, hc, cbytes);
-    int64_t total = 0;
-    std::memcpy(&total, hq, 8);
-    if (total_out) *total_out = total;
-    if (total > capacity)
-      return fail(SFFG_ERR_CAPACITY, "sffg_radius: result buffers hold " + std::to_string(capacity) + " entries, " +
-                                         std::to_string(total) + " needed");
-    std::memcpy(ids_out, hr, (size_t)total * 4);
-    std::memcpy(d2_out, hr + (size_t)capacity * 4, (size_t)total * 4);
-    return SFFG_OK;
-  }
   if (pruned) SFFG_CUDA(launch_radius_count_pruned(v, sv, (const float *)idx->q.p, nq, r2, (int32_t *)idx->counts.p, g_rt.sm_count, st));
   else SFFG_CUDA(launch_radius_count(v, (const float *)idx->q.p, nq, r2, (int32_t *)idx->counts.p, plan, st));
   SFFG_CUDA(cudaMemcpyAsync(small ? (void *)hc : (void *)counts_out, idx->counts.p, cbytes, cudaMemcpyDeviceToHost, st));
