@@ -205,3 +205,33 @@ def test_forest_like_clustered_nodes(sff, orc, dim):
         wc, woff, wid, wd2 = orc.radius_linear(nodes, q, r2)
         assert np.array_equal(c, wc) and np.array_equal(rid, wid), r2
         assert np.array_equal(rd.view(np.uint32), wd2.view(np.uint32)), r2
+
+
+def test_radius_single_call_with_a_guessed_capacity(sff, orc):
+    """the planner's way of calling sffg_radius: one call with a guessed capacity.  Too small a guess reports
+    SFFG_ERR_CAPACITY together with the needed size and never writes past the buffer; any sufficient guess returns the
+    exact rows"""
+    import ctypes as C
+
+    from space_filling_forest_star_b200 import _lib
+    L = _lib.load()
+    for dim, n, r2 in ((6, 20000, 50.0), (6, 3000, 120.0), (2, 30000, 300.0)):
+        nodes, q = cloud(n, dim, 51), cloud(300, dim, 52)
+        idx = sff.Index(nodes)
+        wc, woff, wid, wd2 = orc.radius_linear(nodes, q, r2)
+        total = int(wc.sum())
+        assert 300 < total < 30000, total
+        for cap in (total + 1000, total, total - 1, 1):
+            counts = np.zeros(len(q), dtype=np.int32)
+            ids = np.full(cap + 8, -7, dtype=np.int32)
+            d2 = np.full(cap + 8, -7, dtype=np.float32)
+            got_total = C.c_int64(0)
+            rc = L.sffg_radius(idx._h, q.ctypes.data, len(q), r2, counts.ctypes.data, ids.ctypes.data, d2.ctypes.data, cap, C.byref(got_total))
+            assert got_total.value == total and np.array_equal(counts, wc)
+            assert (ids[cap:] == -7).all() and (d2[cap:] == -7).all()
+            if cap >= total:
+                assert rc == 0
+                assert np.array_equal(ids[:total], wid) and np.array_equal(d2[:total].view(np.uint32), wd2.view(np.uint32))
+            else:
+                assert rc == 5   # SFFG_ERR_CAPACITY
+        idx.close()
