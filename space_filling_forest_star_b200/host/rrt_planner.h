@@ -81,8 +81,13 @@ class RrtPlanner {
     }
     const auto t0 = std::chrono::steady_clock::now();
     while (!solved_ && iter_ < cfg_.max_iterations) {
+      const long iter_before = iter_;
       run_round();
       ++rounds_;
+      if (save_.tree_every > 0) {   // Solver::saveIterCheck, src/problemStruct.h:255-261 (see sff_planner.cpp: dump_periodic)
+        const long last = iter_ / save_.tree_every * save_.tree_every;
+        if (last > iter_before && last > 0) save_trees(prefixed(save_.tree, "iter_" + std::to_string(last) + "_"), view());
+      }
     }
     elapsed_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     connected_trees();

@@ -57,6 +57,9 @@ class TargetHeap {
   bool empty() const { return h_.empty(); }
   int size() const { return (int)h_.size(); }
   bool contains(int id) const { return where_.count(id) != 0; }
+  void append_ids(std::vector<int> &out) const {
+    for (const auto &e : h_) out.push_back(e.second);
+  }
   void push(int id, double key) {
     if (contains(id)) return;
     h_.push_back({key, id});
@@ -223,6 +226,7 @@ class Planner {
       const int B = (int)chosen_nodes.size();
       if (B == 0) break;
       std::vector<char> exhausted(B, 0);
+      const long iter_before = iter_;
       run_round(chosen_nodes, exhausted);
       if (!from_closed) {
         // nodes whose every attempt failed leave the frontier for the closed list (forest.h:160-180); in priority mode the
@@ -248,6 +252,7 @@ class Planner {
           frontier_.pop_back();
         }
       }
+      dump_periodic(iter_before);
       if (goal_reached_) {
         solved = true;   // forest.h:287: the solve loop ends as soon as a new node sees the goal
       } else if (!cfg_.has_goal) {
@@ -269,6 +274,32 @@ class Planner {
     }
     book_.verify(env_, cfg_.has_map, calls_);
     save_tsp(save_.tsp, cfg_, book_, connected_);
+    save_frontiers(save_.frontiers, view(), open_nodes(), use_priority_);   // forest.h:233-235
+  }
+
+  // nodes still open: the plain frontier, or (priority mode) the first heap of every tree -- every open node of a tree is
+  // in all of its heaps (forest.h:527-538)
+  std::vector<int> open_nodes() const {
+    if (!use_priority_) return frontier_;
+    std::vector<int> out;
+    for (const auto &hs : heaps_)
+      if (!hs.empty()) hs.front().append_ids(out);
+    return out;
+  }
+
+  // Solver::saveIterCheck / SpaceForest::saveIterCheck (src/problemStruct.h:255-261, src/forest.h:570-578): a round advances
+  // the iteration counter by many steps, so a dump is written at the end of the round that crossed a multiple of N,
+  // labelled with that multiple
+  void dump_periodic(long iter_before) {
+    for (int which = 0; which < 2; ++which) {
+      const long every = which ? save_.frontiers_every : save_.tree_every;
+      if (every <= 0) continue;
+      const long last = iter_ / every * every;
+      if (last <= iter_before || last == 0) continue;
+      const std::string prefix = "iter_" + std::to_string(last) + "_";
+      if (which) save_frontiers(prefixed(save_.frontiers, prefix), view(), open_nodes(), use_priority_);
+      else save_trees(prefixed(save_.tree, prefix), view());
+    }
   }
 
   void set_save(const SaveOptions &so) { save_ = so; }
@@ -837,7 +868,7 @@ int main(int argc, char **argv) {
   const auto t0 = std::chrono::steady_clock::now();
   check(sffg_init(-1));
   const auto t1 = std::chrono::steady_clock::now();
-  const SaveOptions save = load_save_options(argv[1], run_id, cfg.smoothing);
+  const SaveOptions save = load_save_options(argv[1], run_id, cfg.smoothing, cfg.solver == "sff");
   auto run = [&](auto &planner) {
     planner.set_save(save);
     planner.load();

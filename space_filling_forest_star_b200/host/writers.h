@@ -15,8 +15,17 @@ struct OutFile {   // FileStruct, src/primitives.h:663-666
 };
 
 struct SaveOptions {   // <Save> node, src/main.cpp:359-423
-  OutFile goals, tree, raw_path, smooth_path, tsp;
+  OutFile goals, tree, raw_path, smooth_path, tsp, frontiers;
+  long tree_every = 0, frontiers_every = 0;   // everyIteration attributes (src/main.cpp:372-376, :419-423)
 };
+
+// prefixFileName, src/primitives.h:698-709: the prefix goes behind the last '/' of the path
+inline OutFile prefixed(const OutFile &f, const std::string &prefix) {
+  OutFile r = f;
+  const size_t pos = r.name.find_last_of('/');
+  r.name.insert(pos == std::string::npos ? 0 : pos + 1, prefix);
+  return r;
+}
 
 // getFile, src/main.cpp:439-465: "_<run>" goes in front of the extension when the run id is not 0
 inline OutFile out_file(const Tag &t, const std::string &run_id) {
@@ -39,7 +48,7 @@ inline OutFile out_file(const Tag &t, const std::string &run_id) {
   return f;
 }
 
-inline SaveOptions load_save_options(const std::string &xml_path, const std::string &run_id, bool smoothing) {
+inline SaveOptions load_save_options(const std::string &xml_path, const std::string &run_id, bool smoothing, bool is_sff) {
   std::ifstream f(xml_path);
   std::stringstream ss;
   ss << f.rdbuf();
@@ -49,7 +58,16 @@ inline SaveOptions load_save_options(const std::string &xml_path, const std::str
     if (t.name == "Save") in_save = true;
     if (!in_save) continue;
     if (t.name == "Goals") so.goals = out_file(t, run_id);
-    else if (t.name == "Tree") so.tree = out_file(t, run_id);
+    else if (t.name == "Tree") {
+      so.tree = out_file(t, run_id);
+      auto e = t.attr.find("everyIteration");
+      if (so.tree.set() && e != t.attr.end()) so.tree_every = std::stol(e->second);
+    } else if (t.name == "Frontiers") {
+      so.frontiers = out_file(t, run_id);
+      if (so.frontiers.set() && !is_sff) die("frontiers output is defined only for SFF-based solvers!");
+      auto e = t.attr.find("everyIteration");
+      if (so.frontiers.set() && e != t.attr.end()) so.frontiers_every = std::stol(e->second);
+    }
     else if (t.name == "RawPath") so.raw_path = out_file(t, run_id);
     else if (t.name == "SmoothPath") so.smooth_path = out_file(t, run_id);
     else if (t.name == "TSP") so.tsp = out_file(t, run_id);
@@ -119,6 +137,24 @@ inline void save_trees(const OutFile &f, const NodeView &v) {
           put_point(out, v.pos(v.parent(i)), v.scale);
           out << " " << t << " " << v.age(i) << "\n";
         }
+  }
+}
+
+// SpaceForest::saveFrontiers, src/forest.h:513-566: the open nodes (the priority variant prints positions only in OBJ files)
+inline void save_frontiers(const OutFile &f, const NodeView &v, const std::vector<int> &open_nodes, bool priority) {
+  std::ofstream out;
+  if (!f.set() || !open_out(out, f)) return;
+  if (f.is_obj) out << "o Open nodes\n";
+  for (int id : open_nodes) {
+    if (f.is_obj) {
+      out << "v ";
+      if (priority) put_pos(out, v.pos(id), v.scale);
+      else put_point(out, v.pos(id), v.scale);
+      out << "\n";
+    } else {
+      put_point(out, v.pos(id), v.scale);
+      out << " 1\n";   // "the one in the end is just for plotting purposes"
+    }
   }
 }
 

@@ -134,8 +134,9 @@ def test_reference_validation_rules(exe, tmp_path):
     assert p.returncode == 1 and "Multi-T-RRT with bias is undefined!" in p.stdout
 
 
-SAVE = ('<Save>\n    <Goals file="output/goals.tri" is_obj="false"/>\n    <Tree file="output/tree.obj" is_obj="true"/>\n'
-        '    <RawPath file="output/raw.tri" is_obj="false"/>\n    <TSP file="output/tsp.tsp"/>')
+SAVE = ('<Save>\n    <Goals file="output/goals.tri" is_obj="false"/>\n    <Tree file="output/tree.obj" is_obj="true" everyIteration="200"/>\n'
+        '    <RawPath file="output/raw.tri" is_obj="false"/>\n    <TSP file="output/tsp.tsp"/>\n'
+        '    <Frontiers file="output/front.tri" is_obj="false" everyIteration="400"/>')
 
 
 def _shape(path):
@@ -168,9 +169,16 @@ def test_output_files_follow_the_reference_formats(exe, tmp_path):
     assert tree[0] == "o Trees" and n_l == n_v - 4   # every node but the 4 roots hangs on a parent
     raw = [l.split() for l in (out / "raw_3.tri").read_text().split("\n\n")[0].splitlines()]
     assert all(len(r) == 12 for r in raw) and all(raw[i][6:] == raw[i + 1][:6] for i in range(len(raw) - 1))
+    # open nodes at the end (a solved SFF run has none left: the file exists and is empty) and periodic dumps
+    # (Solver::saveIterCheck / SpaceForest::saveIterCheck: "iter_<N>_" behind the last '/')
+    assert (out / "front_3.tri").read_text() == ""
+    assert (out / "iter_200_tree_3.obj").read_text().startswith("o Trees\n") and (out / "iter_400_front_3.tri").exists()
+    front = (out / "iter_400_front_3.tri").read_text().splitlines()
+    assert front and all(len(l.split()) == 7 and l.split()[-1] == "1" for l in front)
     ref = PU.ROOT / "oracle" / "_ref" / "ref_main_cpu"
     if ref.exists():
         q = subprocess.run([str(ref), cfg.name, "4"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
         assert q.returncode == 0, q.stdout
-        for name in ("tsp_%d.tsp", "goals_%d.tri", "tree_%d.obj", "raw_%d.tri"):
+        for name in ("tsp_%d.tsp", "goals_%d.tri", "tree_%d.obj", "raw_%d.tri", "iter_200_tree_%d.obj", "iter_400_front_%d.tri"):
+            assert (out / (name % 4)).exists(), name
             assert _shape(out / (name % 3)) == _shape(out / (name % 4)), name
