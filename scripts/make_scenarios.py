@@ -99,6 +99,10 @@ def main():
         tag = f"{name}_sffstar_bias"
         (out / f"{tag}.xml").write_text(CONFIG.format(solver="sff", optimize="true", name=tag, points=fmt(sc["points"]), goal="",
                                                       bias="0.95", **rest))
+        # Lazy-TSP (the solver the shipped configs name, src/lazy.h): TSP over the roots + RRT* per tour edge
+        tag = f"{name}_lazy"
+        (out / f"{tag}.xml").write_text(CONFIG.format(solver="lazy", optimize="true", name=tag, points=fmt(sc["points"]), goal="",
+                                                      bias="0", **rest))
         # Multi-T-RRT: every root grows its own RRT, trees merge when they meet (src/rrt.h:219-317); the reference rejects
         # the optimal variant with several roots (src/main.cpp:286-287)
         tag = f"{name}_mtrrt"

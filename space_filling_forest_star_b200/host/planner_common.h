@@ -201,10 +201,15 @@ inline Config load_config(const std::string &path) {
   if (!seen_dist) die("invalid Distances node!");
   if (!seen_iter) die("invalid MaxIterations node!");
   if (c.roots.empty()) die("invalid Points node - insert at least one point!");
-  if (c.solver != "sff" && c.solver != "rrt") die("the batched hosts cover solver=\"sff\" (SFF / SFF*) and solver=\"rrt\" (RRT / RRT* / Multi-T-RRT)");
+  if (c.solver != "sff" && c.solver != "rrt" && c.solver != "lazy")
+    die("unknown solver: the batched hosts cover \"sff\" (SFF / SFF*), \"rrt\" (RRT / RRT* / Multi-T-RRT) and \"lazy\" (Lazy-TSP)");
   if (c.solver == "rrt") {   // the reference's own validation, src/main.cpp:286-288, :327-329
     if (c.optimize && c.roots.size() > 1) die("Multi-T-RRT* is undefined!");
     if (!c.has_goal && c.priority_bias != 0) die("Multi-T-RRT with bias is undefined!");
+  }
+  if (c.solver == "lazy") {   // src/main.cpp:292-293, :330-331
+    if (c.has_goal) die("single point path planning not defined for Lazy solver (use RRT/RRT* solver instead)!");
+    if (c.priority_bias != 0) die("priority bias for Lazy solver is not implemented!");
   }
   c.has_map = !c.obstacles.empty();
   return c;
@@ -229,6 +234,36 @@ inline double dist6(const double *a, const double *b) {   // Point<T>::distance,
     sum += d * d;
   }
   return std::sqrt(sum);
+}
+
+// robot + obstacle meshes -> one engine environment (parseFile, src/main.cpp:161, :254); resolves Range autoDetect from the
+// obstacles' bounding boxes (Environment::processLimits, src/environment.h:46-53)
+inline sffg_env *load_environment(Config &cfg) {
+  double *tris = nullptr;
+  int64_t n = 0;
+  double bbox[6];
+  const double zero[3] = {0, 0, 0};
+  check(sffg_mesh_load(cfg.robot.file.c_str(), cfg.robot.is_obj, zero, cfg.scale, &tris, &n, bbox));
+  std::vector<double> robot(tris, tris + 9 * n);
+  sffg_free(tris);
+  std::vector<double> obst;
+  double lim[6] = {1e308, -1e308, 1e308, -1e308, 1e308, -1e308};
+  for (const MeshRef &m : cfg.obstacles) {
+    check(sffg_mesh_load(m.file.c_str(), m.is_obj, m.pos, cfg.scale, &tris, &n, bbox));
+    obst.insert(obst.end(), tris, tris + 9 * n);
+    sffg_free(tris);
+    for (int k = 0; k < 3; ++k) {
+      lim[2 * k] = std::min(lim[2 * k], bbox[2 * k]);
+      lim[2 * k + 1] = std::max(lim[2 * k + 1], bbox[2 * k + 1]);
+    }
+  }
+  if (cfg.auto_range) {
+    for (int k = 0; k < 6; ++k) cfg.range[k] = lim[k];
+    cfg.auto_range = false;
+  }
+  sffg_env *env = nullptr;
+  check(sffg_env_create(obst.empty() ? nullptr : obst.data(), (int64_t)(obst.size() / 9), robot.data(), (int64_t)(robot.size() / 9), &env));
+  return env;
 }
 
 struct EdgeBatch {

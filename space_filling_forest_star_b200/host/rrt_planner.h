@@ -32,28 +32,14 @@ class RrtPlanner {
     book_.origin = [this](int id) { return origin_of(id); };
   }
 
+  // an environment owned by the caller (the Lazy-TSP host runs many searches in one map)
+  void use_env(sffg_env *env) {
+    env_ = env;
+    own_env_ = false;
+  }
+
   void load() {
-    double *tris = nullptr;
-    int64_t n = 0;
-    double bbox[6];
-    const double zero[3] = {0, 0, 0};
-    check(sffg_mesh_load(cfg_.robot.file.c_str(), cfg_.robot.is_obj, zero, cfg_.scale, &tris, &n, bbox));
-    std::vector<double> robot(tris, tris + 9 * n);
-    sffg_free(tris);
-    std::vector<double> obst;
-    double lim[6] = {1e308, -1e308, 1e308, -1e308, 1e308, -1e308};
-    for (const MeshRef &m : cfg_.obstacles) {
-      check(sffg_mesh_load(m.file.c_str(), m.is_obj, m.pos, cfg_.scale, &tris, &n, bbox));
-      obst.insert(obst.end(), tris, tris + 9 * n);
-      sffg_free(tris);
-      for (int k = 0; k < 3; ++k) {   // Environment::processLimits, src/environment.h:46-53
-        lim[2 * k] = std::min(lim[2 * k], bbox[2 * k]);
-        lim[2 * k + 1] = std::max(lim[2 * k + 1], bbox[2 * k + 1]);
-      }
-    }
-    if (cfg_.auto_range)
-      for (int k = 0; k < 6; ++k) cfg_.range[k] = lim[k];
-    check(sffg_env_create(obst.empty() ? nullptr : obst.data(), (int64_t)(obst.size() / 9), robot.data(), (int64_t)(robot.size() / 9), &env_));
+    if (!env_) env_ = load_environment(cfg_);
     // one tree + one index per root (rrt.h:47-61); the goal is a tree of its own that is never expanded (:64-81)
     const int R = (int)cfg_.roots.size();
     for (int t = 0; t < R + (cfg_.has_goal ? 1 : 0); ++t) {
@@ -133,8 +119,14 @@ class RrtPlanner {
   ~RrtPlanner() {
     for (Tree &t : trees_)
       if (t.idx) sffg_index_destroy(t.idx);
-    if (env_) sffg_env_destroy(env_);
+    if (env_ && own_env_) sffg_env_destroy(env_);
   }
+
+  bool solved() const { return solved_; }
+  long iterations() const { return iter_; }
+  long calls() const { return calls_; }
+  const PlanBook &book() const { return book_; }
+  const double *node_pos(int id) const { return nodes_[id].p; }
 
  private:
   struct RNode {
@@ -568,6 +560,7 @@ class RrtPlanner {
   int batch_;
   bool quiet_;
   sffg_env *env_ = nullptr;
+  bool own_env_ = true;
   std::vector<RNode> nodes_;
   std::vector<int> root_tree_;          // for root nodes: their tree id, -1 otherwise
   std::vector<Tree> trees_;

@@ -18,7 +18,7 @@
 // do not see each other (a candidate that would interact with a node created in the same round is deferred to the
 // next round); stored angles are normalised into [-pi, pi); the RNG is seedable.  This file covers solver="sff" (SFF / SFF*,
 // plain or priority frontiers -- priorityBias, forest.h:79-89, :125-149 --, multi-goal or with a <Goal>, :91-109, :286-287);
-// solver="rrt" (RRT / RRT* / Multi-T-RRT, with or without a goal) is in rrt_planner.h.
+// solver="rrt" (RRT / RRT* / Multi-T-RRT, with or without a goal) is in rrt_planner.h, solver="lazy" (Lazy-TSP) in lazy_planner.h.
 //
 //   sff_planner <config.xml> [run-id] [--seed S] [--batch B] [--paths file] [--quiet]
 //
@@ -30,6 +30,7 @@
 #include "planner_common.h"
 #include "writers.h"
 #include "rrt_planner.h"
+#include "lazy_planner.h"
 
 using namespace planner;
 
@@ -139,27 +140,7 @@ class Planner {
   }
 
   void load() {
-    double *tris = nullptr;
-    int64_t n = 0;
-    double bbox[6];
-    const double zero[3] = {0, 0, 0};
-    check(sffg_mesh_load(cfg_.robot.file.c_str(), cfg_.robot.is_obj, zero, cfg_.scale, &tris, &n, bbox));
-    std::vector<double> robot(tris, tris + 9 * n);
-    sffg_free(tris);
-    std::vector<double> obst;
-    double lim[6] = {1e308, -1e308, 1e308, -1e308, 1e308, -1e308};
-    for (const MeshRef &m : cfg_.obstacles) {
-      check(sffg_mesh_load(m.file.c_str(), m.is_obj, m.pos, cfg_.scale, &tris, &n, bbox));
-      obst.insert(obst.end(), tris, tris + 9 * n);
-      sffg_free(tris);
-      for (int k = 0; k < 3; ++k) {   // Environment::processLimits, src/environment.h:46-53
-        lim[2 * k] = std::min(lim[2 * k], bbox[2 * k]);
-        lim[2 * k + 1] = std::max(lim[2 * k + 1], bbox[2 * k + 1]);
-      }
-    }
-    if (cfg_.auto_range)
-      for (int k = 0; k < 6; ++k) cfg_.range[k] = lim[k];
-    check(sffg_env_create(obst.empty() ? nullptr : obst.data(), (int64_t)(obst.size() / 9), robot.data(), (int64_t)(robot.size() / 9), &env_));
+    env_ = load_environment(cfg_);
     const int T = n_trees_, R = (int)cfg_.roots.size();
     members_.resize(T);
     tree_idx_.resize(T, nullptr);
@@ -883,6 +864,9 @@ int main(int argc, char **argv) {
   };
   if (cfg.solver == "rrt") {
     RrtPlanner planner(cfg, seed, batch, quiet);
+    run(planner);
+  } else if (cfg.solver == "lazy") {
+    LazyPlanner planner(cfg, seed, batch, quiet);
     run(planner);
   } else {
     Planner planner(cfg, seed, batch, quiet);

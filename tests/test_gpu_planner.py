@@ -88,11 +88,22 @@ def test_multi_t_rrt_3d(exe, tmp_path, orc, meshes):
     PU.validate_plans(orc, meshes["triang_s10"], meshes["robot_small_s10"], plans, roots_of("triang"))
 
 
+def test_lazy_tsp_3d(exe, tmp_path, orc, meshes):
+    """Lazy-TSP over six roots in triang.obj: TSP in-process, one batched RRT* search per tour edge (src/lazy.h)"""
+    row, plans, out = PU.run_planner(exe, tmp_path, "triang_lazy", seed=2)
+    assert ",solved," in row, row + out
+    tour = [int(x) for x in row.split("[")[1].split("]")[0].split(";")]
+    assert sorted(tour) == list(range(6))
+    PU.validate_plans(orc, meshes["triang_s10"], meshes["robot_small_s10"], plans, roots_of("triang"))
+    edges = {tuple(sorted((tour[e], tour[(e + 1) % 6]))) for e in range(6)}
+    assert edges <= {(a, b) for a, b, _, _ in plans}
+
+
 def test_engine_and_double_agree_on_a_fixed_seed(exe, tmp_path):
     """same host, same seed: the engine (GPU) and the CPU double behind the same ABI must produce the same params row
     (iterations, solved flag, connected trees, path lengths) -- an end-to-end parity check of verdicts and neighbours"""
     dbl = PU.build_double_host()
-    for scenario in ("2d_mtrrt", "2d_rrtstar_goal", "2d_sffstar", "2d_sffstar_bias", "2d_sffstar_goal"):
+    for scenario in ("2d_mtrrt", "2d_rrtstar_goal", "2d_sffstar", "2d_sffstar_bias", "2d_sffstar_goal", "2d_lazy"):
         row_g, _, _ = PU.run_planner(exe, tmp_path, scenario, seed=9, run_id="g")
         row_c, _, _ = PU.run_planner(dbl, tmp_path, scenario, seed=9, run_id="c")
         assert row_g.split(",")[2:6] == row_c.split(",")[2:6], (scenario, row_g, row_c)

@@ -182,3 +182,49 @@ def test_output_files_follow_the_reference_formats(exe, tmp_path):
         for name in ("tsp_%d.tsp", "goals_%d.tri", "tree_%d.obj", "raw_%d.tri", "iter_200_tree_%d.obj", "iter_400_front_%d.tri"):
             assert (out / (name % 4)).exists(), name
             assert _shape(out / (name % 3)) == _shape(out / (name % 4)), name
+
+
+def test_lazy_tsp_2d(exe, tmp_path, orc, meshes):
+    """Lazy-TSP (src/lazy.h:71-147) with the in-process TSP in place of the non-public obst_tsp: the tour visits every
+    root once, every tour edge has a valid plan, and the reported tour is optimal for the final distance matrix"""
+    import itertools
+    import subprocess
+    PU.run_planner(exe, tmp_path, "2d_lazy", seed=1)
+    cfg = tmp_path / "2d_lazy_w.xml"
+    cfg.write_text((tmp_path / "2d_lazy.xml").read_text().replace("<Save>", '<Save>\n    <TSP file="output/lazy.tsp"/>\n    <RawPath file="output/lazy_raw.tri" is_obj="false"/>'))
+    paths = tmp_path / "lazy_paths.txt"
+    p = subprocess.run([str(exe), cfg.name, "0", "--seed", "1", "--paths", str(paths)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    row = (tmp_path / "output" / "params_2d_lazy.csv").read_text().strip().splitlines()[-1]
+    assert ",solved," in row, row
+    tour = [int(x) for x in row.split("[")[1].split("]")[0].split(";")]
+    lens = [float(x) for x in row.split("[")[2].split("]")[0].split(";")]
+    assert sorted(tour) == [0, 1, 2, 3] and tour[0] == 0 and len(lens) == 4
+    plans = PU.read_plans(paths)
+    PU.validate_plans(orc, meshes["triangles_tri"], meshes["robot_small_s1"], plans, roots_of("2d"))
+    have = {(a, b): d for a, b, d, _ in plans}
+    for e in range(4):
+        a, b = sorted((tour[e], tour[(e + 1) % 4]))
+        assert have[(a, b)] == pytest.approx(lens[e], rel=1e-5)
+    # optimality against the matrix the run ended with (TSPLIB lower-diagonal rows)
+    rows = (tmp_path / "output" / "lazy.tsp").read_text().splitlines()
+    mat = [[float(x) for x in r.split()] for r in rows[rows.index("EDGE_WEIGHT_SECTION") + 1:]]
+    dist = lambda i, j: mat[max(i, j)][min(i, j)]
+    best = min(sum(dist(t[k], t[(k + 1) % 4]) for k in range(4)) for t in ([0] + list(p_) for p_ in itertools.permutations([1, 2, 3])))
+    assert sum(lens) == pytest.approx(best, rel=1e-5)
+    raw = (tmp_path / "output" / "lazy_raw.tri").read_text().strip().split("\n\n")
+    assert len(raw) == 4 and all(len(l.split()) == 12 for blk in raw for l in blk.splitlines())
+
+
+def test_lazy_validation_rules(exe, tmp_path):
+    """src/main.cpp:292-293, :330-331: no single goal and no priority bias for the Lazy solver"""
+    import subprocess
+    PU.run_planner(exe, tmp_path, "2d_mtrrt", seed=1)
+    base = (tmp_path / "2d_lazy.xml").read_text()
+    bad = tmp_path / "bad_lazy.xml"
+    bad.write_text(base.replace('priorityBias="0"', 'priorityBias="0.95"'))
+    p = subprocess.run([str(exe), bad.name], cwd=tmp_path, capture_output=True, text=True)
+    assert p.returncode == 1 and "priority bias for Lazy solver is not implemented!" in p.stdout
+    bad.write_text(base.replace("</Points>", '</Points>\n  <Goal coord="[5; 5; 0]"/>'))
+    p = subprocess.run([str(exe), bad.name], cwd=tmp_path, capture_output=True, text=True)
+    assert p.returncode == 1 and "single point path planning not defined for Lazy solver" in p.stdout
