@@ -170,6 +170,6 @@ def test_host_planner_builds_and_refuses_without_gpu(tmp_path):
     else:
         assert p.returncode == 3 and "no CUDA device" in p.stdout
     bad = tmp_path / "bad.xml"
-    bad.write_text((tmp_path / "2d_sffstar.xml").read_text().replace('solver="sff"', 'solver="lazy"'))
+    bad.write_text((tmp_path / "2d_sffstar.xml").read_text().replace('solver="sff"', 'solver="prm"'))
     p = subprocess.run([str(exe), "bad.xml"], cwd=tmp_path, capture_output=True, text=True)
     assert p.returncode == 1 and "Problem loading error" in p.stdout
