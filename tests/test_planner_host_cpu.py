@@ -228,3 +228,43 @@ def test_lazy_validation_rules(exe, tmp_path):
     bad.write_text(base.replace("</Points>", '</Points>\n  <Goal coord="[5; 5; 0]"/>'))
     p = subprocess.run([str(exe), bad.name], cwd=tmp_path, capture_output=True, text=True)
     assert p.returncode == 1 and "single point path planning not defined for Lazy solver" in p.stdout
+
+
+def test_lazy_tsp_many_roots_without_a_map(exe, tmp_path):
+    """15 roots on a circle, no obstacles (HasMap == false, src/environment.h:307-309): above 13 roots the tour comes from
+    nearest neighbour + 2-opt; on a circle the optimal tour is the polygon, which 2-opt must find"""
+    import math
+    import subprocess
+    PU.run_planner(exe, tmp_path, "2d_lazy", seed=1)   # writes the mesh files
+    n = 15
+    pts = [(50 + 40 * math.cos(2 * math.pi * k / n), 50 + 40 * math.sin(2 * math.pi * k / n)) for k in range(n)]
+    order = [0, 7, 3, 11, 1, 9, 5, 13, 2, 10, 6, 14, 4, 12, 8]     # scrambled input order
+    points = "\n".join('    <Point coord="[%.17g; %.17g; 0]"/>' % pts[k] for k in order)
+    cfg = tmp_path / "circle.xml"
+    cfg.write_text(f"""<?xml version="1.0" ?>
+<Problem solver="lazy" optimize="false" smoothing="false" scale="1" dim="2D">
+  <Robot file="robot_small_s1.obj" is_obj="true"/>
+  <Points>
+{points}
+  </Points>
+  <Range autoDetect="false">
+    <RangeX min="0" max="100" />
+    <RangeY min="0" max="100" />
+    <RangeZ min="0" max="0" />
+  </Range>
+  <Distances dtree="6" circum="4"/>
+  <MaxIterations value="20000"/>
+  <Save>
+    <Params file="output//params_circle.csv" id="circle"/>
+  </Save>
+</Problem>
+""")
+    p = subprocess.run([str(exe), cfg.name, "0", "--seed", "3", "--quiet"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    row = (tmp_path / "output" / "params_circle.csv").read_text().strip().splitlines()[-1]
+    assert ",solved," in row, row
+    tour = [int(x) for x in row.split("[")[1].split("]")[0].split(";")]
+    assert sorted(tour) == list(range(n))
+    ring = [order[t] for t in tour]                                  # positions on the circle in tour order
+    steps = {(ring[(k + 1) % n] - ring[k]) % n for k in range(n)}
+    assert steps in ({1}, {n - 1}), ring                             # neighbours on the circle follow each other
