@@ -351,16 +351,32 @@ class RrtPlanner {
     // ---- 5. nearest node of every other tree (rrt.h:219-229)
     if (frontier_.size() > 1 && !alive.empty()) {
       for (auto &w : who) w.clear();
-      for (int t : frontier_)
+      bool any = false;
+      for (int t : frontier_) {
+        if (trees_[t].members.size() == 1) continue;   // a tree of one node (the goal, a fresh root) needs no search
         for (int ci : alive)
-          if (cand[ci].s.tree != t) who[t].push_back(ci);
-      knn_by_tree(who, qpos, 1, ids, d2, row_of);
+          if (cand[ci].s.tree != t) {
+            who[t].push_back(ci);
+            any = true;
+          }
+      }
+      if (any) knn_by_tree(who, qpos, 1, ids, d2, row_of);
       size_t r = 0;
-      for (int t = 0; t < T; ++t)
+      for (int t = 0; t < T; ++t) {
+        if (trees_[t].eaten_by >= 0 || std::find(frontier_.begin(), frontier_.end(), t) == frontier_.end()) continue;
+        if (trees_[t].members.size() == 1) {
+          for (int ci : alive)
+            if (cand[ci].s.tree != t) {
+              cand[ci].link_tree.push_back(t);
+              cand[ci].link_nb.push_back(trees_[t].members[0]);
+            }
+          continue;
+        }
         for (int qi : who[t]) {
           cand[qi].link_tree.push_back(t);
           cand[qi].link_nb.push_back(trees_[t].members[ids[r++]]);
         }
+      }
     }
     clk_.lap(3);
     // ---- 6. every edge the replay may ask for
