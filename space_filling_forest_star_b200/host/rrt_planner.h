@@ -422,11 +422,16 @@ class RrtPlanner {
       // sequential semantics: the nearest node includes the nodes created earlier in this round
       bool carried = false;
       const double dn = dist6(nodes_[c.nearest].p, c.s.rnd);
-      for (int id : added)
-        if (nodes_[id].tree == tree && dist6(nodes_[id].p, c.s.rnd) < dn) {
+      for (int id : added) {
+        if (nodes_[id].tree != tree) continue;
+        // the translational part bounds the 6-D distance from below: most nodes are settled without wraps and sqrt
+        const double dx = nodes_[id].p[0] - c.s.rnd[0], dy = nodes_[id].p[1] - c.s.rnd[1], dz = nodes_[id].p[2] - c.s.rnd[2];
+        if (dx * dx + dy * dy + dz * dz >= dn * dn) continue;
+        if (dist6(nodes_[id].p, c.s.rnd) < dn) {
           carried = true;
           break;
         }
+      }
       if (carried) {
         carry_.push_back(c.s);
         ++carried_;
