@@ -173,3 +173,13 @@ def test_host_planner_builds_and_refuses_without_gpu(tmp_path):
     bad.write_text((tmp_path / "2d_sffstar.xml").read_text().replace('solver="sff"', 'solver="prm"'))
     p = subprocess.run([str(exe), "bad.xml"], cwd=tmp_path, capture_output=True, text=True)
     assert p.returncode == 1 and "Problem loading error" in p.stdout
+
+
+def test_header_is_plain_c99(tmp_path):
+    """the drop-in boundary is a C ABI: include/sffg.h must compile as strict C99 (no C++-isms, no torch types)"""
+    src = tmp_path / "c99.c"
+    src.write_text('#include "sffg.h"\nint main(void) { sffg_env *e = 0; sffg_index *i = 0; (void)e; (void)i; return SFFG_OK; }\n')
+    cc = "/usr/bin/gcc" if Path("/usr/bin/gcc").exists() else "gcc"
+    p = subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-c", str(src), "-o", str(tmp_path / "c99.o")],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
