@@ -131,6 +131,15 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """all host cores this process may run on -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to every
+    rank, which would silently turn the CPU arm into a single-threaded run"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args):
     """CPU arm: the oracle port of the reference path on all host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -140,7 +149,7 @@ def run_reference(args):
     O.build(ref=False)
     obst, robot = load_meshes()
     mo, mr = O.ObbModel(obst), O.ObbModel(robot)
-    threads = O.num_threads()
+    threads = host_threads()
     sample = args.cpu_sample
     poses = O.gen_poses(SEED, 0, sample, RANGE).astype(np.float64)
     for _ in range(args.warmup):
@@ -174,7 +183,7 @@ def cpu_baseline(sample: int):
     O.build(ref=False)
     obst, robot = load_meshes()
     mo, mr = O.ObbModel(obst), O.ObbModel(robot)
-    threads = O.num_threads()
+    threads = host_threads()
     poses = O.gen_poses(SEED, 0, sample, RANGE).astype(np.float64)
     O.collide_obbtree(mo, mr, poses[: sample // 8], first_contact=False, threads=threads, want_verdicts=False)
     t0 = time.perf_counter()
