@@ -33,8 +33,10 @@ _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 
 
-def build(ref: bool = True) -> None:
-    """Compile the C restatement and, when /root/reference is present, the real FLANN (oracle/_ref)."""
+def build(ref: bool = True, refhost: bool = False) -> None:
+    """Compile the C restatement and, when /root/reference is present, the real FLANN (oracle/_ref); ``refhost`` also
+    compiles the UNMODIFIED reference host against the CPU RAPID stand-in (oracle/_ref/ref_main_cpu, the CPU arm of the
+    end-to-end comparisons) and against the engine's header shims (ref_main_gpu)."""
     stale = (not _LIB_PATH.exists()) or _LIB_PATH.stat().st_mtime < (HERE / "sff_oracle.c").stat().st_mtime
     if stale:
         subprocess.run(["make", "-C", str(HERE)], check=True, capture_output=True)
@@ -42,6 +44,10 @@ def build(ref: bool = True) -> None:
         stale = (not _REF_PATH.exists()) or _REF_PATH.stat().st_mtime < (HERE / "ref_flann.cpp").stat().st_mtime
         if stale:
             subprocess.run(["make", "-C", str(HERE), "ref"], check=True, capture_output=True)
+        if refhost:
+            r = subprocess.run(["make", "-C", str(HERE), "refhost"], capture_output=True, text=True)
+            if r.returncode != 0:   # the comparison binaries are optional: report, do not fail the build of the checker
+                print("oracle: reference host not built:", (r.stderr or r.stdout)[-400:])
 
 
 _lib = None
