@@ -485,7 +485,10 @@ int sffg_env_set_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obs
     return fail(SFFG_ERR_ARG, "sffg_env_set_obstacles: bad arguments");
   SFFG_CUDA(cudaDeviceSynchronize());   // nothing may still be traversing the old hierarchy
   const auto t0 = std::chrono::steady_clock::now();
+  env->dev.n_obst = 0;
+  *env->h_status = 4;                   // until the new set is complete every verdict call reports an error, never "free"
   int rc = set_obstacles(env, obst_tris, n_obst, build_mode);
+  if (rc == SFFG_OK) *env->h_status = 0;
   env->info.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return rc;
 }
@@ -535,6 +538,8 @@ static EnvDev env_view(sffg_env *env, unsigned **base_io) {
 static int check_status(sffg_env *env) {
   const int st = *reinterpret_cast<volatile int *>(env->h_status);
   if (st != 0) {
+    if (st == 4)   // sticky: stays until sffg_env_set_obstacles succeeds
+      return fail(SFFG_ERR_INTERNAL, "the environment has no valid obstacle set: the last sffg_env_set_obstacles failed");
     *env->h_status = 0;
     if (st == 3) return fail(SFFG_ERR_INTERNAL, "peer barrier timed out: a rank of the gather group never signalled");
     return fail(SFFG_ERR_INTERNAL, "BVH traversal stack overflow: results of this call are invalid");
