@@ -10,13 +10,19 @@ loader reads them), Philox pose stream with the distribution of RandGen::randomP
 One step = one pass of the pose->verdict path over one batch of POSES_PER_GPU poses per GPU (weak scaling).
 
   value      poses/s, whole job, poses already resident in HBM (402 MB per batch > 126 MB L2, so every step streams
-             from HBM); N > 1: every rank checks its own shard and the verdict bytes are all-gathered over NCCL
+             from HBM); N > 1: every rank checks its own shard and every rank receives every verdict -- the all-gather and
+             its completion handshake are fused into the kernel (stores to every rank's buffer over NVLink peer memory,
+             sharding.PeerGather); --gather nccl runs kernel + NCCL all-gather instead
   e2e        same metric through the reference-facing host call (sffg_collide_poses_f32 on pinned host buffers):
              H2D of the poses and D2H of the verdicts inside the timed region
-  roofline   dominant kernel = collide_poses_kernel; algorithmic HBM bytes = 25 B/pose (24 B pose in + 1 B verdict out)
+  roofline   dominant kernel = collide_poses_kernel; algorithmic HBM bytes = 25 B/pose (24 B pose in + 1 B verdict out);
+             roofline.issue = the instruction-issue roofline that actually bounds the kernel
   cpu_baseline / --impl reference
              the CPU restatement of the reference path (RAPID-style OBB-tree, ALL_CONTACTS as src/environment.h:274
              calls it) on all host cores; RAPID itself is absent from the reference, so kind = "port"
+  extra      secondary numbers of the same path (not the headline): edges/s, exact k-NN queries/s (sharded at N > 1) and
+             the SFF* solve times of BASELINE.json's third metric -- the batched host on the engine in this arm, the
+             unmodified reference host (oracle/_ref/ref_main_cpu) in the reference arm
 """
 from __future__ import annotations
 
