@@ -183,3 +183,21 @@ def test_header_is_plain_c99(tmp_path):
     p = subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-c", str(src), "-o", str(tmp_path / "c99.o")],
                        capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
+
+
+def test_c_example_builds_and_runs(tmp_path):
+    """examples/minimal.c: the ABI from plain C99.  Links against libsffg.so; exits 0 with the expected answers on a B200
+    and 2 (SFFG_ERR_NO_DEVICE reported) where there is no GPU -- never a CPU answer"""
+    from space_filling_forest_star_b200 import build as B
+    lib = B.build_native()
+    cc = "/usr/bin/gcc" if Path("/usr/bin/gcc").exists() else "gcc"
+    exe = tmp_path / "minimal"
+    p = subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(ROOT / "examples" / "minimal.c"),
+                        "-L", str(lib.parent), "-l:libsffg.so", f"-Wl,-rpath,{lib.parent}", "-o", str(exe)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if _has_gpu():
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "verdicts 1 0 1, edge free 0 (first colliding sample 25), nearest nodes 1 0" in r.stdout
+    else:
+        assert r.returncode == 2 and "no CUDA device" in r.stderr

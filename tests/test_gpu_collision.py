@@ -138,3 +138,21 @@ def test_clearance_grid_is_conservative(sff, orc, meshes, monkeypatch):
     np.testing.assert_array_equal(a, b)
     want, _ = orc.collide_obbtree(orc.ObbModel(meshes[on]), orc.ObbModel(meshes[rn]), poses.astype(np.float64))
     np.testing.assert_array_equal(a, want)
+
+
+def test_c_example_gives_the_expected_answers(tmp_path):
+    """examples/minimal.c (plain C99 on the ABI) on the GPU: exit code 0 = every verdict, first-hit index and neighbour id
+    is the oracle's (see tests/test_abi.py::test_c_example_builds_and_runs for the values)"""
+    import subprocess
+    from pathlib import Path
+
+    from space_filling_forest_star_b200 import build as B
+    root = Path(__file__).resolve().parents[1]
+    lib = B.build_native()
+    cc = "/usr/bin/gcc" if Path("/usr/bin/gcc").exists() else "gcc"
+    exe = tmp_path / "minimal"
+    subprocess.run([cc, "-std=c99", "-I", str(root / "include"), str(root / "examples" / "minimal.c"), "-L", str(lib.parent), "-l:libsffg.so",
+                    f"-Wl,-rpath,{lib.parent}", "-o", str(exe)], check=True, capture_output=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "verdicts 1 0 1, edge free 0 (first colliding sample 25), nearest nodes 1 0" in r.stdout
