@@ -1,0 +1,46 @@
+"""bench.py's reference arm runs on CPU: check the JSON line contract (keys, types, the arm's own e2e / cpu_baseline)."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+KEYS = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+        "data", "config", "cpu_baseline", "e2e"}
+
+
+def run_reference(extra_env=None, args=()):
+    env = dict(os.environ, **(extra_env or {}))
+    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--cpu-sample", "65536",
+                        "--no-extra", *args], capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, p.stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_json_line():
+    d = run_reference()
+    assert KEYS <= set(d), KEYS - set(d)
+    assert d["impl"] == "reference" and d["metric"] == "collision-checked poses/s" and d["unit"] == "poses/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "f64"
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["e2e"] == {"value": d["value"], "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["cores"] >= 1 and "sample" in cb
+
+
+def test_reference_arm_uses_all_cores_under_torchrun_env():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must still use every core it may run on"""
+    d = run_reference({"OMP_NUM_THREADS": "1"})
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    """under torchrun (N > 1) rank 0 alone runs and prints; the other ranks exit 0 without work"""
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=120)
+    assert p.returncode == 0 and p.stdout.strip() == ""
