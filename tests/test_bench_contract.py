@@ -44,3 +44,26 @@ def test_reference_arm_other_ranks_exit_quietly():
     p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, env=env, timeout=120)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_our_arm_json_line_on_the_gpu():
+    """a short run of the GPU arm: every key of the contract is present and consistent"""
+    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "3", "--warmup", "3", "--poses-per-gpu", "1048576", "--no-extra",
+                        "--cpu-sample", "65536"], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert (KEYS - {"impl"}) | {"roofline", "clocks", "gpu_launches"} <= set(d)
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["gpu_launches"] == 3 and d["dtype"] == "f32" and d["scaling"] == "weak"
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert abs(r["achieved"] - 25 * 1048576 / (r["kernel_ms"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 24 * 1048576 and e["d2h_bytes_per_step"] == 1048576 and 0 < e["value"] < d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert d["clocks"]["sm_mhz"] and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
