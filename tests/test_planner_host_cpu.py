@@ -268,3 +268,16 @@ def test_lazy_tsp_many_roots_without_a_map(exe, tmp_path):
     ring = [order[t] for t in tour]                                  # positions on the circle in tour order
     steps = {(ring[(k + 1) % n] - ring[k]) % n for k in range(n)}
     assert steps in ({1}, {n - 1}), ring                             # neighbours on the circle follow each other
+
+
+def test_python_entry_to_the_hosts(exe, tmp_path):
+    """space_filling_forest_star_b200.planner.solve: the reference's command line (config.xml [run-id]) + seed / batch,
+    parsed Params row and plans back (here with the engine double as the binary)"""
+    import subprocess
+    from space_filling_forest_star_b200 import planner
+    subprocess.run([sys.executable, str(PU.ROOT / "scripts" / "make_scenarios.py"), str(tmp_path)], check=True, capture_output=True)
+    r = planner.solve("2d_mtrrt.xml", run_id=2, seed=5, cwd=str(tmp_path), paths_file="p.txt", exe=str(exe))
+    assert r["solved"] and r["run"] == "2" and sorted(r["trees"]) == [0, 1, 2, 3] and len(r["lengths"]) == 6 and len(r["plans"]) == 6
+    assert "carried samples" in r["report"]
+    with pytest.raises(RuntimeError):
+        planner.solve("missing.xml", cwd=str(tmp_path), exe=str(exe))
