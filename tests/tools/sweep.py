@@ -96,7 +96,7 @@ def main():
     # ---------------- edges
     env = S.Environment(m["building_s10"], m["robot_small_s10"])
     mo, mr = O.ObbModel(m["building_s10"]), O.ObbModel(m["robot_small_s10"])
-    for M in ([10 ** 5] if a.quick else [10 ** 5, 10 ** 6]):
+    for M in ([10 ** 5] if a.quick else [10 ** 5, 10 ** 6, 10 ** 7]):
         s = S.gen_poses_device(SEED + 1, 0, M, [-45, 45, -45, 45, 0, 125]).double()
         d = torch.randn((M, 3), device=dev, dtype=torch.float64, generator=torch.Generator(device=dev).manual_seed(1))
         d = d / d.norm(dim=1, keepdim=True)
