@@ -424,6 +424,35 @@ def planner_solves(impl: str, runs: int):
     return out
 
 
+def knn_cpu_baseline(nodes, q, k, gpu_ids):
+    """the CPU neighbour path on the same node set, bounded samples: FLANN exactly as the planner uses it (4 randomised
+    kd-trees, 128 checks, the functor that assigns instead of accumulating -- approximate) from the reference's own
+    vendored sources (oracle/_ref/libflann_ref.so, built in the dev container), and the oracle's exact linear scan, which
+    doubles as a parity check of the GPU rows"""
+    import oracle as O
+    threads = host_threads()
+    out = {"cores": threads}
+    nl = 256
+    t0 = time.perf_counter()
+    wi, _ = O.knn_linear(nodes, q[:nl], k, threads=threads)
+    out["exact_linear_queries_per_s"] = nl / (time.perf_counter() - t0)
+    out["gpu_rows_equal_exact_scan"] = bool(np.array_equal(gpu_ids[:nl], wi))
+    try:
+        if O.have_ref():
+            t0 = time.perf_counter()
+            P = O.RefPlannerIndex(nodes)
+            out["flann_planner_build_s"] = time.perf_counter() - t0
+            nf = 8192
+            t0 = time.perf_counter()
+            fi, _ = P.knn(q[:nf], k, cores=threads)
+            out["flann_planner_queries_per_s"] = nf / (time.perf_counter() - t0)
+            out["flann_planner_recall_vs_exact"] = float(np.mean([len(set(a) & set(b)) / k for a, b in zip(fi[:nl], wi)]))
+            out["sample"] = f"{nf} queries (FLANN kd-tree x4, 128 checks, as src/forest.h:317), {nl} queries (exact scan)"
+    except Exception as ex:
+        out["flann_error"] = repr(ex)
+    return out
+
+
 def sharded_knn_rate(S, torch, dist, dev, rank, world):
     """N > 1: exact k-NN with the node set replicated and the query rows split over the ranks; every rank ends up with all
     rows (packed (id, d2) pairs, one NCCL all-gather).  Same shape per rank as the N = 1 `extra` block (weak scaling)."""
@@ -501,6 +530,7 @@ def extra_metrics(S, env, torch):
         out["knn_queries_per_s"] = nq / sec
         out["knn_config"] = f"N={n} 6-D nodes, Q={nq}, k={k}, exact"
         out["knn_pair_rate_per_s"] = nq * n / sec
+        out["knn_cpu_baseline"] = knn_cpu_baseline(nodes.cpu().numpy(), q.cpu().numpy(), k, ids.cpu().numpy())
     except Exception as ex:   # secondary numbers must never break the headline line
         out["error"] = repr(ex)
     try:
