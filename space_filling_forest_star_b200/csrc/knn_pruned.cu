@@ -109,6 +109,30 @@ __global__ void block_box_kernel(const float *__restrict__ s_coords, long long c
   }
 }
 
+// one warp per superblock of 32 blocks: union of the block boxes
+__global__ void superblock_box_kernel(const float *__restrict__ bb, long long nblk_cap, int nblk, int lin, float *sbb, long long nsb_cap) {
+  const int lane = threadIdx.x & 31;
+  const int sb = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nsb = (nblk + 31) / 32;
+  if (sb >= nsb) return;
+  const int b = sb * 32 + lane;
+  for (int c = 0; c < lin; ++c) {
+    float lo = INFINITY, hi = -INFINITY;
+    if (b < nblk) {
+      lo = bb[(long long)c * nblk_cap + b];
+      hi = bb[(long long)(lin + c) * nblk_cap + b];
+    }
+    for (int s = 16; s > 0; s >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(kFull, lo, s));
+      hi = fmaxf(hi, __shfl_xor_sync(kFull, hi, s));
+    }
+    if (lane == 0) {
+      sbb[(long long)c * nsb_cap + sb] = lo;
+      sbb[(long long)(lin + c) * nsb_cap + sb] = hi;
+    }
+  }
+}
+
 // ---- pruned scan --------------------------------------------------------------------------------------------------
 // lower bound of metric_lin over a box, same operations and order as metric_lin (all monotone): for every node n of the
 // box, box_lb(q) <= metric_lin(n, q) holds exactly in float arithmetic
@@ -165,53 +189,104 @@ __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, cons
   const int nsb = (sv.nblk + 31) / 32;   // superblocks of 32 blocks
   const int sb_begin = slice * sb_per_slice;
   const int sb_end = min(nsb, sb_begin + sb_per_slice);
-  // ---- pass 1: a bound on the k-th distance without touching a node.  G = ceil(k/32) consecutive FULL blocks hold >= k
-  // nodes, all within max_g box_ub(g) (+ the largest possible angular part), so the k-th nearest node cannot be farther.
-  // The bound seeds worst[] (inclusive: worst_id = -1 compares as the largest id), which lets pass 2 prune from the start.
+  // ---- pass 1: a bound on the k-th distance without touching a node.  Superblock level first (lane-per-superblock): a FULL
+  // superblock holds 1024 >= k nodes, all within box_ub of its box.  Inside the best superblock of every query the bound is
+  // refined at block level: G = ceil(k/32) consecutive blocks (all full) hold >= k nodes, all within max_g box_ub(g).  Plus
+  // the largest possible angular part.  The bound seeds worst[] (inclusive: worst_id = -1 compares as the largest id),
+  // which lets pass 2 prune from the start.
   {
     const int G = (k + 31) / 32;
-    const int full_blocks = sv.n_sorted / 32;
+    const int full_sb = sv.n_sorted / 1024;
     float best[QW];
+    int arg[QW];
 #pragma unroll
-    for (int w = 0; w < QW; ++w) best[w] = INFINITY;
-    for (int sb = sb_begin; sb < sb_end; ++sb) {
-      const int blk = sb * 32 + lane;
-      float ub[QW];
-      if (blk < full_blocks) {
+    for (int w = 0; w < QW; ++w) {
+      best[w] = INFINITY;
+      arg[w] = -1;
+    }
+    for (int g = sb_begin; g < sb_end; g += 32) {
+      const int s = g + lane;
+      if (s < sb_end && s < full_sb) {
+        float lo[LIN], hi[LIN];
+#pragma unroll
+        for (int c = 0; c < LIN; ++c) {
+          lo[c] = __ldg(sv.sbb + (long long)c * sv.nsb_cap + s);
+          hi[c] = __ldg(sv.sbb + (long long)(LIN + c) * sv.nsb_cap + s);
+        }
+#pragma unroll
+        for (int w = 0; w < QW; ++w) {
+          const float u = box_ub<LIN>(lo, hi, q[w]);
+          if (u < best[w]) {
+            best[w] = u;
+            arg[w] = s;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < QW; ++w) {
+      float bv = best[w];
+      int bs = arg[w];
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        const float ov = __shfl_xor_sync(kFull, bv, sft);
+        const int os = __shfl_xor_sync(kFull, bs, sft);
+        if (ov < bv || (ov == bv && (unsigned)os < (unsigned)bs)) {
+          bv = ov;
+          bs = os;
+        }
+      }
+      float bound = bv;
+      if (bs >= 0) {   // warp-uniform; every block of a full superblock is full
+        const int blk = bs * 32 + lane;
         float lo[LIN], hi[LIN];
 #pragma unroll
         for (int c = 0; c < LIN; ++c) {
           lo[c] = __ldg(sv.bb + (long long)c * sv.nblk_cap + blk);
           hi[c] = __ldg(sv.bb + (long long)(LIN + c) * sv.nblk_cap + blk);
         }
-#pragma unroll
-        for (int w = 0; w < QW; ++w) ub[w] = box_ub<LIN>(lo, hi, q[w]);
-      } else {
-#pragma unroll
-        for (int w = 0; w < QW; ++w) ub[w] = INFINITY;
-      }
-#pragma unroll
-      for (int w = 0; w < QW; ++w) {
-        float g = ub[w];
+        const float ub = box_ub<LIN>(lo, hi, q[w]);
+        float gmax = ub;
         for (int j = 1; j < G; ++j) {
-          const float o = __shfl_down_sync(kFull, ub[w], j);
-          g = fmaxf(g, lane + j < 32 ? o : INFINITY);
+          const float o = __shfl_down_sync(kFull, ub, j);
+          gmax = fmaxf(gmax, lane + j < 32 ? o : INFINITY);
         }
-        best[w] = fminf(best[w], g);
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) gmax = fminf(gmax, __shfl_xor_sync(kFull, gmax, sft));
+        bound = fminf(bound, gmax);
       }
-    }
-#pragma unroll
-    for (int w = 0; w < QW; ++w) {
-#pragma unroll
-      for (int sft = 16; sft > 0; sft >>= 1) best[w] = fminf(best[w], __shfl_xor_sync(kFull, best[w], sft));
       // angular part of the metric: three wrapped differences, each <= pi  ->  <= 3 * pi^2 = 29.61 (29.7 covers rounding)
-      worst[w] = DIM == 6 ? __fadd_rn(best[w], 29.7f) : best[w];
+      worst[w] = DIM == 6 ? __fadd_rn(bound, 29.7f) : bound;
     }
   }
   float seed[QW];
 #pragma unroll
   for (int w = 0; w < QW; ++w) seed[w] = worst[w];
-  for (int sb = sb_begin; sb < sb_end; ++sb) {
+  // ---- pass 2: superblock boxes first (lane-per-superblock, 32 768 nodes per step), then the block boxes of the superblocks
+  // that can still hold a candidate (lane-per-block), then the nodes of the blocks that can
+  for (int sg = sb_begin; sg < sb_end; sg += 32) {
+    float lbs[QW];
+    bool need_s = false;
+    if (sg + lane < sb_end) {
+      float lo[LIN], hi[LIN];
+#pragma unroll
+      for (int c = 0; c < LIN; ++c) {
+        lo[c] = __ldg(sv.sbb + (long long)c * sv.nsb_cap + sg + lane);
+        hi[c] = __ldg(sv.sbb + (long long)(LIN + c) * sv.nsb_cap + sg + lane);
+      }
+#pragma unroll
+      for (int w = 0; w < QW; ++w) {
+        lbs[w] = box_lb<LIN>(lo, hi, q[w]);
+        need_s |= !(lbs[w] > worst[w]);
+      }
+    } else {
+#pragma unroll
+      for (int w = 0; w < QW; ++w) lbs[w] = INFINITY;
+    }
+    unsigned todo_s = __ballot_sync(kFull, need_s);
+  while (todo_s) {
+    const int sl = __ffs(todo_s) - 1;
+    const int sb = sg + sl;
     const int blk = sb * 32 + lane;
     float lb[QW];
     bool need = false;
@@ -282,6 +357,12 @@ __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, cons
       for (int w = 0; w < QW; ++w) need |= !(lb[w] > worst[w]);
       todo = __ballot_sync(kFull, need && lane > bl);
     }
+    // ... and which of the remaining superblocks of this group
+    need_s = false;
+#pragma unroll
+    for (int w = 0; w < QW; ++w) need_s |= !(lbs[w] > worst[w]);
+    todo_s = __ballot_sync(kFull, need_s && lane > sl);
+  }
   }
 #pragma unroll
   for (int w = 0; w < QW; ++w) {
@@ -409,6 +490,8 @@ cudaError_t launch_sorted_build(const IndexDev &idx, int n, const SortedBuildBuf
   gather_kernel<<<blocks, threads, 0, st>>>(idx.coords, idx.capacity, idx.dim, n, b.vals_out, b.s_coords, b.cap_s, b.s_ids);
   const int nblk = (n + 31) / 32;
   block_box_kernel<<<(nblk * 32 + threads - 1) / threads, threads, 0, st>>>(b.s_coords, b.cap_s, n, lin, b.bb, b.nblk_cap);
+  const int nsb = (nblk + 31) / 32;
+  superblock_box_kernel<<<(nsb * 32 + threads - 1) / threads, threads, 0, st>>>(b.bb, b.nblk_cap, nblk, lin, b.sbb, b.nsb_cap);
   return cudaGetLastError();
 }
 

@@ -14,8 +14,10 @@ struct SortedDev {
   const float *coords;   // SoA, coordinate c of sorted position p at coords[c * cap_s + p]
   const int *ids;        // original (insertion-order) id of sorted position p
   const float *bb;       // block boxes over the translational coordinates: lo_c at bb[c * nblk_cap + b], hi_c at bb[(LIN + c) * nblk_cap + b]
+  const float *sbb;      // superblock boxes (32 blocks = 1024 nodes), same layout with stride nsb_cap
   long long cap_s;
   long long nblk_cap;
+  long long nsb_cap;
   int n_sorted;
   int nblk;
 };
@@ -30,6 +32,8 @@ struct SortedBuildBuffers {
   int *s_ids;
   float *bb;
   long long nblk_cap;
+  float *sbb;
+  long long nsb_cap;
 };
 
 size_t sorted_build_temp_bytes(int n);

@@ -981,7 +981,8 @@ static int ensure_sorted(sffg_index *idx, cudaStream_t st) {
   }
   int rc = idx->s_coords.reserve((size_t)idx->s_cap * idx->dim * 4);
   if (rc == SFFG_OK) rc = idx->s_ids.reserve((size_t)idx->s_cap * 4);
-  if (rc == SFFG_OK) rc = idx->s_bb.reserve((size_t)idx->s_nblk_cap * 2 * lin * 4);
+  // block boxes followed by superblock boxes (one per 32 blocks)
+  if (rc == SFFG_OK) rc = idx->s_bb.reserve(((size_t)idx->s_nblk_cap + (size_t)(idx->s_nblk_cap / 32 + 2)) * 2 * lin * 4);
   if (rc == SFFG_OK) rc = idx->s_keys.reserve((size_t)idx->s_cap * 8);
   if (rc == SFFG_OK) rc = idx->s_vals.reserve((size_t)idx->s_cap * 8);
   if (rc == SFFG_OK) rc = idx->s_temp.reserve(sorted_build_temp_bytes((int)idx->s_cap));
@@ -1000,6 +1001,8 @@ static int ensure_sorted(sffg_index *idx, cudaStream_t st) {
   b.s_ids = (int *)idx->s_ids.p;
   b.bb = (float *)idx->s_bb.p;
   b.nblk_cap = idx->s_nblk_cap;
+  b.nsb_cap = idx->s_nblk_cap / 32 + 2;
+  b.sbb = b.bb + (size_t)idx->s_nblk_cap * 2 * lin;
   IndexDev v{idx->d_coords, idx->cap, idx->n, idx->dim};
   SFFG_CUDA(launch_sorted_build(v, n, b, st));
   idx->n_sorted = n;
@@ -1013,6 +1016,8 @@ static SortedDev sorted_view(const sffg_index *idx) {
   sv.bb = (const float *)idx->s_bb.p;
   sv.cap_s = idx->s_cap;
   sv.nblk_cap = idx->s_nblk_cap;
+  sv.nsb_cap = idx->s_nblk_cap / 32 + 2;
+  sv.sbb = sv.bb + (size_t)idx->s_nblk_cap * 2 * (idx->dim == 6 ? 3 : 2);
   sv.n_sorted = (int)idx->n_sorted;
   sv.nblk = (int)((idx->n_sorted + 31) / 32);
   return sv;
