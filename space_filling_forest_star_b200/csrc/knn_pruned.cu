@@ -189,7 +189,52 @@ __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, cons
   const int nsb = (sv.nblk + 31) / 32;   // superblocks of 32 blocks
   const int sb_begin = slice * sb_per_slice;
   const int sb_end = min(nsb, sb_begin + sb_per_slice);
-  // ---- pass 1: a bound on the k-th distance without touching a node.  Superblock level first (lane-per-superblock): a FULL
+  // ---- pass 1: a bound on the k-th distance without touching a node.
+  // Slices of up to 128 superblocks scan every block box of the slice: G = ceil(k/32) consecutive FULL blocks hold >= k nodes,
+  // all within max_g box_ub(g) (+ the largest possible angular part), so the k-th nearest node cannot be farther -- the
+  // tightest bound, at one step per superblock.  Larger slices take the superblock route below.
+  // The bound seeds worst[] (inclusive: worst_id = -1 compares as the largest id), which lets pass 2 prune from the start.
+  if (sb_end - sb_begin <= 128) {
+    const int G = (k + 31) / 32;
+    const int full_blocks = sv.n_sorted / 32;
+    float best[QW];
+#pragma unroll
+    for (int w = 0; w < QW; ++w) best[w] = INFINITY;
+    for (int sb = sb_begin; sb < sb_end; ++sb) {
+      const int blk = sb * 32 + lane;
+      float ub[QW];
+      if (blk < full_blocks) {
+        float lo[LIN], hi[LIN];
+#pragma unroll
+        for (int c = 0; c < LIN; ++c) {
+          lo[c] = __ldg(sv.bb + (long long)c * sv.nblk_cap + blk);
+          hi[c] = __ldg(sv.bb + (long long)(LIN + c) * sv.nblk_cap + blk);
+        }
+#pragma unroll
+        for (int w = 0; w < QW; ++w) ub[w] = box_ub<LIN>(lo, hi, q[w]);
+      } else {
+#pragma unroll
+        for (int w = 0; w < QW; ++w) ub[w] = INFINITY;
+      }
+#pragma unroll
+      for (int w = 0; w < QW; ++w) {
+        float g = ub[w];
+        for (int j = 1; j < G; ++j) {
+          const float o = __shfl_down_sync(kFull, ub[w], j);
+          g = fmaxf(g, lane + j < 32 ? o : INFINITY);
+        }
+        best[w] = fminf(best[w], g);
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < QW; ++w) {
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) best[w] = fminf(best[w], __shfl_xor_sync(kFull, best[w], sft));
+      // angular part of the metric: three wrapped differences, each <= pi  ->  <= 3 * pi^2 = 29.61 (29.7 covers rounding)
+      worst[w] = DIM == 6 ? __fadd_rn(best[w], 29.7f) : best[w];
+    }
+  } else
+  // Superblock route (lane-per-superblock first): a FULL
   // superblock holds 1024 >= k nodes, all within box_ub of its box.  Inside the best superblock of every query the bound is
   // refined at block level: G = ceil(k/32) consecutive blocks (all full) hold >= k nodes, all within max_g box_ub(g).  Plus
   // the largest possible angular part.  The bound seeds worst[] (inclusive: worst_id = -1 compares as the largest id),
