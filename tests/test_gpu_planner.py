@@ -125,3 +125,21 @@ def test_path_cost_within_tolerance_of_the_reference(exe, tmp_path, scenario):
         assert ",solved," in row, row
         means.append(np.mean([d for _, _, d, _ in plans]))
     assert np.mean(means) <= (1.0 + TOLERANCE) * REFERENCE_MEAN_LENGTH[scenario], (np.mean(means), REFERENCE_MEAN_LENGTH[scenario])
+
+
+def _golden_rows():
+    import json
+    return json.loads((PU.ROOT / "tests" / "golden" / "planner_rows.json").read_text())
+
+
+@pytest.mark.parametrize("case", sorted(_golden_rows()))
+def test_engine_reproduces_the_golden_planner_rows(exe, tmp_path, case):
+    """the committed rows were produced with the oracle behind the C ABI (tests/golden/gen_planner_rows.py); the engine must
+    lead the same host to the same iterations, trees and path lengths: every verdict and neighbour list of a whole solve
+    agrees with the oracle"""
+    scenario, seed = case.split("@")
+    want = _golden_rows()[case]
+    row, plans, _ = PU.run_planner(exe, tmp_path, scenario, seed=int(seed), batch=128)
+    f = row.split(",")
+    assert ",".join(f[:1] + f[2:-1]) == want["row"]
+    assert len(plans) == want["plans"] and sum(len(p[3]) for p in plans) == want["nodes_on_plans"]

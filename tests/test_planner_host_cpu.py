@@ -281,3 +281,26 @@ def test_python_entry_to_the_hosts(exe, tmp_path):
     assert "carried samples" in r["report"]
     with pytest.raises(RuntimeError):
         planner.solve("missing.xml", cwd=str(tmp_path), exe=str(exe))
+
+
+def _golden_rows():
+    import json
+    return json.loads((PU.ROOT / "tests" / "golden" / "planner_rows.json").read_text())
+
+
+def _row_key(row):
+    f = row.split(",")
+    return ",".join(f[:1] + f[2:-1])
+
+
+@pytest.mark.parametrize("case", sorted(_golden_rows()))
+def test_golden_planner_rows(exe, tmp_path, case):
+    """tests/golden/planner_rows.json (generated by tests/golden/gen_planner_rows.py with the engine double): iterations,
+    solved flag, connected trees and every path length of a fixed-seed solve.  Pins the host logic (sampling order, replay
+    rules, path extraction) -- the rows depend on libstdc++'s std::mt19937_64 / uniform_real_distribution, i.e. on this
+    image's toolchain."""
+    scenario, seed = case.split("@")
+    want = _golden_rows()[case]
+    row, plans, _ = PU.run_planner(exe, tmp_path, scenario, seed=int(seed), batch=128)
+    assert _row_key(row) == want["row"]
+    assert len(plans) == want["plans"] and sum(len(p[3]) for p in plans) == want["nodes_on_plans"]
