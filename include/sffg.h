@@ -36,7 +36,7 @@ extern "C" {
 #define SFFG_ERR_ARG 3          /* bad argument (null pointer, negative size, dim not 2 or 6, k out of range)  */
 #define SFFG_ERR_IO 4           /* mesh file unreadable / malformed                                            */
 #define SFFG_ERR_CAPACITY 5     /* caller-provided result buffer too small (needed size is reported)           */
-#define SFFG_ERR_DOMAIN 6       /* angle outside the range for which the float metric is bit-exact (|a|<=7)    */
+#define SFFG_ERR_DOMAIN 6       /* reserved (no longer returned: the metric is exact for every float angle)    */
 #define SFFG_ERR_INTERNAL 7     /* traversal stack overflow or similar -- a bug, never a silent wrong answer   */
 
 #define SFFG_ROT_REFERENCE 0    /* interior edge samples carry identity rotation (src/problemStruct.h:157-163) */

@@ -14,14 +14,42 @@ constexpr int kThreads = kWarps * 32;
 constexpr float kTwoPiHi = 6.28318548202514648f;      // float(2*pi)
 constexpr float kTwoPiLoNeg = 1.74845553146951715e-07f;  // float(2*pi) - 2*pi, nearest float
 
-// |wrap(b - a)| of NormalizeAngle<float> (reference src/primitives.h:277-292: the +-2*pi is done in double and
-// narrowed).  Exhaustively verified equal for every float |b - a| < 14 (tests/test_metric_wrap.py):
-//   |d| >= float(pi)  ->  |(|d| - hi) + lo'|   (first subtraction exact by Sterbenz, second correctly rounded)
-//   otherwise         ->  |d|, and min() selects between the two without a branch
+constexpr double kTwoPiD = 6.283185307179586476925286766559;   // 2 * M_PI as the reference's double arithmetic sees it
+constexpr float kWideFrom = 12.5f;   // the FP32 form below is exact for |b - a| < 14 (needs |b - a| <= 2 * float(2*pi) for Sterbenz)
+
+// |wrap(b - a)| of NormalizeAngle<float> (reference src/primitives.h:277-292: ONE +-2*pi, done in double and narrowed;
+// stored angles are never re-normalised, src/primitives.h:237-250, so |b - a| is unbounded).
+//   |d| <  kWideFrom: FP32 only, verified equal for every float in [pi, 14) by tests/test_metric_wrap.py:
+//     |d| >= float(pi)  ->  |(|d| - hi) + lo'|   (first subtraction exact by Sterbenz, second correctly rounded)
+//     otherwise         ->  |d|, and min() selects between the two without a branch
+//   WIDE (a warp-uniform decision of the caller, see wide_needed()): differences of kWideFrom and more take the
+//     reference's own float -> double -> float route, so the result is exact for every float.
+template <bool WIDE>
 __device__ __forceinline__ float wrapped_abs(float qa, float na) {
   const float a = fabsf(__fsub_rn(qa, na));
   const float t = __fadd_rn(__fsub_rn(a, kTwoPiHi), kTwoPiLoNeg);
-  return fminf(a, fabsf(t));
+  float r = fminf(a, fabsf(t));
+  if (WIDE) {
+    if (!(a < kWideFrom)) r = fabsf(__double2float_rn(__dsub_rn((double)a, kTwoPiD)));
+  }
+  return r;
+}
+
+// Can |query angle - node angle| reach kWideFrom?  node_amax = largest |angle| stored in the index (kept by the append
+// kernel), rounding of the sum and of the difference are both monotone, so fl(|qa| + node_amax) < kWideFrom proves
+// fl(|qa - na|) < kWideFrom for every node.  NaN anywhere selects the wide path (which propagates it like the reference).
+__device__ __forceinline__ bool wide_needed(const float *q, float node_amax) {
+  const float qm = fmaxf(fmaxf(fabsf(q[3]), fabsf(q[4])), fabsf(q[5]));
+  return !(__fadd_rn(qm, node_amax) < kWideFrom) || q[3] != q[3] || q[4] != q[4] || q[5] != q[5];
+}
+
+// upper bound of the angular part of the metric over every node of the index (seeds of the pruned search): each wrapped
+// difference is at most max(pi, A - 2*pi) with A >= |qa| + |na|.  The caller adds a relative margin for the roundings.
+__device__ __forceinline__ float angular_part_ub(const float *q, float node_amax) {
+  const float qm = fmaxf(fmaxf(fabsf(q[3]), fabsf(q[4])), fabsf(q[5]));
+  const float A = __fadd_ru(qm, node_amax);
+  const float m = fmaxf(3.1415928f, __fsub_ru(A, 6.28f));
+  return __fmul_ru(__fmul_ru(m, m), 3.0001f);
 }
 
 // translational part (all of the metric for DIM == 2): ((dx^2 + dy^2) + dz^2), float, unfused
@@ -40,18 +68,19 @@ __device__ __forceinline__ float metric_lin(const float *nd, const float *q) {
 // angular part continues the same accumulator: (((r + wy^2) + wp^2) + wr^2).  Every term is >= 0 and round-to-nearest
 // addition is monotone, so metric_lin() is a lower bound of the full distance: a 32-node block whose translational
 // parts all reach the current k-th distance cannot contain a candidate and its angles are never loaded.
+template <bool WIDE = false>
 __device__ __forceinline__ float metric_ang(float r, const float *na, const float *q) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float w = wrapped_abs(q[3 + c], na[c]);
+    const float w = wrapped_abs<WIDE>(q[3 + c], na[c]);
     r = __fadd_rn(r, __fmul_rn(w, w));
   }
   return r;
 }
-template <int DIM>
+template <int DIM, bool WIDE = false>
 __device__ __forceinline__ float metric(const float *nd, const float *q) {
   float r = metric_lin<DIM>(nd, q);
-  if (DIM == 6) r = metric_ang(r, nd + 3, q);
+  if (DIM == 6) r = metric_ang<WIDE>(r, nd + 3, q);
   return r;
 }
 

@@ -49,6 +49,13 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(IndexDev idx, const 
     top[w].init();
     worst[w] = INFINITY;
   }
+  // un-normalised angles (the reference lets them drift): one warp-uniform decision selects the exact wide wrap
+  bool wide = false;
+  if (DIM == 6) {
+    const float node_amax = __uint_as_float(__ldg(idx.amax));
+#pragma unroll
+    for (int w = 0; w < QW; ++w) wide |= wide_needed(q[w], node_amax);
+  }
   // the scan covers nodes [first, idx.n): the whole index, or the not-yet-sorted tail behind a sorted view
   const long long begin = first + (long long)slice * slice_len;
   long long end = begin + slice_len;
@@ -101,8 +108,13 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(IndexDev idx, const 
           float ang[3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) ang[c] = __ldg(ang_base + (long long)c * idx.capacity + b);
+          if (!wide) {
 #pragma unroll
-          for (int w = 0; w < QW; ++w) d[w] = valid ? metric_ang(d[w], ang, q[w]) : INFINITY;
+            for (int w = 0; w < QW; ++w) d[w] = valid ? metric_ang<false>(d[w], ang, q[w]) : INFINITY;
+          } else {
+#pragma unroll
+            for (int w = 0; w < QW; ++w) d[w] = valid ? metric_ang<true>(d[w], ang, q[w]) : INFINITY;
+          }
         }
 #pragma unroll
         for (int w = 0; w < QW; ++w) {
@@ -205,6 +217,12 @@ __global__ void __launch_bounds__(kThreads) radius_scan_kernel(IndexDev idx, con
     for (int c = 0; c < DIM; ++c) q[w][c] = __ldg(queries + qi * DIM + c);
     cnt[w] = 0;
   }
+  bool wide = false;
+  if (DIM == 6) {
+    const float node_amax = __uint_as_float(__ldg(idx.amax));
+#pragma unroll
+    for (int w = 0; w < QW; ++w) wide |= wide_needed(q[w], node_amax);
+  }
   const long long begin = first + (long long)slice * slice_len;
   long long end = begin + slice_len;
   if (end > idx.n) end = idx.n;
@@ -217,7 +235,7 @@ __global__ void __launch_bounds__(kThreads) radius_scan_kernel(IndexDev idx, con
     for (int c = 0; c < DIM; ++c) nd[c] = valid ? __ldg(idx.coords + (long long)c * idx.capacity + i) : 0.f;
 #pragma unroll
     for (int w = 0; w < QW; ++w) {
-      const float d = valid ? metric<DIM>(nd, q[w]) : INFINITY;
+      const float d = !valid ? INFINITY : (wide ? metric<DIM, true>(nd, q[w]) : metric<DIM, false>(nd, q[w]));
       const bool in = d < r2;
       const unsigned mask = __ballot_sync(kFull, in);
       if (FILL) {
@@ -289,12 +307,20 @@ __global__ void __launch_bounds__(kThreads) radius_sort_kernel(unsigned long lon
 }
 
 __global__ void index_append_kernel(float *coords, long long capacity, int dim, long long at, const float *__restrict__ pts,
-                                    long long n) {
+                                    long long n, unsigned *amax) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n * dim) return;
-  const long long i = t / dim;
-  const int c = (int)(t - i * dim);
-  coords[(long long)c * capacity + at + i] = pts[t];
+  unsigned mag = 0;   // float bits of |angle|: for non-negative floats the unsigned order is the float order, NaN sorts above inf
+  if (t < n * dim) {
+    const long long i = t / dim;
+    const int c = (int)(t - i * dim);
+    const float v = pts[t];
+    coords[(long long)c * capacity + at + i] = v;
+    if (c >= 3) mag = __float_as_uint(fabsf(v));
+  }
+  if (dim == 6) {
+    mag = __reduce_max_sync(kFull, mag);
+    if ((threadIdx.x & 31) == 0 && mag > *(volatile unsigned *)amax) atomicMax(amax, mag);
+  }
 }
 
 template <int DIM, int QW>
@@ -422,10 +448,10 @@ cudaError_t launch_radius_sort(unsigned long long *d_keys, const int64_t *d_offs
 }
 
 cudaError_t launch_index_append(float *d_coords, int64_t capacity, int dim, int64_t at, const float *d_pts, int64_t n,
-                                cudaStream_t stream) {
+                                unsigned *d_amax, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   const long long total = (long long)n * dim;
-  index_append_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_coords, capacity, dim, at, d_pts, n);
+  index_append_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_coords, capacity, dim, at, d_pts, n, d_amax);
   return cudaGetLastError();
 }
 

@@ -12,6 +12,7 @@ struct IndexDev {
   int64_t capacity;
   int64_t n;
   int dim;   // 2 or 6
+  const unsigned *amax;   // one word: float bits of the largest |angle| ever appended (dim 6), kept by the append kernel
 };
 
 struct KnnPlan {
@@ -49,6 +50,6 @@ cudaError_t launch_radius_sort(unsigned long long *d_keys, const int64_t *d_offs
 
 // AoS [n][dim] -> SoA append at position `at`
 cudaError_t launch_index_append(float *d_coords, int64_t capacity, int dim, int64_t at, const float *d_pts, int64_t n,
-                                cudaStream_t stream);
+                                unsigned *d_amax, cudaStream_t stream);
 
 }  // namespace sffg

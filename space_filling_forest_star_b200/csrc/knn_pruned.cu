@@ -186,6 +186,17 @@ __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, cons
     worst[w] = INFINITY;
     worst_id[w] = -1;
   }
+  // un-normalised angles: warp-uniform choice of the exact wide wrap, and the seed's bound on the angular part
+  bool wide = false;
+  float ang_ub[QW];
+  if (DIM == 6) {
+    const float node_amax = __uint_as_float(__ldg(sv.amax));
+#pragma unroll
+    for (int w = 0; w < QW; ++w) {
+      wide |= wide_needed(q[w], node_amax);
+      ang_ub[w] = angular_part_ub(q[w], node_amax);
+    }
+  }
   const int nsb = (sv.nblk + 31) / 32;   // superblocks of 32 blocks
   const int sb_begin = slice * sb_per_slice;
   const int sb_end = min(nsb, sb_begin + sb_per_slice);
@@ -230,8 +241,8 @@ __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, cons
     for (int w = 0; w < QW; ++w) {
 #pragma unroll
       for (int sft = 16; sft > 0; sft >>= 1) best[w] = fminf(best[w], __shfl_xor_sync(kFull, best[w], sft));
-      // angular part of the metric: three wrapped differences, each <= pi  ->  <= 3 * pi^2 = 29.61 (29.7 covers rounding)
-      worst[w] = DIM == 6 ? __fadd_rn(best[w], 29.7f) : best[w];
+      // + the largest possible angular part; the relative margin covers the three roundings of the accumulation
+      worst[w] = DIM == 6 ? __fmul_ru(__fadd_ru(best[w], ang_ub[w]), 1.000001f) : best[w];
     }
   } else
   // Superblock route (lane-per-superblock first): a FULL
@@ -300,8 +311,7 @@ __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, cons
         for (int sft = 16; sft > 0; sft >>= 1) gmax = fminf(gmax, __shfl_xor_sync(kFull, gmax, sft));
         bound = fminf(bound, gmax);
       }
-      // angular part of the metric: three wrapped differences, each <= pi  ->  <= 3 * pi^2 = 29.61 (29.7 covers rounding)
-      worst[w] = DIM == 6 ? __fadd_rn(bound, 29.7f) : bound;
+      worst[w] = DIM == 6 ? __fmul_ru(__fadd_ru(bound, ang_ub[w]), 1.000001f) : bound;
     }
   }
   float seed[QW];
@@ -374,8 +384,13 @@ __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, cons
           float ang[3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) ang[c] = valid ? __ldg(sv.coords + (long long)(3 + c) * sv.cap_s + pos) : 0.f;
+          if (!wide) {
 #pragma unroll
-          for (int w = 0; w < QW; ++w) d[w] = valid ? metric_ang(d[w], ang, q[w]) : INFINITY;
+            for (int w = 0; w < QW; ++w) d[w] = valid ? metric_ang<false>(d[w], ang, q[w]) : INFINITY;
+          } else {
+#pragma unroll
+            for (int w = 0; w < QW; ++w) d[w] = valid ? metric_ang<true>(d[w], ang, q[w]) : INFINITY;
+          }
         }
 #pragma unroll
         for (int w = 0; w < QW; ++w) {
@@ -447,6 +462,12 @@ __global__ void __launch_bounds__(kThreads) radius_pruned_kernel(SortedDev sv, c
     for (int c = 0; c < DIM; ++c) q[w][c] = __ldg(queries + qi * DIM + c);
     cnt[w] = 0;
   }
+  bool wide = false;
+  if (DIM == 6) {
+    const float node_amax = __uint_as_float(__ldg(sv.amax));
+#pragma unroll
+    for (int w = 0; w < QW; ++w) wide |= wide_needed(q[w], node_amax);
+  }
   const unsigned lt = (1u << lane) - 1u;
   const int nsb = (sv.nblk + 31) / 32;
   const int sb_begin = slice * sb_per_slice;
@@ -476,7 +497,7 @@ __global__ void __launch_bounds__(kThreads) radius_pruned_kernel(SortedDev sv, c
       const int id = (FILL && valid) ? __ldg(sv.ids + pos) : 0;
 #pragma unroll
       for (int w = 0; w < QW; ++w) {
-        const float d = valid ? metric<DIM>(nd, q[w]) : INFINITY;
+        const float d = !valid ? INFINITY : (wide ? metric<DIM, true>(nd, q[w]) : metric<DIM, false>(nd, q[w]));
         const bool in = d < r2;
         const unsigned mask = __ballot_sync(kFull, in);
         if (FILL) {

@@ -20,6 +20,7 @@ struct SortedDev {
   long long nsb_cap;
   int n_sorted;
   int nblk;
+  const unsigned *amax;  // as IndexDev::amax
 };
 
 struct SortedBuildBuffers {

@@ -107,6 +107,7 @@ struct sffg_env {
 struct sffg_index {
   int dim = 0;
   float *d_coords = nullptr;
+  unsigned *d_amax = nullptr;   // float bits of the largest |angle| stored (dim 6): selects the kernels' exact wide wrap
   int64_t cap = 0, n = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev = nullptr;   // fork / join of multi-index calls
@@ -847,8 +848,12 @@ int sffg_index_create(int dim, sffg_index **out) {
     idx->cap = 4096 + 128;
     e = cudaMalloc((void **)&idx->d_coords, (size_t)idx->cap * dim * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(idx->d_coords, 0, (size_t)idx->cap * dim * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&idx->d_amax, 256);
+    if (e == cudaSuccess) e = cudaMemset(idx->d_amax, 0, 256);
   }
   if (e != cudaSuccess) {
+    cudaFree(idx->d_coords);
+    cudaFree(idx->d_amax);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     if (idx->ev) cudaEventDestroy(idx->ev);
     if (idx->h_small) cudaFreeHost(idx->h_small);
@@ -863,6 +868,7 @@ int sffg_index_destroy(sffg_index *idx) {
   if (!idx) return SFFG_OK;
   if (idx->stream) cudaStreamSynchronize(idx->stream);
   cudaFree(idx->d_coords);
+  cudaFree(idx->d_amax);
   DevBuf *bufs[] = {&idx->q, &idx->ids, &idx->d2, &idx->scratch, &idx->counts, &idx->offsets, &idx->cursor, &idx->keys, &idx->stage,
                     &idx->s_coords, &idx->s_ids, &idx->s_bb, &idx->s_keys, &idx->s_vals, &idx->s_temp, &idx->s_bounds};
   for (DevBuf *b : bufs) b->release();
@@ -891,24 +897,13 @@ static int index_grow(sffg_index *idx, int64_t need, cudaStream_t st) {
   return SFFG_OK;
 }
 
-// the float metric is bit-exact against the reference only while |angle difference| < 14 rad
-static int check_angles(const float *pts, int64_t n, int dim) {
-  if (dim != 6) return SFFG_OK;
-  for (int64_t i = 0; i < n; ++i)
-    for (int c = 3; c < 6; ++c) {
-      const float a = pts[i * 6 + c];
-      if (!(a >= -7.0f && a <= 7.0f)) return fail(SFFG_ERR_DOMAIN, "angle outside [-7, 7] rad (or NaN) in point/query " + std::to_string(i));
-    }
-  return SFFG_OK;
-}
-
 int sffg_index_add_device(sffg_index *idx, const float *d_pts, int64_t n, void *stream) {
   if (!idx || n < 0 || (n > 0 && !d_pts)) return fail(SFFG_ERR_ARG, "sffg_index_add_device: bad arguments");
   if (n == 0) return SFFG_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = index_grow(idx, idx->n + n, st);
   if (rc != SFFG_OK) return rc;
-  SFFG_CUDA(launch_index_append(idx->d_coords, idx->cap, idx->dim, idx->n, d_pts, n, st));
+  SFFG_CUDA(launch_index_append(idx->d_coords, idx->cap, idx->dim, idx->n, d_pts, n, idx->d_amax, st));
   idx->n += n;
   return SFFG_OK;
 }
@@ -916,9 +911,7 @@ int sffg_index_add_device(sffg_index *idx, const float *d_pts, int64_t n, void *
 int sffg_index_add(sffg_index *idx, const float *pts, int64_t n) {
   if (!idx || n < 0 || (n > 0 && !pts)) return fail(SFFG_ERR_ARG, "sffg_index_add: bad arguments");
   if (n == 0) return SFFG_OK;
-  int rc = check_angles(pts, n, idx->dim);
-  if (rc != SFFG_OK) return rc;
-  rc = idx->stage.reserve((size_t)n * idx->dim * sizeof(float));
+  int rc = idx->stage.reserve((size_t)n * idx->dim * sizeof(float));
   if (rc != SFFG_OK) return rc;
   SFFG_CUDA(cudaMemcpyAsync(idx->stage.p, pts, (size_t)n * idx->dim * sizeof(float), cudaMemcpyHostToDevice, idx->stream));
   rc = sffg_index_add_device(idx, (const float *)idx->stage.p, n, idx->stream);
@@ -937,8 +930,7 @@ int sffg_index_add_multi(sffg_index *const *idx, const int64_t *n_per, int n_idx
   }
   if (total == 0) return SFFG_OK;
   if (!pts) return fail(SFFG_ERR_ARG, "sffg_index_add_multi: null points");
-  int rc = check_angles(pts, total, dim);
-  if (rc != SFFG_OK) return rc;
+  int rc;
   sffg_index *lead = idx[0];   // one staging buffer, one upload, one synchronisation for all indices
   cudaStream_t st = lead->stream;
   const size_t bytes = (size_t)total * dim * sizeof(float);
@@ -1003,7 +995,7 @@ static int ensure_sorted(sffg_index *idx, cudaStream_t st) {
   b.nblk_cap = idx->s_nblk_cap;
   b.nsb_cap = idx->s_nblk_cap / 32 + 2;
   b.sbb = b.bb + (size_t)idx->s_nblk_cap * 2 * lin;
-  IndexDev v{idx->d_coords, idx->cap, idx->n, idx->dim};
+  IndexDev v{idx->d_coords, idx->cap, idx->n, idx->dim, idx->d_amax};
   SFFG_CUDA(launch_sorted_build(v, n, b, st));
   idx->n_sorted = n;
   return SFFG_OK;
@@ -1020,6 +1012,7 @@ static SortedDev sorted_view(const sffg_index *idx) {
   sv.sbb = sv.bb + (size_t)idx->s_nblk_cap * 2 * (idx->dim == 6 ? 3 : 2);
   sv.n_sorted = (int)idx->n_sorted;
   sv.nblk = (int)((idx->n_sorted + 31) / 32);
+  sv.amax = idx->d_amax;
   return sv;
 }
 
@@ -1029,7 +1022,7 @@ int sffg_knn_device(sffg_index *idx, const float *d_queries, int64_t nq, int k, 
     return fail(SFFG_ERR_ARG, "sffg_knn_device: bad arguments (1 <= k <= 128)");
   if (nq == 0) return SFFG_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  IndexDev v{idx->d_coords, idx->cap, idx->n, idx->dim};
+  IndexDev v{idx->d_coords, idx->cap, idx->n, idx->dim, idx->d_amax};
   int rc = ensure_sorted(idx, st);
   if (rc != SFFG_OK) return rc;
   if (idx->n_sorted > 0) {
@@ -1051,8 +1044,7 @@ int sffg_knn(sffg_index *idx, const float *queries, int64_t nq, int k, int32_t *
   if (!idx || nq < 0 || k < 1 || k > SFFG_MAX_K || (nq > 0 && (!queries || !ids_out || !d2_out)))
     return fail(SFFG_ERR_ARG, "sffg_knn: bad arguments (1 <= k <= 128)");
   if (nq == 0) return SFFG_OK;
-  int rc = check_angles(queries, nq, idx->dim);
-  if (rc != SFFG_OK) return rc;
+  int rc;
   const size_t qbytes = (size_t)nq * idx->dim * 4, obytes = (size_t)nq * k * 4;
   if (qbytes <= (64 << 10) && 2 * obytes <= kSmallBytes - (64 << 10)) {
     // planner-sized call: queries and results live in pinned mapped memory, one synchronisation
@@ -1094,8 +1086,7 @@ int sffg_knn_multi(sffg_index *const *idx, const int64_t *nq_per, int n_idx, con
   }
   if (total == 0) return SFFG_OK;
   if (!queries || !ids_out || !d2_out) return fail(SFFG_ERR_ARG, "sffg_knn_multi: null buffers");
-  int rc = check_angles(queries, total, dim);
-  if (rc != SFFG_OK) return rc;
+  int rc;
   sffg_index *lead = idx[0];   // its stream and staging carry the whole call
   cudaStream_t st = lead->stream;
   const size_t qbytes = (size_t)total * dim * 4, obytes = (size_t)total * k * 4;
@@ -1147,10 +1138,9 @@ int sffg_radius(sffg_index *idx, const float *queries, int64_t nq, float r2, int
     return fail(SFFG_ERR_ARG, "sffg_radius: bad arguments");
   if (total_out) *total_out = 0;
   if (nq == 0) return SFFG_OK;
-  int rc = check_angles(queries, nq, idx->dim);
-  if (rc != SFFG_OK) return rc;
+  int rc;
   cudaStream_t st = idx->stream;
-  IndexDev v{idx->d_coords, idx->cap, idx->n, idx->dim};
+  IndexDev v{idx->d_coords, idx->cap, idx->n, idx->dim, idx->d_amax};
   KnnPlan plan = plan_knn(nq, idx->n, g_rt.sm_count);
   const size_t qbytes = (size_t)nq * idx->dim * 4, cbytes = (size_t)nq * 4;
   // planner-sized calls stage through pinned memory so that every copy is an asynchronous DMA

@@ -37,6 +37,11 @@ def gold_knn():
 
 
 @pytest.fixture(scope="session")
+def gold_knn_wide():
+    return dict(np.load(GOLDEN / "knn_wide.npz"))
+
+
+@pytest.fixture(scope="session")
 def orc():
     import oracle
     oracle.build(ref=True)

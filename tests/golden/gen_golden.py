@@ -9,6 +9,7 @@ What comes from where
                  travel as data.  The product loader (sffg_mesh_load) is checked against these in the tests.
   knn.npz        outputs of the REAL vendored FLANN 1.9.1 LinearIndex (oracle/_ref, built from /root/reference) with
                  the fixed D6Distance functor: the pinned reference answers for exact k-NN / radius.
+  knn_wide.npz   the same for nodes / queries with un-normalised angles (+-50 rad).
   collision.npz  seeded poses + verdicts of the oracle's all-pairs double-precision SAT (ground truth definition;
                  RAPID itself is absent from the reference: "parity unpinned") + per-pose clearance margins.
   edges.npz      seeded edges + isPathFree results of the oracle.
@@ -74,6 +75,37 @@ def knn():
         out[f"rad{dim}_r2"] = np.float32(r2)
         out[f"rad{dim}_counts"], out[f"rad{dim}_ids"], out[f"rad{dim}_d2"] = c, ids, d2
     np.savez_compressed(OUT / "knn.npz", **out)
+
+
+def wide_cloud(n, seed, spread):
+    """6-D nodes whose angles have drifted out of [-pi, pi), as the unmodified reference host stores them
+    (getStateInDistance never re-normalises, src/primitives.h:237-250)"""
+    r = np.random.RandomState(seed)
+    pts = cloud(n, 6, seed)
+    pts[:, 3:] = r.uniform(-spread, spread, (n, 3)).astype(np.float32)
+    return pts
+
+
+def knn_wide():
+    """knn_wide.npz: REAL FLANN LinearIndex + FixedD6 on angles in +-50 rad (single wrap done in double and narrowed,
+    src/primitives.h:277-292); `small` stays below the engine's sorted-view threshold, `large` is above it"""
+    out = {}
+    for tag, n in (("small", 2000), ("large", 10000)):
+        nodes, q = wide_cloud(n, 31, 50.0), wide_cloud(128, 32, 50.0)
+        nodes[50:60] = nodes[0:10]            # ties
+        q[:8] = nodes[:8]
+        q[8:16, 3:] = -q[8:16, 3:]
+        nodes[100:110, 3:] = np.float32(12.5)  # the engine's fast/wide switch-over
+        q[16:24, 3:] = np.float32(-12.5)
+        out[f"{tag}_nodes"], out[f"{tag}_queries"] = nodes, q
+        for k in (1, 16, 50):
+            ids, d2 = O.ref_knn_linear(nodes, q, k)
+            out[f"{tag}_ids_k{k}"], out[f"{tag}_d2_k{k}"] = ids, d2
+        r2 = float(np.median(out[f"{tag}_d2_k16"][:, -1]))
+        c, off, ids, d2 = O.ref_radius_linear(nodes, q, r2)
+        out[f"{tag}_r2"] = np.float32(r2)
+        out[f"{tag}_rad_counts"], out[f"{tag}_rad_ids"], out[f"{tag}_rad_d2"] = c, ids, d2
+    np.savez_compressed(OUT / "knn_wide.npz", **out)
 
 
 def near_surface_poses(obst, n, seed, spread):
@@ -160,6 +192,7 @@ if __name__ == "__main__":
     O.build()
     m = meshes()
     knn()
+    knn_wide()
     collision(m)
     edges(m)
     for f in sorted(OUT.glob("*.npz")):

@@ -81,7 +81,7 @@ def test_radius_large_rows_and_empty_rows(sff, orc):
         assert np.all(np.diff(row) >= 0) and np.all(row < 67600.0)
 
 
-def test_argument_and_domain_errors(sff):
+def test_argument_errors(sff):
     idx = sff.Index(cloud(10, 6, 1))
     with pytest.raises(sff.SffgError) as ei:
         idx.knnSearch(cloud(2, 6, 2), 0)
@@ -89,11 +89,10 @@ def test_argument_and_domain_errors(sff):
     with pytest.raises(sff.SffgError) as ei:
         idx.knnSearch(cloud(2, 6, 2), 129)
     assert ei.value.code == 3
-    bad = cloud(2, 6, 2)
-    bad[1, 4] = 9.0
-    with pytest.raises(sff.SffgError) as ei:
-        idx.addPoints(bad)
-    assert ei.value.code == 6
+    wide = cloud(2, 6, 2)
+    wide[1, 4] = 9.0          # un-normalised angles are data, not an error (src/primitives.h:237-250 never re-normalises)
+    idx.addPoints(wide)
+    assert idx.size() == 12
     with pytest.raises(sff.SffgError):
         sff.Index(dim=3)
 
@@ -235,3 +234,70 @@ def test_radius_single_call_with_a_guessed_capacity(sff, orc):
             else:
                 assert rc == 5   # SFFG_ERR_CAPACITY
         idx.close()
+
+
+def wide_cloud(n, seed, spread):
+    """nodes as the unmodified reference host stores them: angles random-walk away from [-pi, pi) (src/primitives.h:237-250)"""
+    r = np.random.RandomState(seed)
+    pts = cloud(n, 6, seed)
+    pts[:, 3:] = r.uniform(-spread, spread, (n, 3)).astype(np.float32)
+    pts[::7, 3:] = r.uniform(-np.pi, np.pi, (len(pts[::7]), 3)).astype(np.float32)   # a normalised minority
+    return pts
+
+
+def test_wide_angles_golden_real_flann(sff, gold_knn_wide):
+    """angles in +-50 rad vs the reference's vendored FLANN LinearIndex with the FixedD6 functor (single wrap in double,
+    src/primitives.h:277-292): ids AND float bits, exhaustive kernel (N < 8192) and Morton-pruned kernel (N >= 8192)"""
+    g = gold_knn_wide
+    for tag in ("small", "large"):
+        idx = sff.Index(g[f"{tag}_nodes"])
+        q = g[f"{tag}_queries"]
+        for k in (1, 16, 50):
+            ids, d2 = idx.knnSearch(q, k)
+            np.testing.assert_array_equal(ids, g[f"{tag}_ids_k{k}"])
+            np.testing.assert_array_equal(d2.view(np.uint32), g[f"{tag}_d2_k{k}"].view(np.uint32))
+        c, off, ids, d2 = idx.radiusSearch(q, float(g[f"{tag}_r2"]))
+        np.testing.assert_array_equal(c, g[f"{tag}_rad_counts"])
+        np.testing.assert_array_equal(ids, g[f"{tag}_rad_ids"])
+        np.testing.assert_array_equal(d2.view(np.uint32), g[f"{tag}_rad_d2"].view(np.uint32))
+
+
+@pytest.mark.parametrize("n,nq,k,spread", [(60000, 9000, 16, 50.0), (60000, 1500, 5, 50.0), (60000, 3, 33, 50.0), (3000, 40, 8, 50.0),
+                                           (20000, 9000, 16, 7.0), (20000, 9000, 4, 1000.0)])
+def test_wide_angles_vs_oracle_and_ref(sff, orc, n, nq, k, spread):
+    """every queries-per-warp variant (8 / 4 / 1), sliced + merged small batches, unsorted tail, radius count + fill"""
+    nodes, q = wide_cloud(n, 11, spread), wide_cloud(nq, 12, spread)
+    idx = sff.Index(nodes[: n - 700])
+    idx.knnSearch(q[:1], 1)            # builds the sorted view now ...
+    idx.addPoints(nodes[n - 700:])     # ... so that these stay in the unsorted tail
+    ids, d2 = idx.knnSearch(q, k)
+    wi, wd = orc.knn_linear(nodes, q, k)
+    np.testing.assert_array_equal(ids, wi)
+    np.testing.assert_array_equal(d2.view(np.uint32), wd.view(np.uint32))
+    r2 = float(np.median(wd[:, -1]))
+    c, off, rid, rd = idx.radiusSearch(q[:2000], r2)
+    wc, woff, wrid, wrd = orc.radius_linear(nodes, q[:2000], r2)
+    np.testing.assert_array_equal(c, wc)
+    np.testing.assert_array_equal(rid, wrid)
+    np.testing.assert_array_equal(rd.view(np.uint32), wrd.view(np.uint32))
+    if orc._REF_PATH.exists():         # the real FLANN travels to the GPU box as oracle/_ref/libflann_ref.so
+        fi, fd = orc.ref_knn_linear(nodes, q[:300], k)
+        np.testing.assert_array_equal(ids[:300], fi)
+        np.testing.assert_array_equal(d2[:300].view(np.uint32), fd.view(np.uint32))
+
+
+def test_normalised_queries_against_wide_index_and_back(sff, orc):
+    """the wide decision is per warp (query angles + the index's largest stored angle): mixed batches stay exact"""
+    nodes = wide_cloud(30000, 21, 3.0)
+    q = np.concatenate([wide_cloud(4096, 22, 3.0), wide_cloud(4096, 23, 40.0)])
+    idx = sff.Index(nodes)
+    ids, d2 = idx.knnSearch(q, 8)
+    wi, wd = orc.knn_linear(nodes, q, 8)
+    np.testing.assert_array_equal(ids, wi)
+    np.testing.assert_array_equal(d2.view(np.uint32), wd.view(np.uint32))
+    idx.addPoints(wide_cloud(10, 24, 60.0))      # one far-out node flips every later query to the wide path
+    allnodes = np.concatenate([nodes, wide_cloud(10, 24, 60.0)])
+    ids, d2 = idx.knnSearch(q, 8)
+    wi, wd = orc.knn_linear(allnodes, q, 8)
+    np.testing.assert_array_equal(ids, wi)
+    np.testing.assert_array_equal(d2.view(np.uint32), wd.view(np.uint32))
