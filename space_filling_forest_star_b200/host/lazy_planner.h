@@ -54,6 +54,7 @@ class LazyPlanner {
       tour_ = n_ >= 2 ? solve_tsp() : std::vector<int>{0};
       now = 0;
       bool all_reachable = true;
+      const long searches_before = searches_;
       for (size_t e = 0; e < tour_.size() && n_ >= 2; ++e) {
         const int a = tour_[e], b = tour_[(e + 1) % tour_.size()];
         if (!book_.link(a, b).exists() && d(a, b) < kUnreachable) search_edge(a, b);
@@ -63,6 +64,9 @@ class LazyPlanner {
       ++passes_;
       solved_ = all_reachable && now >= prev - kTol && now <= prev + kTol;   // lazy.h:130
       if (n_ < 2) solved_ = true;
+      // a pass that searched nothing leaves the matrix, hence the next tour and `now`, unchanged: with an unreachable tour
+      // edge that is the reference's `newDist == prevDist` exit (lazy.h:128), reported as unsolved instead of spinning
+      if (!all_reachable && searches_ == searches_before) break;
     }
     elapsed_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     tour_length_ = now;

@@ -230,6 +230,26 @@ def test_lazy_validation_rules(exe, tmp_path):
     assert p.returncode == 1 and "single point path planning not defined for Lazy solver" in p.stdout
 
 
+def test_lazy_terminates_when_a_tour_edge_is_unreachable(exe, tmp_path):
+    """two roots and a budget far too small to link them: the edge search fails, the edge becomes unreachable, and the next
+    pass has nothing left to search -- the reference leaves its loop there (newDist == prevDist, src/lazy.h:128); the host
+    must report `unsolved` instead of spinning (run under a timeout)"""
+    import re
+    import subprocess
+    PU.run_planner(exe, tmp_path, "2d_lazy", seed=1)
+    txt = (tmp_path / "2d_lazy.xml").read_text()
+    pts = re.findall(r"\s*<Point [^>]*/>\n", txt)
+    for extra in pts[2:]:
+        txt = txt.replace(extra, "\n", 1)
+    txt = txt.replace('MaxIterations value="100000"', 'MaxIterations value="5"').replace("params_2d_lazy", "params_lazy_unreach")
+    cfg = tmp_path / "lazy_unreach.xml"
+    cfg.write_text(txt)
+    p = subprocess.run([str(exe), cfg.name, "0", "--seed", "1", "--quiet"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0, p.stdout + p.stderr
+    row = (tmp_path / "output" / "params_lazy_unreach.csv").read_text().strip().splitlines()[-1]
+    assert ",unsolved," in row, row
+
+
 def test_lazy_tsp_many_roots_without_a_map(exe, tmp_path):
     """15 roots on a circle, no obstacles (HasMap == false, src/environment.h:307-309): above 13 roots the tour comes from
     nearest neighbour + 2-opt; on a circle the optimal tour is the polygon, which 2-opt must find"""
