@@ -284,6 +284,29 @@ void build_wide_bvh(const double *tris, int64_t n, HostBvh *out) {
   c.tri_pos.resize((size_t)n);
   for (int64_t i = 0; i < n; ++i) c.tri_pos[(size_t)b.idx[(size_t)i]] = (int32_t)i;
   c.emit(0, 0);
+  // emit() numbers the nodes depth-first; the kernels stage the first few hundred nodes in shared memory, so renumber
+  // breadth-first: the top levels of the hierarchy become one contiguous prefix (what the device builder produces anyway)
+  {
+    const size_t nn = out->slots.size() / kWide;
+    std::vector<int32_t> order;   // new index -> old index
+    order.reserve(nn);
+    order.push_back(0);
+    for (size_t head = 0; head < order.size(); ++head)
+      for (int i = 0; i < kWide; ++i) {
+        const int32_t ch = out->slots[(size_t)order[head] * kWide + i].child;
+        if (ch >= 0 && ch != kEmptyChild) order.push_back(ch);
+      }
+    std::vector<int32_t> new_of(nn, -1);
+    for (size_t i = 0; i < order.size(); ++i) new_of[(size_t)order[i]] = (int32_t)i;
+    std::vector<ChildSlot> re(out->slots.size());
+    for (size_t i = 0; i < order.size(); ++i)
+      for (int k2 = 0; k2 < kWide; ++k2) {
+        ChildSlot s2 = out->slots[(size_t)order[i] * kWide + k2];
+        if (s2.child >= 0 && s2.child != kEmptyChild) s2.child = new_of[(size_t)s2.child];
+        re[i * kWide + k2] = s2;
+      }
+    out->slots.swap(re);
+  }
   for (int k = 0; k < 3; ++k) {
     out->root_lo[k] = all.lo[k];
     out->root_hi[k] = all.hi[k];

@@ -3,18 +3,24 @@
 // Replaces the inside of Environment<T>::Collide -> Obstacle<T>::Collide -> RAPID_Collide
 // (reference src/environment.h:306-316, :269-276) and of Solver<T,R>::isPathFree (src/problemStruct.h:154-168).
 //
-// Execution model (one warp = one pose at a time):
-//   phase A  lane-per-pose: load 32 poses, cull the robot's bounding sphere against the obstacle AABB, build R
-//   phase B  warp-per-pose for the survivors:
-//            - 8-wide AABB BVH, warp-shared DFS stack in shared memory; each step pops up to 4 nodes and the 32
-//              lanes test the 4x8 child boxes against the robot's oriented box (6-axis conservative SAT)
-//            - surviving leaf triangles are transformed into the robot frame (as RAPID does) lane-per-triangle,
-//              then lane-per-(obstacle triangle, robot triangle) pair runs the 17-axis separating-axis test in FP32
-//              as a *certificate* test: an axis only counts when its gap exceeds a rigorous rounding bound
-//            - pairs without an FP32 certificate are decided by the exact stage: the same 17 axes in FP64 with the
-//              operation order of the CPU oracle, one axis per lane; __all_sync gives the pair verdict
-//            - __ballot/__any early-out on the first confirmed contact (verdict-equivalent to RAPID's ALL_CONTACTS
-//              because the caller only looks at num_contacts != 0)
+// Execution model (one warp = one unit of 32 poses, its survivors share one task pool):
+//   phase A  lane-per-pose: load 32 poses, cull the robot's bounding sphere against the obstacle AABB and the clearance
+//            grid, build R; every surviving lane writes its pose record (R, T, oriented-box constants) to shared memory
+//   phase B  the warp works through ONE pool of tasks of all survivors of the unit, so that every stage runs on (close
+//            to) full lanes whatever the individual poses need:
+//            - 8-wide AABB BVH; the top of the hierarchy (a <=32-box cut + the first levels, breadth-first node order)
+//              is staged in shared memory per CTA.  The warp-shared stack holds (pose slot, node) items of all poses;
+//              each step pops up to 4 items and the 32 lanes test the 4x8 child boxes against the oriented box of
+//              *their item's* pose (6-axis conservative SAT, pose record read from shared memory)
+//            - surviving leaf triangles go to a shared (pose slot, triangle) list; the triangle stage transforms 32 of
+//              them into their robot frames (as RAPID does) lane-per-item, then lane-per-(obstacle triangle, robot
+//              triangle) pair runs the cheap half of the 17-axis separating-axis test in FP32 as a *certificate* test:
+//              an axis only counts when its gap exceeds a rigorous rounding bound
+//            - open pairs get the 9 edge x edge axes + 6 contact certificates cooperatively, TWO pairs per pass (one per
+//              half-warp, 15 lanes each); pairs without an FP32 certificate are decided by the exact stage: the same
+//              17 axes in FP64 with the operation order of the CPU oracle, one axis per lane
+//            - a confirmed contact retires its pose: pending items of that pose are dropped when they surface
+//              (verdict-equivalent to RAPID's ALL_CONTACTS because the caller only looks at num_contacts != 0)
 // The result equals "OR over all triangle pairs of the double-precision SAT" -- the oracle's ground truth.
 #include <cstdint>
 
@@ -27,13 +33,23 @@ namespace {
 #define SFFG_WARPS 16
 #endif
 #ifndef SFFG_TRI_FLUSH
-#define SFFG_TRI_FLUSH 1
+#define SFFG_TRI_FLUSH 32
+#endif
+#ifndef SFFG_START_BELOW
+#define SFFG_START_BELOW 8
+#endif
+#ifndef SFFG_SEQ_ADMIT
+#define SFFG_SEQ_ADMIT 0
 #endif
 constexpr int kWarpsPerBlock = SFFG_WARPS;
 constexpr int kThreads = kWarpsPerBlock * 32;
-constexpr int kStackCap = 384;   // node ids pending for one pose
-constexpr int kTriCap = 64;      // candidate triangles pending for one pose
-constexpr int kTriFlush = SFFG_TRI_FLUSH;    // run the triangle stage once this many candidates are pending
+constexpr int kStackCap = 384;   // (pose slot, node) items pending for one unit
+constexpr int kTriCap = 96;      // (pose slot, triangle) candidates pending for one unit
+constexpr bool kSeqAdmit = SFFG_SEQ_ADMIT != 0;   // 1: a pose enters only when the pool is empty (one pose at a time)
+constexpr int kStartBelow = SFFG_START_BELOW;   // a new pose enters the pool when fewer items than this are pending
+constexpr int kItemBits = 26;    // item = slot << 26 | index  (node / triangle index < 2^26, slot = lane of the pose)
+constexpr int kItemMask = (1 << kItemBits) - 1;
+constexpr int kTriFlush = SFFG_TRI_FLUSH;    // run the triangle stage once this many candidates of the pool are pending
 constexpr unsigned kFull = 0xffffffffu;
 #ifndef SFFG_MIN_BLOCKS
 #define SFFG_MIN_BLOCKS 1
@@ -46,14 +62,40 @@ struct XTri {        // obstacle triangle in the robot frame (FP32); 13 words = 
   float err;         // absolute position error bound of these 9 values
   float mabs;        // max |v|
   int tri;           // triangle index (leaf order) for the exact stage
-  int pad;
+  int slot;          // pose slot (lane of the pose inside its unit) whose robot frame this is
 };
 
-struct WarpScratch {
+// Record of one surviving pose, written by the pose's own lane in phase A and read per item in phase B.  Six float4;
+// the stride of 7 float4 (28 words) puts 8 consecutive slots on 8 distinct bank quads.
+struct __align__(16) PoseRec {
+  float R[9];          // row-major, world <- robot
+  float Thi[3];        // T = Thi + Tlo (+ negligible)
+  float o[3];          // R * (robot box centre) + Tlo
+  float rob_sz;
+  float ra[3];         // world-axis radii of the robot box
+  float pad0;
+  float Tlo[3];
+  float pad1;
+  float pad2[4];
+};
+static_assert(sizeof(PoseRec) == 112, "PoseRec stride");
+
+struct __align__(16) WarpScratch {
+  PoseRec rec[32];
   int stack[kStackCap];
   int tri[kTriCap];
   XTri xt[32];
 };
+static_assert(sizeof(WarpScratch) % 16 == 0, "WarpScratch must keep 16-byte alignment");
+
+// what a CTA stages once: the robot records, the top cut and the first nodes of the (breadth-first) hierarchy
+struct CtaShared {
+  const RobotTri *rob;
+  const float4 *top;     // 2 float4 per slot, E.n_top slots
+  const float4 *nodes;   // 16 float4 per node, n_stage nodes
+  int n_stage;
+};
+constexpr int kTopSlots = 32;
 
 // ---------------------------------------------------------------------------------------------------------
 // FP32 certificate SAT
@@ -137,29 +179,29 @@ __device__ __forceinline__ bool edge_pierces(const float *a, const float *b, con
   return (v0 > bound && v1 > bound && v2 > bound) || (v0 < -bound && v1 < -bound && v2 < -bound);
 }
 
-// Stage P2, warp-per-pair (all lanes call with the same pair): the nine edge x edge axes e_i x f_j on lanes 0..8 and the
-// six edge-pierces-triangle contact certificates on lanes 9..14, all at once.
-// Returns 0 = proven disjoint, 1 = proven contact, 2 = undecided (FP64 stage).
-__device__ __forceinline__ int pair_cooperative_verdict(const XTri &x, const RobotTri &rt, int lane) {
+// Stage P2, ten lanes per open pair, three pairs per pass (lanes 0..9, 10..19, 20..29; k = lane % 10):
+//   pass a  lanes k < 9 evaluate the nine edge x edge axes e_i x f_j        -> pairs proven disjoint
+//   pass b  (only for pairs pass a left open) lanes k < 6 evaluate the six edge-pierces-triangle contact certificates
+// Most open pairs are separated by an edge x edge axis, so pass b is skipped for most passes.
+__device__ __forceinline__ bool open_pair_axis(const XTri &x, const RobotTri &rt, int k) {
   const float *p = x.v;
+  const float errpos = 2.0f * x.err + kEpsSat * fmaxf(x.mabs, rt.qmax);
+  const int i = k / 3, j = k - 3 * i, i1 = i == 2 ? 0 : i + 1;
+  const float e[3] = {p[3 * i1] - p[3 * i], p[3 * i1 + 1] - p[3 * i + 1], p[3 * i1 + 2] - p[3 * i + 2]};
+  const float ax = e[1] * rt.f[j][2] - e[2] * rt.f[j][1], ay = e[2] * rt.f[j][0] - e[0] * rt.f[j][2],
+              az = e[0] * rt.f[j][1] - e[1] * rt.f[j][0];
+  return axis_certifies(ax, ay, az, p, rt.q, errpos);
+}
+__device__ __forceinline__ bool open_pair_pierce(const XTri &x, const RobotTri &rt, int c) {
   const float M = fmaxf(x.mabs, rt.qmax);
-  const float errpos = 2.0f * x.err + kEpsSat * M;
-  bool sep = false, con = false;
-  if (lane < 9) {
-    const int i = lane / 3, j = lane - 3 * i, i1 = i == 2 ? 0 : i + 1;
-    const float e[3] = {p[3 * i1] - p[3 * i], p[3 * i1 + 1] - p[3 * i + 1], p[3 * i1 + 2] - p[3 * i + 2]};
-    const float ax = e[1] * rt.f[j][2] - e[2] * rt.f[j][1], ay = e[2] * rt.f[j][0] - e[0] * rt.f[j][2],
-                az = e[0] * rt.f[j][1] - e[1] * rt.f[j][0];
-    sep = axis_certifies(ax, ay, az, p, rt.q, errpos);
-  } else if (lane < 15) {
-    const float bound = 256.0f * errpos * M * M;
-    const int c = lane - 9, ed = c < 3 ? c : c - 3, ed1 = ed == 2 ? 0 : ed + 1;
-    if (c < 3) con = edge_pierces(x.v + 3 * ed, x.v + 3 * ed1, rt.q[0], rt.q[1], rt.q[2], bound);
-    else con = edge_pierces(rt.q[ed], rt.q[ed1], x.v, x.v + 3, x.v + 6, bound);
-  }
-  if (__any_sync(kFull, sep)) return 0;
-  if (__any_sync(kFull, con)) return 1;
-  return 2;
+  const float bound = 256.0f * (2.0f * x.err + kEpsSat * M) * M * M;
+  // c < 3: obstacle edge c against the robot triangle; c >= 3: robot edge c - 3 against the obstacle triangle.  The operands
+  // are selected first so that both kinds share ONE inlined body instead of two divergent ones.
+  const int ed = c < 3 ? c : c - 3, ed1 = ed == 2 ? 0 : ed + 1;
+  const bool obst_edge = c < 3;
+  const float *a = obst_edge ? x.v + 3 * ed : rt.q[ed], *b = obst_edge ? x.v + 3 * ed1 : rt.q[ed1];
+  const float *c0 = obst_edge ? rt.q[0] : x.v, *c1 = obst_edge ? rt.q[1] : x.v + 3, *c2 = obst_edge ? rt.q[2] : x.v + 6;
+  return edge_pierces(a, b, c0, c1, c2, bound);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -371,81 +413,131 @@ __device__ __forceinline__ void LanePose<kFmtEulerF64>::rot32(float *R) const {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// per-pose warp traversal
+// phase B: one task pool per unit
 // ---------------------------------------------------------------------------------------------------------
-struct PoseU {          // warp-uniform copy of one pose
-  float R[9];           // row-major, world <- robot
-  float Thi[3], Tlo[3]; // T = Thi + Tlo (+ negligible)
-};
-
 struct Tally { unsigned long long past_root, box, pair, exact, steps, tri_passes, tris, exact_run, past_grid; };
 
-struct BoxTest {        // per-pose constants of the oriented-box test
-  float o[3], ra[3], rob_sz;
-};
+// the pose's own lane fills its record (phase A)
+__device__ __forceinline__ void write_pose_record(const EnvDev &E, PoseRec &rec, const float *R, const float *thi, const float *tlo) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k) rec.R[k] = R[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    rec.Thi[k] = thi[k];
+    rec.Tlo[k] = tlo[k];
+    rec.o[k] = R[3 * k] * E.rob_c[0] + R[3 * k + 1] * E.rob_c[1] + R[3 * k + 2] * E.rob_c[2] + tlo[k];
+    rec.ra[k] = fabsf(R[3 * k]) * E.rob_h[0] + fabsf(R[3 * k + 1]) * E.rob_h[1] + fabsf(R[3 * k + 2]) * E.rob_h[2];
+  }
+  rec.rob_sz = 2.0f * E.rob_radius + fabsf(tlo[0]) + fabsf(tlo[1]) + fabsf(tlo[2]);
+}
 
 // robot oriented box (centre T + R c, axes R, half extents h) against an AABB slot; conservative.  Straight-line code:
 // lanes of one step almost never agree on an early exit, so all six axes are evaluated and combined without branches.
-__device__ __forceinline__ bool slot_overlaps(const EnvDev &E, const PoseU &P, const BoxTest &bt, const float4 a, const float4 b) {
-  const float tx = (a.x - P.Thi[0]) - bt.o[0], ty = (a.y - P.Thi[1]) - bt.o[1], tz = (a.z - P.Thi[2]) - bt.o[2];
-  const float pad = kEpsBox * (fabsf(tx) + fabsf(ty) + fabsf(tz) + b.x + b.y + b.z + bt.rob_sz);
-  const float s0 = P.R[0] * tx + P.R[3] * ty + P.R[6] * tz, s1 = P.R[1] * tx + P.R[4] * ty + P.R[7] * tz,
-              s2 = P.R[2] * tx + P.R[5] * ty + P.R[8] * tz;
-  const float r0 = fabsf(P.R[0]) * b.x + fabsf(P.R[3]) * b.y + fabsf(P.R[6]) * b.z,
-              r1 = fabsf(P.R[1]) * b.x + fabsf(P.R[4]) * b.y + fabsf(P.R[7]) * b.z,
-              r2 = fabsf(P.R[2]) * b.x + fabsf(P.R[5]) * b.y + fabsf(P.R[8]) * b.z;
+// The pose constants come from the item's record in shared memory (five 16-byte loads).
+__device__ __forceinline__ bool slot_overlaps(const EnvDev &E, const PoseRec &rec, const float4 a, const float4 b) {
+  const float4 *rp = reinterpret_cast<const float4 *>(&rec);
+  const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2], q3 = rp[3], q4 = rp[4];
+  // q0 = R0 R1 R2 R3 | q1 = R4 R5 R6 R7 | q2 = R8 Thi0 Thi1 Thi2 | q3 = o0 o1 o2 rob_sz | q4 = ra0 ra1 ra2 -
+  const float tx = (a.x - q2.y) - q3.x, ty = (a.y - q2.z) - q3.y, tz = (a.z - q2.w) - q3.z;
+  const float pad = kEpsBox * (fabsf(tx) + fabsf(ty) + fabsf(tz) + b.x + b.y + b.z + q3.w);
+  const float s0 = q0.x * tx + q0.w * ty + q1.z * tz, s1 = q0.y * tx + q1.x * ty + q1.w * tz,
+              s2 = q0.z * tx + q1.y * ty + q2.x * tz;
+  const float r0 = fabsf(q0.x) * b.x + fabsf(q0.w) * b.y + fabsf(q1.z) * b.z,
+              r1 = fabsf(q0.y) * b.x + fabsf(q1.x) * b.y + fabsf(q1.w) * b.z,
+              r2 = fabsf(q0.z) * b.x + fabsf(q1.y) * b.y + fabsf(q2.x) * b.z;
   // the largest excess over the allowed distance on any axis; overlap iff none is positive
-  const float ex = fmaxf(fmaxf(fabsf(tx) - (b.x + bt.ra[0]), fabsf(ty) - (b.y + bt.ra[1])), fabsf(tz) - (b.z + bt.ra[2]));
+  const float ex = fmaxf(fmaxf(fabsf(tx) - (b.x + q4.x), fabsf(ty) - (b.y + q4.y)), fabsf(tz) - (b.z + q4.z));
   const float eb = fmaxf(fmaxf(fabsf(s0) - (E.rob_h[0] + r0), fabsf(s1) - (E.rob_h[1] + r1)), fabsf(s2) - (E.rob_h[2] + r2));
   return !(fmaxf(ex, eb) > pad);
 }
 
-template <int FMT, bool COUNT>
-__device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *srob, const PoseU &P,
-                              const LanePose<FMT> &lp, int src, int lane, Tally &tally) {
-  BoxTest bt;
+// obstacle triangle t into the robot frame of a pose record (what RAPID does: x = R2^T (p - T2)), FP32
+__device__ __forceinline__ void transform_tri(const EnvDev &E, const PoseRec &rec, int t, int slot, XTri &x) {
+  const float4 v0 = __ldg(E.tris32 + 3 * (size_t)t), v1 = __ldg(E.tris32 + 3 * (size_t)t + 1), v2 = __ldg(E.tris32 + 3 * (size_t)t + 2);
+  const float4 *rp = reinterpret_cast<const float4 *>(&rec);
+  const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2], q5 = rp[5];
+  const float R[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+  const float w[9] = {(v0.x - q2.y) - q5.x, (v0.y - q2.z) - q5.y, (v0.z - q2.w) - q5.z,
+                      (v1.x - q2.y) - q5.x, (v1.y - q2.z) - q5.y, (v1.z - q2.w) - q5.z,
+                      (v2.x - q2.y) - q5.x, (v2.y - q2.z) - q5.y, (v2.z - q2.w) - q5.z};
+  float mabs = 0.f;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    bt.o[k] = P.R[3 * k] * E.rob_c[0] + P.R[3 * k + 1] * E.rob_c[1] + P.R[3 * k + 2] * E.rob_c[2] + P.Tlo[k];
-    bt.ra[k] = fabsf(P.R[3 * k]) * E.rob_h[0] + fabsf(P.R[3 * k + 1]) * E.rob_h[1] + fabsf(P.R[3 * k + 2]) * E.rob_h[2];
-  }
-  bt.rob_sz = 2.0f * E.rob_radius + fabsf(P.Tlo[0]) + fabsf(P.Tlo[1]) + fabsf(P.Tlo[2]);
+  for (int v = 0; v < 3; ++v)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float val = R[c] * w[3 * v] + R[3 + c] * w[3 * v + 1] + R[6 + c] * w[3 * v + 2];
+      x.v[3 * v + c] = val;
+      mabs = fmaxf(mabs, fabsf(val));
+    }
+  x.err = v0.w;
+  x.mabs = mabs;
+  x.tri = t;
+  x.slot = slot;
+}
+
+__device__ __forceinline__ unsigned settled_slots(unsigned hit, bool first_only) {
+  return (first_only && hit) ? (hit | ~((hit & (0u - hit)) - 1u)) : hit;
+}
+
+// `todo`: lanes whose pose survived phase A (their records are in ws.rec).  Returns the mask of colliding lanes; with
+// `first_only` only its lowest bit is meaningful (an edge needs the first colliding sample) and work for slots above a
+// known hit is dropped.
+template <int FMT, bool COUNT>
+__device__ unsigned pool_hits(const EnvDev &E, WarpScratch &ws, const CtaShared &cs, unsigned todo, const LanePose<FMT> &lp,
+                              int lane, bool first_only, Tally &tally) {
   const unsigned lt = (1u << lane) - 1u;
-
+  const RobotTri *srob = cs.rob;
+  unsigned pending = todo, hit = 0;
   int sp = 0, ntri = 0;
-  bool hit = false;
-  bool have_R2 = false;
+  const float inv_n_robot = 1.0f / (float)E.n_robot;
+  const int grp10 = lane / 10, k10 = lane - 10 * grp10;
+  int r2_slot = -1;
   double R2[9], T2[3];
-  if (COUNT) tally.past_root += 1;
-
-  bool first = true;   // step 0 tests the precomputed <=32-box cut of the top of the hierarchy with all lanes
   while (true) {
-    if (first || (sp > 0 && ntri <= kTriCap - 32)) {
+    // slots whose outcome is settled: hit, or (first_only) above the lowest hit
+    const unsigned dead = (first_only && hit) ? (hit | ~((hit & (0u - hit)) - 1u)) : hit;
+    if (first_only && hit) pending = 0;   // poses enter in increasing slot order: everything still pending is above the hit
+    const bool start = pending != 0 && (kSeqAdmit ? (sp == 0 && ntri == 0) : (sp < kStartBelow && ntri <= kTriCap - 32));
+    if (start || (sp > 0 && ntri <= kTriCap - 32)) {
       bool ov = false;
-      int child = kEmptyChild;
+      int child = kEmptyChild, slot = 0;
       bool active;
-      if (first) {
+      if (start) {
+        // a new pose enters: all lanes test the precomputed <=32-box cut through the top of the hierarchy
+        slot = __ffs(pending) - 1;
+        pending &= pending - 1;
+        if (COUNT) tally.past_root += 1;
         active = lane < E.n_top;
         if (active) {
-          const float4 a = __ldg(E.top + 2 * lane), b = __ldg(E.top + 2 * lane + 1);
+          const float4 a = cs.top[2 * lane], b = cs.top[2 * lane + 1];
           child = __float_as_int(a.w);
-          ov = slot_overlaps(E, P, bt, a, b);
+          ov = slot_overlaps(E, ws.rec[slot], a, b);
         }
-        first = false;
       } else {
-        // 4 nodes per step while there is room; near the cap fall back to strict depth-first (1 node per step grows the
+        // 4 items per step while there is room; near the cap fall back to strict depth-first (1 item per step grows the
         // stack by at most 7 per level), which keeps any hierarchy of depth <= 45 inside the stack
         const int take = sp > kStackCap - 64 ? 1 : (sp < 4 ? sp : 4);
         const int grp = lane >> 3;
         active = grp < take;
-        const int node = active ? ws.stack[sp - 1 - grp] : 0;
+        const int item = active ? ws.stack[sp - 1 - grp] : 0;
         __syncwarp();
         sp -= take;
+        slot = item >> kItemBits;
+        const int node = item & kItemMask;
+        active = active && !((dead >> slot) & 1u);
         if (active) {
-          const float4 *s = E.slots + ((size_t)node * kWide + (lane & 7)) * 2;
-          const float4 a = __ldg(s), b = __ldg(s + 1);
+          float4 a, b;
+          if (node < cs.n_stage) {
+            const float4 *sn = cs.nodes + ((size_t)node * kWide + (lane & 7)) * 2;
+            a = sn[0];
+            b = sn[1];
+          } else {
+            const float4 *gn = E.slots + ((size_t)node * kWide + (lane & 7)) * 2;
+            a = __ldg(gn);
+            b = __ldg(gn + 1);
+          }
           child = __float_as_int(a.w);
-          if (child != kEmptyChild) ov = slot_overlaps(E, P, bt, a, b);
+          if (child != kEmptyChild) ov = slot_overlaps(E, ws.rec[slot], a, b);
         }
       }
       const unsigned m_int = __ballot_sync(kFull, ov && child >= 0);
@@ -453,9 +545,9 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *
       if (COUNT) { tally.box += __popc(__ballot_sync(kFull, active && child != kEmptyChild)); tally.steps += 1; }
       if (ov && child >= 0) {
         const int pos = sp + __popc(m_int & lt);
-        if (pos < kStackCap) ws.stack[pos] = child;
+        if (pos < kStackCap) ws.stack[pos] = (slot << kItemBits) | child;
       }
-      if (ov && child < 0) ws.tri[ntri + __popc(m_leaf & lt)] = ~child;
+      if (ov && child < 0) ws.tri[ntri + __popc(m_leaf & lt)] = (slot << kItemBits) | (~child);
       sp += __popc(m_int);
       ntri += __popc(m_leaf);
       if (sp > kStackCap) {     // never silently drop work: flag the launch as failed
@@ -463,45 +555,35 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *
         sp = kStackCap;
       }
       __syncwarp();
-      if (sp > 0 && ntri < kTriFlush) continue;
+      // keep traversing while that can still fill the triangle list (full lanes in the triangle stage)
+      if ((sp > 0 || pending != 0) && ntri < kTriFlush && ntri <= kTriCap - 32) continue;
     }
     if (ntri == 0) {
-      if (sp == 0) break;
+      if (sp == 0 && pending == 0) break;
       continue;
     }
     // ---------------- triangle stage ----------------
-    for (int base = 0; base < ntri && !hit; base += 32) {
+    const unsigned hit_before = hit;
+    for (int base = 0; base < ntri; base += 32) {
       const int cnt = (ntri - base) < 32 ? (ntri - base) : 32;
+      const unsigned dead_t = (first_only && hit) ? (hit | ~((hit & (0u - hit)) - 1u)) : hit;
       bool keep = false;
       XTri x;
       if (lane < cnt) {
-        const int t = ws.tri[base + lane];
-        const float4 v0 = __ldg(E.tris32 + 3 * (size_t)t), v1 = __ldg(E.tris32 + 3 * (size_t)t + 1),
-                     v2 = __ldg(E.tris32 + 3 * (size_t)t + 2);
-        const float w[9] = {(v0.x - P.Thi[0]) - P.Tlo[0], (v0.y - P.Thi[1]) - P.Tlo[1], (v0.z - P.Thi[2]) - P.Tlo[2],
-                            (v1.x - P.Thi[0]) - P.Tlo[0], (v1.y - P.Thi[1]) - P.Tlo[1], (v1.z - P.Thi[2]) - P.Tlo[2],
-                            (v2.x - P.Thi[0]) - P.Tlo[0], (v2.y - P.Thi[1]) - P.Tlo[1], (v2.z - P.Thi[2]) - P.Tlo[2]};
-        float mabs = 0.f;
-#pragma unroll
-        for (int v = 0; v < 3; ++v)
+        const int item = ws.tri[base + lane];
+        const int slot = item >> kItemBits, t = item & kItemMask;
+        if (!((dead_t >> slot) & 1u)) {
+          transform_tri(E, ws.rec[slot], t, slot, x);
+          const float mabs = x.mabs;
+          const float padT = 2.0f * x.err + kEpsSat * fmaxf(mabs, E.rob_radius);
+          keep = true;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float val = P.R[c] * w[3 * v] + P.R[3 + c] * w[3 * v + 1] + P.R[6 + c] * w[3 * v + 2];
-            x.v[3 * v + c] = val;
-            mabs = fmaxf(mabs, fabsf(val));
+            const float lo = min3f(x.v[c], x.v[3 + c], x.v[6 + c]) - padT, hi = max3f(x.v[c], x.v[3 + c], x.v[6 + c]) + padT;
+            const float rc = c == 0 ? E.rob_c[0] : (c == 1 ? E.rob_c[1] : E.rob_c[2]);
+            const float rh = c == 0 ? E.rob_h[0] : (c == 1 ? E.rob_h[1] : E.rob_h[2]);
+            if (lo > rc + rh || hi < rc - rh) keep = false;
           }
-        x.err = v0.w;
-        x.mabs = mabs;
-        x.tri = t;
-        x.pad = 0;
-        const float padT = 2.0f * x.err + kEpsSat * fmaxf(mabs, E.rob_radius);
-        keep = true;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float lo = min3f(x.v[c], x.v[3 + c], x.v[6 + c]) - padT, hi = max3f(x.v[c], x.v[3 + c], x.v[6 + c]) + padT;
-          const float rc = c == 0 ? E.rob_c[0] : (c == 1 ? E.rob_c[1] : E.rob_c[2]);
-          const float rh = c == 0 ? E.rob_h[0] : (c == 1 ? E.rob_h[1] : E.rob_h[2]);
-          if (lo > rc + rh || hi < rc - rh) keep = false;
         }
       }
       const unsigned km = __ballot_sync(kFull, keep);
@@ -510,12 +592,14 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *
       if (keep) ws.xt[__popc(km & lt)] = x;
       __syncwarp();
       const int npairs = nx * E.n_robot;
-      for (int pb = 0; pb < npairs && !hit; pb += 32) {
+      for (int pb = 0; pb < npairs; pb += 32) {
         const int pidx = pb + lane;
+        const unsigned dead_p = settled_slots(hit, first_only);
         bool undecided = false;
+        // (triangle, robot triangle) of this lane's pair; the quotient by float reciprocal is exact for pidx < 2^20
+        const int xi = (int)(((float)pidx + 0.5f) * inv_n_robot), r = pidx - xi * E.n_robot;
         if (pidx < npairs) {
-          const int xi = pidx / E.n_robot, r = pidx - xi * E.n_robot;
-          undecided = !pair_quick_disjoint(ws.xt[xi], srob[r]);
+          if (!((dead_p >> ws.xt[xi].slot) & 1u)) undecided = !pair_quick_disjoint(ws.xt[xi], srob[r]);
         }
         unsigned um = __ballot_sync(kFull, undecided);
         if (COUNT) {
@@ -524,33 +608,67 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const RobotTri *
           tally.exact += __popc(um);   // pairs the lane-per-pair stage P1 left open
         }
         while (um) {
-          const int l = __ffs(um) - 1;
+          // up to three open pairs per cooperative pass, ten lanes each: group g takes the g-th open pair
+          const int l0 = __ffs(um) - 1;
           um &= um - 1;
-          const int pp = pb + l;
-          const int xi = pp / E.n_robot, r = pp - xi * E.n_robot;
-          const int verdict = pair_cooperative_verdict(ws.xt[xi], srob[r], lane);
-          if (verdict == 0) continue;
-          if (verdict == 1) {
-            hit = true;
-            break;
-          }
-          if (COUNT) tally.exact_run += 1;
-          if (!have_R2) {
-            lp.exact(src, R2, T2, lane);
-            have_R2 = true;
-          }
-          const int t = ws.xt[xi].tri;
-          if (exact_pair_contact(R2, T2, E.tris64 + 9 * (size_t)t, E.robot64 + 9 * (size_t)r, lane)) {
-            hit = true;
-            break;
+          const int l1 = um ? __ffs(um) - 1 : -1;
+          um &= um - 1;   // (0 stays 0)
+          const int l2 = um ? __ffs(um) - 1 : -1;
+          um &= um - 1;
+          const int lmine = grp10 == 0 ? l0 : (grp10 == 1 ? l1 : (grp10 == 2 ? l2 : -1));
+          const int xim = __shfl_sync(kFull, xi, lmine & 31), rm = __shfl_sync(kFull, r, lmine & 31);
+          bool sep = false;
+          if (lmine >= 0 && k10 < 9) sep = open_pair_axis(ws.xt[xim], srob[rm], k10);
+          const unsigned bs = __ballot_sync(kFull, sep);
+          // groups whose pair no axis separated
+          unsigned open_g = 0;
+          if (!(bs & 0x3ffu)) open_g |= 1u;
+          if (l1 >= 0 && !(bs & (0x3ffu << 10))) open_g |= 2u;
+          if (l2 >= 0 && !(bs & (0x3ffu << 20))) open_g |= 4u;
+          if (open_g == 0) continue;
+          bool con = false;
+          if (lmine >= 0 && k10 < 6 && ((open_g >> grp10) & 1u)) con = open_pair_pierce(ws.xt[xim], srob[rm], k10);
+          const unsigned bc = __ballot_sync(kFull, con);
+          while (open_g) {
+            const int g = __ffs(open_g) - 1;
+            open_g &= open_g - 1;
+            const int lg = g == 0 ? l0 : (g == 1 ? l1 : l2);
+            const int xg = __shfl_sync(kFull, xi, lg), rg = __shfl_sync(kFull, r, lg);
+            const int slot = ws.xt[xg].slot;
+            if ((settled_slots(hit, first_only) >> slot) & 1u) continue;   // settled a moment ago
+            if (bc & (0x3ffu << (10 * g))) {
+              hit |= 1u << slot;
+              continue;
+            }
+            if (COUNT) tally.exact_run += 1;
+            if (r2_slot != slot) {
+              lp.exact(slot, R2, T2, lane);
+              r2_slot = slot;
+            }
+            const int t = ws.xt[xg].tri;
+            if (exact_pair_contact(R2, T2, E.tris64 + 9 * (size_t)t, E.robot64 + 9 * (size_t)rg, lane)) hit |= 1u << slot;
           }
         }
       }
       __syncwarp();
     }
-    if (hit) break;
     ntri = 0;
-    if (sp == 0) break;
+    if (hit != hit_before && sp > 0) {
+      // poses were retired: take their pending items off the stack now instead of popping them one step at a time
+      const unsigned dead_s = settled_slots(hit, first_only);
+      int out = 0;
+      for (int base = 0; base < sp; base += 32) {
+        const int v = base + lane < sp ? ws.stack[base + lane] : 0;
+        const bool keep_it = base + lane < sp && !((dead_s >> (v >> kItemBits)) & 1u);
+        const unsigned km2 = __ballot_sync(kFull, keep_it);
+        __syncwarp();
+        if (keep_it) ws.stack[out + __popc(km2 & lt)] = v;
+        out += __popc(km2);
+        __syncwarp();
+      }
+      sp = out;
+    }
+    if (sp == 0 && pending == 0) break;
   }
   return hit;
 }
@@ -577,12 +695,32 @@ __device__ __forceinline__ bool sphere_hits_root(const EnvDev &E, float tx, floa
   return dx * dx + dy * dy + dz * dz <= r * r * 1.000001f;
 }
 
-__device__ __forceinline__ void stage_robot(const EnvDev &E, RobotTri *srob) {
-  const int words = E.n_robot * (int)(sizeof(RobotTri) / 4);
-  const float *g = reinterpret_cast<const float *>(E.robot);
-  float *s = reinterpret_cast<float *>(srob);
-  for (int i = threadIdx.x; i < words; i += blockDim.x) s[i] = __ldg(g + i);
+// robot records, top cut and the first `n_stage` nodes of the hierarchy -> shared memory (once per CTA)
+__device__ __forceinline__ CtaShared stage_cta(const EnvDev &E, unsigned char *smem, int n_stage) {
+  RobotTri *srob = reinterpret_cast<RobotTri *>(smem);
+  float4 *stop = reinterpret_cast<float4 *>(smem + (size_t)E.n_robot * sizeof(RobotTri));
+  float4 *snodes = stop + 2 * kTopSlots;
+  {
+    const int words = E.n_robot * (int)(sizeof(RobotTri) / 4);
+    const float *g = reinterpret_cast<const float *>(E.robot);
+    float *d = reinterpret_cast<float *>(srob);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) d[i] = __ldg(g + i);
+  }
+  for (int i = threadIdx.x; i < 2 * E.n_top; i += blockDim.x) stop[i] = __ldg(E.top + i);
+  const int nv = n_stage * kWide * 2;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) snodes[i] = __ldg(E.slots + i);
   __syncthreads();
+  CtaShared cs;
+  cs.rob = srob;
+  cs.top = stop;
+  cs.nodes = snodes;
+  cs.n_stage = n_stage;
+  return cs;
+}
+__device__ __forceinline__ WarpScratch &warp_scratch(const EnvDev &E, unsigned char *smem, int warp) {
+  unsigned char *base = smem + (size_t)E.n_robot * sizeof(RobotTri) + (size_t)2 * kTopSlots * sizeof(float4) +
+                        (size_t)E.n_stage_max * kWide * 2 * sizeof(float4);
+  return reinterpret_cast<WarpScratch *>(base)[warp];
 }
 
 __device__ __forceinline__ void flush_tally(const EnvDev &E, const Tally &t, unsigned long long poses, int lane) {
@@ -600,37 +738,27 @@ __device__ __forceinline__ void flush_tally(const EnvDev &E, const Tally &t, uns
   }
 }
 
-// phase A (lane-per-pose cull + rotation) then phase B over the surviving lanes; returns the mask of colliding lanes
-// (stops at the first hit when `first_only`, which is what an edge needs)
+// phase A (lane-per-pose cull + rotation + pose record) then phase B over the pool of the surviving lanes; returns the
+// mask of colliding lanes (with `first_only` only the lowest bit counts, which is what an edge needs)
 template <int FMT, bool COUNT>
-__device__ __forceinline__ unsigned check_32_poses(const EnvDev &E, WarpScratch &ws, const RobotTri *srob, bool valid,
+__device__ __forceinline__ unsigned check_32_poses(const EnvDev &E, WarpScratch &ws, const CtaShared &cs, bool valid,
                                                    const LanePose<FMT> &lp, int lane, bool first_only, Tally &tally) {
-  float thi[3], tlo[3], R[9];
+  float thi[3], tlo[3];
   lp.split(thi, tlo);
   bool alive = valid && E.n_obst > 0 &&
                sphere_hits_root(E, thi[0], thi[1], thi[2], fabsf(tlo[0]) + fabsf(tlo[1]) + fabsf(tlo[2]));
   if (alive && E.grid_n[0] > 0) alive = !clearance_says_free(E, thi[0], thi[1], thi[2]);
-  if (COUNT) tally.past_grid += __popc(__ballot_sync(kFull, alive));
-  if (alive) lp.rot32(R);
-  unsigned todo = __ballot_sync(kFull, alive);
-  unsigned hitmask = 0;
-  while (todo) {
-    const int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    PoseU P;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) P.R[k] = __shfl_sync(kFull, R[k], src);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      P.Thi[k] = __shfl_sync(kFull, thi[k], src);
-      P.Tlo[k] = FMT == kFmtEulerF32 ? 0.f : __shfl_sync(kFull, tlo[k], src);
-    }
-    if (warp_pose_hit<FMT, COUNT>(E, ws, srob, P, lp, src, lane, tally)) {
-      hitmask |= 1u << src;
-      if (first_only) break;
-    }
+  const unsigned todo = __ballot_sync(kFull, alive);
+  if (COUNT) tally.past_grid += __popc(todo);
+  if (todo == 0) return 0;
+  if (alive) {
+    float R[9];
+    lp.rot32(R);
+    if (FMT == kFmtEulerF32) tlo[0] = tlo[1] = tlo[2] = 0.f;
+    write_pose_record(E, ws.rec[lane], R, thi, tlo);
   }
-  return hitmask;
+  __syncwarp();
+  return pool_hits<FMT, COUNT>(E, ws, cs, todo, lp, lane, first_only, tally);
 }
 
 // spins (one thread) until every rank has published an epoch >= `epoch` in the local flag words; bounded by a 10 s timeout
@@ -655,13 +783,12 @@ __device__ __forceinline__ void wait_flags(const FlagSet &f, unsigned epoch, int
 
 template <int FMT, bool COUNT>
 __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) collide_poses_kernel(EnvDev E, const void *poses, long long n,
-                                                                                  OutSet outs, GatherSync gs, int chunk) {
+                                                                                  OutSet outs, GatherSync gs, int chunk, int n_stage) {
   extern __shared__ __align__(16) unsigned char smem[];
-  RobotTri *srob = reinterpret_cast<RobotTri *>(smem);
   if (gs.flags.n > 0 && gs.wait_epoch != 0 && threadIdx.x == 0) wait_flags(gs.flags, gs.wait_epoch, E.status);
-  stage_robot(E, srob);   // (its __syncthreads also releases the CTA from the wait above)
+  const CtaShared cs = stage_cta(E, smem, n_stage);   // (its __syncthreads also releases the CTA from the wait above)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + (size_t)E.n_robot * sizeof(RobotTri))[warp];
+  WarpScratch &ws = warp_scratch(E, smem, warp);
   // a work unit is `chunk` (1..32) consecutive poses: 32 for large batches (full lanes in phase A), fewer when the
   // batch is too small to give every resident warp a unit (planner-sized calls are latency-, not throughput-bound)
   const long long nchunks = (n + chunk - 1) / chunk;
@@ -678,7 +805,7 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) collide_poses_kerne
     if (mine) lp.load(poses, i);
     else lp.clear();
     if (COUNT) nposes += mine ? 1 : 0;
-    const unsigned hitmask = check_32_poses<FMT, COUNT>(E, ws, srob, mine, lp, lane, false, tally);
+    const unsigned hitmask = check_32_poses<FMT, COUNT>(E, ws, cs, mine, lp, lane, false, tally);
     if (outs.n == 1) {
       if (mine) outs.p[0][i] = (uint8_t)((hitmask >> lane) & 1u);
     } else if (chunk == 32 && (long long)c * 32 + 32 <= n) {
@@ -736,12 +863,11 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(EnvDev E, const double *starts,
                                                                                 const double *ends, long long m, double sample,
                                                                                 int rot_mode, uint8_t *free_out,
-                                                                                int32_t *first_hit, int split, int *fh) {
+                                                                                int32_t *first_hit, int split, int *fh, int n_stage) {
   extern __shared__ __align__(16) unsigned char smem[];
-  RobotTri *srob = reinterpret_cast<RobotTri *>(smem);
-  stage_robot(E, srob);
+  const CtaShared cs = stage_cta(E, smem, n_stage);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + (size_t)E.n_robot * sizeof(RobotTri))[warp];
+  WarpScratch &ws = warp_scratch(E, smem, warp);
   Tally tally = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long nposes = 0;
   const long long units = m * split;
@@ -795,7 +921,7 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(
         for (int k = 0; k < 3; ++k) lp.a[k] = dadd(s[3 + k], __ddiv_rn(dmul(di, adir[k]), parts));
       }
       if (COUNT) nposes += valid ? 1 : 0;
-      const unsigned hm = check_32_poses<kFmtEulerF64, COUNT>(E, ws, srob, valid, lp, lane, true, tally);
+      const unsigned hm = check_32_poses<kFmtEulerF64, COUNT>(E, ws, cs, valid, lp, lane, true, tally);
       if (hm) hit_index = (int)(base + (long long)(__ffs(hm) - 1) * split);
     }
     if (lane == 0) {
@@ -972,17 +1098,26 @@ static const KernelCfg &kernel_cfg(size_t smem) {
   return c;
 }
 
-size_t collide_smem_bytes(int n_robot) {
-  return (size_t)n_robot * sizeof(RobotTri) + (size_t)kWarpsPerBlock * sizeof(WarpScratch);
+size_t collide_smem_bytes(int n_robot, int n_stage_max) {
+  return (size_t)n_robot * sizeof(RobotTri) + (size_t)2 * kTopSlots * sizeof(float4) +
+         (size_t)n_stage_max * kWide * 2 * sizeof(float4) + (size_t)kWarpsPerBlock * sizeof(WarpScratch);
+}
+
+// nodes of the hierarchy a launch stages per CTA: everything that fits for a large batch, the first three levels for a
+// planner-sized one (staging 100 KB would cost more than the few poses of such a call ever read)
+static int stage_nodes_for(const EnvDev &env, long long units) {
+  const int small = env.n_stage_max < 73 ? env.n_stage_max : 73;
+  return units >= 4096 ? env.n_stage_max : small;
 }
 
 
 template <int FMT>
 static cudaError_t launch_poses_fmt(const EnvDev &env, const void *d_poses, int64_t n, const OutSet &d_verdict, const GatherSync &gs,
                                     cudaStream_t stream, const LaunchCfg &cfg, bool count, int chunk, int *grid_out) {
-  const size_t smem = collide_smem_bytes(env.n_robot);
+  const size_t smem = collide_smem_bytes(env.n_robot, env.n_stage_max);
   const long long chunks = (n + chunk - 1) / chunk;
   const long long want = (chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int n_stage = stage_nodes_for(env, chunks);
   cudaError_t e;
   if (count) {
     const KernelCfg &kc = kernel_cfg<collide_poses_kernel<FMT, true>>(smem);
@@ -990,14 +1125,14 @@ static cudaError_t launch_poses_fmt(const EnvDev &env, const void *d_poses, int6
     int grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;
     *grid_out = grid;
-    collide_poses_kernel<FMT, true><<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict, gs, chunk);
+    collide_poses_kernel<FMT, true><<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict, gs, chunk, n_stage);
   } else {
     const KernelCfg &kc = kernel_cfg<collide_poses_kernel<FMT, false>>(smem);
     if ((e = kc.err) != cudaSuccess) return e;
     int grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;
     *grid_out = grid;
-    collide_poses_kernel<FMT, false><<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict, gs, chunk);
+    collide_poses_kernel<FMT, false><<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict, gs, chunk, n_stage);
   }
   return cudaGetLastError();
 }
@@ -1070,7 +1205,7 @@ cudaError_t launch_check_edges(const EnvDev &env_in, const double *d_starts, con
   if (m <= 0) return cudaSuccess;
   EnvDev env = env_in;
   env.work_base = *work_base_io;
-  const size_t smem = collide_smem_bytes(env.n_robot);
+  const size_t smem = collide_smem_bytes(env.n_robot, env.n_stage_max);
   // warps per edge: enough units for ~2 per resident warp, at most 32 (needs the scratch array)
   int split = 1;
   const long long warps = (long long)cfg.sm_count * 2 * kWarpsPerBlock * 2;
@@ -1078,6 +1213,7 @@ cudaError_t launch_check_edges(const EnvDev &env_in, const double *d_starts, con
     while (split < 32 && m * split < warps) split <<= 1;
   const long long units = m * split;
   const long long want = (units + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int n_stage = stage_nodes_for(env, units);
   cudaError_t e;
   if (split > 1 && (e = cudaMemsetAsync(d_fh_scratch, 0x7f, (size_t)m * sizeof(int), stream)) != cudaSuccess) return e;
   int grid;
@@ -1086,13 +1222,13 @@ cudaError_t launch_check_edges(const EnvDev &env_in, const double *d_starts, con
     if ((e = kc.err) != cudaSuccess) return e;
     grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;
-    check_edges_kernel<true><<<grid, kThreads, smem, stream>>>(env, d_starts, d_ends, (long long)m, sample_dist, rot_mode, d_free, d_first_hit, split, d_fh_scratch);
+    check_edges_kernel<true><<<grid, kThreads, smem, stream>>>(env, d_starts, d_ends, (long long)m, sample_dist, rot_mode, d_free, d_first_hit, split, d_fh_scratch, n_stage);
   } else {
     const KernelCfg &kc = kernel_cfg<check_edges_kernel<false>>(smem);
     if ((e = kc.err) != cudaSuccess) return e;
     grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;
-    check_edges_kernel<false><<<grid, kThreads, smem, stream>>>(env, d_starts, d_ends, (long long)m, sample_dist, rot_mode, d_free, d_first_hit, split, d_fh_scratch);
+    check_edges_kernel<false><<<grid, kThreads, smem, stream>>>(env, d_starts, d_ends, (long long)m, sample_dist, rot_mode, d_free, d_first_hit, split, d_fh_scratch, n_stage);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -10,6 +10,7 @@ struct EnvDev {
   const float4 *slots;      // 2 float4 per child slot, kWide slots per node
   const float4 *top;        // <= 32 slots: a cut through the top of the hierarchy, tested by all lanes in step 0
   int n_top;
+  int n_stage_max;          // leading nodes (breadth-first order) a CTA may stage in shared memory; fixes the smem layout
   const float4 *tris32;     // 3 float4 per obstacle triangle (BVH leaf order); p[0].w = representation error bound
   const double *tris64;     // 9 doubles per obstacle triangle (BVH leaf order) -- exact stage
   const RobotTri *robot;    // n_robot records (FP32, robot frame)
@@ -79,7 +80,11 @@ cudaError_t launch_check_edges(const EnvDev &env, const double *d_starts, const 
 cudaError_t launch_gen_poses(uint64_t seed, uint64_t first, int64_t n, const float range[6], float *d_out,
                              cudaStream_t stream);
 
-size_t collide_smem_bytes(int n_robot);
+size_t collide_smem_bytes(int n_robot, int n_stage_max);
+#ifndef SFFG_STAGE_NODES
+#define SFFG_STAGE_NODES 384
+#endif
+constexpr int kStageNodesCap = SFFG_STAGE_NODES;   // staged hierarchy per CTA at most (256 B per node)
 
 // marks every cell whose centre is within `reach` of an obstacle triangle (one warp per triangle)
 cudaError_t launch_build_clearance(const float4 *d_tris32, int n_tris, const float origin[3], float h, const int n[3], float reach,

@@ -36,6 +36,7 @@ struct Runtime {
   bool ready = false;
   int device = -1;
   int sm_count = 0;
+  int smem_optin = 0;   // largest dynamic shared memory a CTA may ask for
 };
 Runtime g_rt;
 
@@ -152,6 +153,7 @@ int sffg_init(int device) {
                                         std::to_string(prop.minor) + "; libsffg.so carries sm_100a code only");
   g_rt.device = device;
   g_rt.sm_count = prop.multiProcessorCount;
+  g_rt.smem_optin = (int)prop.sharedMemPerBlockOptin;
   g_rt.ready = true;
   return SFFG_OK;
 }
@@ -346,6 +348,8 @@ static int set_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obst,
   }
   // ---- clearance grid (free-space bitmap) over the obstacle AABB dilated by the robot's reach
   d.clear_bits = nullptr;
+  env->info.grid_cells = 0;
+  env->info.grid_cell_size = 0;
   d.grid_n[0] = d.grid_n[1] = d.grid_n[2] = 0;
   d.grid_inv_h = 0.f;
   d.grid_o[0] = d.grid_o[1] = d.grid_o[2] = 0.f;
@@ -387,6 +391,11 @@ static int set_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obst,
   d.slots = reinterpret_cast<const float4 *>(env->d_slots);
   d.top = reinterpret_cast<const float4 *>(env->d_top);
   d.n_top = (int)top.size();
+  {
+    // leading (breadth-first) nodes a CTA stages in shared memory: what fits next to the robot and the warp scratch
+    const int64_t room = ((int64_t)g_rt.smem_optin - 1024 - (int64_t)collide_smem_bytes(d.n_robot, 0)) / (int64_t)(kWide * sizeof(ChildSlot));
+    d.n_stage_max = (int)std::max<int64_t>(0, std::min<int64_t>({n_nodes, (int64_t)kStageNodesCap, room}));
+  }
   d.tris32 = reinterpret_cast<const float4 *>(env->d_tris32);
   d.tris64 = reinterpret_cast<const double *>(env->d_tris64);
   env->info.n_obst_tris = n_obst;
@@ -401,9 +410,16 @@ int sffg_env_create_ex(const double *obst_tris, int64_t n_obst, const double *ro
                        sffg_env **out) {
   if (!out || n_obst < 0 || n_robot <= 0 || !robot_tris || (n_obst > 0 && !obst_tris) || build_mode < 0 || build_mode > 2)
     return fail(SFFG_ERR_ARG, "sffg_env_create: bad arguments");
-  if (n_obst > 0x3fffffff || n_robot > 4096) return fail(SFFG_ERR_ARG, "sffg_env_create: mesh too large");
+  if (n_obst >= (1 << 26) || n_robot > 4096) return fail(SFFG_ERR_ARG, "sffg_env_create: mesh too large");
   int rc = ensure_runtime();
   if (rc != SFFG_OK) return rc;
+  // the kernels keep the whole robot in shared memory next to the per-warp scratch: refuse what cannot fit instead of
+  // building an environment whose every call would fail to launch
+  if (collide_smem_bytes((int)n_robot, 0) + 1024 > (size_t)g_rt.smem_optin) {
+    const size_t room = (size_t)g_rt.smem_optin - 1024 - collide_smem_bytes(0, 0);
+    return fail(SFFG_ERR_ARG, "sffg_env_create: robot mesh of " + std::to_string(n_robot) + " triangles does not fit the kernels' "
+                              "shared-memory staging (at most " + std::to_string(room / sizeof(RobotTri)) + " on this device)");
+  }
   const auto t0 = std::chrono::steady_clock::now();
 
   sffg_env *env = new sffg_env();
@@ -482,7 +498,7 @@ int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot
 }
 
 int sffg_env_set_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obst, int build_mode) {
-  if (!env || n_obst < 0 || (n_obst > 0 && !obst_tris) || n_obst > 0x3fffffff || build_mode < 0 || build_mode > 2)
+  if (!env || n_obst < 0 || (n_obst > 0 && !obst_tris) || n_obst >= (1 << 26) || build_mode < 0 || build_mode > 2)
     return fail(SFFG_ERR_ARG, "sffg_env_set_obstacles: bad arguments");
   SFFG_CUDA(cudaDeviceSynchronize());   // nothing may still be traversing the old hierarchy
   const auto t0 = std::chrono::steady_clock::now();
