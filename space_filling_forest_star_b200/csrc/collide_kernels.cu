@@ -3,24 +3,22 @@
 // Replaces the inside of Environment<T>::Collide -> Obstacle<T>::Collide -> RAPID_Collide
 // (reference src/environment.h:306-316, :269-276) and of Solver<T,R>::isPathFree (src/problemStruct.h:154-168).
 //
-// Execution model (one warp = one unit of 32 poses, its survivors share one task pool):
-//   phase A  lane-per-pose: load 32 poses, cull the robot's bounding sphere against the obstacle AABB and the clearance
-//            grid, build R; every surviving lane writes its pose record (R, T, oriented-box constants) to shared memory
-//   phase B  the warp works through ONE pool of tasks of all survivors of the unit, so that every stage runs on (close
-//            to) full lanes whatever the individual poses need:
-//            - 8-wide AABB BVH; the top of the hierarchy (a <=32-box cut + the first levels, breadth-first node order)
-//              is staged in shared memory per CTA.  The warp-shared stack holds (pose slot, node) items of all poses;
-//              each step pops up to 4 items and the 32 lanes test the 4x8 child boxes against the oriented box of
-//              *their item's* pose (6-axis conservative SAT, pose record read from shared memory)
-//            - surviving leaf triangles go to a shared (pose slot, triangle) list; the triangle stage transforms 32 of
-//              them into their robot frames (as RAPID does) lane-per-item, then lane-per-(obstacle triangle, robot
-//              triangle) pair runs the cheap half of the 17-axis separating-axis test in FP32 as a *certificate* test:
-//              an axis only counts when its gap exceeds a rigorous rounding bound
-//            - open pairs get the 9 edge x edge axes + 6 contact certificates cooperatively, TWO pairs per pass (one per
-//              half-warp, 15 lanes each); pairs without an FP32 certificate are decided by the exact stage: the same
-//              17 axes in FP64 with the operation order of the CPU oracle, one axis per lane
-//            - a confirmed contact retires its pose: pending items of that pose are dropped when they surface
-//              (verdict-equivalent to RAPID's ALL_CONTACTS because the caller only looks at num_contacts != 0)
+// Execution model (one warp = one pose at a time):
+//   phase A  lane-per-pose: load 32 poses, cull the robot's bounding sphere against the obstacle AABB, build R
+//   phase B  warp-per-pose for the survivors:
+//            - 8-wide AABB BVH (breadth-first node order); the top of the hierarchy -- a <=32-box cut tested by all lanes
+//              in step 0 and the first three levels of nodes -- is staged in shared memory once per CTA; warp-shared DFS
+//              stack in shared memory; each step pops up to 4 nodes and the 32 lanes test the 4x8 child boxes against
+//              the robot's oriented box (6-axis conservative SAT)
+//            - surviving leaf triangles are transformed into the robot frame (as RAPID does) lane-per-triangle,
+//              then lane-per-(obstacle triangle, robot triangle) pair runs the 17-axis separating-axis test in FP32
+//              as a *certificate* test: an axis only counts when its gap exceeds a rigorous rounding bound
+//            - pairs the lane-per-pair stage leaves open get the 9 edge x edge axes and, only if those fail, the 6
+//              contact certificates cooperatively, three pairs per pass on ten lanes each
+//            - pairs without an FP32 certificate are decided by the exact stage: the same 17 axes in FP64 with the
+//              operation order of the CPU oracle, one axis per lane; __all_sync gives the pair verdict
+//            - __ballot/__any early-out on the first confirmed contact (verdict-equivalent to RAPID's ALL_CONTACTS
+//              because the caller only looks at num_contacts != 0)
 // The result equals "OR over all triangle pairs of the double-precision SAT" -- the oracle's ground truth.
 #include <cstdint>
 
@@ -33,23 +31,13 @@ namespace {
 #define SFFG_WARPS 16
 #endif
 #ifndef SFFG_TRI_FLUSH
-#define SFFG_TRI_FLUSH 32
-#endif
-#ifndef SFFG_START_BELOW
-#define SFFG_START_BELOW 8
-#endif
-#ifndef SFFG_SEQ_ADMIT
-#define SFFG_SEQ_ADMIT 0
+#define SFFG_TRI_FLUSH 1
 #endif
 constexpr int kWarpsPerBlock = SFFG_WARPS;
 constexpr int kThreads = kWarpsPerBlock * 32;
-constexpr int kStackCap = 384;   // (pose slot, node) items pending for one unit
-constexpr int kTriCap = 96;      // (pose slot, triangle) candidates pending for one unit
-constexpr bool kSeqAdmit = SFFG_SEQ_ADMIT != 0;   // 1: a pose enters only when the pool is empty (one pose at a time)
-constexpr int kStartBelow = SFFG_START_BELOW;   // a new pose enters the pool when fewer items than this are pending
-constexpr int kItemBits = 26;    // item = slot << 26 | index  (node / triangle index < 2^26, slot = lane of the pose)
-constexpr int kItemMask = (1 << kItemBits) - 1;
-constexpr int kTriFlush = SFFG_TRI_FLUSH;    // run the triangle stage once this many candidates of the pool are pending
+constexpr int kStackCap = 384;   // node ids pending for one pose
+constexpr int kTriCap = 64;      // candidate triangles pending for one pose
+constexpr int kTriFlush = SFFG_TRI_FLUSH;    // run the triangle stage once this many candidates are pending
 constexpr unsigned kFull = 0xffffffffu;
 #ifndef SFFG_MIN_BLOCKS
 #define SFFG_MIN_BLOCKS 1
@@ -62,31 +50,14 @@ struct XTri {        // obstacle triangle in the robot frame (FP32); 13 words = 
   float err;         // absolute position error bound of these 9 values
   float mabs;        // max |v|
   int tri;           // triangle index (leaf order) for the exact stage
-  int slot;          // pose slot (lane of the pose inside its unit) whose robot frame this is
+  int pad;
 };
 
-// Record of one surviving pose, written by the pose's own lane in phase A and read per item in phase B.  Six float4;
-// the stride of 7 float4 (28 words) puts 8 consecutive slots on 8 distinct bank quads.
-struct __align__(16) PoseRec {
-  float R[9];          // row-major, world <- robot
-  float Thi[3];        // T = Thi + Tlo (+ negligible)
-  float o[3];          // R * (robot box centre) + Tlo
-  float rob_sz;
-  float ra[3];         // world-axis radii of the robot box
-  float pad0;
-  float Tlo[3];
-  float pad1;
-  float pad2[4];
-};
-static_assert(sizeof(PoseRec) == 112, "PoseRec stride");
-
-struct __align__(16) WarpScratch {
-  PoseRec rec[32];
+struct WarpScratch {
   int stack[kStackCap];
   int tri[kTriCap];
   XTri xt[32];
 };
-static_assert(sizeof(WarpScratch) % 16 == 0, "WarpScratch must keep 16-byte alignment");
 
 // what a CTA stages once: the robot records, the top cut and the first nodes of the (breadth-first) hierarchy
 struct CtaShared {
@@ -182,7 +153,6 @@ __device__ __forceinline__ bool edge_pierces(const float *a, const float *b, con
 // Stage P2, ten lanes per open pair, three pairs per pass (lanes 0..9, 10..19, 20..29; k = lane % 10):
 //   pass a  lanes k < 9 evaluate the nine edge x edge axes e_i x f_j        -> pairs proven disjoint
 //   pass b  (only for pairs pass a left open) lanes k < 6 evaluate the six edge-pierces-triangle contact certificates
-// Most open pairs are separated by an edge x edge axis, so pass b is skipped for most passes.
 __device__ __forceinline__ bool open_pair_axis(const XTri &x, const RobotTri &rt, int k) {
   const float *p = x.v;
   const float errpos = 2.0f * x.err + kEpsSat * fmaxf(x.mabs, rt.qmax);
@@ -195,8 +165,6 @@ __device__ __forceinline__ bool open_pair_axis(const XTri &x, const RobotTri &rt
 __device__ __forceinline__ bool open_pair_pierce(const XTri &x, const RobotTri &rt, int c) {
   const float M = fmaxf(x.mabs, rt.qmax);
   const float bound = 256.0f * (2.0f * x.err + kEpsSat * M) * M * M;
-  // c < 3: obstacle edge c against the robot triangle; c >= 3: robot edge c - 3 against the obstacle triangle.  The operands
-  // are selected first so that both kinds share ONE inlined body instead of two divergent ones.
   const int ed = c < 3 ? c : c - 3, ed1 = ed == 2 ? 0 : ed + 1;
   const bool obst_edge = c < 3;
   const float *a = obst_edge ? x.v + 3 * ed : rt.q[ed], *b = obst_edge ? x.v + 3 * ed1 : rt.q[ed1];
@@ -413,121 +381,81 @@ __device__ __forceinline__ void LanePose<kFmtEulerF64>::rot32(float *R) const {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// phase B: one task pool per unit
+// per-pose warp traversal
 // ---------------------------------------------------------------------------------------------------------
+struct PoseU {          // warp-uniform copy of one pose
+  float R[9];           // row-major, world <- robot
+  float Thi[3], Tlo[3]; // T = Thi + Tlo (+ negligible)
+};
+
 struct Tally { unsigned long long past_root, box, pair, exact, steps, tri_passes, tris, exact_run, past_grid; };
 
-// the pose's own lane fills its record (phase A)
-__device__ __forceinline__ void write_pose_record(const EnvDev &E, PoseRec &rec, const float *R, const float *thi, const float *tlo) {
-#pragma unroll
-  for (int k = 0; k < 9; ++k) rec.R[k] = R[k];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    rec.Thi[k] = thi[k];
-    rec.Tlo[k] = tlo[k];
-    rec.o[k] = R[3 * k] * E.rob_c[0] + R[3 * k + 1] * E.rob_c[1] + R[3 * k + 2] * E.rob_c[2] + tlo[k];
-    rec.ra[k] = fabsf(R[3 * k]) * E.rob_h[0] + fabsf(R[3 * k + 1]) * E.rob_h[1] + fabsf(R[3 * k + 2]) * E.rob_h[2];
-  }
-  rec.rob_sz = 2.0f * E.rob_radius + fabsf(tlo[0]) + fabsf(tlo[1]) + fabsf(tlo[2]);
-}
+struct BoxTest {        // per-pose constants of the oriented-box test
+  float o[3], ra[3], rob_sz;
+};
 
 // robot oriented box (centre T + R c, axes R, half extents h) against an AABB slot; conservative.  Straight-line code:
 // lanes of one step almost never agree on an early exit, so all six axes are evaluated and combined without branches.
-// The pose constants come from the item's record in shared memory (five 16-byte loads).
-__device__ __forceinline__ bool slot_overlaps(const EnvDev &E, const PoseRec &rec, const float4 a, const float4 b) {
-  const float4 *rp = reinterpret_cast<const float4 *>(&rec);
-  const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2], q3 = rp[3], q4 = rp[4];
-  // q0 = R0 R1 R2 R3 | q1 = R4 R5 R6 R7 | q2 = R8 Thi0 Thi1 Thi2 | q3 = o0 o1 o2 rob_sz | q4 = ra0 ra1 ra2 -
-  const float tx = (a.x - q2.y) - q3.x, ty = (a.y - q2.z) - q3.y, tz = (a.z - q2.w) - q3.z;
-  const float pad = kEpsBox * (fabsf(tx) + fabsf(ty) + fabsf(tz) + b.x + b.y + b.z + q3.w);
-  const float s0 = q0.x * tx + q0.w * ty + q1.z * tz, s1 = q0.y * tx + q1.x * ty + q1.w * tz,
-              s2 = q0.z * tx + q1.y * ty + q2.x * tz;
-  const float r0 = fabsf(q0.x) * b.x + fabsf(q0.w) * b.y + fabsf(q1.z) * b.z,
-              r1 = fabsf(q0.y) * b.x + fabsf(q1.x) * b.y + fabsf(q1.w) * b.z,
-              r2 = fabsf(q0.z) * b.x + fabsf(q1.y) * b.y + fabsf(q2.x) * b.z;
+__device__ __forceinline__ bool slot_overlaps(const EnvDev &E, const PoseU &P, const BoxTest &bt, const float4 a, const float4 b) {
+  const float tx = (a.x - P.Thi[0]) - bt.o[0], ty = (a.y - P.Thi[1]) - bt.o[1], tz = (a.z - P.Thi[2]) - bt.o[2];
+  const float pad = kEpsBox * (fabsf(tx) + fabsf(ty) + fabsf(tz) + b.x + b.y + b.z + bt.rob_sz);
+  const float s0 = P.R[0] * tx + P.R[3] * ty + P.R[6] * tz, s1 = P.R[1] * tx + P.R[4] * ty + P.R[7] * tz,
+              s2 = P.R[2] * tx + P.R[5] * ty + P.R[8] * tz;
+  const float r0 = fabsf(P.R[0]) * b.x + fabsf(P.R[3]) * b.y + fabsf(P.R[6]) * b.z,
+              r1 = fabsf(P.R[1]) * b.x + fabsf(P.R[4]) * b.y + fabsf(P.R[7]) * b.z,
+              r2 = fabsf(P.R[2]) * b.x + fabsf(P.R[5]) * b.y + fabsf(P.R[8]) * b.z;
   // the largest excess over the allowed distance on any axis; overlap iff none is positive
-  const float ex = fmaxf(fmaxf(fabsf(tx) - (b.x + q4.x), fabsf(ty) - (b.y + q4.y)), fabsf(tz) - (b.z + q4.z));
+  const float ex = fmaxf(fmaxf(fabsf(tx) - (b.x + bt.ra[0]), fabsf(ty) - (b.y + bt.ra[1])), fabsf(tz) - (b.z + bt.ra[2]));
   const float eb = fmaxf(fmaxf(fabsf(s0) - (E.rob_h[0] + r0), fabsf(s1) - (E.rob_h[1] + r1)), fabsf(s2) - (E.rob_h[2] + r2));
   return !(fmaxf(ex, eb) > pad);
 }
 
-// obstacle triangle t into the robot frame of a pose record (what RAPID does: x = R2^T (p - T2)), FP32
-__device__ __forceinline__ void transform_tri(const EnvDev &E, const PoseRec &rec, int t, int slot, XTri &x) {
-  const float4 v0 = __ldg(E.tris32 + 3 * (size_t)t), v1 = __ldg(E.tris32 + 3 * (size_t)t + 1), v2 = __ldg(E.tris32 + 3 * (size_t)t + 2);
-  const float4 *rp = reinterpret_cast<const float4 *>(&rec);
-  const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2], q5 = rp[5];
-  const float R[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
-  const float w[9] = {(v0.x - q2.y) - q5.x, (v0.y - q2.z) - q5.y, (v0.z - q2.w) - q5.z,
-                      (v1.x - q2.y) - q5.x, (v1.y - q2.z) - q5.y, (v1.z - q2.w) - q5.z,
-                      (v2.x - q2.y) - q5.x, (v2.y - q2.z) - q5.y, (v2.z - q2.w) - q5.z};
-  float mabs = 0.f;
-#pragma unroll
-  for (int v = 0; v < 3; ++v)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float val = R[c] * w[3 * v] + R[3 + c] * w[3 * v + 1] + R[6 + c] * w[3 * v + 2];
-      x.v[3 * v + c] = val;
-      mabs = fmaxf(mabs, fabsf(val));
-    }
-  x.err = v0.w;
-  x.mabs = mabs;
-  x.tri = t;
-  x.slot = slot;
-}
-
-__device__ __forceinline__ unsigned settled_slots(unsigned hit, bool first_only) {
-  return (first_only && hit) ? (hit | ~((hit & (0u - hit)) - 1u)) : hit;
-}
-
-// `todo`: lanes whose pose survived phase A (their records are in ws.rec).  Returns the mask of colliding lanes; with
-// `first_only` only its lowest bit is meaningful (an edge needs the first colliding sample) and work for slots above a
-// known hit is dropped.
 template <int FMT, bool COUNT>
-__device__ unsigned pool_hits(const EnvDev &E, WarpScratch &ws, const CtaShared &cs, unsigned todo, const LanePose<FMT> &lp,
-                              int lane, bool first_only, Tally &tally) {
-  const unsigned lt = (1u << lane) - 1u;
+__device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const CtaShared &cs, const PoseU &P,
+                              const LanePose<FMT> &lp, int src, int lane, Tally &tally) {
   const RobotTri *srob = cs.rob;
-  unsigned pending = todo, hit = 0;
+  BoxTest bt;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    bt.o[k] = P.R[3 * k] * E.rob_c[0] + P.R[3 * k + 1] * E.rob_c[1] + P.R[3 * k + 2] * E.rob_c[2] + P.Tlo[k];
+    bt.ra[k] = fabsf(P.R[3 * k]) * E.rob_h[0] + fabsf(P.R[3 * k + 1]) * E.rob_h[1] + fabsf(P.R[3 * k + 2]) * E.rob_h[2];
+  }
+  bt.rob_sz = 2.0f * E.rob_radius + fabsf(P.Tlo[0]) + fabsf(P.Tlo[1]) + fabsf(P.Tlo[2]);
+  const unsigned lt = (1u << lane) - 1u;
+
   int sp = 0, ntri = 0;
-  const float inv_n_robot = 1.0f / (float)E.n_robot;
   const int grp10 = lane / 10, k10 = lane - 10 * grp10;
-  int r2_slot = -1;
+  bool hit = false;
+  bool have_R2 = false;
   double R2[9], T2[3];
+  if (COUNT) tally.past_root += 1;
+
+  bool first = true;   // step 0 tests the precomputed <=32-box cut of the top of the hierarchy with all lanes
   while (true) {
-    // slots whose outcome is settled: hit, or (first_only) above the lowest hit
-    const unsigned dead = (first_only && hit) ? (hit | ~((hit & (0u - hit)) - 1u)) : hit;
-    if (first_only && hit) pending = 0;   // poses enter in increasing slot order: everything still pending is above the hit
-    const bool start = pending != 0 && (kSeqAdmit ? (sp == 0 && ntri == 0) : (sp < kStartBelow && ntri <= kTriCap - 32));
-    if (start || (sp > 0 && ntri <= kTriCap - 32)) {
+    if (first || (sp > 0 && ntri <= kTriCap - 32)) {
       bool ov = false;
-      int child = kEmptyChild, slot = 0;
+      int child = kEmptyChild;
       bool active;
-      if (start) {
-        // a new pose enters: all lanes test the precomputed <=32-box cut through the top of the hierarchy
-        slot = __ffs(pending) - 1;
-        pending &= pending - 1;
-        if (COUNT) tally.past_root += 1;
+      if (first) {
         active = lane < E.n_top;
         if (active) {
           const float4 a = cs.top[2 * lane], b = cs.top[2 * lane + 1];
           child = __float_as_int(a.w);
-          ov = slot_overlaps(E, ws.rec[slot], a, b);
+          ov = slot_overlaps(E, P, bt, a, b);
         }
+        first = false;
       } else {
-        // 4 items per step while there is room; near the cap fall back to strict depth-first (1 item per step grows the
+        // 4 nodes per step while there is room; near the cap fall back to strict depth-first (1 node per step grows the
         // stack by at most 7 per level), which keeps any hierarchy of depth <= 45 inside the stack
         const int take = sp > kStackCap - 64 ? 1 : (sp < 4 ? sp : 4);
         const int grp = lane >> 3;
         active = grp < take;
-        const int item = active ? ws.stack[sp - 1 - grp] : 0;
+        const int node = active ? ws.stack[sp - 1 - grp] : 0;
         __syncwarp();
         sp -= take;
-        slot = item >> kItemBits;
-        const int node = item & kItemMask;
-        active = active && !((dead >> slot) & 1u);
         if (active) {
           float4 a, b;
-          if (node < cs.n_stage) {
+          if (node < cs.n_stage) {   // (nodes of one step are popped together: mostly one side of this branch)
             const float4 *sn = cs.nodes + ((size_t)node * kWide + (lane & 7)) * 2;
             a = sn[0];
             b = sn[1];
@@ -537,7 +465,7 @@ __device__ unsigned pool_hits(const EnvDev &E, WarpScratch &ws, const CtaShared 
             b = __ldg(gn + 1);
           }
           child = __float_as_int(a.w);
-          if (child != kEmptyChild) ov = slot_overlaps(E, ws.rec[slot], a, b);
+          if (child != kEmptyChild) ov = slot_overlaps(E, P, bt, a, b);
         }
       }
       const unsigned m_int = __ballot_sync(kFull, ov && child >= 0);
@@ -545,9 +473,9 @@ __device__ unsigned pool_hits(const EnvDev &E, WarpScratch &ws, const CtaShared 
       if (COUNT) { tally.box += __popc(__ballot_sync(kFull, active && child != kEmptyChild)); tally.steps += 1; }
       if (ov && child >= 0) {
         const int pos = sp + __popc(m_int & lt);
-        if (pos < kStackCap) ws.stack[pos] = (slot << kItemBits) | child;
+        if (pos < kStackCap) ws.stack[pos] = child;
       }
-      if (ov && child < 0) ws.tri[ntri + __popc(m_leaf & lt)] = (slot << kItemBits) | (~child);
+      if (ov && child < 0) ws.tri[ntri + __popc(m_leaf & lt)] = ~child;
       sp += __popc(m_int);
       ntri += __popc(m_leaf);
       if (sp > kStackCap) {     // never silently drop work: flag the launch as failed
@@ -555,35 +483,45 @@ __device__ unsigned pool_hits(const EnvDev &E, WarpScratch &ws, const CtaShared 
         sp = kStackCap;
       }
       __syncwarp();
-      // keep traversing while that can still fill the triangle list (full lanes in the triangle stage)
-      if ((sp > 0 || pending != 0) && ntri < kTriFlush && ntri <= kTriCap - 32) continue;
+      if (sp > 0 && ntri < kTriFlush) continue;
     }
     if (ntri == 0) {
-      if (sp == 0 && pending == 0) break;
+      if (sp == 0) break;
       continue;
     }
     // ---------------- triangle stage ----------------
-    const unsigned hit_before = hit;
-    for (int base = 0; base < ntri; base += 32) {
+    for (int base = 0; base < ntri && !hit; base += 32) {
       const int cnt = (ntri - base) < 32 ? (ntri - base) : 32;
-      const unsigned dead_t = (first_only && hit) ? (hit | ~((hit & (0u - hit)) - 1u)) : hit;
       bool keep = false;
       XTri x;
       if (lane < cnt) {
-        const int item = ws.tri[base + lane];
-        const int slot = item >> kItemBits, t = item & kItemMask;
-        if (!((dead_t >> slot) & 1u)) {
-          transform_tri(E, ws.rec[slot], t, slot, x);
-          const float mabs = x.mabs;
-          const float padT = 2.0f * x.err + kEpsSat * fmaxf(mabs, E.rob_radius);
-          keep = true;
+        const int t = ws.tri[base + lane];
+        const float4 v0 = __ldg(E.tris32 + 3 * (size_t)t), v1 = __ldg(E.tris32 + 3 * (size_t)t + 1),
+                     v2 = __ldg(E.tris32 + 3 * (size_t)t + 2);
+        const float w[9] = {(v0.x - P.Thi[0]) - P.Tlo[0], (v0.y - P.Thi[1]) - P.Tlo[1], (v0.z - P.Thi[2]) - P.Tlo[2],
+                            (v1.x - P.Thi[0]) - P.Tlo[0], (v1.y - P.Thi[1]) - P.Tlo[1], (v1.z - P.Thi[2]) - P.Tlo[2],
+                            (v2.x - P.Thi[0]) - P.Tlo[0], (v2.y - P.Thi[1]) - P.Tlo[1], (v2.z - P.Thi[2]) - P.Tlo[2]};
+        float mabs = 0.f;
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float lo = min3f(x.v[c], x.v[3 + c], x.v[6 + c]) - padT, hi = max3f(x.v[c], x.v[3 + c], x.v[6 + c]) + padT;
-            const float rc = c == 0 ? E.rob_c[0] : (c == 1 ? E.rob_c[1] : E.rob_c[2]);
-            const float rh = c == 0 ? E.rob_h[0] : (c == 1 ? E.rob_h[1] : E.rob_h[2]);
-            if (lo > rc + rh || hi < rc - rh) keep = false;
+            const float val = P.R[c] * w[3 * v] + P.R[3 + c] * w[3 * v + 1] + P.R[6 + c] * w[3 * v + 2];
+            x.v[3 * v + c] = val;
+            mabs = fmaxf(mabs, fabsf(val));
           }
+        x.err = v0.w;
+        x.mabs = mabs;
+        x.tri = t;
+        x.pad = 0;
+        const float padT = 2.0f * x.err + kEpsSat * fmaxf(mabs, E.rob_radius);
+        keep = true;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float lo = min3f(x.v[c], x.v[3 + c], x.v[6 + c]) - padT, hi = max3f(x.v[c], x.v[3 + c], x.v[6 + c]) + padT;
+          const float rc = c == 0 ? E.rob_c[0] : (c == 1 ? E.rob_c[1] : E.rob_c[2]);
+          const float rh = c == 0 ? E.rob_h[0] : (c == 1 ? E.rob_h[1] : E.rob_h[2]);
+          if (lo > rc + rh || hi < rc - rh) keep = false;
         }
       }
       const unsigned km = __ballot_sync(kFull, keep);
@@ -592,14 +530,12 @@ __device__ unsigned pool_hits(const EnvDev &E, WarpScratch &ws, const CtaShared 
       if (keep) ws.xt[__popc(km & lt)] = x;
       __syncwarp();
       const int npairs = nx * E.n_robot;
-      for (int pb = 0; pb < npairs; pb += 32) {
+      for (int pb = 0; pb < npairs && !hit; pb += 32) {
         const int pidx = pb + lane;
-        const unsigned dead_p = settled_slots(hit, first_only);
         bool undecided = false;
-        // (triangle, robot triangle) of this lane's pair; the quotient by float reciprocal is exact for pidx < 2^20
-        const int xi = (int)(((float)pidx + 0.5f) * inv_n_robot), r = pidx - xi * E.n_robot;
         if (pidx < npairs) {
-          if (!((dead_p >> ws.xt[xi].slot) & 1u)) undecided = !pair_quick_disjoint(ws.xt[xi], srob[r]);
+          const int xi = pidx / E.n_robot, r = pidx - xi * E.n_robot;
+          undecided = !pair_quick_disjoint(ws.xt[xi], srob[r]);
         }
         unsigned um = __ballot_sync(kFull, undecided);
         if (COUNT) {
@@ -607,8 +543,8 @@ __device__ unsigned pool_hits(const EnvDev &E, WarpScratch &ws, const CtaShared 
           tally.pair += np;
           tally.exact += __popc(um);   // pairs the lane-per-pair stage P1 left open
         }
-        while (um) {
-          // up to three open pairs per cooperative pass, ten lanes each: group g takes the g-th open pair
+        const int xi_l = pidx / E.n_robot, r_l = pidx - xi_l * E.n_robot;
+        while (um && !hit) {
           const int l0 = __ffs(um) - 1;
           um &= um - 1;
           const int l1 = um ? __ffs(um) - 1 : -1;
@@ -616,11 +552,10 @@ __device__ unsigned pool_hits(const EnvDev &E, WarpScratch &ws, const CtaShared 
           const int l2 = um ? __ffs(um) - 1 : -1;
           um &= um - 1;
           const int lmine = grp10 == 0 ? l0 : (grp10 == 1 ? l1 : (grp10 == 2 ? l2 : -1));
-          const int xim = __shfl_sync(kFull, xi, lmine & 31), rm = __shfl_sync(kFull, r, lmine & 31);
+          const int xim = __shfl_sync(kFull, xi_l, lmine & 31), rm = __shfl_sync(kFull, r_l, lmine & 31);
           bool sep = false;
           if (lmine >= 0 && k10 < 9) sep = open_pair_axis(ws.xt[xim], srob[rm], k10);
           const unsigned bs = __ballot_sync(kFull, sep);
-          // groups whose pair no axis separated
           unsigned open_g = 0;
           if (!(bs & 0x3ffu)) open_g |= 1u;
           if (l1 >= 0 && !(bs & (0x3ffu << 10))) open_g |= 2u;
@@ -628,47 +563,33 @@ __device__ unsigned pool_hits(const EnvDev &E, WarpScratch &ws, const CtaShared 
           if (open_g == 0) continue;
           bool con = false;
           if (lmine >= 0 && k10 < 6 && ((open_g >> grp10) & 1u)) con = open_pair_pierce(ws.xt[xim], srob[rm], k10);
-          const unsigned bc = __ballot_sync(kFull, con);
+          if (__any_sync(kFull, con)) {
+            hit = true;
+            break;
+          }
           while (open_g) {
             const int g = __ffs(open_g) - 1;
             open_g &= open_g - 1;
             const int lg = g == 0 ? l0 : (g == 1 ? l1 : l2);
-            const int xg = __shfl_sync(kFull, xi, lg), rg = __shfl_sync(kFull, r, lg);
-            const int slot = ws.xt[xg].slot;
-            if ((settled_slots(hit, first_only) >> slot) & 1u) continue;   // settled a moment ago
-            if (bc & (0x3ffu << (10 * g))) {
-              hit |= 1u << slot;
-              continue;
-            }
+            const int xg = __shfl_sync(kFull, xi_l, lg), rg = __shfl_sync(kFull, r_l, lg);
             if (COUNT) tally.exact_run += 1;
-            if (r2_slot != slot) {
-              lp.exact(slot, R2, T2, lane);
-              r2_slot = slot;
+            if (!have_R2) {
+              lp.exact(src, R2, T2, lane);
+              have_R2 = true;
             }
             const int t = ws.xt[xg].tri;
-            if (exact_pair_contact(R2, T2, E.tris64 + 9 * (size_t)t, E.robot64 + 9 * (size_t)rg, lane)) hit |= 1u << slot;
+            if (exact_pair_contact(R2, T2, E.tris64 + 9 * (size_t)t, E.robot64 + 9 * (size_t)rg, lane)) {
+              hit = true;
+              break;
+            }
           }
         }
       }
       __syncwarp();
     }
+    if (hit) break;
     ntri = 0;
-    if (hit != hit_before && sp > 0) {
-      // poses were retired: take their pending items off the stack now instead of popping them one step at a time
-      const unsigned dead_s = settled_slots(hit, first_only);
-      int out = 0;
-      for (int base = 0; base < sp; base += 32) {
-        const int v = base + lane < sp ? ws.stack[base + lane] : 0;
-        const bool keep_it = base + lane < sp && !((dead_s >> (v >> kItemBits)) & 1u);
-        const unsigned km2 = __ballot_sync(kFull, keep_it);
-        __syncwarp();
-        if (keep_it) ws.stack[out + __popc(km2 & lt)] = v;
-        out += __popc(km2);
-        __syncwarp();
-      }
-      sp = out;
-    }
-    if (sp == 0 && pending == 0) break;
+    if (sp == 0) break;
   }
   return hit;
 }
@@ -738,27 +659,37 @@ __device__ __forceinline__ void flush_tally(const EnvDev &E, const Tally &t, uns
   }
 }
 
-// phase A (lane-per-pose cull + rotation + pose record) then phase B over the pool of the surviving lanes; returns the
-// mask of colliding lanes (with `first_only` only the lowest bit counts, which is what an edge needs)
+// phase A (lane-per-pose cull + rotation) then phase B over the surviving lanes; returns the mask of colliding lanes
+// (stops at the first hit when `first_only`, which is what an edge needs)
 template <int FMT, bool COUNT>
 __device__ __forceinline__ unsigned check_32_poses(const EnvDev &E, WarpScratch &ws, const CtaShared &cs, bool valid,
                                                    const LanePose<FMT> &lp, int lane, bool first_only, Tally &tally) {
-  float thi[3], tlo[3];
+  float thi[3], tlo[3], R[9];
   lp.split(thi, tlo);
   bool alive = valid && E.n_obst > 0 &&
                sphere_hits_root(E, thi[0], thi[1], thi[2], fabsf(tlo[0]) + fabsf(tlo[1]) + fabsf(tlo[2]));
   if (alive && E.grid_n[0] > 0) alive = !clearance_says_free(E, thi[0], thi[1], thi[2]);
-  const unsigned todo = __ballot_sync(kFull, alive);
-  if (COUNT) tally.past_grid += __popc(todo);
-  if (todo == 0) return 0;
-  if (alive) {
-    float R[9];
-    lp.rot32(R);
-    if (FMT == kFmtEulerF32) tlo[0] = tlo[1] = tlo[2] = 0.f;
-    write_pose_record(E, ws.rec[lane], R, thi, tlo);
+  if (COUNT) tally.past_grid += __popc(__ballot_sync(kFull, alive));
+  if (alive) lp.rot32(R);
+  unsigned todo = __ballot_sync(kFull, alive);
+  unsigned hitmask = 0;
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    PoseU P;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) P.R[k] = __shfl_sync(kFull, R[k], src);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      P.Thi[k] = __shfl_sync(kFull, thi[k], src);
+      P.Tlo[k] = FMT == kFmtEulerF32 ? 0.f : __shfl_sync(kFull, tlo[k], src);
+    }
+    if (warp_pose_hit<FMT, COUNT>(E, ws, cs, P, lp, src, lane, tally)) {
+      hitmask |= 1u << src;
+      if (first_only) break;
+    }
   }
-  __syncwarp();
-  return pool_hits<FMT, COUNT>(E, ws, cs, todo, lp, lane, first_only, tally);
+  return hitmask;
 }
 
 // spins (one thread) until every rank has published an epoch >= `epoch` in the local flag words; bounded by a 10 s timeout
@@ -783,10 +714,10 @@ __device__ __forceinline__ void wait_flags(const FlagSet &f, unsigned epoch, int
 
 template <int FMT, bool COUNT>
 __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) collide_poses_kernel(EnvDev E, const void *poses, long long n,
-                                                                                  OutSet outs, GatherSync gs, int chunk, int n_stage) {
+                                                                                  OutSet outs, GatherSync gs, int chunk) {
   extern __shared__ __align__(16) unsigned char smem[];
   if (gs.flags.n > 0 && gs.wait_epoch != 0 && threadIdx.x == 0) wait_flags(gs.flags, gs.wait_epoch, E.status);
-  const CtaShared cs = stage_cta(E, smem, n_stage);   // (its __syncthreads also releases the CTA from the wait above)
+  const CtaShared cs = stage_cta(E, smem, E.n_stage_max);   // (its __syncthreads also releases the CTA from the wait above)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpScratch &ws = warp_scratch(E, smem, warp);
   // a work unit is `chunk` (1..32) consecutive poses: 32 for large batches (full lanes in phase A), fewer when the
@@ -863,9 +794,9 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(EnvDev E, const double *starts,
                                                                                 const double *ends, long long m, double sample,
                                                                                 int rot_mode, uint8_t *free_out,
-                                                                                int32_t *first_hit, int split, int *fh, int n_stage) {
+                                                                                int32_t *first_hit, int split, int *fh) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const CtaShared cs = stage_cta(E, smem, n_stage);
+  const CtaShared cs = stage_cta(E, smem, E.n_stage_max);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpScratch &ws = warp_scratch(E, smem, warp);
   Tally tally = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1103,13 +1034,6 @@ size_t collide_smem_bytes(int n_robot, int n_stage_max) {
          (size_t)n_stage_max * kWide * 2 * sizeof(float4) + (size_t)kWarpsPerBlock * sizeof(WarpScratch);
 }
 
-// nodes of the hierarchy a launch stages per CTA: everything that fits for a large batch, the first three levels for a
-// planner-sized one (staging 100 KB would cost more than the few poses of such a call ever read)
-static int stage_nodes_for(const EnvDev &env, long long units) {
-  const int small = env.n_stage_max < 73 ? env.n_stage_max : 73;
-  return units >= 4096 ? env.n_stage_max : small;
-}
-
 
 template <int FMT>
 static cudaError_t launch_poses_fmt(const EnvDev &env, const void *d_poses, int64_t n, const OutSet &d_verdict, const GatherSync &gs,
@@ -1117,7 +1041,6 @@ static cudaError_t launch_poses_fmt(const EnvDev &env, const void *d_poses, int6
   const size_t smem = collide_smem_bytes(env.n_robot, env.n_stage_max);
   const long long chunks = (n + chunk - 1) / chunk;
   const long long want = (chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const int n_stage = stage_nodes_for(env, chunks);
   cudaError_t e;
   if (count) {
     const KernelCfg &kc = kernel_cfg<collide_poses_kernel<FMT, true>>(smem);
@@ -1125,14 +1048,14 @@ static cudaError_t launch_poses_fmt(const EnvDev &env, const void *d_poses, int6
     int grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;
     *grid_out = grid;
-    collide_poses_kernel<FMT, true><<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict, gs, chunk, n_stage);
+    collide_poses_kernel<FMT, true><<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict, gs, chunk);
   } else {
     const KernelCfg &kc = kernel_cfg<collide_poses_kernel<FMT, false>>(smem);
     if ((e = kc.err) != cudaSuccess) return e;
     int grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;
     *grid_out = grid;
-    collide_poses_kernel<FMT, false><<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict, gs, chunk, n_stage);
+    collide_poses_kernel<FMT, false><<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict, gs, chunk);
   }
   return cudaGetLastError();
 }
@@ -1213,7 +1136,6 @@ cudaError_t launch_check_edges(const EnvDev &env_in, const double *d_starts, con
     while (split < 32 && m * split < warps) split <<= 1;
   const long long units = m * split;
   const long long want = (units + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const int n_stage = stage_nodes_for(env, units);
   cudaError_t e;
   if (split > 1 && (e = cudaMemsetAsync(d_fh_scratch, 0x7f, (size_t)m * sizeof(int), stream)) != cudaSuccess) return e;
   int grid;
@@ -1222,13 +1144,13 @@ cudaError_t launch_check_edges(const EnvDev &env_in, const double *d_starts, con
     if ((e = kc.err) != cudaSuccess) return e;
     grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;
-    check_edges_kernel<true><<<grid, kThreads, smem, stream>>>(env, d_starts, d_ends, (long long)m, sample_dist, rot_mode, d_free, d_first_hit, split, d_fh_scratch, n_stage);
+    check_edges_kernel<true><<<grid, kThreads, smem, stream>>>(env, d_starts, d_ends, (long long)m, sample_dist, rot_mode, d_free, d_first_hit, split, d_fh_scratch);
   } else {
     const KernelCfg &kc = kernel_cfg<check_edges_kernel<false>>(smem);
     if ((e = kc.err) != cudaSuccess) return e;
     grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;
-    check_edges_kernel<false><<<grid, kThreads, smem, stream>>>(env, d_starts, d_ends, (long long)m, sample_dist, rot_mode, d_free, d_first_hit, split, d_fh_scratch, n_stage);
+    check_edges_kernel<false><<<grid, kThreads, smem, stream>>>(env, d_starts, d_ends, (long long)m, sample_dist, rot_mode, d_free, d_first_hit, split, d_fh_scratch);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -81,10 +81,13 @@ cudaError_t launch_gen_poses(uint64_t seed, uint64_t first, int64_t n, const flo
                              cudaStream_t stream);
 
 size_t collide_smem_bytes(int n_robot, int n_stage_max);
+// Staged hierarchy per CTA at most: the first three levels (1 + 8 + 64 nodes, 18.7 KB).  Shared memory and L1 come out
+// of the same 256 KB per SM; 384 staged nodes (96 KB) measured no faster than 73 because L1 holds the deeper levels
+// and the triangles (profiles/r02_collide_variants.md).
 #ifndef SFFG_STAGE_NODES
-#define SFFG_STAGE_NODES 384
+#define SFFG_STAGE_NODES 73
 #endif
-constexpr int kStageNodesCap = SFFG_STAGE_NODES;   // staged hierarchy per CTA at most (256 B per node)
+constexpr int kStageNodesCap = SFFG_STAGE_NODES;
 
 // marks every cell whose centre is within `reach` of an obstacle triangle (one warp per triangle)
 cudaError_t launch_build_clearance(const float4 *d_tris32, int n_tris, const float origin[3], float h, const int n[3], float reach,

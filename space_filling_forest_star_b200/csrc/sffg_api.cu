@@ -410,7 +410,7 @@ int sffg_env_create_ex(const double *obst_tris, int64_t n_obst, const double *ro
                        sffg_env **out) {
   if (!out || n_obst < 0 || n_robot <= 0 || !robot_tris || (n_obst > 0 && !obst_tris) || build_mode < 0 || build_mode > 2)
     return fail(SFFG_ERR_ARG, "sffg_env_create: bad arguments");
-  if (n_obst >= (1 << 26) || n_robot > 4096) return fail(SFFG_ERR_ARG, "sffg_env_create: mesh too large");
+  if (n_obst > 0x3fffffff || n_robot > 4096) return fail(SFFG_ERR_ARG, "sffg_env_create: mesh too large");
   int rc = ensure_runtime();
   if (rc != SFFG_OK) return rc;
   // the kernels keep the whole robot in shared memory next to the per-warp scratch: refuse what cannot fit instead of
@@ -498,7 +498,7 @@ int sffg_env_create(const double *obst_tris, int64_t n_obst, const double *robot
 }
 
 int sffg_env_set_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obst, int build_mode) {
-  if (!env || n_obst < 0 || (n_obst > 0 && !obst_tris) || n_obst >= (1 << 26) || build_mode < 0 || build_mode > 2)
+  if (!env || n_obst < 0 || (n_obst > 0 && !obst_tris) || n_obst > 0x3fffffff || build_mode < 0 || build_mode > 2)
     return fail(SFFG_ERR_ARG, "sffg_env_set_obstacles: bad arguments");
   SFFG_CUDA(cudaDeviceSynchronize());   // nothing may still be traversing the old hierarchy
   const auto t0 = std::chrono::steady_clock::now();
