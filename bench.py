@@ -15,8 +15,15 @@ One step = one pass of the pose->verdict path over one batch of POSES_PER_GPU po
              sharding.PeerGather); --gather nccl runs kernel + NCCL all-gather instead
   e2e        same metric through the reference-facing host call (sffg_collide_poses_f32 on pinned host buffers):
              H2D of the poses and D2H of the verdicts inside the timed region
-  roofline   dominant kernel = collide_poses_kernel; algorithmic HBM bytes = 25 B/pose (24 B pose in + 1 B verdict out);
-             roofline.issue = the instruction-issue roofline that actually bounds the kernel
+             N > 1: after the timed loop every byte of the gathered buffer is compared with an NCCL all-gather of verdicts
+             recomputed locally, and rank r also recomputes rank (r+1) % N's whole shard itself (gather_verified)
+  e2e.edges  second end-to-end figure, through the call the planner actually makes: sffg_check_edges on pinned host
+             buffers (96 B per edge up, 1 B down, 39 sample poses per edge) -- not PCIe-bound
+  e2e.h2d_probe  plain pinned cudaMemcpyAsync host->device on all ranks at once: the host-side ceiling of the pose e2e
+  roofline   dominant kernel = collide_poses_kernel.  It is instruction-issue bound (bound = "issue"): achieved = warp
+             instructions per launch (committed ncu capture, refused when its source hash is not the current kernel's)
+             / the kernel time measured live here; peak = SMs x 4 schedulers x sampled SM clock.  roofline.hbm keeps the
+             HBM view (25 B/pose algorithmic: 24 B pose in + 1 B verdict out) and roofline.traffic the measured DRAM bytes
   cpu_baseline / --impl reference
              the CPU restatement of the reference path (RAPID-style OBB-tree, ALL_CONTACTS as src/environment.h:274
              calls it) on all host cores; RAPID itself is absent from the reference, so kind = "port"
@@ -52,16 +59,28 @@ def load_meshes():
     return m["building_s10"], m["robot_small_s10"]
 
 
-def measured_traffic(poses_per_launch):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json)"""
-    p = ROOT / "profiles" / "traffic.json"
+def _source_sha16(files):
+    import hashlib
+    h = hashlib.sha256()
+    for f in files:
+        h.update((ROOT / "space_filling_forest_star_b200" / "csrc" / f).read_bytes())
+    return h.hexdigest()[:16]
+
+
+def committed_counters(name, files):
+    """per-launch ncu counters committed under profiles/ (scripts/summarize_profile.py); None when the capture belongs to
+    older kernel sources than the ones libsffg.so was built from -- stale counters are never reported"""
     try:
-        t = json.loads(p.read_text())
-        if int(t["poses_per_launch"]) == int(poses_per_launch):
-            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"]), t
+        t = json.loads((ROOT / "profiles" / name).read_text())
     except Exception:
-        pass
-    return None, None
+        return None, "no committed capture"
+    if t.get("source_sha16") != _source_sha16(files):
+        return None, f"profiles/{name} was captured from other kernel sources (hash {t.get('source_sha16')}); re-profile"
+    return t, None
+
+
+COLLIDE_SOURCES = ["collide_kernels.cu", "collide_kernels.cuh", "common.h"]
+KNN_SOURCES = ["knn_pruned.cu", "knn_common.cuh", "knn_kernels.cu"]
 
 
 def measured_peak_hbm():
@@ -74,22 +93,42 @@ def measured_peak_hbm():
     return 6650.0, "fallback"
 
 
+def _parse_cpulist(txt):
+    out = []
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        out.extend(range(int(lo), int(hi or lo) + 1))
+    return out
+
+
 def bind_to_gpu_numa_node(index: int):
-    """N > 1: pin this rank to the CPUs next to its GPU (NVML's ideal affinity) before any pinned host buffer is allocated,
-    so that the e2e leg's H2D stream reads from the local NUMA node instead of crossing the socket interconnect."""
+    """Before any pinned host buffer exists: run this rank on the CPUs next to its GPU where the container allows it (sysfs
+    local_cpulist of the GPU's PCI function) and make the GPU's NUMA node the preferred node for new pages (set_mempolicy),
+    so the e2e leg's H2D stream reads host memory on the GPU's own socket.  Returns what was done, for the JSON line."""
+    info = {"numa_node": None, "cpus": None, "cpus_local_to_gpu": 0, "mempolicy": False}
     try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
-        cpus = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1]
-        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        dev = Path("/sys/bus/pci/devices") / f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int((dev / "numa_node").read_text())
+        info["numa_node"] = node
+        allowed = sorted(set(_parse_cpulist((dev / "local_cpulist").read_text())) & os.sched_getaffinity(0))
         if allowed:
             os.sched_setaffinity(0, allowed)
-            return len(allowed)
-    except Exception:
-        pass
-    return None
+        info["cpus"] = len(os.sched_getaffinity(0))
+        info["cpus_local_to_gpu"] = len(allowed)
+        if node >= 0:
+            import ctypes
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            MPOL_PREFERRED = 1
+            rc = libc.syscall(238, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))   # __NR_set_mempolicy (x86-64)
+            info["mempolicy"] = rc == 0
+    except Exception as ex:
+        info["error"] = repr(ex)[:120]
+    return info
 
 
 class ClockSampler:
@@ -146,8 +185,17 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def bench_config(args, obst, robot):
+    """identical in both arms: the workload one step covers, per GPU"""
+    n = args.gpus
+    return {"workload": WORKLOAD, "poses_per_gpu_per_step": args.poses_per_gpu, "pose_seed": SEED, "obstacle_tris": int(len(obst)),
+            "robot_tris": int(len(robot)), "l2_policy": "inputs larger than L2 (24 B/pose streamed from HBM, 402 MB per 2^24 poses)",
+            "parallelism": f"pose-shard x{n} + verdict all-gather" if n > 1 else "single GPU"}
+
+
 def run_reference(args):
-    """CPU arm: the oracle port of the reference path on all host cores (rank 0 only)."""
+    """CPU arm: the oracle port of the reference path on all host cores (rank 0 only), one step = the same number of
+    poses one GPU checks per step in the other arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -156,7 +204,7 @@ def run_reference(args):
     obst, robot = load_meshes()
     mo, mr = O.ObbModel(obst), O.ObbModel(robot)
     threads = host_threads()
-    sample = args.cpu_sample
+    sample = args.poses_per_gpu
     poses = O.gen_poses(SEED, 0, sample, RANGE).astype(np.float64)
     for _ in range(args.warmup):
         O.collide_obbtree(mo, mr, poses[: sample // 8], first_contact=False, threads=threads, want_verdicts=False)
@@ -169,7 +217,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "poses_per_step": sample, "pose_seed": SEED},
+        "config": bench_config(args, obst, robot),
         "cpu_baseline": {"value": value, "unit": "poses/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} poses/step, RAPID-restatement OBB-tree (oracle/sff_oracle.c), ALL_CONTACTS, "
                                    f"OpenMP over poses; RAPID 2.01 itself is not vendored in the reference"},
@@ -295,15 +343,29 @@ def run_ours(args):
         dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     kernel_ms = float(kern_ms.item())
-    if pg is not None:
-        # every rank must hold every rank's verdicts: compare each gathered slice with the count its owner reports
-        full = pg.view(last_buf[0], dev)
-        verdict.copy_(full[rank, :P])
-        mine = torch.tensor([int(verdict.sum().item())], device=dev, dtype=torch.int64)
-        counts = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(counts, mine)
-        seen = [int(full[r, :P].sum().item()) for r in range(world)]
-        assert seen == [int(c.item()) for c in counts], ("peer gather mismatch", seen, counts)
+    # ---- N > 1: byte-exact verification of the gathered verdicts (outside the timed region) ------------------------
+    gather_check = None
+    if world > 1:
+        env.collide_device(poses, out=verdict)                       # this rank's shard, computed locally
+        dist.all_gather_into_tensor(gathered, verdict)               # NCCL reference gather of the same verdicts
+        nxt = (rank + 1) % world
+        poses_n = S.gen_poses_device(SEED, nxt * P, P, RANGE)        # rank (r+1) % N's whole shard, recomputed here
+        verdict_n = env.collide_device(poses_n)
+        del poses_n
+        if pg is not None:
+            full = pg.view(last_buf[0], dev)                         # [world, per]: what the fused gather left on this rank
+            got = full[:, :P].reshape(-1)
+        else:
+            got = gathered                                           # (nccl mode: the timed loop's own last gather)
+        ok_all = bool(torch.equal(got, gathered))                    # every byte of every slice against the NCCL result
+        ok_next = bool(torch.equal(got[nxt * P:(nxt + 1) * P], verdict_n))
+        flag = torch.tensor([1.0 if (ok_all and ok_next) else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_check = {"gather_verified": bool(flag.item() > 0), "bytes_compared_per_rank": int(world * P + P),
+                        "how": "gathered buffer == NCCL all-gather of locally recomputed verdicts (all slices, byte for byte) "
+                               "and slice (r+1)%N == that shard recomputed on rank r", "mode": gather_mode}
+        assert gather_check["gather_verified"], ("gathered verdicts differ", rank, ok_all, ok_next)
+        del verdict_n
     hits = int(verdict.sum().item())
 
     # ---- end-to-end leg: pinned host buffers through the host C-ABI call ----------------------------------------
@@ -326,49 +388,110 @@ def run_ours(args):
     e2e_hits = int(h_out.sum().item())
     assert e2e_hits == hits, (e2e_hits, hits)
 
+    # host-side ceiling of that leg: the same pinned buffer through plain cudaMemcpyAsync, all ranks at the same time
+    probe = torch.empty_like(poses)
+    for _ in range(2):
+        probe.copy_(h_poses, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pa.record()
+    for _ in range(4):
+        probe.copy_(h_poses, non_blocking=True)
+    pb.record()
+    torch.cuda.synchronize()
+    gbs = torch.tensor([4 * P * 24 / (pa.elapsed_time(pb) * 1e-3) / 1e9], device=dev)
+    gbs_min, gbs_sum = gbs.clone(), gbs.clone()
+    if world > 1:
+        dist.all_reduce(gbs_min, op=dist.ReduceOp.MIN)
+        dist.all_reduce(gbs_sum, op=dist.ReduceOp.SUM)
+    del probe
+    h2d_probe = {"gbs_per_rank_min": float(gbs_min.item()), "gbs_aggregate": float(gbs_sum.item()),
+                 "what": "pinned host -> device cudaMemcpyAsync of the same 24 B/pose buffer, all ranks concurrently"}
+    e2e_frac = e2e_value * 24 / 1e9 / float(gbs_sum.item())
+
+    # second e2e figure: the call the planner makes -- sffg_check_edges on pinned host buffers (96 B/edge up, 1 B down)
+    edges_e2e = None
+    try:
+        m_e = 1 << 20
+        s_e = S.gen_poses_device(SEED + 1, rank * m_e, m_e, [-45, 45, -45, 45, 0, 125]).double()
+        d_e = torch.randn((m_e, 3), device=dev, dtype=torch.float64, generator=torch.Generator(device=dev).manual_seed(1 + rank))
+        e_e = s_e.clone()
+        e_e[:, :3] += 4.0 * d_e / d_e.norm(dim=1, keepdim=True)
+        h_s = torch.empty((m_e, 6), dtype=torch.float64, pin_memory=True)
+        h_e = torch.empty((m_e, 6), dtype=torch.float64, pin_memory=True)
+        h_s.copy_(s_e)
+        h_e.copy_(e_e)
+        h_free = torch.empty(m_e, dtype=torch.uint8, pin_memory=True)
+        torch.cuda.synchronize()
+        del s_e, e_e, d_e
+        env.edges_host_buffers(h_s.data_ptr(), h_e.data_ptr(), m_e, h_free.data_ptr())
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            env.edges_host_buffers(h_s.data_ptr(), h_e.data_ptr(), m_e, h_free.data_ptr())
+        ed = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(ed, op=dist.ReduceOp.MAX)
+        eps = world * m_e * 3 / float(ed.item())
+        edges_e2e = {"edges_per_s": eps, "pose_equivalents_per_s": eps * 39, "samples_per_edge": 39,
+                     "h2d_bytes_per_step": m_e * 96, "d2h_bytes_per_step": m_e, "edges_per_gpu_per_step": m_e,
+                     "free_fraction": float(h_free.float().mean().item()),
+                     "api": "sffg_check_edges on pinned host buffers (edges of 6-D length 4 in building.obj, sample 0.1, "
+                            "isPathFree semantics: an edge stops at its first colliding sample)"}
+    except Exception as ex:
+        edges_e2e = {"error": repr(ex)}
+
     knn_multi = None
     if world > 1 and not args.no_extra:
         knn_multi = sharded_knn_rate(S, torch, dist, dev, rank, world)
     if rank == 0:
         peak, which = measured_peak_hbm()
         achieved = ALGO_BYTES_PER_POSE * P / (kernel_ms * 1e-3) / 1e9
-        traffic, tinfo = measured_traffic(P)
+        tinfo, stale = committed_counters("traffic.json", COLLIDE_SOURCES)
+        if tinfo is not None and int(tinfo.get("poses_per_launch", 0)) != int(P):
+            tinfo, stale = None, "committed capture is for another batch size"
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue_peak = sms * 4 * (clocks["sm_mhz"] or 1965) * 1e6 / 1e9
+        hbm = {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
+               "algorithmic_bytes_per_pose": ALGO_BYTES_PER_POSE, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POSE * P}
+        if tinfo is not None:
+            # the roofline that bounds this kernel: warp-instruction issue.  achieved = ncu count of executed warp instructions
+            # per launch (capture committed with the hash of the kernel sources it was taken from) / the kernel time measured
+            # live here; peak = SMs x 4 schedulers x the SM clock sampled during the timed region
+            ach = tinfo["warp_instructions"] / (kernel_ms * 1e-3) / 1e9
+            roof = {"bound": "issue", "achieved": ach, "peak": issue_peak, "unit": "G warp-instructions/s", "frac": ach / issue_peak,
+                    "traffic": tinfo["dram_bytes_read"] + tinfo["dram_bytes_write"],
+                    "ncu": {"warp_instructions_per_pose": tinfo["warp_instructions"] / P, "issue_slots_active_pct": tinfo["issue_active_pct"],
+                            "active_lanes_per_instruction": tinfo.get("active_lanes_per_inst"), "source": tinfo["source"],
+                            "source_sha16": tinfo["source_sha16"]}}
+        else:
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "ncu": {"unavailable": stale}}
+        roof.update({"kernel": "collide_poses_kernel<f32>", "kernel_ms": kernel_ms, "hbm": hbm,
+                     "note": "instruction-issue / latency bound, not HBM bound (25 B/pose of algorithmic traffic); DESIGN.md 4.1"})
         line = {
             "metric": METRIC, "value": world * P * args.steps / (total_ms * 1e-3), "unit": "poses/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "poses_per_gpu_per_step": P, "pose_seed": SEED, "obstacle_tris": int(len(obst)),
-                       "robot_tris": int(len(robot)), "l2_policy": "inputs larger than L2 (402 MB of poses per step)",
-                       "parallelism": (f"pose-shard x{world} + verdict all-gather fused into the kernel's stores over NVLink peer memory"
-                                       if gather_mode == "fused" else
-                                       f"pose-shard x{world} + NCCL all-gather of verdict bytes" if world > 1 else "single GPU"),
-                       "hit_fraction": hits / P, "cpus_bound_per_rank": numa},
+            "config": bench_config(args, obst, robot),
+            "run": {"gather": gather_mode, "hit_fraction": hits / P, "host_binding": numa},
             "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": P * 24, "d2h_bytes_per_step": P,
-                    "steps": e_steps, "api": "sffg_collide_poses_f32 on pinned host buffers"},
+                    "steps": e_steps, "api": "sffg_collide_poses_f32 on pinned host buffers",
+                    "h2d_probe": h2d_probe, "frac_of_h2d_probe": e2e_frac, "edges": edges_e2e},
             # collide_poses_kernel per step (gather and completion signal are inside it) + one final wait kernel
             "gpu_launches": args.steps + (1 if gather_mode == "fused" else 0),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": which, "kernel": "collide_poses_kernel<f32>",
-                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_pose": ALGO_BYTES_PER_POSE,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POSE * P,
-                         "ncu": ({"warp_instructions_per_pose": tinfo["warp_instructions"] / tinfo["poses_per_launch"],
-                                  "issue_slots_active_pct": tinfo["issue_active_pct"], "source": tinfo["source"]} if tinfo else None),
-                         # the roofline that does bound this kernel: warp-instruction issue.  achieved = committed ncu count of
-                         # executed warp instructions per launch / the kernel time measured live here; peak = SMs x 4 schedulers
-                         # x the SM clock sampled during the timed region (one warp instruction per scheduler per cycle)
-                         "issue": ({"achieved": tinfo["warp_instructions"] / (kernel_ms * 1e-3) / 1e9,
-                                    "peak": torch.cuda.get_device_properties(dev).multi_processor_count * 4 * (clocks["sm_mhz"] or 1965) * 1e6 / 1e9,
-                                    "unit": "G warp-instructions/s"} if tinfo else None),
-                         "note": "the path is instruction-issue / L2-latency bound, not HBM bound (SURVEY 8d): the informative "
-                                 "fraction is issue_slots_active_pct; see DESIGN.md 4.1"},
+            "roofline": roof,
         }
-        if line["roofline"].get("issue"):
-            line["roofline"]["issue"]["frac"] = line["roofline"]["issue"]["achieved"] / line["roofline"]["issue"]["peak"]
+        if gather_check is not None:
+            line.update(gather_check)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
         if world == 1 and not args.no_extra:
-            line["extra"] = extra_metrics(S, env, torch)
+            line["extra"] = extra_metrics(S, env, torch, clocks)
         if knn_multi is not None:
             line["extra"] = knn_multi
         print(json.dumps(line), flush=True)
@@ -397,13 +520,15 @@ def planner_solves(impl: str, runs: int):
     subprocess.run([sys.executable, str(ROOT / "scripts" / "make_scenarios.py"), str(work)], check=True, capture_output=True)
     out = {}
     for sc in PLANNER_SCENARIOS:
-        secs, lens, solved, iters = [], [], 0, []
+        secs, lens, solved, iters, walls = [], [], 0, [], []
         for r in range(runs):
             cmd = [str(exe), f"{sc}.xml", str(r)] + (["--seed", str(100 + r), "--quiet"] if impl == "ours" else [])
+            t0 = time.perf_counter()
             try:
                 p = subprocess.run(cmd, cwd=work, capture_output=True, text=True, timeout=300)
             except subprocess.TimeoutExpired:
                 break
+            walls.append(time.perf_counter() - t0)
             if p.returncode != 0:
                 break
             row = (work / "output" / f"params_{sc}.csv").read_text().strip().splitlines()[-1]
@@ -417,7 +542,8 @@ def planner_solves(impl: str, runs: int):
                 lens.append(sum(d) / len(d))
             secs.append(float(m.group(4)))
         if secs:
-            out[sc] = {"solve_s_mean": sum(secs) / len(secs), "runs": len(secs), "solved": solved, "iterations_mean": sum(iters) / len(iters),
+            out[sc] = {"solve_s_mean": sum(secs) / len(secs), "process_wall_s_mean": sum(walls[:len(secs)]) / len(secs),
+                       "runs": len(secs), "solved": solved, "iterations_mean": sum(iters) / len(iters),
                        "mean_path_length": (sum(lens) / len(lens)) if lens else None}
         else:
             out[sc] = {"error": "no result"}
@@ -453,24 +579,49 @@ def knn_cpu_baseline(nodes, q, k, gpu_ids):
     return out
 
 
+KNN_Q = 100_000          # BASELINE.json configs[4]: 1e5 queries, 1e4..1e7 nodes, k = 1..32
+
+
+def knn_cloud(torch, dev, n, seed):
+    lo = torch.tensor([-70, -70, 0, -3.14159, -3.14159, -3.14159], device=dev)
+    hi = torch.tensor([70, 70, 140, 3.14159, 3.14159, 3.14159], device=dev)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    return (lo + (hi - lo) * torch.rand((n, 6), device=dev, generator=g)).float().contiguous()
+
+
+def knn_rate(torch, idx, q, k, reps=3):
+    """device-resident exact k-NN rate through sffg_knn_device (CUDA events on the current stream) -> (queries/s, ids)"""
+    nq = q.shape[0]
+    ids = torch.empty((nq, k), dtype=torch.int32, device=q.device)
+    d2 = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+    idx.knn_device(q, k, ids, d2)          # (first call also builds the Morton-sorted view)
+    idx.knn_device(q, k, ids, d2)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        idx.knn_device(q, k, ids, d2)
+    b.record()
+    torch.cuda.synchronize()
+    return nq / (a.elapsed_time(b) * 1e-3 / reps), ids
+
+
 def sharded_knn_rate(S, torch, dist, dev, rank, world):
     """N > 1: exact k-NN with the node set replicated and the query rows split over the ranks; every rank ends up with all
-    rows (packed (id, d2) pairs, one NCCL all-gather).  Same shape per rank as the N = 1 `extra` block (weak scaling)."""
+    rows: the search writes into its slice of the gathered layout and two in-place NCCL all-gathers exchange the slices.
+    Q = 1e5 query rows per GPU (weak scaling, the N = 1 `extra.knn` shape), rows checked against a local search."""
     try:
         from space_filling_forest_star_b200.sharding import sharded_knn
-        n, nq, k = 1_000_000, 1 << 15, 16
-        lo = torch.tensor([-70, -70, 0, -3.14159, -3.14159, -3.14159], device=dev)
-        hi = torch.tensor([70, 70, 140, 3.14159, 3.14159, 3.14159], device=dev)
-        g = torch.Generator(device=dev).manual_seed(2)           # the same node set on every rank
-        nodes = (lo + (hi - lo) * torch.rand((n, 6), device=dev, generator=g)).float().contiguous()
-        gq = torch.Generator(device=dev).manual_seed(3)
-        q = (lo + (hi - lo) * torch.rand((world * nq, 6), device=dev, generator=gq)).float().contiguous()
+        n, nq, k = 1_000_000, KNN_Q, 16
+        nodes = knn_cloud(torch, dev, n, 2)            # the same node set on every rank
+        q = knn_cloud(torch, dev, world * nq, 3)
         idx = S.Index(dim=6)
         idx.add_device(nodes)
         for _ in range(2):
             sharded_knn(idx, q, k)
         torch.cuda.synchronize()
         dist.barrier()
+        dist.all_reduce(torch.zeros(1, device=dev))
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(5):
@@ -479,16 +630,28 @@ def sharded_knn_rate(S, torch, dist, dev, rank, world):
         torch.cuda.synchronize()
         ms = torch.tensor([a.elapsed_time(b) / 5], device=dev)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        # every rank checks another rank's slice of the gathered rows against its own search
+        nxt = (rank + 1) % world
+        li, ld = idx.knn_device(q[nxt * nq:(nxt + 1) * nq].contiguous(), k)
+        ok = torch.tensor([1.0 if (torch.equal(li, ids[nxt * nq:(nxt + 1) * nq]) and torch.equal(ld, d2[nxt * nq:(nxt + 1) * nq])) else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        rate1, _ = knn_rate(torch, idx, q[rank * nq:(rank + 1) * nq].contiguous(), k, reps=5)
+        r1 = torch.tensor([rate1], device=dev)
+        dist.all_reduce(r1, op=dist.ReduceOp.MIN)
         idx.close()
-        return {"knn_queries_per_s": world * nq / (float(ms.item()) * 1e-3),
-                "knn_config": f"N={n} 6-D nodes replicated, Q={nq} per GPU, k={k}, exact, rows all-gathered over NCCL"}
+        total = world * nq / (float(ms.item()) * 1e-3)
+        return {"knn": {"queries_per_s": total, "single_gpu_kernel_only_queries_per_s": float(r1.item()),
+                        "efficiency_vs_kernel_only": total / (world * float(r1.item())), "rows_verified": bool(ok.item() > 0),
+                        "config": f"N={n} 6-D nodes replicated, Q={nq} per GPU, k={k}, exact, rows written into the gathered layout + "
+                                  f"2 in-place NCCL all-gathers"}}
     except Exception as ex:
-        return {"error": repr(ex)}
+        return {"knn": {"error": repr(ex)}}
 
 
-def extra_metrics(S, env, torch):
+def extra_metrics(S, env, torch, clocks):
     """secondary numbers of the same hot path (not the headline): edges/s and exact k-NN queries/s"""
     out = {}
+    dev = torch.device("cuda", torch.cuda.current_device())
     try:
         m = 1 << 18
         s = S.gen_poses_device(SEED + 1, 0, m, [-45, 45, -45, 45, 0, 125]).double()
@@ -509,36 +672,65 @@ def extra_metrics(S, env, torch):
         out["edges_per_s"] = 3 * m / (a.elapsed_time(b) * 1e-3)
         out["edge_config"] = "2^18 edges of length 4 (39 samples @0.1) in building.obj, reference rotation mode"
         out["edge_free_fraction"] = float(free.float().mean().item())
-        n, nq, k = 1_000_000, 1 << 15, 16
-        g = torch.Generator(device=s.device).manual_seed(2)
-        lo = torch.tensor([-70, -70, 0, -3.14159, -3.14159, -3.14159], device=s.device)
-        hi = torch.tensor([70, 70, 140, 3.14159, 3.14159, 3.14159], device=s.device)
-        nodes = (lo + (hi - lo) * torch.rand((n, 6), device=s.device, generator=g)).float().contiguous()
-        q = (lo + (hi - lo) * torch.rand((nq, 6), device=s.device, generator=g)).float().contiguous()
-        idx = S.Index(dim=6)
-        idx.add_device(nodes)
-        ids = torch.empty((nq, k), dtype=torch.int32, device=s.device)
-        d2 = torch.empty((nq, k), dtype=torch.float32, device=s.device)
-        idx.knn_device(q, k, ids, d2)
-        torch.cuda.synchronize()
-        a.record()
-        for _ in range(3):
-            idx.knn_device(q, k, ids, d2)
-        b.record()
-        torch.cuda.synchronize()
-        sec = a.elapsed_time(b) * 1e-3 / 3
-        out["knn_queries_per_s"] = nq / sec
-        out["knn_config"] = f"N={n} 6-D nodes, Q={nq}, k={k}, exact"
-        out["knn_pair_rate_per_s"] = nq * n / sec
-        out["knn_cpu_baseline"] = knn_cpu_baseline(nodes.cpu().numpy(), q.cpu().numpy(), k, ids.cpu().numpy())
+        del s, e, d, free
     except Exception as ex:   # secondary numbers must never break the headline line
-        out["error"] = repr(ex)
+        out["edges_error"] = repr(ex)
+    # ---- exact k-NN at BASELINE.json's configuration: Q = 1e5 queries, N = 1e6 and 1e7 nodes, k = 16 (+ 1, 32) -------------
+    try:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue_peak = sms * 4 * (clocks["sm_mhz"] or 1965) * 1e6 / 1e9
+        kinfo, stale = committed_counters("knn_counters.json", KNN_SOURCES)
+        knn = {"metric": "exact k-NN queries/s", "queries": KNN_Q, "dtype": "f32",
+               "metric_flops_per_pair": 23, "rows": {}}
+        q = knn_cloud(torch, dev, KNN_Q, 3)
+        for n in (1_000_000, 10_000_000):
+            nodes = knn_cloud(torch, dev, n, 2)
+            idx = S.Index(dim=6)
+            idx.add_device(nodes)
+            for k in (16, 1, 32):
+                rate, ids = knn_rate(torch, idx, q, k)
+                row = {"queries_per_s": rate, "pairs_equiv_per_s": rate * n, "flop_equiv_per_s": 23.0 * rate * n}
+                if n == 1_000_000 and k == 16:
+                    # issue-rate roofline of knn_pruned_kernel: committed ncu instruction count of exactly this launch /
+                    # the time measured here (sort of the query rows included in the time, not in the count)
+                    if kinfo is not None:
+                        ach = kinfo["warp_instructions"] / (KNN_Q / rate) / 1e9
+                        row["roofline"] = {"bound": "issue", "achieved": ach, "peak": issue_peak, "unit": "G warp-instructions/s",
+                                           "frac": ach / issue_peak, "traffic": kinfo["dram_bytes_read"] + kinfo["dram_bytes_write"],
+                                           "ncu": {"issue_slots_active_pct": kinfo["issue_active_pct"],
+                                                   "active_lanes_per_instruction": kinfo.get("active_lanes_per_inst"),
+                                                   "source": kinfo["source"], "source_sha16": kinfo["source_sha16"]}}
+                    else:
+                        row["roofline"] = {"unavailable": stale}
+                    row["cpu_baseline"] = knn_cpu_baseline(nodes.cpu().numpy(), q.cpu().numpy(), k, ids.cpu().numpy())
+                if n == 10_000_000 and k == 16:
+                    row["cpu_baseline"] = knn_cpu_exact_only(nodes.cpu().numpy(), q.cpu().numpy(), k, ids.cpu().numpy())
+                knn["rows"][f"N={n},k={k}"] = row
+            idx.close()
+            del nodes, idx
+        out["knn"] = knn
+        out["knn_queries_per_s"] = knn["rows"]["N=1000000,k=16"]["queries_per_s"]
+        out["knn_config"] = f"N=1000000 6-D nodes, Q={KNN_Q}, k=16, exact (all rows: extra.knn.rows)"
+    except Exception as ex:
+        out["knn_error"] = repr(ex)
     try:
         env.sync_check()
         out["sffstar_solve"] = planner_solves("ours", 3)
     except Exception as ex:
         out["sffstar_solve"] = {"error": repr(ex)}
     return out
+
+
+def knn_cpu_exact_only(nodes, q, k, gpu_ids):
+    """N = 1e7: building the planner's kd-tree index one addPoints at a time would take minutes, so only the exact CPU scan
+    (which doubles as a parity check of the GPU rows) is timed, on a small sample"""
+    import oracle as O
+    threads = host_threads()
+    nl = 64
+    t0 = time.perf_counter()
+    wi, _ = O.knn_linear(nodes, q[:nl], k, threads=threads)
+    return {"cores": threads, "exact_linear_queries_per_s": nl / (time.perf_counter() - t0),
+            "gpu_rows_equal_exact_scan": bool(np.array_equal(gpu_ids[:nl], wi)), "sample": f"{nl} queries (exact scan)"}
 
 
 def main():

@@ -71,6 +71,47 @@ def raw(rep):
     return "\n".join(out) + "\n"
 
 
+def source_sha16(files):
+    """hash of the kernel sources a counter file belongs to: bench.py refuses counters of an older kernel"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in files:
+        h.update((ROOT / "space_filling_forest_star_b200" / "csrc" / f).read_bytes())
+    return h.hexdigest()[:16]
+
+
+COLLIDE_SOURCES = ["collide_kernels.cu", "collide_kernels.cuh", "common.h"]
+KNN_SOURCES = ["knn_pruned.cu", "knn_common.cuh", "knn_kernels.cu"]
+
+
+def counters(tag):
+    """profiles/traffic.json (collide) and profiles/knn_counters.json: the per-launch ncu counters bench.py turns into the
+    issue-rate roofline, stamped with the hash of the kernel sources they were captured from"""
+    import json
+    for name, out, files, extra in (("collide", "traffic.json", COLLIDE_SOURCES, {"kernel": "collide_poses_kernel<f32>", "poses_per_launch": 1 << 24}),
+                                    ("knn", "knn_counters.json", KNN_SOURCES, {"kernel": "knn_pruned_kernel<6,8,1>", "config": "N=1000000 Q=100000 k=16"})):
+        rep = SRC / f"{tag}_{name}.ncu-rep"
+        if not rep.exists():
+            continue
+        txt = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(txt.splitlines()))
+        d = dict(zip(rows[0], rows[2]))
+        unit = dict(zip(rows[0], rows[1]))
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rec = dict(extra)
+        rec.update({
+            "dram_bytes_read": float(d["dram__bytes_read.sum"]) * scale.get(unit["dram__bytes_read.sum"], 1.0),
+            "dram_bytes_write": float(d["dram__bytes_write.sum"]) * scale.get(unit["dram__bytes_write.sum"], 1.0),
+            "warp_instructions": float(d["smsp__inst_executed.sum"]),
+            "issue_active_pct": float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
+            "active_lanes_per_inst": float(d["smsp__thread_inst_executed_per_inst_executed.ratio"]),
+            "source": f"profiles/{tag}_{name}.txt (ncu --set full --clock-control none, one launch)",
+            "source_sha16": source_sha16(files),
+        })
+        (OUT / out).write_text(json.dumps(rec, indent=1))
+        print("wrote", OUT / out)
+
+
 def main():
     tag = sys.argv[1]
     OUT.mkdir(exist_ok=True)
@@ -88,6 +129,7 @@ def main():
         body += "\n# hottest source lines (share of stall samples / of executed warp instructions / avg active lanes)\n" + lines
         (OUT / f"{tag}_{name}.txt").write_text(body)
         print("wrote", OUT / f"{tag}_{name}.txt")
+    counters(tag)
 
 
 if __name__ == "__main__":

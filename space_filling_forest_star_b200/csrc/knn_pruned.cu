@@ -14,6 +14,8 @@
 // "tail") are covered by the exhaustive kernel; the partial lists are merged by knn_merge_kernel.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstdlib>
+
 #include "knn_common.cuh"
 #include "knn_kernels.cuh"
 #include "knn_pruned.cuh"
@@ -76,6 +78,22 @@ __global__ void morton_kernel(const float *__restrict__ coords, long long cap, i
     q[c] = (unsigned)fminf(fmaxf(t * levels, 0.f), levels);
   }
   keys[i] = lin == 3 ? (spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2)) : (spread2(q[0]) | (spread2(q[1]) << 1));
+  vals[i] = (unsigned)i;
+}
+
+// Morton key of every query row (AoS [nq][dim]) on the grid the node set was sorted with; rows outside it clamp
+__global__ void query_morton_kernel(const float *__restrict__ q, int nq, int dim, int lin, const int *bounds, unsigned *keys, unsigned *vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  unsigned c3[3] = {0, 0, 0};
+  const float levels = lin == 3 ? 1023.f : 32767.f;
+  for (int c = 0; c < lin; ++c) {
+    const float lo = order_float(bounds[c]), hi = order_float(bounds[3 + c]);
+    const float span = hi - lo;
+    const float t = span > 0.f ? (q[(long long)i * dim + c] - lo) / span : 0.f;
+    c3[c] = (unsigned)fminf(fmaxf(t * levels, 0.f), levels);   // (NaN -> 0)
+  }
+  keys[i] = lin == 3 ? (spread3(c3[0]) | (spread3(c3[1]) << 1) | (spread3(c3[2]) << 2)) : (spread2(c3[0]) | (spread2(c3[1]) << 1));
   vals[i] = (unsigned)i;
 }
 
@@ -165,7 +183,7 @@ __device__ __forceinline__ float box_ub(const float *lo, const float *hi, const 
 template <int DIM, int QW, int KPL>
 __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, const float *__restrict__ queries, long long nq, int k,
                                                               int slices, int sb_per_slice, float *out_d, int *out_i,
-                                                              int slot_base, int slots_total) {
+                                                              int slot_base, int slots_total, const unsigned *__restrict__ perm) {
   constexpr int LIN = DIM == 6 ? 3 : 2;
   const int lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
@@ -176,12 +194,14 @@ __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, cons
   TopK<KPL> top[QW];
   float worst[QW];
   int worst_id[QW];
+  long long row[QW];   // caller's row of the w-th query of this warp (perm: visiting order -> row)
 #pragma unroll
   for (int w = 0; w < QW; ++w) {
     long long qi = group * QW + w;
     if (qi >= nq) qi = nq - 1;
+    row[w] = perm ? (long long)__ldg(perm + qi) : qi;
 #pragma unroll
-    for (int c = 0; c < DIM; ++c) q[w][c] = __ldg(queries + qi * DIM + c);
+    for (int c = 0; c < DIM; ++c) q[w][c] = __ldg(queries + row[w] * DIM + c);
     top[w].init();
     worst[w] = INFINITY;
     worst_id[w] = -1;
@@ -426,8 +446,8 @@ __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, cons
   }
 #pragma unroll
   for (int w = 0; w < QW; ++w) {
-    const long long qi = group * QW + w;
-    if (qi >= nq) break;
+    if (group * QW + w >= nq) break;
+    const long long qi = row[w];
 #pragma unroll
     for (int s = 0; s < KPL; ++s) {
       const int pos = lane * KPL + s;
@@ -525,10 +545,10 @@ __global__ void __launch_bounds__(kThreads) radius_pruned_kernel(SortedDev sv, c
 
 template <int DIM, int QW>
 cudaError_t launch_pruned_kpl(const SortedDev &sv, const float *q, int64_t nq, int k, int slices, int sb_per_slice, float *od, int *oi,
-                              int slot_base, int slots_total, unsigned grid, cudaStream_t st) {
-  if (k <= 32) knn_pruned_kernel<DIM, QW, 1><<<grid, kThreads, 0, st>>>(sv, q, nq, k, slices, sb_per_slice, od, oi, slot_base, slots_total);
-  else if (k <= 64) knn_pruned_kernel<DIM, QW, 2><<<grid, kThreads, 0, st>>>(sv, q, nq, k, slices, sb_per_slice, od, oi, slot_base, slots_total);
-  else knn_pruned_kernel<DIM, QW, 4><<<grid, kThreads, 0, st>>>(sv, q, nq, k, slices, sb_per_slice, od, oi, slot_base, slots_total);
+                              int slot_base, int slots_total, unsigned grid, const unsigned *perm, cudaStream_t st) {
+  if (k <= 32) knn_pruned_kernel<DIM, QW, 1><<<grid, kThreads, 0, st>>>(sv, q, nq, k, slices, sb_per_slice, od, oi, slot_base, slots_total, perm);
+  else if (k <= 64) knn_pruned_kernel<DIM, QW, 2><<<grid, kThreads, 0, st>>>(sv, q, nq, k, slices, sb_per_slice, od, oi, slot_base, slots_total, perm);
+  else knn_pruned_kernel<DIM, QW, 4><<<grid, kThreads, 0, st>>>(sv, q, nq, k, slices, sb_per_slice, od, oi, slot_base, slots_total, perm);
   return cudaGetLastError();
 }
 
@@ -588,12 +608,25 @@ PrunedPlan plan_pruned(int64_t nq, const SortedDev &sv, int64_t tail, int sm_cou
     p.tail_len = len;
     p.tail_slices = (int)((tail + len - 1) / len);
   }
+  const char *qs = std::getenv("SFFG_KNN_QUERY_SORT");
+  p.sort_queries = nq >= 4096 && nq < (int64_t(1) << 31) && !(qs && qs[0] == '0');
+  p.sort_temp_bytes = 0;
+  if (p.sort_queries) {
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const unsigned *)nullptr, (unsigned *)nullptr, (const unsigned *)nullptr,
+                                    (unsigned *)nullptr, (int)nq, 0, 30);
+    p.sort_temp_bytes = tmp + 256;
+  }
   return p;
 }
 
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
 size_t pruned_scratch_bytes(const PrunedPlan &p, int64_t nq, int k) {
   const int slots = p.slices + p.tail_slices;
-  return slots <= 1 ? 0 : (size_t)nq * slots * k * 8;
+  size_t bytes = slots <= 1 ? 0 : align256((size_t)nq * slots * k * 8);
+  if (p.sort_queries) bytes += 4 * align256((size_t)nq * 4) + p.sort_temp_bytes;
+  return bytes;
 }
 
 cudaError_t launch_knn_pruned(const IndexDev &idx, const SortedDev &sv, const float *d_queries, int64_t nq, int k, int32_t *d_ids,
@@ -609,14 +642,29 @@ cudaError_t launch_knn_pruned(const IndexDev &idx, const SortedDev &sv, const fl
   const int64_t groups = (nq + p.qw - 1) / p.qw;
   const unsigned grid = (unsigned)((groups * p.slices + kWarps - 1) / kWarps);
   cudaError_t e;
+  const unsigned *perm = nullptr;
+  if (p.sort_queries) {
+    // visiting order of the query rows: Morton keys on the node grid, one radix sort of (key, row)
+    unsigned char *base = reinterpret_cast<unsigned char *>(d_scratch) + (slots > 1 ? align256((size_t)nq * slots * k * 8) : 0);
+    const size_t arr = align256((size_t)nq * 4);
+    unsigned *keys_in = reinterpret_cast<unsigned *>(base), *keys_out = reinterpret_cast<unsigned *>(base + arr);
+    unsigned *vals_in = reinterpret_cast<unsigned *>(base + 2 * arr), *vals_out = reinterpret_cast<unsigned *>(base + 3 * arr);
+    void *tmp = base + 4 * arr;
+    size_t tmp_bytes = p.sort_temp_bytes;
+    const int lin = idx.dim == 6 ? 3 : 2;
+    query_morton_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(d_queries, (int)nq, idx.dim, lin, sv.bounds, keys_in, vals_in);
+    e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)nq, 0, 30, st);
+    if (e != cudaSuccess) return e;
+    perm = vals_out;
+  }
   if (idx.dim == 6) {
-    if (p.qw == 8) e = launch_pruned_kpl<6, 8>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, st);
-    else if (p.qw == 4) e = launch_pruned_kpl<6, 4>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, st);
-    else e = launch_pruned_kpl<6, 1>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, st);
+    if (p.qw == 8) e = launch_pruned_kpl<6, 8>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, st);
+    else if (p.qw == 4) e = launch_pruned_kpl<6, 4>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, st);
+    else e = launch_pruned_kpl<6, 1>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, st);
   } else {
-    if (p.qw == 8) e = launch_pruned_kpl<2, 8>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, st);
-    else if (p.qw == 4) e = launch_pruned_kpl<2, 4>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, st);
-    else e = launch_pruned_kpl<2, 1>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, st);
+    if (p.qw == 8) e = launch_pruned_kpl<2, 8>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, st);
+    else if (p.qw == 4) e = launch_pruned_kpl<2, 4>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, st);
+    else e = launch_pruned_kpl<2, 1>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, st);
   }
   if (e != cudaSuccess) return e;
   if (p.tail_slices > 0) {

@@ -21,6 +21,7 @@ struct SortedDev {
   int n_sorted;
   int nblk;
   const unsigned *amax;  // as IndexDev::amax
+  const int *bounds;     // 6 ordered ints: min / max of the translational coordinates at build time (Morton quantisation)
 };
 
 struct SortedBuildBuffers {
@@ -46,6 +47,10 @@ struct PrunedPlan {
   int sb_per_slice;
   int tail_slices;    // slices of the exhaustive scan over the unsorted tail
   int64_t tail_len;
+  // large batches: the query rows are visited in Morton order of their translational part (same curve as the nodes), so the
+  // queries that share a warp are neighbours in space and need the same blocks; results still land in the caller's row order
+  bool sort_queries;
+  size_t sort_temp_bytes;
 };
 PrunedPlan plan_pruned(int64_t nq, const SortedDev &sv, int64_t tail, int sm_count);
 size_t pruned_scratch_bytes(const PrunedPlan &p, int64_t nq, int k);

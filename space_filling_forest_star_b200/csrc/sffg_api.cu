@@ -1029,6 +1029,7 @@ static SortedDev sorted_view(const sffg_index *idx) {
   sv.n_sorted = (int)idx->n_sorted;
   sv.nblk = (int)((idx->n_sorted + 31) / 32);
   sv.amax = idx->d_amax;
+  sv.bounds = (const int *)idx->s_bounds.p;
   return sv;
 }
 

@@ -124,6 +124,11 @@ class Environment:
         fn = self._L.sffg_collide_poses_f64 if is_f64 else self._L.sffg_collide_poses_f32
         check(fn(self._h, poses_ptr, n, out_ptr))
 
+    def edges_host_buffers(self, starts_ptr: int, ends_ptr: int, m: int, free_ptr: int, sample_dist: float = COLLISION_SAMPLE_SIZE,
+                           rot_mode: int = ROT_REFERENCE) -> None:
+        """Raw host-pointer form of isPathFree (pinned float64 [m][6] buffers from the caller), used by bench.py's e2e leg."""
+        check(self._L.sffg_check_edges(self._h, starts_ptr, ends_ptr, m, float(sample_dist), rot_mode, free_ptr, None))
+
     def collide_device(self, poses, out=None, stream: Optional[int] = None):
         """poses: torch CUDA tensor [n][6] float32/float64; returns a torch uint8 tensor (enqueued, not synchronised)."""
         import torch

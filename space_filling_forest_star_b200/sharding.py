@@ -61,18 +61,26 @@ def sharded_edges(env, starts: torch.Tensor, ends: torch.Tensor, sample_dist: fl
 
 
 def sharded_knn(index, queries: torch.Tensor, k: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Node set replicated, query rows split.  (ids, d2) rows are packed as one int32 pair tensor for a single gather."""
+    """Node set replicated, query rows split (the pattern of FLANN's MPI index, lib/flann/src/cpp/flann/mpi/index.h:196-226,
+    without its merge step: every rank owns whole rows).  The search kernel writes this rank's (ids, d2) rows straight into
+    its slice of the gathered layout and the two all-gathers run in place on those buffers -- no staging copies."""
     nq = queries.shape[0]
-
-    def compute(b, e, out):
-        ids = out[: e - b, :, 0]
-        d2 = out[: e - b, :, 1].view(torch.float32)
-        i_tmp, d_tmp = index.knn_device(queries[b:e].contiguous(), k)
-        ids.copy_(i_tmp)
-        d2.copy_(d_tmp)
-
-    packed = sharded_rows(nq, (k, 2), torch.int32, queries.device, compute, group)
-    return packed[:, :, 0].contiguous(), packed[:, :, 1].contiguous().view(torch.float32)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    b, e, per = shard_bounds(nq, rank, world)
+    dev = queries.device
+    ids = torch.empty((world * per, k), dtype=torch.int32, device=dev)
+    d2 = torch.empty((world * per, k), dtype=torch.float32, device=dev)
+    lo = rank * per
+    if e > b:
+        index.knn_device(queries[b:e], k, ids[lo:lo + (e - b)], d2[lo:lo + (e - b)])
+    if per > e - b:          # ragged tail: rows that exist only as padding of the equal-sized slices
+        ids[lo + (e - b):lo + per].fill_(-1)
+        d2[lo + (e - b):lo + per].fill_(float("inf"))
+    if world > 1:
+        dist.all_gather_into_tensor(ids, ids[lo:lo + per], group=group)
+        dist.all_gather_into_tensor(d2, d2[lo:lo + per], group=group)
+    return ids[:nq], d2[:nq]
 
 
 class PeerGather:

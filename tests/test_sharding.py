@@ -55,3 +55,34 @@ def test_sharded_rows_gloo_world2(tmp_path, n):
     port = 29500 + (os.getpid() + n) % 2000
     mp.spawn(_worker, args=(2, port, n, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").read_text() == "True" and (tmp_path / "ok1").read_text() == "True"
+
+
+class _FakeIndex:
+    """stands in for engine.Index.knn_device on CPU tensors: row i of the result is a function of query row i only"""
+
+    def knn_device(self, queries, k, ids_out, d2_out):
+        base = queries[:, 0].to(torch.int32)
+        ids_out.copy_(base[:, None] * 100 + torch.arange(k, dtype=torch.int32)[None, :])
+        d2_out.copy_(queries[:, 1:2] + torch.arange(k, dtype=torch.float32)[None, :])
+
+
+def _knn_worker(rank, world, port, nq, k, tmp):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from space_filling_forest_star_b200.sharding import sharded_knn
+    q = torch.stack([torch.arange(nq, dtype=torch.float32), torch.arange(nq, dtype=torch.float32) * 0.5], 1).contiguous()
+    ids, d2 = sharded_knn(_FakeIndex(), q, k)
+    want_i = torch.arange(nq, dtype=torch.int32)[:, None] * 100 + torch.arange(k, dtype=torch.int32)[None, :]
+    want_d = q[:, 1:2] + torch.arange(k, dtype=torch.float32)[None, :]
+    ok = ids.shape == (nq, k) and torch.equal(ids, want_i) and torch.equal(d2, want_d)
+    Path(tmp, f"ok{rank}").write_text(str(ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nq", [0, 1, 7, 64, 1001])
+def test_sharded_knn_in_place_gather_gloo_world2(tmp_path, nq):
+    """the search writes its rows into its slice of the gathered buffers and the all-gathers run in place on them"""
+    port = 31500 + (os.getpid() + nq) % 2000
+    mp.spawn(_knn_worker, args=(2, port, nq, 5, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").read_text() == "True" and (tmp_path / "ok1").read_text() == "True"
