@@ -70,6 +70,15 @@ SCENARIOS = {
     "triang": dict(dim="3D", robot="robot_small_s10.obj", obstacle="triang_s10.obj", obst_is_obj="true",
                    points=[[-15, 40, 30], [29, 3, 70], [27, -34, 50], [-39.6, -24, 10], [42, 35, 10], [-43, 35, 80]],
                    r=[-100, 100, -100, 100, 0, 100], dtree=5, circum=4, maxiter=100000),
+    # 3-D scenarios that BOTH hosts solve every time within 20 000 iterations (the shipped root sets above never connect all
+    # their trees in either program within 100 000): roots of the same scenes moved into mutual reach.  These carry the
+    # two-sided end-to-end path-cost comparison (tests/test_gpu_planner.py, north_star "within stated tolerance").
+    "triangpair": dict(dim="3D", robot="robot_small_s10.obj", obstacle="triang_s10.obj", obst_is_obj="true",
+                       points=[[29, 3, 70], [27, -34, 50]],
+                       r=[-100, 100, -100, 100, 0, 100], dtree=5, circum=4, maxiter=20000),
+    "buildingnear": dict(dim="3D", robot="robot_small_s10.obj", obstacle="building_s10.obj", obst_is_obj="true",
+                         points=[[3.03, 0.57, 70], [30, 0.57, 70], [3.03, 25, 70]],
+                         r=[-70, 70, -70, 70, 0, 140], dtree=5, circum=4, maxiter=20000),
     # BASELINE.json configs[0]: 2-D SFF* on maps/triangles.tri (test_2D.xml distances: dtree 100, circum 80)
     "2d": dict(dim="2D", robot="robot_small_s1.obj", obstacle="triangles.tri", obst_is_obj="false",
                points=[[60, 60, 0], [950, 650, 0], [80, 640, 0], [930, 70, 0]],

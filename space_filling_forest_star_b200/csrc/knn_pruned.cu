@@ -492,47 +492,65 @@ __global__ void __launch_bounds__(kThreads) radius_pruned_kernel(SortedDev sv, c
   const int nsb = (sv.nblk + 31) / 32;
   const int sb_begin = slice * sb_per_slice;
   const int sb_end = min(nsb, sb_begin + sb_per_slice);
-  for (int sb = sb_begin; sb < sb_end; ++sb) {
-    const int blk = sb * 32 + lane;
-    bool need = false;
-    if (blk < sv.nblk) {
+  // two levels, as in the k-NN kernel: 32 superblock boxes per step (lane-per-superblock, 32 768 nodes), then the block
+  // boxes of the superblocks whose box is within reach, then the nodes of the blocks that are
+  for (int sg = sb_begin; sg < sb_end; sg += 32) {
+    bool need_s = false;
+    if (sg + lane < sb_end) {
       float lo[LIN], hi[LIN];
 #pragma unroll
       for (int c = 0; c < LIN; ++c) {
-        lo[c] = __ldg(sv.bb + (long long)c * sv.nblk_cap + blk);
-        hi[c] = __ldg(sv.bb + (long long)(LIN + c) * sv.nblk_cap + blk);
+        lo[c] = __ldg(sv.sbb + (long long)c * sv.nsb_cap + sg + lane);
+        hi[c] = __ldg(sv.sbb + (long long)(LIN + c) * sv.nsb_cap + sg + lane);
       }
 #pragma unroll
-      for (int w = 0; w < QW; ++w) need |= box_lb<LIN>(lo, hi, q[w]) < r2;
+      for (int w = 0; w < QW; ++w) need_s |= box_lb<LIN>(lo, hi, q[w]) < r2;
     }
-    unsigned todo = __ballot_sync(kFull, need);
-    while (todo) {
-      const int bl = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int pos = (sb * 32 + bl) * 32 + lane;
-      const bool valid = pos < sv.n_sorted;
-      float nd[DIM];
-#pragma unroll
-      for (int c = 0; c < DIM; ++c) nd[c] = valid ? __ldg(sv.coords + (long long)c * sv.cap_s + pos) : 0.f;
-      const int id = (FILL && valid) ? __ldg(sv.ids + pos) : 0;
-#pragma unroll
-      for (int w = 0; w < QW; ++w) {
-        const float d = !valid ? INFINITY : (wide ? metric<DIM, true>(nd, q[w]) : metric<DIM, false>(nd, q[w]));
-        const bool in = d < r2;
-        const unsigned mask = __ballot_sync(kFull, in);
-        if (FILL) {
-          const long long qi = group * QW + w;
-          if (mask && qi < nq) {
-            int at = 0;
-            if (lane == 0) at = atomicAdd(cursor + qi, __popc(mask));
-            at = __shfl_sync(kFull, at, 0);
-            if (in) keys[offsets[qi] + at + __popc(mask & lt)] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)id;
+    unsigned todo_s = __ballot_sync(kFull, need_s);
+    while (todo_s) {
+      const int sb = sg + __ffs(todo_s) - 1;
+      todo_s &= todo_s - 1;
+      const int blk = sb * 32 + lane;
+      bool need = false;
+      if (blk < sv.nblk) {
+        float lo[LIN], hi[LIN];
+  #pragma unroll
+        for (int c = 0; c < LIN; ++c) {
+          lo[c] = __ldg(sv.bb + (long long)c * sv.nblk_cap + blk);
+          hi[c] = __ldg(sv.bb + (long long)(LIN + c) * sv.nblk_cap + blk);
+        }
+  #pragma unroll
+        for (int w = 0; w < QW; ++w) need |= box_lb<LIN>(lo, hi, q[w]) < r2;
+      }
+      unsigned todo = __ballot_sync(kFull, need);
+      while (todo) {
+        const int bl = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int pos = (sb * 32 + bl) * 32 + lane;
+        const bool valid = pos < sv.n_sorted;
+        float nd[DIM];
+  #pragma unroll
+        for (int c = 0; c < DIM; ++c) nd[c] = valid ? __ldg(sv.coords + (long long)c * sv.cap_s + pos) : 0.f;
+        const int id = (FILL && valid) ? __ldg(sv.ids + pos) : 0;
+  #pragma unroll
+        for (int w = 0; w < QW; ++w) {
+          const float d = !valid ? INFINITY : (wide ? metric<DIM, true>(nd, q[w]) : metric<DIM, false>(nd, q[w]));
+          const bool in = d < r2;
+          const unsigned mask = __ballot_sync(kFull, in);
+          if (FILL) {
+            const long long qi = group * QW + w;
+            if (mask && qi < nq) {
+              int at = 0;
+              if (lane == 0) at = atomicAdd(cursor + qi, __popc(mask));
+              at = __shfl_sync(kFull, at, 0);
+              if (in) keys[offsets[qi] + at + __popc(mask & lt)] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)id;
+            }
+          } else {
+            cnt[w] += __popc(mask);
           }
-        } else {
-          cnt[w] += __popc(mask);
         }
       }
-    }
+  }
   }
   if (!FILL && lane == 0) {
 #pragma unroll

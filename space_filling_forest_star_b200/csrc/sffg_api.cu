@@ -146,14 +146,18 @@ int sffg_init(int device) {
   }
   if (device >= n) return fail(SFFG_ERR_ARG, "device ordinal out of range");
   SFFG_CUDA(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  SFFG_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10)
-    return fail(SFFG_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
-                                        std::to_string(prop.minor) + "; libsffg.so carries sm_100a code only");
+  // (attributes, not cudaGetDeviceProperties: the full property query costs tens of milliseconds of every process start)
+  int major = 0, minor = 0, sms = 0, optin = 0;
+  SFFG_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  SFFG_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  SFFG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  SFFG_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  if (major != 10)
+    return fail(SFFG_ERR_NO_DEVICE, "device " + std::to_string(device) + " is sm_" + std::to_string(major) + std::to_string(minor) +
+                                        "; libsffg.so carries sm_100a code only");
   g_rt.device = device;
-  g_rt.sm_count = prop.multiProcessorCount;
-  g_rt.smem_optin = (int)prop.sharedMemPerBlockOptin;
+  g_rt.sm_count = sms;
+  g_rt.smem_optin = optin;
   g_rt.ready = true;
   return SFFG_OK;
 }
