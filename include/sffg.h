@@ -47,6 +47,15 @@ extern "C" {
 typedef struct sffg_env sffg_env;       /* obstacle BVH + robot mesh resident on one GPU  (Environment<T>)     */
 typedef struct sffg_index sffg_index;   /* append-only node set resident on one GPU        (flann::Index)      */
 
+/* ---- threads and streams ----------------------------------------------------------------------------------
+ * A handle (sffg_env, sffg_index) may be used from one host thread at a time; different handles may be used from
+ * different threads.  Host-pointer calls block until their results are in the caller's buffers.  The *_device calls
+ * only enqueue work on the caller's stream.  Launches of ONE environment share launch state (a ring of work counters,
+ * scratch for small edge batches), so the library keeps them in order across streams: a *_device call on another stream
+ * than the previous call of that environment first waits (on the device, cudaStreamWaitEvent) for that previous launch.
+ * Use one environment per stream for launches that should overlap.  An sffg_index is bound the same way to the stream
+ * of its last call for as long as work is in flight (its scratch buffers are reused by the next search).              */
+
 /* ---- library ------------------------------------------------------------------------------------------ */
 SFFG_API int sffg_version(void);
 SFFG_API const char *sffg_last_error(void);              /* thread-local, valid until the next call on this thread      */
@@ -104,8 +113,11 @@ SFFG_API int sffg_env_info(const sffg_env *env, sffg_env_info_t *out);
  *      = RAPID_Collide(I, 0, obstacle, R(pose), T(pose), robot) != 0 contacts, :269-276 ---------------------- */
 SFFG_API int sffg_collide_poses_f32(sffg_env *env, const float *poses, int64_t n, uint8_t *verdict_out);
 SFFG_API int sffg_collide_poses_f64(sffg_env *env, const double *poses, int64_t n, uint8_t *verdict_out);
-/* RAPID_Collide's own argument form: rt = [n][12] doubles, R2 row-major (9) then T2 (3); obstacle at identity.
- * This is what a RAPID.H shim forwards (src/environment.h:274). */
+/* RAPID_Collide's own argument form: rt = [n][12] doubles, R2 row-major (9) then T2 (3).  Model 1 (the obstacle soup) sits
+ * at identity -- the only placement the planner ever passes (eyeRotation and a zero vector, src/environment.h:89, :270,
+ * :274).  This is what the RAPID.H shim forwards; the shim terminates the process (like the reference's own fatal paths,
+ * src/main.cpp:427-433) when a caller hands RAPID_Collide a model 1 that is rotated or translated, because this engine
+ * bakes the obstacle placement into the hierarchy at sffg_env_create. */
 SFFG_API int sffg_collide_transforms_f64(sffg_env *env, const double *rt, int64_t n, uint8_t *verdict_out);
 SFFG_API int sffg_collide_poses_device(sffg_env *env, const void *d_poses, int poses_are_f64, int64_t n,
                               uint8_t *d_verdict_out, void *stream);

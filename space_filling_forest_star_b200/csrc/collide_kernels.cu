@@ -21,6 +21,7 @@
 //              because the caller only looks at num_contacts != 0)
 // The result equals "OR over all triangle pairs of the double-precision SAT" -- the oracle's ground truth.
 #include <cstdint>
+#include <mutex>
 
 #include "collide_kernels.cuh"
 
@@ -1015,8 +1016,10 @@ struct KernelCfg {
   cudaError_t err = cudaSuccess;
 };
 template <auto Kernel>
-static const KernelCfg &kernel_cfg(size_t smem) {
+static KernelCfg kernel_cfg(size_t smem) {
   static KernelCfg c;
+  static std::mutex mu;   // environments of different host threads share the per-kernel cache
+  std::lock_guard<std::mutex> lock(mu);
   if (c.smem != smem) {
     c.smem = smem;
     c.err = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1043,14 +1046,14 @@ static cudaError_t launch_poses_fmt(const EnvDev &env, const void *d_poses, int6
   const long long want = (chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
   cudaError_t e;
   if (count) {
-    const KernelCfg &kc = kernel_cfg<collide_poses_kernel<FMT, true>>(smem);
+    const KernelCfg kc = kernel_cfg<collide_poses_kernel<FMT, true>>(smem);
     if ((e = kc.err) != cudaSuccess) return e;
     int grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;
     *grid_out = grid;
     collide_poses_kernel<FMT, true><<<grid, kThreads, smem, stream>>>(env, d_poses, (long long)n, d_verdict, gs, chunk);
   } else {
-    const KernelCfg &kc = kernel_cfg<collide_poses_kernel<FMT, false>>(smem);
+    const KernelCfg kc = kernel_cfg<collide_poses_kernel<FMT, false>>(smem);
     if ((e = kc.err) != cudaSuccess) return e;
     int grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;
@@ -1140,13 +1143,13 @@ cudaError_t launch_check_edges(const EnvDev &env_in, const double *d_starts, con
   if (split > 1 && (e = cudaMemsetAsync(d_fh_scratch, 0x7f, (size_t)m * sizeof(int), stream)) != cudaSuccess) return e;
   int grid;
   if (count) {
-    const KernelCfg &kc = kernel_cfg<check_edges_kernel<true>>(smem);
+    const KernelCfg kc = kernel_cfg<check_edges_kernel<true>>(smem);
     if ((e = kc.err) != cudaSuccess) return e;
     grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;
     check_edges_kernel<true><<<grid, kThreads, smem, stream>>>(env, d_starts, d_ends, (long long)m, sample_dist, rot_mode, d_free, d_first_hit, split, d_fh_scratch);
   } else {
-    const KernelCfg &kc = kernel_cfg<check_edges_kernel<false>>(smem);
+    const KernelCfg kc = kernel_cfg<check_edges_kernel<false>>(smem);
     if ((e = kc.err) != cudaSuccess) return e;
     grid = cfg.sm_count * kc.per_sm;
     if (want < grid) grid = (int)want;

@@ -98,6 +98,12 @@ struct sffg_env {
   int work_next = 0;
   unsigned char *h_small = nullptr;   // pinned + device-mapped staging for small calls (planner-sized batches)
   cudaStream_t streams[2] = {nullptr, nullptr};
+  // launches of one environment share state (the ring of work counters, the first-hit scratch `fh`), so they are kept in
+  // order across whatever streams the caller uses: every *_device launch records order_ev, and a launch on another
+  // stream (or an internal stream of the host-pointer calls) first waits for it
+  cudaEvent_t order_ev = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool order_pending = false;
   DevBuf in[2], out[2], aux[2], fh;   // fh: per-edge first-hit scratch of small edge batches
   bool count = false;
   int64_t robot_bytes = 0;
@@ -244,6 +250,7 @@ int sffg_env_destroy(sffg_env *env) {
   cudaFree(env->d_robot);
   cudaFree(env->d_robot64);
   cudaFree(env->d_counters);
+  if (env->order_ev) cudaEventDestroy(env->order_ev);
   if (env->h_status) cudaFreeHost(env->h_status);
   if (env->h_small) cudaFreeHost(env->h_small);
   cudaFree(env->d_work);
@@ -479,6 +486,7 @@ int sffg_env_create_ex(const double *obst_tris, int64_t n_obst, const double *ro
   SFFG_ENV_CUDA(cudaMalloc((void **)&env->d_work, 8 * sizeof(unsigned)));
   SFFG_ENV_CUDA(cudaMemset(env->d_work, 0, 8 * sizeof(unsigned)));
   for (int s = 0; s < 2; ++s) SFFG_ENV_CUDA(cudaStreamCreateWithFlags(&env->streams[s], cudaStreamNonBlocking));
+  SFFG_ENV_CUDA(cudaEventCreateWithFlags(&env->order_ev, cudaEventDisableTiming));
   d.robot = reinterpret_cast<const RobotTri *>(env->d_robot);
   d.robot64 = reinterpret_cast<const double *>(env->d_robot64);
   d.counters = nullptr;
@@ -555,6 +563,27 @@ static EnvDev env_view(sffg_env *env, unsigned **base_io) {
   return v;
 }
 
+// stream ordering of the launches of one environment (see sffg_env::order_ev)
+static int env_enter(sffg_env *env, cudaStream_t st) {
+  if (env->order_pending && env->last_stream != st) SFFG_CUDA(cudaStreamWaitEvent(st, env->order_ev, 0));
+  return SFFG_OK;
+}
+static int env_leave(sffg_env *env, cudaStream_t st) {
+  SFFG_CUDA(cudaEventRecord(env->order_ev, st));
+  env->last_stream = st;
+  env->order_pending = true;
+  return SFFG_OK;
+}
+// host-pointer calls run on the environment's own two streams and synchronise before they return
+static int env_enter_host(sffg_env *env) {
+  if (env->order_pending) {
+    SFFG_CUDA(cudaStreamWaitEvent(env->streams[0], env->order_ev, 0));
+    SFFG_CUDA(cudaStreamWaitEvent(env->streams[1], env->order_ev, 0));
+    env->order_pending = false;   // everything recorded so far is complete once this call has synchronised
+  }
+  return SFFG_OK;
+}
+
 // call after the streams were synchronised
 static int check_status(sffg_env *env) {
   const int st = *reinterpret_cast<volatile int *>(env->h_status);
@@ -578,10 +607,12 @@ int sffg_collide_poses_device(sffg_env *env, const void *d_poses, int poses_are_
                               void *stream) {
   if (!env || n < 0 || (n > 0 && (!d_poses || !d_verdict_out))) return fail(SFFG_ERR_ARG, "sffg_collide_poses_device: bad arguments");
   unsigned *base;
+  int rc = env_enter(env, (cudaStream_t)stream);
+  if (rc != SFFG_OK) return rc;
   EnvDev v = env_view(env, &base);
   SFFG_CUDA(launch_collide_poses(v, d_poses, poses_are_f64 ? 1 : 0, n, d_verdict_out, (cudaStream_t)stream, env->cfg,
                                  env->count, base));
-  return SFFG_OK;
+  return env_leave(env, (cudaStream_t)stream);
 }
 
 // ---- multi-GPU: verdict all-gather fused into the kernel's stores -----------------------------------------
@@ -649,9 +680,11 @@ int sffg_collide_poses_gather_device(sffg_env *env, const void *d_poses, int pos
   if (rc != SFFG_OK) return rc;
   GatherSync none{};
   unsigned *base;
+  rc = env_enter(env, (cudaStream_t)stream);
+  if (rc != SFFG_OK) return rc;
   EnvDev v = env_view(env, &base);
   SFFG_CUDA(launch_collide_poses_gather(v, d_poses, poses_are_f64 ? 1 : 0, n, outs, none, (cudaStream_t)stream, env->cfg, env->count, base));
-  return SFFG_OK;
+  return env_leave(env, (cudaStream_t)stream);
 }
 
 int sffg_collide_poses_gather_sync_device(sffg_env *env, const void *d_poses, int poses_are_f64, int64_t n, uint8_t *const *d_outs,
@@ -668,9 +701,11 @@ int sffg_collide_poses_gather_sync_device(sffg_env *env, const void *d_poses, in
   gs.wait_epoch = wait_epoch;
   gs.done_counter = d_done_counter;
   unsigned *base;
+  rc = env_enter(env, (cudaStream_t)stream);
+  if (rc != SFFG_OK) return rc;
   EnvDev v = env_view(env, &base);
   SFFG_CUDA(launch_collide_poses_gather(v, d_poses, poses_are_f64 ? 1 : 0, n, outs, gs, (cudaStream_t)stream, env->cfg, env->count, base));
-  return SFFG_OK;
+  return env_leave(env, (cudaStream_t)stream);
 }
 
 int sffg_peer_wait_device(sffg_env *env, uint32_t *const *d_flags, int n_ranks, int my_rank, uint32_t epoch, void *stream) {
@@ -697,6 +732,10 @@ static int collide_poses_host(sffg_env *env, const void *poses, int fmt, int64_t
   if (n == 0) return SFFG_OK;
   const size_t psz = fmt == 0 ? 24 : (fmt == 1 ? 48 : 96);
   unsigned *base;
+  {
+    const int rc0 = env_enter_host(env);
+    if (rc0 != SFFG_OK) return rc0;
+  }
   if ((size_t)n * psz <= kSmallIn && (size_t)n <= kSmallBytes - kSmallIn) {
     // planner-sized call: one kernel reading/writing pinned mapped memory, one synchronisation, no DMA copies
     cudaStream_t st = env->streams[0];
@@ -742,16 +781,19 @@ int sffg_check_edges_device(sffg_env *env, const double *d_starts, const double 
       (rot_mode != SFFG_ROT_REFERENCE && rot_mode != SFFG_ROT_INTERPOLATE))
     return fail(SFFG_ERR_ARG, "sffg_check_edges_device: bad arguments");
   unsigned *base;
+  int rc = env_enter(env, (cudaStream_t)stream);
+  if (rc != SFFG_OK) return rc;
   EnvDev v = env_view(env, &base);
   int *scratch = nullptr;
   if (m < 8192) {   // small batches: several warps per edge (needs a scratch word per edge)
-    int rc = env->fh.reserve((size_t)m * sizeof(int));
+    if ((size_t)m * sizeof(int) > env->fh.cap) SFFG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));   // (growing frees the old block)
+    rc = env->fh.reserve((size_t)m * sizeof(int));
     if (rc != SFFG_OK) return rc;
     scratch = (int *)env->fh.p;
   }
   SFFG_CUDA(launch_check_edges(v, d_starts, d_ends, m, sample_dist, rot_mode, d_free_out, d_first_hit_out,
                                (cudaStream_t)stream, env->cfg, env->count, base, scratch));
-  return SFFG_OK;
+  return env_leave(env, (cudaStream_t)stream);
 }
 
 int sffg_check_edges(sffg_env *env, const double *starts, const double *ends, int64_t m, double sample_dist, int rot_mode,
@@ -761,6 +803,10 @@ int sffg_check_edges(sffg_env *env, const double *starts, const double *ends, in
     return fail(SFFG_ERR_ARG, "sffg_check_edges: bad arguments");
   if (m == 0) return SFFG_OK;
   unsigned *base;
+  {
+    const int rc0 = env_enter_host(env);
+    if (rc0 != SFFG_OK) return rc0;
+  }
   if ((size_t)m * 96 <= kSmallIn && (size_t)m * 5 <= kSmallBytes - kSmallIn) {
     // planner-sized call.  The endpoints are re-read by every warp that shares an edge, so they go to device memory with
     // one DMA from the pinned staging area; the results are written straight into pinned mapped memory.
@@ -814,6 +860,10 @@ int sffg_check_moves(sffg_env *env, const double *starts, const double *ends, in
     return fail(SFFG_ERR_ARG, "sffg_check_moves: bad arguments");
   if (m == 0) return SFFG_OK;
   unsigned *base;
+  {
+    const int rc0 = env_enter_host(env);
+    if (rc0 != SFFG_OK) return rc0;
+  }
   if ((size_t)m * 96 <= kSmallIn && (size_t)m * 6 <= kSmallBytes - kSmallIn) {
     // planner-sized call: one upload, the pose kernel on the end points and the edge kernel on the segments back to back
     // on one stream, results straight into pinned mapped memory, one synchronisation

@@ -156,3 +156,25 @@ def test_c_example_gives_the_expected_answers(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "verdicts 1 0 1, edge free 0 (first colliding sample 25), nearest nodes 1 0" in r.stdout
+
+
+def test_many_launches_on_different_streams_stay_exact(sff, orc, meshes):
+    """the *_device calls of one environment share a ring of 8 work counters: 24 launches enqueued on three streams without
+    any host synchronisation must still answer every pose (the library orders the launches of an environment across streams)"""
+    import torch
+    on, rn, rng = CASES["T"]
+    env = make_env(sff, meshes, "T")
+    n = 20000
+    poses = orc.gen_poses(SEED + 77, 0, 24 * n, rng)
+    want, _ = orc.collide_obbtree(orc.ObbModel(meshes[on]), orc.ObbModel(meshes[rn]), poses.astype(np.float64))
+    d_poses = torch.from_numpy(poses).cuda()
+    outs = [torch.full((n,), 7, dtype=torch.uint8, device="cuda") for _ in range(24)]
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    torch.cuda.synchronize()
+    for j in range(24):
+        st = streams[j % 3]
+        env.collide_device(d_poses[j * n:(j + 1) * n], out=outs[j], stream=st.cuda_stream)
+    torch.cuda.synchronize()
+    env.sync_check()
+    got = torch.cat(outs).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
