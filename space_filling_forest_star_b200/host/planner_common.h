@@ -45,15 +45,21 @@ inline void check(int rc) {
 struct Tag {
   std::string name;
   std::map<std::string, std::string> attr;
+  std::string parent;   // name of the enclosing element ("" at top level): the reference reads children of named nodes only
 };
 
 inline std::vector<Tag> scan_tags(const std::string &t) {
   std::vector<Tag> out;
+  std::vector<std::string> open;   // element nesting
   size_t i = 0;
   while ((i = t.find('<', i)) != std::string::npos) {
     ++i;
     if (i >= t.size()) break;
-    if (t[i] == '?' || t[i] == '/') continue;
+    if (t[i] == '?') continue;
+    if (t[i] == '/') {
+      if (!open.empty()) open.pop_back();
+      continue;
+    }
     if (t.compare(i, 3, "!--") == 0) {
       size_t e = t.find("-->", i);
       i = e == std::string::npos ? t.size() : e + 3;
@@ -74,6 +80,9 @@ inline std::vector<Tag> scan_tags(const std::string &t) {
       ++i;
       tag.attr[key] = val;
     }
+    tag.parent = open.empty() ? std::string() : open.back();
+    const bool self_closing = i > 0 && i < t.size() && t[i] == '>' && t[i - 1] == '/';
+    if (!self_closing) open.push_back(tag.name);
     out.push_back(tag);
   }
   return out;
@@ -150,14 +159,14 @@ inline Config load_config(const std::string &path) {
       if (auto v = get("file")) c.robot.file = *v; else die("invalid file node in Robot node!");
       if (auto v = get("is_obj")) c.robot.is_obj = *v == "true";
       if (auto v = get("fix_mesh")) if (*v == "true" && c.robot.is_obj) c.robot.is_obj = SFFG_MESH_OBJ_FIXED;
-    } else if (t.name == "Obstacle") {
+    } else if (t.name == "Obstacle" && t.parent == "Environment") {   // src/main.cpp:241-258: children of <Environment>
       MeshRef m;
       if (auto v = get("file")) m.file = *v; else die("invalid file attribute in Obstacle node!");
       if (auto v = get("is_obj")) m.is_obj = *v == "true";
       if (auto v = get("fix_mesh")) if (*v == "true" && m.is_obj) m.is_obj = SFFG_MESH_OBJ_FIXED;
       if (auto v = get("position")) if (!parse_point(*v, 1.0, m.pos)) die("Unknown format of point");
       c.obstacles.push_back(m);
-    } else if (t.name == "Point") {
+    } else if (t.name == "Point" && t.parent == "Points") {           // src/main.cpp:166-186: children of <Points>
       std::array<double, 3> p;
       auto v = get("coord");
       if (!v || !parse_point(*v, c.scale, p.data())) die("invalid coord attribute in Point node!");
@@ -190,7 +199,7 @@ inline Config load_config(const std::string &path) {
       if (auto v = get("value")) c.max_iterations = std::stol(*v); else die("invalid MaxIterations node!");
     } else if (t.name == "Save") {
       in_save = true;
-    } else if (t.name == "Params" && in_save) {
+    } else if (t.name == "Params" && in_save && t.parent == "Save") {   // src/main.cpp:394-399: a child of <Save>
       if (auto v = get("file")) c.params_file = *v;
       if (auto v = get("id")) c.id = *v;
     }

@@ -216,6 +216,22 @@ def test_lazy_tsp_2d(exe, tmp_path, orc, meshes):
     assert len(raw) == 4 and all(len(l.split()) == 12 for blk in raw for l in blk.splitlines())
 
 
+def test_config_reads_points_and_obstacles_only_where_the_reference_does(exe, tmp_path):
+    """src/main.cpp:166-186, :241-258: <Point> is read as a child of <Points>, <Obstacle> as a child of <Environment>; the same
+    tags elsewhere in the file are not roots / obstacles"""
+    import subprocess
+    PU.run_planner(exe, tmp_path, "2d_sffstar", seed=1)
+    base = (tmp_path / "2d_sffstar.xml").read_text()
+    stray = tmp_path / "stray.xml"
+    stray.write_text(base.replace("<Save>", '<Point coord="[500; 350; 0]"/>\n  <Obstacle file="missing.tri" is_obj="false"/>\n  <Save>')
+                     .replace("params_2d_sffstar", "params_stray"))
+    p = subprocess.run([str(exe), stray.name, "0", "--seed", "1", "--quiet"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    row = (tmp_path / "output" / "params_stray.csv").read_text().strip().splitlines()[-1]
+    want = (tmp_path / "output" / "params_2d_sffstar.csv").read_text().strip().splitlines()[-1]
+    assert row.split(",")[2:6] == want.split(",")[2:6]      # same four roots, same map, same seed -> same solve
+
+
 def test_lazy_validation_rules(exe, tmp_path):
     """src/main.cpp:292-293, :330-331: no single goal and no priority bias for the Lazy solver"""
     import subprocess
