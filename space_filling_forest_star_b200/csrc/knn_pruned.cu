@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, cons
   const int nsb = (sv.nblk + 31) / 32;   // superblocks of 32 blocks
   const int sb_begin = slice * sb_per_slice;
   const int sb_end = min(nsb, sb_begin + sb_per_slice);
+  int near_sb = -1;   // a superblock close to the warp's queries (they are neighbours in space): pass 2 starts there
   // ---- pass 1: a bound on the k-th distance without touching a node.
   // Slices of up to 128 superblocks scan every block box of the slice: G = ceil(k/32) consecutive FULL blocks hold >= k nodes,
   // all within max_g box_ub(g) (+ the largest possible angular part), so the k-th nearest node cannot be farther -- the
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, cons
         }
       }
       float bound = bv;
+      if (w == 0) near_sb = bs;
       if (bs >= 0) {   // warp-uniform; every block of a full superblock is full
         const int blk = bs * 32 + lane;
         float lo[LIN], hi[LIN];
@@ -339,9 +341,18 @@ __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, cons
   for (int w = 0; w < QW; ++w) seed[w] = worst[w];
   // ---- pass 2: superblock boxes first (lane-per-superblock, 32 768 nodes per step), then the block boxes of the superblocks
   // that can still hold a candidate (lane-per-block), then the nodes of the blocks that can
-  for (int sg = sb_begin; sg < sb_end; sg += 32) {
+  // Visiting order: nearest first at every level (the group of 32 superblocks around `near_sb` first, then inside a group
+  // the superblock and inside a superblock the block whose box is closest to any of the warp's queries): the k-th
+  // distances tighten after a few blocks, and almost everything visited later fails the `d < worst` vote without a
+  // single insertion.  The order changes nothing in the result -- insertion is (d2, id)-keyed.
+  const int first_sg = near_sb >= 0 ? sb_begin + ((near_sb - sb_begin) & ~31) : -1;
+  for (int gi = first_sg >= 0 ? -1 : 0;; ++gi) {
+    const int sg = gi < 0 ? first_sg : sb_begin + gi * 32;
+    if (gi >= 0 && sg >= sb_end) break;
+    if (gi >= 0 && sg == first_sg) continue;
     float lbs[QW];
     bool need_s = false;
+    float key_s = INFINITY;
     if (sg + lane < sb_end) {
       float lo[LIN], hi[LIN];
 #pragma unroll
@@ -353,96 +364,103 @@ __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, cons
       for (int w = 0; w < QW; ++w) {
         lbs[w] = box_lb<LIN>(lo, hi, q[w]);
         need_s |= !(lbs[w] > worst[w]);
+        key_s = fminf(key_s, lbs[w]);
       }
     } else {
 #pragma unroll
       for (int w = 0; w < QW; ++w) lbs[w] = INFINITY;
     }
     unsigned todo_s = __ballot_sync(kFull, need_s);
-  while (todo_s) {
-    const int sl = __ffs(todo_s) - 1;
-    const int sb = sg + sl;
-    const int blk = sb * 32 + lane;
-    float lb[QW];
-    bool need = false;
-    if (blk < sv.nblk) {
-      float lo[LIN], hi[LIN];
+    const unsigned pk_s = (__float_as_uint(key_s) & 0xffffffe0u) | (unsigned)lane;   // (key >= 0: bit order = value order)
+    while (todo_s) {
+      const int sl = (int)(__reduce_min_sync(kFull, ((todo_s >> lane) & 1u) ? pk_s : 0xffffffffu) & 31u);
+      todo_s &= ~(1u << sl);
+      const int sb = sg + sl;
+      const int blk = sb * 32 + lane;
+      float lb[QW];
+      bool need = false;
+      float key_b = INFINITY;
+      if (blk < sv.nblk) {
+        float lo[LIN], hi[LIN];
 #pragma unroll
-      for (int c = 0; c < LIN; ++c) {
-        lo[c] = __ldg(sv.bb + (long long)c * sv.nblk_cap + blk);
-        hi[c] = __ldg(sv.bb + (long long)(LIN + c) * sv.nblk_cap + blk);
-      }
-#pragma unroll
-      for (int w = 0; w < QW; ++w) {
-        lb[w] = box_lb<LIN>(lo, hi, q[w]);
-        need |= !(lb[w] > worst[w]);
-      }
-    } else {
-#pragma unroll
-      for (int w = 0; w < QW; ++w) lb[w] = INFINITY;
-    }
-    unsigned todo = __ballot_sync(kFull, need);
-    while (todo) {
-      const int bl = __ffs(todo) - 1;
-      // ---- visit block sb*32 + bl: lane-per-node
-      const int base = (sb * 32 + bl) * 32;
-      const int pos = base + lane;
-      const bool valid = pos < sv.n_sorted;
-      float nd[LIN];
-#pragma unroll
-      for (int c = 0; c < LIN; ++c) nd[c] = valid ? __ldg(sv.coords + (long long)c * sv.cap_s + pos) : 0.f;
-      float d[QW];
-      bool any = false;
-#pragma unroll
-      for (int w = 0; w < QW; ++w) {
-        d[w] = valid ? metric_lin<DIM>(nd, q[w]) : INFINITY;
-        any |= !(d[w] > worst[w]);
-      }
-      if (__any_sync(kFull, any)) {
-        const int id = valid ? __ldg(sv.ids + pos) : -1;
-        if (DIM == 6) {
-          float ang[3];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) ang[c] = valid ? __ldg(sv.coords + (long long)(3 + c) * sv.cap_s + pos) : 0.f;
-          if (!wide) {
-#pragma unroll
-            for (int w = 0; w < QW; ++w) d[w] = valid ? metric_ang<false>(d[w], ang, q[w]) : INFINITY;
-          } else {
-#pragma unroll
-            for (int w = 0; w < QW; ++w) d[w] = valid ? metric_ang<true>(d[w], ang, q[w]) : INFINITY;
-          }
+        for (int c = 0; c < LIN; ++c) {
+          lo[c] = __ldg(sv.bb + (long long)c * sv.nblk_cap + blk);
+          hi[c] = __ldg(sv.bb + (long long)(LIN + c) * sv.nblk_cap + blk);
         }
 #pragma unroll
         for (int w = 0; w < QW; ++w) {
-          unsigned mask = __ballot_sync(kFull, valid && (d[w] < worst[w] || (d[w] == worst[w] && (unsigned)id < (unsigned)worst_id[w])));
-          while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float cd = __shfl_sync(kFull, d[w], src);
-            const int ci = __shfl_sync(kFull, id, src);
-            if (cd < worst[w] || (cd == worst[w] && (unsigned)ci < (unsigned)worst_id[w])) {
-              top[w].insert_keyed(cd, ci, lane);
-              const float kd = top[w].kth(k);
-              if (kd <= seed[w]) {          // list full and at least as tight as the seed bound
-                worst[w] = kd;
-                worst_id[w] = top[w].kth_id(k);
+          lb[w] = box_lb<LIN>(lo, hi, q[w]);
+          need |= !(lb[w] > worst[w]);
+          key_b = fminf(key_b, lb[w]);
+        }
+      } else {
+#pragma unroll
+        for (int w = 0; w < QW; ++w) lb[w] = INFINITY;
+      }
+      unsigned todo = __ballot_sync(kFull, need);
+      const unsigned pk_b = (__float_as_uint(key_b) & 0xffffffe0u) | (unsigned)lane;
+      while (todo) {
+        const int bl = (int)(__reduce_min_sync(kFull, ((todo >> lane) & 1u) ? pk_b : 0xffffffffu) & 31u);
+        todo &= ~(1u << bl);
+        // ---- visit block sb*32 + bl: lane-per-node
+        const int base = (sb * 32 + bl) * 32;
+        const int pos = base + lane;
+        const bool valid = pos < sv.n_sorted;
+        float nd[LIN];
+#pragma unroll
+        for (int c = 0; c < LIN; ++c) nd[c] = valid ? __ldg(sv.coords + (long long)c * sv.cap_s + pos) : 0.f;
+        float d[QW];
+        bool any = false;
+#pragma unroll
+        for (int w = 0; w < QW; ++w) {
+          d[w] = valid ? metric_lin<DIM>(nd, q[w]) : INFINITY;
+          any |= !(d[w] > worst[w]);
+        }
+        if (__any_sync(kFull, any)) {
+          const int id = valid ? __ldg(sv.ids + pos) : -1;
+          if (DIM == 6) {
+            float ang[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) ang[c] = valid ? __ldg(sv.coords + (long long)(3 + c) * sv.cap_s + pos) : 0.f;
+            if (!wide) {
+#pragma unroll
+              for (int w = 0; w < QW; ++w) d[w] = valid ? metric_ang<false>(d[w], ang, q[w]) : INFINITY;
+            } else {
+#pragma unroll
+              for (int w = 0; w < QW; ++w) d[w] = valid ? metric_ang<true>(d[w], ang, q[w]) : INFINITY;
+            }
+          }
+#pragma unroll
+          for (int w = 0; w < QW; ++w) {
+            unsigned mask = __ballot_sync(kFull, valid && (d[w] < worst[w] || (d[w] == worst[w] && (unsigned)id < (unsigned)worst_id[w])));
+            while (mask) {
+              const int src = __ffs(mask) - 1;
+              mask &= mask - 1;
+              const float cd = __shfl_sync(kFull, d[w], src);
+              const int ci = __shfl_sync(kFull, id, src);
+              if (cd < worst[w] || (cd == worst[w] && (unsigned)ci < (unsigned)worst_id[w])) {
+                top[w].insert_keyed(cd, ci, lane);
+                const float kd = top[w].kth(k);
+                if (kd <= seed[w]) {          // list full and at least as tight as the seed bound
+                  worst[w] = kd;
+                  worst_id[w] = top[w].kth_id(k);
+                }
               }
             }
           }
         }
+        // the k-th distances may have shrunk: drop the remaining blocks of this superblock that no longer matter
+        need = false;
+#pragma unroll
+        for (int w = 0; w < QW; ++w) need |= !(lb[w] > worst[w]);
+        todo &= __ballot_sync(kFull, need);
       }
-      // the k-th distances may have shrunk: re-evaluate which of the remaining blocks of this step still matter
-      need = false;
+      // ... and the remaining superblocks of this group
+      need_s = false;
 #pragma unroll
-      for (int w = 0; w < QW; ++w) need |= !(lb[w] > worst[w]);
-      todo = __ballot_sync(kFull, need && lane > bl);
+      for (int w = 0; w < QW; ++w) need_s |= !(lbs[w] > worst[w]);
+      todo_s &= __ballot_sync(kFull, need_s);
     }
-    // ... and which of the remaining superblocks of this group
-    need_s = false;
-#pragma unroll
-    for (int w = 0; w < QW; ++w) need_s |= !(lbs[w] > worst[w]);
-    todo_s = __ballot_sync(kFull, need_s && lane > sl);
-  }
   }
 #pragma unroll
   for (int w = 0; w < QW; ++w) {
