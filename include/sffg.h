@@ -96,6 +96,13 @@ SFFG_API int sffg_env_create_ex(const double *obst_tris, int64_t n_obst, const d
  * delete and re-create its Obstacle objects, src/main.cpp:254): rebuilds hierarchy, triangle arrays and clearance grid,
  * keeps robot, streams, staging buffers and counters.  Blocks until the device is idle, then until the rebuild is done. */
 SFFG_API int sffg_env_set_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obst, int build_mode);
+/* the same n_obst triangles in the same order, at new positions (rigid motion or deformation between frames): the
+ * hierarchy keeps its topology and only the triangle arrays, every slot box (bottom-up, outward rounded), the top cut,
+ * the root box and the clearance grid are recomputed on the GPU -- several times cheaper than a rebuild.  Verdicts stay
+ * exact whatever the motion (boxes are refitted conservatively, every surviving pair is still tested exactly); only the
+ * culling power degrades as the soup drifts away from the shape the topology was built for -- rebuild from time to time.
+ * SFFG_ERR_ARG when the triangle count differs from the current set.                                               */
+SFFG_API int sffg_env_refit_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obst);
 
 typedef struct {
   int64_t n_obst_tris, n_robot_tris;

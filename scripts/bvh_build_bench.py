@@ -58,7 +58,23 @@ for levels in (0, 2, 3):
         t1 = time.perf_counter()
         env.set_obstacles(soup, build=mode)
         rebuild = time.perf_counter() - t1
-        rows.append({"triangles": int(len(soup)), "builder": name, "create_s": wall, "set_obstacles_s": rebuild, "n_nodes": info["n_nodes"],
+        # ... and what it costs when the topology is kept (refit: boxes, triangle arrays, top cut, clearance grid)
+        moved = soup + np.array([0.5, -0.25, 0.125])
+        env.refit_obstacles(moved)
+        t2 = time.perf_counter()
+        env.refit_obstacles(moved)
+        refit = time.perf_counter() - t2
+        env.collide_device(poses, out=out)
+        torch.cuda.synchronize()
+        ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev2[0].record()
+        for _ in range(3):
+            env.collide_device(poses, out=out)
+        ev2[1].record()
+        torch.cuda.synchronize()
+        env.sync_check()
+        rows.append({"triangles": int(len(soup)), "builder": name, "create_s": wall, "set_obstacles_s": rebuild, "refit_s": refit,
+                     "poses_per_s_after_refit": (1 << 22) / (ev2[0].elapsed_time(ev2[1]) * 1e-3 / 3), "n_nodes": info["n_nodes"],
                      "depth": info["depth"], "poses_per_s": (1 << 22) / sec, "hits": hits})
         print(json.dumps(rows[-1]), flush=True)
         env.close()

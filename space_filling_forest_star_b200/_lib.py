@@ -48,6 +48,7 @@ SIGNATURES = {
     "sffg_env_destroy": (C.c_int, [_p]),
     "sffg_env_create_ex": (C.c_int, [_p, C.c_int64, _p, C.c_int64, C.c_int, C.POINTER(_p)]),
     "sffg_env_set_obstacles": (C.c_int, [_p, _p, C.c_int64, C.c_int]),
+    "sffg_env_refit_obstacles": (C.c_int, [_p, _p, C.c_int64]),
     "sffg_env_info": (C.c_int, [_p, C.POINTER(EnvInfo)]),
     "sffg_collide_poses_f32": (C.c_int, [_p, _p, C.c_int64, _p]),
     "sffg_collide_poses_f64": (C.c_int, [_p, _p, C.c_int64, _p]),

@@ -291,11 +291,17 @@ void build_wide_bvh(const double *tris, int64_t n, HostBvh *out) {
     std::vector<int32_t> order;   // new index -> old index
     order.reserve(nn);
     order.push_back(0);
-    for (size_t head = 0; head < order.size(); ++head)
-      for (int i = 0; i < kWide; ++i) {
-        const int32_t ch = out->slots[(size_t)order[head] * kWide + i].child;
-        if (ch >= 0 && ch != kEmptyChild) order.push_back(ch);
-      }
+    out->level_base.clear();
+    out->level_count.clear();
+    for (size_t begin = 0, end = 1; begin < end; begin = end, end = order.size()) {
+      out->level_base.push_back((int)begin);
+      out->level_count.push_back((int)(end - begin));
+      for (size_t head = begin; head < end; ++head)
+        for (int i = 0; i < kWide; ++i) {
+          const int32_t ch = out->slots[(size_t)order[head] * kWide + i].child;
+          if (ch >= 0 && ch != kEmptyChild) order.push_back(ch);
+        }
+    }
     std::vector<int32_t> new_of(nn, -1);
     for (size_t i = 0; i < order.size(); ++i) new_of[(size_t)order[i]] = (int32_t)i;
     std::vector<ChildSlot> re(out->slots.size());

@@ -399,6 +399,39 @@ cudaError_t build_bvh_device(const double *d_soup, int n, cudaStream_t st, Devic
   out->d_order = vals_out;
   out->n_nodes = n_nodes;
   out->depth = (int)level_base.size();
+  out->level_base = level_base;
+  out->level_count = level_count;
+  return cudaSuccess;
+}
+
+cudaError_t refit_bvh_device(const double *d_soup, int n, ChildSlot *d_slots, double *d_tris64, float4 *d_tris32, const int *d_order,
+                             const std::vector<int> &level_base, const std::vector<int> &level_count, cudaStream_t st,
+                             double root_lo[3], double root_hi[3]) {
+  if (n <= 0) return cudaSuccess;
+  Scratch tmp;
+  float *tbox;
+  int *bounds;
+  BD_CUDA(tmp.get(&tbox, 6 * (size_t)n));
+  BD_CUDA(tmp.get(&bounds, 8));
+  const int T = 256, G = (n + T - 1) / T;
+  init_bounds_kernel<<<1, 32, 0, st>>>(bounds);
+  tri_prepare_kernel<<<G, T, 0, st>>>(d_soup, n, tbox, bounds);
+  gather_tris_kernel<<<G, T, 0, st>>>(d_soup, d_order, n, d_tris64, d_tris32);
+  for (int l = (int)level_base.size() - 1; l >= 0; --l) {
+    const int threads = level_count[l] * 8;
+    fit_level_kernel<<<(threads + 255) / 256, 256, 0, st>>>(d_slots, level_base[l], level_count[l], tbox, d_order);
+  }
+  int hb[6];
+  BD_CUDA(cudaMemcpyAsync(hb, bounds, sizeof hb, cudaMemcpyDeviceToHost, st));
+  BD_CUDA(cudaStreamSynchronize(st));
+  BD_CUDA(cudaGetLastError());
+  for (int k = 0; k < 6; ++k) {
+    const int i = hb[k];
+    const int bits = i >= 0 ? i : i ^ 0x7fffffff;
+    float f;
+    memcpy(&f, &bits, 4);
+    (k < 3 ? root_lo[k] : root_hi[k - 3]) = (double)f;
+  }
   return cudaSuccess;
 }
 

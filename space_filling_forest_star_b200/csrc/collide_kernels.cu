@@ -426,6 +426,7 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const CtaShared 
 
   int sp = 0, ntri = 0;
   const int grp10 = lane / 10, k10 = lane - 10 * grp10;
+  const float inv_n_robot = 1.0f / (float)E.n_robot;
   bool hit = false;
   bool have_R2 = false;
   double R2[9], T2[3];
@@ -440,7 +441,7 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const CtaShared 
       if (first) {
         active = lane < E.n_top;
         if (active) {
-          const float4 a = cs.top[2 * lane], b = cs.top[2 * lane + 1];
+          const float4 a = cs.top[lane], b = cs.top[kTopSlots + lane];
           child = __float_as_int(a.w);
           ov = slot_overlaps(E, P, bt, a, b);
         }
@@ -457,9 +458,9 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const CtaShared 
         if (active) {
           float4 a, b;
           if (node < cs.n_stage) {   // (nodes of one step are popped together: mostly one side of this branch)
-            const float4 *sn = cs.nodes + ((size_t)node * kWide + (lane & 7)) * 2;
-            a = sn[0];
-            b = sn[1];
+            const int si = node * kWide + (lane & 7);
+            a = cs.nodes[si];                             // staged as two arrays (all `a` halves, then all `b` halves):
+            b = cs.nodes[cs.n_stage * kWide + si];        // 8 lanes read 128 contiguous bytes, no bank conflicts
           } else {
             const float4 *gn = E.slots + ((size_t)node * kWide + (lane & 7)) * 2;
             a = __ldg(gn);
@@ -534,17 +535,15 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const CtaShared 
       for (int pb = 0; pb < npairs && !hit; pb += 32) {
         const int pidx = pb + lane;
         bool undecided = false;
-        if (pidx < npairs) {
-          const int xi = pidx / E.n_robot, r = pidx - xi * E.n_robot;
-          undecided = !pair_quick_disjoint(ws.xt[xi], srob[r]);
-        }
+        // (triangle, robot triangle) of this lane's pair; the quotient by float reciprocal is exact for pidx < 2^20
+        const int xi_l = (int)(((float)pidx + 0.5f) * inv_n_robot), r_l = pidx - xi_l * E.n_robot;
+        if (pidx < npairs) undecided = !pair_quick_disjoint(ws.xt[xi_l], srob[r_l]);
         unsigned um = __ballot_sync(kFull, undecided);
         if (COUNT) {
           const int np = (npairs - pb) < 32 ? (npairs - pb) : 32;
           tally.pair += np;
           tally.exact += __popc(um);   // pairs the lane-per-pair stage P1 left open
         }
-        const int xi_l = pidx / E.n_robot, r_l = pidx - xi_l * E.n_robot;
         while (um && !hit) {
           const int l0 = __ffs(um) - 1;
           um &= um - 1;
@@ -628,9 +627,10 @@ __device__ __forceinline__ CtaShared stage_cta(const EnvDev &E, unsigned char *s
     float *d = reinterpret_cast<float *>(srob);
     for (int i = threadIdx.x; i < words; i += blockDim.x) d[i] = __ldg(g + i);
   }
-  for (int i = threadIdx.x; i < 2 * E.n_top; i += blockDim.x) stop[i] = __ldg(E.top + i);
+  // slot = 2 float4 (a, b) in global memory; shared memory keeps all `a` halves first, then all `b` halves
+  for (int i = threadIdx.x; i < 2 * E.n_top; i += blockDim.x) stop[(i & 1) * kTopSlots + (i >> 1)] = __ldg(E.top + i);
   const int nv = n_stage * kWide * 2;
-  for (int i = threadIdx.x; i < nv; i += blockDim.x) snodes[i] = __ldg(E.slots + i);
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) snodes[(i & 1) * n_stage * kWide + (i >> 1)] = __ldg(E.slots + i);
   __syncthreads();
   CtaShared cs;
   cs.rob = srob;

@@ -53,6 +53,7 @@ struct HostBvh {
   std::vector<int32_t> tri_order;     // BVH leaf order -> original triangle index
   int depth = 0;
   double root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
+  std::vector<int> level_base, level_count;   // nodes are stored breadth-first: level l = [level_base[l], +level_count[l])
 };
 
 // picks <= 32 slots forming a cut through the top of the hierarchy (largest boxes expanded first)

@@ -91,6 +91,9 @@ using namespace sffg;
 struct sffg_env {
   EnvDev dev{};
   void *d_slots = nullptr, *d_top = nullptr, *d_clear = nullptr, *d_tris32 = nullptr, *d_tris64 = nullptr, *d_robot = nullptr, *d_robot64 = nullptr;
+  void *d_order = nullptr;                       // leaf position -> caller's triangle index (refit)
+  std::vector<int> level_base, level_count;      // breadth-first level table of the hierarchy (refit)
+  int64_t obst_bytes = 0;
   unsigned long long *d_counters = nullptr;
   int *h_status = nullptr;      // pinned + device-mapped: the kernels raise it, the host reads it without a copy
   unsigned *d_work = nullptr;   // ring of 8 work counters (never reset; see launch_collide_poses)
@@ -243,6 +246,7 @@ int sffg_env_destroy(sffg_env *env) {
     if (env->streams[s]) cudaStreamSynchronize(env->streams[s]);
   }
   cudaFree(env->d_slots);
+  cudaFree(env->d_order);
   cudaFree(env->d_top);
   cudaFree(env->d_clear);
   cudaFree(env->d_tris32);
@@ -269,15 +273,14 @@ int sffg_env_destroy(sffg_env *env) {
 // The robot side of `env` must already be in place (the grid is dilated by the robot's bounding radius).
 constexpr int64_t kDeviceBuildMin = 1 << 18;   // SFFG_BUILD_AUTO: triangle count from which the hierarchy is built on the GPU
 
-static int set_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obst, int build_mode) {
-  const bool on_device = n_obst > 0 && (build_mode == SFFG_BUILD_DEVICE || (build_mode == SFFG_BUILD_AUTO && n_obst >= kDeviceBuildMin));
-  void **olds[] = {&env->d_slots, &env->d_top, &env->d_clear, &env->d_tris32, &env->d_tris64};
-  for (void **p : olds) {
-    cudaFree(*p);
-    *p = nullptr;
-  }
+// everything that hangs off a finished hierarchy: top cut, root box, clearance grid, device view, info
+static int finish_obstacles(sffg_env *env, const std::vector<ChildSlot> &top, const double root_lo[3], const double root_hi[3],
+                            int64_t n_obst, int64_t n_nodes, int depth, bool on_device, size_t bytes) {
   EnvDev &d = env->dev;
-  size_t bytes = 0;
+  cudaFree(env->d_top);
+  env->d_top = nullptr;
+  cudaFree(env->d_clear);
+  env->d_clear = nullptr;
   auto upload = [&](void **dst, const void *src, size_t n) -> cudaError_t {
     cudaError_t e = cudaMalloc(dst, std::max<size_t>(n, 16));
     if (e != cudaSuccess) return e;
@@ -285,71 +288,6 @@ static int set_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obst,
     if (n) e = cudaMemcpy(*dst, src, n, cudaMemcpyHostToDevice);
     return e;
   };
-  double root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
-  std::vector<ChildSlot> top;
-  int64_t n_nodes = 0;
-  int depth = 0;
-  if (!on_device) {
-    // ---- host: binned-SAH hierarchy + FP32 / FP64 triangle arrays in leaf order
-    HostBvh bvh;
-    build_wide_bvh(obst_tris, n_obst, &bvh);
-    std::vector<TriF32> t32((size_t)n_obst);
-    std::vector<double> t64(9 * (size_t)n_obst);
-    for (int64_t i = 0; i < n_obst; ++i) {
-      const double *src = obst_tris + 9 * (size_t)bvh.tri_order[(size_t)i];
-      std::memcpy(&t64[9 * (size_t)i], src, 9 * sizeof(double));
-      double err = 0;
-      for (int v = 0; v < 3; ++v) {
-        for (int k = 0; k < 3; ++k) {
-          float f = (float)src[3 * v + k];
-          t32[(size_t)i].p[v][k] = f;
-          err = std::max(err, std::fabs(src[3 * v + k] - (double)f));
-        }
-        t32[(size_t)i].p[v][3] = 0.f;
-      }
-      t32[(size_t)i].p[0][3] = round_up_f32(err * 1.0000001);
-    }
-    SFFG_CUDA(upload(&env->d_slots, bvh.slots.data(), bvh.slots.size() * sizeof(ChildSlot)));
-    SFFG_CUDA(upload(&env->d_tris32, t32.data(), t32.size() * sizeof(TriF32)));
-    SFFG_CUDA(upload(&env->d_tris64, t64.data(), t64.size() * sizeof(double)));
-    top_cut(bvh, &top);
-    n_nodes = (int64_t)(bvh.slots.size() / kWide);
-    depth = bvh.depth;
-    for (int k = 0; k < 3; ++k) {
-      root_lo[k] = bvh.root_lo[k];
-      root_hi[k] = bvh.root_hi[k];
-    }
-  } else {
-    // ---- device: Morton-ordered 8-wide hierarchy built by bvh_device.cu from the uploaded soup
-    void *d_soup = nullptr;
-    size_t dummy = 0;
-    (void)dummy;
-    SFFG_CUDA(cudaMalloc(&d_soup, 9 * (size_t)n_obst * sizeof(double)));
-    cudaError_t e = cudaMemcpyAsync(d_soup, obst_tris, 9 * (size_t)n_obst * sizeof(double), cudaMemcpyHostToDevice, env->streams[0]);
-    DeviceBvh db;
-    if (e == cudaSuccess) e = build_bvh_device((const double *)d_soup, (int)n_obst, env->streams[0], &db);
-    cudaFree(d_soup);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      return fail(SFFG_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString(e));
-    }
-    env->d_slots = db.d_slots;
-    env->d_tris32 = db.d_tris32;
-    env->d_tris64 = db.d_tris64;
-    cudaFree(db.d_order);
-    bytes += (size_t)db.n_nodes * kWide * sizeof(ChildSlot) + (size_t)n_obst * (sizeof(TriF32) + 9 * sizeof(double));
-    // the cut through the top of the hierarchy is chosen on the host from the first levels (nodes are stored level by level)
-    HostBvh head;
-    head.slots.resize((size_t)std::min<int64_t>(db.n_nodes, 1 + 8 + 64) * kWide);
-    SFFG_CUDA(cudaMemcpy(head.slots.data(), env->d_slots, head.slots.size() * sizeof(ChildSlot), cudaMemcpyDeviceToHost));
-    top_cut(head, &top);
-    n_nodes = db.n_nodes;
-    depth = db.depth;
-    for (int k = 0; k < 3; ++k) {
-      root_lo[k] = db.root_lo[k];
-      root_hi[k] = db.root_hi[k];
-    }
-  }
   SFFG_CUDA(upload(&env->d_top, top.data(), top.size() * sizeof(ChildSlot)));
   d.n_obst = (int)n_obst;
   for (int k = 0; k < 3; ++k) {
@@ -415,6 +353,98 @@ static int set_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obst,
   env->info.device_bytes = env->robot_bytes + (int64_t)bytes;
   env->info.built_on_device = on_device ? 1 : 0;
   return SFFG_OK;
+}
+
+static int set_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obst, int build_mode) {
+  const bool on_device = n_obst > 0 && (build_mode == SFFG_BUILD_DEVICE || (build_mode == SFFG_BUILD_AUTO && n_obst >= kDeviceBuildMin));
+  void **olds[] = {&env->d_slots, &env->d_tris32, &env->d_tris64, &env->d_order};
+  env->level_base.clear();
+  env->level_count.clear();
+  for (void **p : olds) {
+    cudaFree(*p);
+    *p = nullptr;
+  }
+  EnvDev &d = env->dev;
+  size_t bytes = 0;
+  auto upload = [&](void **dst, const void *src, size_t n) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, std::max<size_t>(n, 16));
+    if (e != cudaSuccess) return e;
+    bytes += n;
+    if (n) e = cudaMemcpy(*dst, src, n, cudaMemcpyHostToDevice);
+    return e;
+  };
+  double root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
+  std::vector<ChildSlot> top;
+  int64_t n_nodes = 0;
+  int depth = 0;
+  if (!on_device) {
+    // ---- host: binned-SAH hierarchy + FP32 / FP64 triangle arrays in leaf order
+    HostBvh bvh;
+    build_wide_bvh(obst_tris, n_obst, &bvh);
+    std::vector<TriF32> t32((size_t)n_obst);
+    std::vector<double> t64(9 * (size_t)n_obst);
+    for (int64_t i = 0; i < n_obst; ++i) {
+      const double *src = obst_tris + 9 * (size_t)bvh.tri_order[(size_t)i];
+      std::memcpy(&t64[9 * (size_t)i], src, 9 * sizeof(double));
+      double err = 0;
+      for (int v = 0; v < 3; ++v) {
+        for (int k = 0; k < 3; ++k) {
+          float f = (float)src[3 * v + k];
+          t32[(size_t)i].p[v][k] = f;
+          err = std::max(err, std::fabs(src[3 * v + k] - (double)f));
+        }
+        t32[(size_t)i].p[v][3] = 0.f;
+      }
+      t32[(size_t)i].p[0][3] = round_up_f32(err * 1.0000001);
+    }
+    SFFG_CUDA(upload(&env->d_slots, bvh.slots.data(), bvh.slots.size() * sizeof(ChildSlot)));
+    SFFG_CUDA(upload(&env->d_tris32, t32.data(), t32.size() * sizeof(TriF32)));
+    SFFG_CUDA(upload(&env->d_tris64, t64.data(), t64.size() * sizeof(double)));
+    SFFG_CUDA(upload(&env->d_order, bvh.tri_order.data(), bvh.tri_order.size() * sizeof(int32_t)));
+    env->level_base = bvh.level_base;
+    env->level_count = bvh.level_count;
+    top_cut(bvh, &top);
+    n_nodes = (int64_t)(bvh.slots.size() / kWide);
+    depth = bvh.depth;
+    for (int k = 0; k < 3; ++k) {
+      root_lo[k] = bvh.root_lo[k];
+      root_hi[k] = bvh.root_hi[k];
+    }
+  } else {
+    // ---- device: Morton-ordered 8-wide hierarchy built by bvh_device.cu from the uploaded soup
+    void *d_soup = nullptr;
+    size_t dummy = 0;
+    (void)dummy;
+    SFFG_CUDA(cudaMalloc(&d_soup, 9 * (size_t)n_obst * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d_soup, obst_tris, 9 * (size_t)n_obst * sizeof(double), cudaMemcpyHostToDevice, env->streams[0]);
+    DeviceBvh db;
+    if (e == cudaSuccess) e = build_bvh_device((const double *)d_soup, (int)n_obst, env->streams[0], &db);
+    cudaFree(d_soup);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(SFFG_ERR_CUDA, std::string("device BVH build: ") + cudaGetErrorString(e));
+    }
+    env->d_slots = db.d_slots;
+    env->d_tris32 = db.d_tris32;
+    env->d_tris64 = db.d_tris64;
+    env->d_order = db.d_order;
+    env->level_base = db.level_base;
+    env->level_count = db.level_count;
+    bytes += (size_t)db.n_nodes * kWide * sizeof(ChildSlot) + (size_t)n_obst * (sizeof(TriF32) + 9 * sizeof(double));
+    // the cut through the top of the hierarchy is chosen on the host from the first levels (nodes are stored level by level)
+    HostBvh head;
+    head.slots.resize((size_t)std::min<int64_t>(db.n_nodes, 1 + 8 + 64) * kWide);
+    SFFG_CUDA(cudaMemcpy(head.slots.data(), env->d_slots, head.slots.size() * sizeof(ChildSlot), cudaMemcpyDeviceToHost));
+    top_cut(head, &top);
+    n_nodes = db.n_nodes;
+    depth = db.depth;
+    for (int k = 0; k < 3; ++k) {
+      root_lo[k] = db.root_lo[k];
+      root_hi[k] = db.root_hi[k];
+    }
+  }
+  env->obst_bytes = (int64_t)bytes;
+  return finish_obstacles(env, top, root_lo, root_hi, n_obst, n_nodes, depth, on_device, bytes);
 }
 
 int sffg_env_create_ex(const double *obst_tris, int64_t n_obst, const double *robot_tris, int64_t n_robot, int build_mode,
@@ -517,6 +547,39 @@ int sffg_env_set_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obs
   env->dev.n_obst = 0;
   *env->h_status = 4;                   // until the new set is complete every verdict call reports an error, never "free"
   int rc = set_obstacles(env, obst_tris, n_obst, build_mode);
+  if (rc == SFFG_OK) *env->h_status = 0;
+  env->info.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
+}
+
+int sffg_env_refit_obstacles(sffg_env *env, const double *obst_tris, int64_t n_obst) {
+  if (!env || !obst_tris || n_obst <= 0) return fail(SFFG_ERR_ARG, "sffg_env_refit_obstacles: bad arguments");
+  if (n_obst != env->info.n_obst_tris || !env->d_order || env->level_base.empty())
+    return fail(SFFG_ERR_ARG, "sffg_env_refit_obstacles: the soup must have the " + std::to_string(env->info.n_obst_tris) +
+                                  " triangles of the current obstacle set, in the same order (use sffg_env_set_obstacles otherwise)");
+  SFFG_CUDA(cudaDeviceSynchronize());   // nothing may still be traversing the boxes that are about to move
+  const auto t0 = std::chrono::steady_clock::now();
+  *env->h_status = 4;                   // until the refit is complete every verdict call reports an error, never "free"
+  void *d_soup = nullptr;
+  SFFG_CUDA(cudaMalloc(&d_soup, 9 * (size_t)n_obst * sizeof(double)));
+  cudaError_t e = cudaMemcpyAsync(d_soup, obst_tris, 9 * (size_t)n_obst * sizeof(double), cudaMemcpyHostToDevice, env->streams[0]);
+  double root_lo[3], root_hi[3];
+  if (e == cudaSuccess)
+    e = refit_bvh_device((const double *)d_soup, (int)n_obst, (ChildSlot *)env->d_slots, (double *)env->d_tris64, (float4 *)env->d_tris32,
+                         (const int *)env->d_order, env->level_base, env->level_count, env->streams[0], root_lo, root_hi);
+  cudaFree(d_soup);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(SFFG_ERR_CUDA, std::string("refit: ") + cudaGetErrorString(e));
+  }
+  // the cut through the top of the hierarchy is re-chosen from the refitted head (its boxes changed)
+  HostBvh head;
+  head.slots.resize((size_t)std::min<int64_t>(env->info.n_nodes, 1 + 8 + 64) * kWide);
+  SFFG_CUDA(cudaMemcpy(head.slots.data(), env->d_slots, head.slots.size() * sizeof(ChildSlot), cudaMemcpyDeviceToHost));
+  std::vector<ChildSlot> top;
+  top_cut(head, &top);
+  int rc = finish_obstacles(env, top, root_lo, root_hi, n_obst, env->info.n_nodes, env->info.depth, env->info.built_on_device != 0,
+                            (size_t)env->obst_bytes);
   if (rc == SFFG_OK) *env->h_status = 0;
   env->info.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return rc;

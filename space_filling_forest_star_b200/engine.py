@@ -72,6 +72,12 @@ class Environment:
         o = np.ascontiguousarray(np.asarray(obstacle_tris, dtype=np.float64).reshape(-1, 9))
         check(self._L.sffg_env_set_obstacles(self._h, _ptr(o) if len(o) else None, len(o), int(build)))
 
+    def refit_obstacles(self, obstacle_tris) -> None:
+        """the same triangles (count and order) at new positions: boxes, triangle arrays, top cut and clearance grid are
+        recomputed, the topology of the hierarchy is kept (sffg_env_refit_obstacles)"""
+        o = np.ascontiguousarray(np.asarray(obstacle_tris, dtype=np.float64).reshape(-1, 9))
+        check(self._L.sffg_env_refit_obstacles(self._h, _ptr(o), len(o)))
+
     @classmethod
     def from_files(cls, robot_file: str, robot_is_obj: bool, obstacles: Sequence[Tuple[str, bool, Sequence[float]]],
                    scale: float = 1.0) -> "Environment":

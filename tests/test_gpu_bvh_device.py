@@ -68,6 +68,38 @@ def test_set_obstacles_replaces_the_map_in_place(sff, orc, meshes):
     env.close()
 
 
+@pytest.mark.parametrize("mode", ["host", "device"])
+def test_refit_keeps_verdicts_exact_for_moving_and_deforming_obstacles(sff, orc, meshes, mode):
+    """sffg_env_refit_obstacles: same triangles at new positions (rigid motion, then a deformation), topology of the hierarchy
+    kept from either builder; verdicts equal the oracle on the new soup every frame, and equal a fresh rebuild"""
+    on, rn, rng = CASES["B"]
+    robot = meshes[rn]
+    base = meshes[on].reshape(-1, 3, 3)
+    env = sff.Environment(base, robot, build=sff.BUILD_HOST if mode == "host" else sff.BUILD_DEVICE)
+    nodes0 = env.info["n_nodes"]
+    poses = orc.gen_poses(SEED + 9, 0, 30000, rng).astype(np.float64)
+    c, s_ = np.cos(0.3), np.sin(0.3)
+    rot = np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1.0]])
+    frames = [base + np.array([3.0, -2.0, 1.5]),                                   # translation
+              base @ rot.T + np.array([-1.0, 4.0, 0.0]),                           # rotation about z + translation
+              base + 0.8 * np.sin(base[..., [1, 2, 0]] * 0.2)]                     # smooth deformation of every vertex
+    for f, soup in enumerate(frames):
+        soup = np.ascontiguousarray(soup)
+        env.refit_obstacles(soup)
+        assert env.info["n_nodes"] == nodes0 and env.info["n_obst_tris"] == len(base)
+        want, _ = orc.collide_obbtree(orc.ObbModel(soup), orc.ObbModel(robot), poses)
+        got = env.Collide(poses)
+        assert np.array_equal(got, want), (mode, f, np.nonzero(got != want)[0][:8])
+        assert 0.01 < want.mean() < 0.9
+    fresh = sff.Environment(frames[-1], robot)
+    assert np.array_equal(fresh.Collide(poses), env.Collide(poses))
+    fresh.close()
+    with pytest.raises(sff.SffgError) as ei:                                       # another triangle count is a rebuild, not a refit
+        env.refit_obstacles(base[:-1])
+    assert ei.value.code == 3
+    env.close()
+
+
 def test_multi_destination_stores_on_one_gpu(sff, orc, meshes):
     """the peer-store gather of the multi-GPU path, exercised on a single GPU: two local destination buffers stand in for
     two ranks' buffers; both must hold the plain kernel's verdicts for full 32-pose units (packed-word stores), ragged
