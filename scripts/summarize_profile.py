@@ -47,8 +47,8 @@ def launches(tag):
     out = [f"# {tag}: ncu launch list of `python bench.py --steps 5 --warmup 3 --no-cpu --no-extra` (gpu__time_duration.sum, --clock-control none)",
            "# per-launch times are cold-cache and serialised: compare SHARES, not absolutes",
            "# the timed region of `value` launches collide_poses_kernel only (1 launch per step = 100 % of the step);",
-           "# the remaining collide launches are the chunked e2e leg (16 chunks per host call); the secondary `extra` block",
-           "# (edges, k-NN, planner solves) is switched off for this pass", ""]
+           "# the remaining collide launches are the chunked e2e leg (16 chunks per host call), the check_edges launches are the",
+           "# edge e2e leg (4 chunks per host call); the secondary `extra` block (edges, k-NN, planner solves) is switched off", ""]
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f"{t / 1e6:10.3f} ms  {n:4d} launches  {100 * t / tot:5.1f} %  {k}")
     return "\n".join(out) + "\n"
