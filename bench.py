@@ -403,11 +403,18 @@ def run_ours(args):
     torch.cuda.synchronize()
     gbs = torch.tensor([4 * P * 24 / (pa.elapsed_time(pb) * 1e-3) / 1e9], device=dev)
     gbs_min, gbs_sum = gbs.clone(), gbs.clone()
+    per_rank = [float(gbs.item())]
     if world > 1:
         dist.all_reduce(gbs_min, op=dist.ReduceOp.MIN)
         dist.all_reduce(gbs_sum, op=dist.ReduceOp.SUM)
+        allg = [torch.zeros_like(gbs) for _ in range(world)]
+        dist.all_gather(allg, gbs)
+        per_rank = [float(x.item()) for x in allg]
     del probe
-    h2d_probe = {"gbs_per_rank_min": float(gbs_min.item()), "gbs_aggregate": float(gbs_sum.item()),
+    # every rank moves the same number of poses per step and the step ends with the slowest rank, so the ceiling of the e2e
+    # leg is world x the slowest rank's link, not the sum of the links
+    h2d_probe = {"gbs_per_rank_min": float(gbs_min.item()), "gbs_aggregate": float(gbs_sum.item()), "gbs_per_rank": per_rank,
+                 "e2e_frac_of_slowest_rank_ceiling": e2e_value * 24 / 1e9 / (world * float(gbs_min.item())),
                  "what": "pinned host -> device cudaMemcpyAsync of the same 24 B/pose buffer, all ranks concurrently"}
     e2e_frac = e2e_value * 24 / 1e9 / float(gbs_sum.item())
 
