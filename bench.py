@@ -615,42 +615,63 @@ def knn_rate(torch, idx, q, k, reps=3):
 
 def sharded_knn_rate(S, torch, dist, dev, rank, world):
     """N > 1: exact k-NN with the node set replicated and the query rows split over the ranks; every rank ends up with all
-    rows: the search writes into its slice of the gathered layout and two in-place NCCL all-gathers exchange the slices.
-    Q = 1e5 query rows per GPU (weak scaling, the N = 1 `extra.knn` shape), rows checked against a local search."""
+    rows.  Fused form (sharding.PeerRows): the search kernels store every finished row into every rank's gathered buffers
+    over NVLink peer memory, a flag barrier follows.  The NCCL form (rows written into the gathered layout + two in-place
+    all-gathers) is timed beside it.  Q = 1e5 query rows per GPU (weak scaling, the N = 1 `extra.knn` shape); a slice of
+    another rank's rows is checked against a local search on every rank."""
     try:
-        from space_filling_forest_star_b200.sharding import sharded_knn
+        from space_filling_forest_star_b200.sharding import PeerRows, sharded_knn
         n, nq, k = 1_000_000, KNN_Q, 16
         nodes = knn_cloud(torch, dev, n, 2)            # the same node set on every rank
         q = knn_cloud(torch, dev, world * nq, 3)
+        mine = q[rank * nq:(rank + 1) * nq].contiguous()
         idx = S.Index(dim=6)
         idx.add_device(nodes)
-        for _ in range(2):
-            sharded_knn(idx, q, k)
-        torch.cuda.synchronize()
-        dist.barrier()
-        dist.all_reduce(torch.zeros(1, device=dev))
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(5):
-            ids, d2 = sharded_knn(idx, q, k)
-        b.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([a.elapsed_time(b) / 5], device=dev)
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+
+        def timed(fn, reps=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            dist.all_reduce(torch.zeros(1, device=dev))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                out = fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([a.elapsed_time(b) / reps], device=dev)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item()), out
+
+        ms_nccl, (ids_n, d2_n) = timed(lambda: sharded_knn(idx, q, k))
+        res = {"config": f"N={n} 6-D nodes replicated, Q={nq} per GPU, k={k}, exact",
+               "nccl": {"queries_per_s": world * nq / (ms_nccl * 1e-3), "how": "rows written into the gathered layout + 2 in-place NCCL all-gathers"}}
+        mode = "nccl"
+        ids, d2 = ids_n, d2_n
+        try:
+            pr = PeerRows(nq, k)
+            ms_fused, (ids_f, d2_f) = timed(lambda: pr.knn(idx, mine, k))
+            same = bool(torch.equal(ids_f, ids_n) and torch.equal(d2_f, d2_n))   # every gathered byte against the NCCL result
+            res["fused"] = {"queries_per_s": world * nq / (ms_fused * 1e-3), "equals_nccl_result": same,
+                            "how": "rows stored by the search kernels into every rank's buffers over NVLink peer memory + flag barrier"}
+            if same:
+                mode, ids, d2 = "fused", ids_f, d2_f
+        except Exception as ex:
+            res["fused"] = {"error": repr(ex)}
         # every rank checks another rank's slice of the gathered rows against its own search
         nxt = (rank + 1) % world
         li, ld = idx.knn_device(q[nxt * nq:(nxt + 1) * nq].contiguous(), k)
         ok = torch.tensor([1.0 if (torch.equal(li, ids[nxt * nq:(nxt + 1) * nq]) and torch.equal(ld, d2[nxt * nq:(nxt + 1) * nq])) else 0.0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        rate1, _ = knn_rate(torch, idx, q[rank * nq:(rank + 1) * nq].contiguous(), k, reps=5)
+        rate1, _ = knn_rate(torch, idx, mine, k, reps=5)
         r1 = torch.tensor([rate1], device=dev)
         dist.all_reduce(r1, op=dist.ReduceOp.MIN)
+        total = res[mode]["queries_per_s"]
+        res.update({"queries_per_s": total, "mode": mode, "single_gpu_kernel_only_queries_per_s": float(r1.item()),
+                    "efficiency_vs_kernel_only": total / (world * float(r1.item())), "rows_verified": bool(ok.item() > 0)})
         idx.close()
-        total = world * nq / (float(ms.item()) * 1e-3)
-        return {"knn": {"queries_per_s": total, "single_gpu_kernel_only_queries_per_s": float(r1.item()),
-                        "efficiency_vs_kernel_only": total / (world * float(r1.item())), "rows_verified": bool(ok.item() > 0),
-                        "config": f"N={n} 6-D nodes replicated, Q={nq} per GPU, k={k}, exact, rows written into the gathered layout + "
-                                  f"2 in-place NCCL all-gathers"}}
+        return {"knn": res}
     except Exception as ex:
         return {"knn": {"error": repr(ex)}}
 

@@ -149,6 +149,8 @@ SFFG_API int sffg_collide_poses_device(sffg_env *env, const void *d_poses, int p
  *   sffg_peer_wait_device     enqueue "wait until every rank has published >= epoch": what a consumer of call `epoch`'s
  *                             gathered results puts in front of its work
  *   sffg_peer_barrier_device  signal + wait in one call (stand-alone barrier on the same flag words)
+ *                             env may be NULL for both (a barrier between index searches): a timeout then aborts the
+ *                             launch (the next CUDA call of the process fails) instead of raising the env's status
  * A rank that never arrives raises SFFG_ERR_INTERNAL at the next sffg_env_sync_check after 10 s instead of hanging the GPU. */
 SFFG_API int sffg_peer_buffer_create(int64_t bytes, void **d_ptr_out, uint8_t handle_out[64]);
 SFFG_API int sffg_peer_buffer_open(const uint8_t handle[64], void **d_ptr_out);
@@ -219,6 +221,14 @@ SFFG_API int64_t sffg_index_size(const sffg_index *idx);
 SFFG_API int sffg_knn(sffg_index *idx, const float *queries, int64_t nq, int k, int32_t *ids_out, float *d2_out);
 SFFG_API int sffg_knn_device(sffg_index *idx, const float *d_queries, int64_t nq, int k, int32_t *d_ids_out, float *d2_out,
                     void *stream);
+/* multi-GPU form of sffg_knn_device (node set replicated, query rows split over the ranks): the kernel that finishes a
+ * row stores it to d_ids_dests[r] / d_d2_dests[r] for every r < n_dests -- this rank's row range inside every rank's
+ * gathered [Q][k] buffers (sffg_peer_buffer_create / _open) -- so the row exchange rides on the search's own stores over
+ * NVLink.  Follow it with sffg_peer_barrier_device(NULL, ...) on the same stream before anyone reads the gathered rows;
+ * with two sets of gathered buffers used alternately and results read (on that stream) before the next call but one,
+ * no further synchronisation is needed.                                                                            */
+SFFG_API int sffg_knn_gather_device(sffg_index *idx, const float *d_queries, int64_t nq, int k, int32_t *const *d_ids_dests,
+                           float *const *d_d2_dests, int n_dests, void *stream);
 
 /* several indices in one call (the planner keeps one index per tree, src/forest.h:72): queries are concatenated in index
  * order, nq_per[i] rows for idx[i]; one upload, the per-index searches run concurrently on the indices' own streams, one

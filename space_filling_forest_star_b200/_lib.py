@@ -78,6 +78,7 @@ SIGNATURES = {
     "sffg_index_size": (C.c_int64, [_p]),
     "sffg_knn": (C.c_int, [_p, _p, C.c_int64, C.c_int, _p, _p]),
     "sffg_knn_device": (C.c_int, [_p, _p, C.c_int64, C.c_int, _p, _p, _p]),
+    "sffg_knn_gather_device": (C.c_int, [_p, _p, C.c_int64, C.c_int, _p, _p, C.c_int, _p]),
     "sffg_knn_multi": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, _p, _p]),
     "sffg_radius": (C.c_int, [_p, _p, C.c_int64, C.c_float, _p, _p, _p, C.c_int64, C.POINTER(C.c_int64)]),
 }

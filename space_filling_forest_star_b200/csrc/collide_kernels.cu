@@ -706,6 +706,7 @@ __device__ __forceinline__ void wait_flags(const FlagSet &f, unsigned epoch, int
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if (t1 - t0 > 10000000000ull) {   // a peer died or never launched -- flag it, never hang the GPU
         if (status) atomicExch(status, 3);
+        else __trap();                  // no status word to raise (barrier without an environment): fail the launch loudly
         return;
       }
       __nanosleep(100);

@@ -84,6 +84,17 @@ __device__ __forceinline__ float metric(const float *nd, const float *q) {
   return r;
 }
 
+// final row of query qi (position pos < k) -> every destination
+template <class Dests>
+__device__ __forceinline__ void store_row_entry(const Dests &out, long long qi, int k, int pos, float d, int id) {
+  const long long o = qi * k + pos;
+#pragma unroll 1
+  for (int r = 0; r < out.n; ++r) {
+    out.d2[r][o] = d;
+    out.ids[r][o] = id;
+  }
+}
+
 // sorted (ascending) list of 32*KPL entries spread over the warp: position j lives in lane j / KPL, slot j % KPL
 template <int KPL>
 struct TopK {

@@ -31,7 +31,8 @@ using namespace knn;
 template <int DIM, int QW, int KPL>
 __global__ void __launch_bounds__(kThreads) knn_scan_kernel(IndexDev idx, const float *__restrict__ queries, long long nq,
                                                             int k, int slices, long long slice_len, float *out_d,
-                                                            int *out_i, long long first, int slot_base, int slots_total) {
+                                                            int *out_i, long long first, int slot_base, int slots_total,
+                                                            RowDests rows) {
   const int lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   const long long group = item / slices;
@@ -145,9 +146,13 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(IndexDev idx, const 
     for (int s = 0; s < KPL; ++s) {
       const int pos = lane * KPL + s;
       if (pos < k) {
-        const long long o = (qi * slots_total + slot_base + slice) * k + pos;
-        out_d[o] = top[w].d[s];
-        out_i[o] = top[w].id[s];
+        if (slots_total == 1) {
+          store_row_entry(rows, qi, k, pos, top[w].d[s], top[w].id[s]);
+        } else {
+          const long long o = (qi * slots_total + slot_base + slice) * k + pos;
+          out_d[o] = top[w].d[s];
+          out_i[o] = top[w].id[s];
+        }
       }
     }
   }
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(IndexDev idx, const 
 // slices, from the spatially sorted view and from the unsorted tail, in any id order.
 template <int KPL>
 __global__ void __launch_bounds__(kThreads) knn_merge_kernel(const float *__restrict__ part_d, const int *__restrict__ part_i,
-                                                             long long nq, int k, int slices, float *out_d, int *out_i) {
+                                                             long long nq, int k, int slices, RowDests rows) {
   const int lane = threadIdx.x & 31;
   const long long qi = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   if (qi >= nq) return;
@@ -188,10 +193,7 @@ __global__ void __launch_bounds__(kThreads) knn_merge_kernel(const float *__rest
 #pragma unroll
   for (int s = 0; s < KPL; ++s) {
     const int pos = lane * KPL + s;
-    if (pos < k) {
-      out_d[qi * k + pos] = top.d[s];
-      out_i[qi * k + pos] = top.id[s];
-    }
+    if (pos < k) store_row_entry(rows, qi, k, pos, top.d[s], top.id[s]);
   }
 }
 
@@ -325,10 +327,11 @@ __global__ void index_append_kernel(float *coords, long long capacity, int dim, 
 
 template <int DIM, int QW>
 cudaError_t launch_knn_kpl(const IndexDev &idx, const float *q, int64_t nq, int k, int slices, int64_t slice_len,
-                           float *od, int *oi, unsigned grid, cudaStream_t st, long long first, int slot_base, int slots_total) {
-  if (k <= 32) knn_scan_kernel<DIM, QW, 1><<<grid, kThreads, 0, st>>>(idx, q, nq, k, slices, slice_len, od, oi, first, slot_base, slots_total);
-  else if (k <= 64) knn_scan_kernel<DIM, QW, 2><<<grid, kThreads, 0, st>>>(idx, q, nq, k, slices, slice_len, od, oi, first, slot_base, slots_total);
-  else knn_scan_kernel<DIM, QW, 4><<<grid, kThreads, 0, st>>>(idx, q, nq, k, slices, slice_len, od, oi, first, slot_base, slots_total);
+                           float *od, int *oi, unsigned grid, cudaStream_t st, long long first, int slot_base, int slots_total,
+                           const RowDests &rows) {
+  if (k <= 32) knn_scan_kernel<DIM, QW, 1><<<grid, kThreads, 0, st>>>(idx, q, nq, k, slices, slice_len, od, oi, first, slot_base, slots_total, rows);
+  else if (k <= 64) knn_scan_kernel<DIM, QW, 2><<<grid, kThreads, 0, st>>>(idx, q, nq, k, slices, slice_len, od, oi, first, slot_base, slots_total, rows);
+  else knn_scan_kernel<DIM, QW, 4><<<grid, kThreads, 0, st>>>(idx, q, nq, k, slices, slice_len, od, oi, first, slot_base, slots_total, rows);
   return cudaGetLastError();
 }
 
@@ -365,43 +368,43 @@ size_t knn_scratch_bytes(const KnnPlan &p, int64_t nq, int k) {
 // slots_total (slots_total == 1: od / oi are the final [nq][k] outputs)
 cudaError_t launch_knn_scan_range(const IndexDev &idx, const float *d_queries, int64_t nq, int k, int qw, int slices,
                                   int64_t slice_len, int64_t first, float *od, int *oi, int slot_base, int slots_total,
-                                  cudaStream_t stream) {
+                                  const RowDests &rows, cudaStream_t stream) {
   if (nq <= 0 || slices <= 0) return cudaSuccess;
   const int64_t groups = (nq + qw - 1) / qw;
   const int64_t items = groups * slices;
   const unsigned grid = (unsigned)((items + kWarps - 1) / kWarps);
   if (idx.dim == 6) {
-    if (qw == 8) return launch_knn_kpl<6, 8>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total);
-    if (qw == 4) return launch_knn_kpl<6, 4>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total);
-    return launch_knn_kpl<6, 1>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total);
+    if (qw == 8) return launch_knn_kpl<6, 8>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total, rows);
+    if (qw == 4) return launch_knn_kpl<6, 4>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total, rows);
+    return launch_knn_kpl<6, 1>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total, rows);
   }
-  if (qw == 8) return launch_knn_kpl<2, 8>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total);
-  if (qw == 4) return launch_knn_kpl<2, 4>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total);
-  return launch_knn_kpl<2, 1>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total);
+  if (qw == 8) return launch_knn_kpl<2, 8>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total, rows);
+  if (qw == 4) return launch_knn_kpl<2, 4>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total, rows);
+  return launch_knn_kpl<2, 1>(idx, d_queries, nq, k, slices, slice_len, od, oi, grid, stream, first, slot_base, slots_total, rows);
 }
 
-cudaError_t launch_knn_merge(const float *part_d, const int *part_i, int64_t nq, int k, int slots, float *d_d2, int32_t *d_ids,
+cudaError_t launch_knn_merge(const float *part_d, const int *part_i, int64_t nq, int k, int slots, const RowDests &rows,
                              cudaStream_t stream) {
   if (nq <= 0) return cudaSuccess;
   const unsigned mg = (unsigned)((nq + kWarps - 1) / kWarps);
-  if (k <= 32) knn_merge_kernel<1><<<mg, kThreads, 0, stream>>>(part_d, part_i, nq, k, slots, d_d2, d_ids);
-  else if (k <= 64) knn_merge_kernel<2><<<mg, kThreads, 0, stream>>>(part_d, part_i, nq, k, slots, d_d2, d_ids);
-  else knn_merge_kernel<4><<<mg, kThreads, 0, stream>>>(part_d, part_i, nq, k, slots, d_d2, d_ids);
+  if (k <= 32) knn_merge_kernel<1><<<mg, kThreads, 0, stream>>>(part_d, part_i, nq, k, slots, rows);
+  else if (k <= 64) knn_merge_kernel<2><<<mg, kThreads, 0, stream>>>(part_d, part_i, nq, k, slots, rows);
+  else knn_merge_kernel<4><<<mg, kThreads, 0, stream>>>(part_d, part_i, nq, k, slots, rows);
   return cudaGetLastError();
 }
 
-cudaError_t launch_knn(const IndexDev &idx, const float *d_queries, int64_t nq, int k, int32_t *d_ids, float *d_d2,
+cudaError_t launch_knn(const IndexDev &idx, const float *d_queries, int64_t nq, int k, const RowDests &out,
                        void *d_scratch, const KnnPlan &plan, cudaStream_t stream) {
   if (nq <= 0) return cudaSuccess;
-  float *od = d_d2;
-  int *oi = d_ids;
+  float *od = nullptr;
+  int *oi = nullptr;
   if (plan.slices > 1) {
     od = reinterpret_cast<float *>(d_scratch);
     oi = reinterpret_cast<int *>(od + (size_t)nq * plan.slices * k);
   }
-  cudaError_t e = launch_knn_scan_range(idx, d_queries, nq, k, plan.qw, plan.slices, plan.slice_len, 0, od, oi, 0, plan.slices, stream);
+  cudaError_t e = launch_knn_scan_range(idx, d_queries, nq, k, plan.qw, plan.slices, plan.slice_len, 0, od, oi, 0, plan.slices, out, stream);
   if (e != cudaSuccess) return e;
-  if (plan.slices > 1) e = launch_knn_merge(od, oi, nq, k, plan.slices, d_d2, d_ids, stream);
+  if (plan.slices > 1) e = launch_knn_merge(od, oi, nq, k, plan.slices, out, stream);
   return e;
 }
 

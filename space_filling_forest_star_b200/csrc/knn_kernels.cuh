@@ -15,6 +15,23 @@ struct IndexDev {
   const unsigned *amax;   // one word: float bits of the largest |angle| ever appended (dim 6), kept by the append kernel
 };
 
+// Destinations of the final result rows: the caller's buffers, or (multi-GPU) the same row range in every rank's gathered
+// buffer, mapped through CUDA IPC -- the kernel that finishes a row stores it to all of them, so the row exchange rides on
+// the search's own stores over NVLink instead of a collective after it.
+constexpr int kMaxRowDests = 8;
+struct RowDests {
+  float *d2[kMaxRowDests];
+  int32_t *ids[kMaxRowDests];
+  int n;
+};
+inline RowDests single_dest(int32_t *ids, float *d2) {
+  RowDests r{};
+  r.n = 1;
+  r.ids[0] = ids;
+  r.d2[0] = d2;
+  return r;
+}
+
 struct KnnPlan {
   int qw;        // queries per warp
   int slices;    // node slices per query group
@@ -26,13 +43,14 @@ KnnPlan plan_knn(int64_t nq, int64_t n, int sm_count);
 // partial scratch: slices > 1 needs nq * slices * k (float,int) pairs = 8 bytes each
 size_t knn_scratch_bytes(const KnnPlan &p, int64_t nq, int k);
 
-cudaError_t launch_knn(const IndexDev &idx, const float *d_queries, int64_t nq, int k, int32_t *d_ids, float *d_d2,
+cudaError_t launch_knn(const IndexDev &idx, const float *d_queries, int64_t nq, int k, const RowDests &out,
                        void *d_scratch, const KnnPlan &plan, cudaStream_t stream);
 
+// od / oi: partial lists [nq][slots_total][k] when slots_total > 1; with slots_total == 1 the rows go to `out`
 cudaError_t launch_knn_scan_range(const IndexDev &idx, const float *d_queries, int64_t nq, int k, int qw, int slices,
                                   int64_t slice_len, int64_t first, float *od, int *oi, int slot_base, int slots_total,
-                                  cudaStream_t stream);
-cudaError_t launch_knn_merge(const float *part_d, const int *part_i, int64_t nq, int k, int slots, float *d_d2, int32_t *d_ids,
+                                  const RowDests &out, cudaStream_t stream);
+cudaError_t launch_knn_merge(const float *part_d, const int *part_i, int64_t nq, int k, int slots, const RowDests &out,
                              cudaStream_t stream);
 
 // the radius scans cover nodes [first, idx.n); counts are accumulated with atomicAdd (zero them first)

@@ -183,7 +183,8 @@ __device__ __forceinline__ float box_ub(const float *lo, const float *hi, const 
 template <int DIM, int QW, int KPL>
 __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, const float *__restrict__ queries, long long nq, int k,
                                                               int slices, int sb_per_slice, float *out_d, int *out_i,
-                                                              int slot_base, int slots_total, const unsigned *__restrict__ perm) {
+                                                              int slot_base, int slots_total, const unsigned *__restrict__ perm,
+                                                              RowDests rows) {
   constexpr int LIN = DIM == 6 ? 3 : 2;
   const int lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
@@ -470,9 +471,13 @@ __global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, cons
     for (int s = 0; s < KPL; ++s) {
       const int pos = lane * KPL + s;
       if (pos < k) {
-        const long long o = (qi * slots_total + slot_base + slice) * k + pos;
-        out_d[o] = top[w].d[s];
-        out_i[o] = top[w].id[s];
+        if (slots_total == 1) {
+          store_row_entry(rows, qi, k, pos, top[w].d[s], top[w].id[s]);
+        } else {
+          const long long o = (qi * slots_total + slot_base + slice) * k + pos;
+          out_d[o] = top[w].d[s];
+          out_i[o] = top[w].id[s];
+        }
       }
     }
   }
@@ -581,10 +586,10 @@ __global__ void __launch_bounds__(kThreads) radius_pruned_kernel(SortedDev sv, c
 
 template <int DIM, int QW>
 cudaError_t launch_pruned_kpl(const SortedDev &sv, const float *q, int64_t nq, int k, int slices, int sb_per_slice, float *od, int *oi,
-                              int slot_base, int slots_total, unsigned grid, const unsigned *perm, cudaStream_t st) {
-  if (k <= 32) knn_pruned_kernel<DIM, QW, 1><<<grid, kThreads, 0, st>>>(sv, q, nq, k, slices, sb_per_slice, od, oi, slot_base, slots_total, perm);
-  else if (k <= 64) knn_pruned_kernel<DIM, QW, 2><<<grid, kThreads, 0, st>>>(sv, q, nq, k, slices, sb_per_slice, od, oi, slot_base, slots_total, perm);
-  else knn_pruned_kernel<DIM, QW, 4><<<grid, kThreads, 0, st>>>(sv, q, nq, k, slices, sb_per_slice, od, oi, slot_base, slots_total, perm);
+                              int slot_base, int slots_total, unsigned grid, const unsigned *perm, const RowDests &rows, cudaStream_t st) {
+  if (k <= 32) knn_pruned_kernel<DIM, QW, 1><<<grid, kThreads, 0, st>>>(sv, q, nq, k, slices, sb_per_slice, od, oi, slot_base, slots_total, perm, rows);
+  else if (k <= 64) knn_pruned_kernel<DIM, QW, 2><<<grid, kThreads, 0, st>>>(sv, q, nq, k, slices, sb_per_slice, od, oi, slot_base, slots_total, perm, rows);
+  else knn_pruned_kernel<DIM, QW, 4><<<grid, kThreads, 0, st>>>(sv, q, nq, k, slices, sb_per_slice, od, oi, slot_base, slots_total, perm, rows);
   return cudaGetLastError();
 }
 
@@ -665,12 +670,12 @@ size_t pruned_scratch_bytes(const PrunedPlan &p, int64_t nq, int k) {
   return bytes;
 }
 
-cudaError_t launch_knn_pruned(const IndexDev &idx, const SortedDev &sv, const float *d_queries, int64_t nq, int k, int32_t *d_ids,
-                              float *d_d2, void *d_scratch, const PrunedPlan &p, cudaStream_t st) {
+cudaError_t launch_knn_pruned(const IndexDev &idx, const SortedDev &sv, const float *d_queries, int64_t nq, int k, const RowDests &out,
+                              void *d_scratch, const PrunedPlan &p, cudaStream_t st) {
   if (nq <= 0) return cudaSuccess;
   const int slots = p.slices + p.tail_slices;
-  float *od = d_d2;
-  int *oi = d_ids;
+  float *od = nullptr;
+  int *oi = nullptr;
   if (slots > 1) {
     od = reinterpret_cast<float *>(d_scratch);
     oi = reinterpret_cast<int *>(od + (size_t)nq * slots * k);
@@ -694,20 +699,20 @@ cudaError_t launch_knn_pruned(const IndexDev &idx, const SortedDev &sv, const fl
     perm = vals_out;
   }
   if (idx.dim == 6) {
-    if (p.qw == 8) e = launch_pruned_kpl<6, 8>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, st);
-    else if (p.qw == 4) e = launch_pruned_kpl<6, 4>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, st);
-    else e = launch_pruned_kpl<6, 1>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, st);
+    if (p.qw == 8) e = launch_pruned_kpl<6, 8>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, out, st);
+    else if (p.qw == 4) e = launch_pruned_kpl<6, 4>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, out, st);
+    else e = launch_pruned_kpl<6, 1>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, out, st);
   } else {
-    if (p.qw == 8) e = launch_pruned_kpl<2, 8>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, st);
-    else if (p.qw == 4) e = launch_pruned_kpl<2, 4>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, st);
-    else e = launch_pruned_kpl<2, 1>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, st);
+    if (p.qw == 8) e = launch_pruned_kpl<2, 8>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, out, st);
+    else if (p.qw == 4) e = launch_pruned_kpl<2, 4>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, out, st);
+    else e = launch_pruned_kpl<2, 1>(sv, d_queries, nq, k, p.slices, p.sb_per_slice, od, oi, 0, slots, grid, perm, out, st);
   }
   if (e != cudaSuccess) return e;
   if (p.tail_slices > 0) {
-    e = launch_knn_scan_range(idx, d_queries, nq, k, p.qw, p.tail_slices, p.tail_len, sv.n_sorted, od, oi, p.slices, slots, st);
+    e = launch_knn_scan_range(idx, d_queries, nq, k, p.qw, p.tail_slices, p.tail_len, sv.n_sorted, od, oi, p.slices, slots, out, st);
     if (e != cudaSuccess) return e;
   }
-  if (slots > 1) e = launch_knn_merge(od, oi, nq, k, slots, d_d2, d_ids, st);
+  if (slots > 1) e = launch_knn_merge(od, oi, nq, k, slots, out, st);
   return e;
 }
 

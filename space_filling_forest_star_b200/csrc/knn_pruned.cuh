@@ -54,8 +54,8 @@ struct PrunedPlan {
 };
 PrunedPlan plan_pruned(int64_t nq, const SortedDev &sv, int64_t tail, int sm_count);
 size_t pruned_scratch_bytes(const PrunedPlan &p, int64_t nq, int k);
-cudaError_t launch_knn_pruned(const IndexDev &idx, const SortedDev &sv, const float *d_queries, int64_t nq, int k, int32_t *d_ids,
-                              float *d_d2, void *d_scratch, const PrunedPlan &p, cudaStream_t st);
+cudaError_t launch_knn_pruned(const IndexDev &idx, const SortedDev &sv, const float *d_queries, int64_t nq, int k, const RowDests &out,
+                              void *d_scratch, const PrunedPlan &p, cudaStream_t st);
 
 // radius search over sorted view + tail (counts must be zeroed / cursor zeroed by the caller)
 cudaError_t launch_radius_count_pruned(const IndexDev &idx, const SortedDev &sv, const float *d_queries, int64_t nq, float r2,

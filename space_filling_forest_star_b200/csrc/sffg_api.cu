@@ -772,21 +772,19 @@ int sffg_collide_poses_gather_sync_device(sffg_env *env, const void *d_poses, in
 }
 
 int sffg_peer_wait_device(sffg_env *env, uint32_t *const *d_flags, int n_ranks, int my_rank, uint32_t epoch, void *stream) {
-  if (!env) return fail(SFFG_ERR_ARG, "sffg_peer_wait_device: null env");
   FlagSet f;
   int rc = fill_flags(&f, d_flags, n_ranks, my_rank, "sffg_peer_wait_device");
   if (rc != SFFG_OK) return rc;
-  SFFG_CUDA(launch_peer_barrier(f, epoch, false, env->h_status, (cudaStream_t)stream));
+  SFFG_CUDA(launch_peer_barrier(f, epoch, false, env ? env->h_status : nullptr, (cudaStream_t)stream));
   return SFFG_OK;
 }
 
 int sffg_peer_barrier_device(sffg_env *env, uint32_t *const *d_flags, int n_ranks, int my_rank, uint32_t epoch, void *stream) {
-  if (!env) return fail(SFFG_ERR_ARG, "sffg_peer_barrier_device: null env");
   FlagSet f;
   int rc = fill_flags(&f, d_flags, n_ranks, my_rank, "sffg_peer_barrier_device");
   if (rc != SFFG_OK) return rc;
   SFFG_CUDA(launch_peer_barrier(f, epoch, true, nullptr, (cudaStream_t)stream));
-  SFFG_CUDA(launch_peer_barrier(f, epoch, false, env->h_status, (cudaStream_t)stream));
+  SFFG_CUDA(launch_peer_barrier(f, epoch, false, env ? env->h_status : nullptr, (cudaStream_t)stream));
   return SFFG_OK;
 }
 
@@ -1150,12 +1148,7 @@ static SortedDev sorted_view(const sffg_index *idx) {
   return sv;
 }
 
-int sffg_knn_device(sffg_index *idx, const float *d_queries, int64_t nq, int k, int32_t *d_ids_out, float *d_d2_out,
-                    void *stream) {
-  if (!idx || nq < 0 || k < 1 || k > SFFG_MAX_K || (nq > 0 && (!d_queries || !d_ids_out || !d_d2_out)))
-    return fail(SFFG_ERR_ARG, "sffg_knn_device: bad arguments (1 <= k <= 128)");
-  if (nq == 0) return SFFG_OK;
-  cudaStream_t st = (cudaStream_t)stream;
+static int knn_rows_device(sffg_index *idx, const float *d_queries, int64_t nq, int k, const RowDests &out, cudaStream_t st) {
   IndexDev v{idx->d_coords, idx->cap, idx->n, idx->dim, idx->d_amax};
   int rc = ensure_sorted(idx, st);
   if (rc != SFFG_OK) return rc;
@@ -1164,14 +1157,38 @@ int sffg_knn_device(sffg_index *idx, const float *d_queries, int64_t nq, int k, 
     const PrunedPlan plan = plan_pruned(nq, sv, idx->n - idx->n_sorted, g_rt.sm_count);
     rc = idx->scratch.reserve(pruned_scratch_bytes(plan, nq, k));
     if (rc != SFFG_OK) return rc;
-    SFFG_CUDA(launch_knn_pruned(v, sv, d_queries, nq, k, d_ids_out, d_d2_out, idx->scratch.p, plan, st));
+    SFFG_CUDA(launch_knn_pruned(v, sv, d_queries, nq, k, out, idx->scratch.p, plan, st));
     return SFFG_OK;
   }
   KnnPlan plan = plan_knn(nq, idx->n, g_rt.sm_count);
   rc = idx->scratch.reserve(knn_scratch_bytes(plan, nq, k));
   if (rc != SFFG_OK) return rc;
-  SFFG_CUDA(launch_knn(v, d_queries, nq, k, d_ids_out, d_d2_out, idx->scratch.p, plan, st));
+  SFFG_CUDA(launch_knn(v, d_queries, nq, k, out, idx->scratch.p, plan, st));
   return SFFG_OK;
+}
+
+int sffg_knn_device(sffg_index *idx, const float *d_queries, int64_t nq, int k, int32_t *d_ids_out, float *d_d2_out,
+                    void *stream) {
+  if (!idx || nq < 0 || k < 1 || k > SFFG_MAX_K || (nq > 0 && (!d_queries || !d_ids_out || !d_d2_out)))
+    return fail(SFFG_ERR_ARG, "sffg_knn_device: bad arguments (1 <= k <= 128)");
+  if (nq == 0) return SFFG_OK;
+  return knn_rows_device(idx, d_queries, nq, k, single_dest(d_ids_out, d_d2_out), (cudaStream_t)stream);
+}
+
+int sffg_knn_gather_device(sffg_index *idx, const float *d_queries, int64_t nq, int k, int32_t *const *d_ids_dests,
+                           float *const *d_d2_dests, int n_dests, void *stream) {
+  if (!idx || nq < 0 || k < 1 || k > SFFG_MAX_K || !d_ids_dests || !d_d2_dests || n_dests < 1 || n_dests > kMaxRowDests ||
+      (nq > 0 && !d_queries))
+    return fail(SFFG_ERR_ARG, "sffg_knn_gather_device: bad arguments (1 <= k <= 128, 1..8 destinations)");
+  RowDests out{};
+  out.n = n_dests;
+  for (int r = 0; r < n_dests; ++r) {
+    if (!d_ids_dests[r] || !d_d2_dests[r]) return fail(SFFG_ERR_ARG, "sffg_knn_gather_device: null destination");
+    out.ids[r] = d_ids_dests[r];
+    out.d2[r] = d_d2_dests[r];
+  }
+  if (nq == 0) return SFFG_OK;
+  return knn_rows_device(idx, d_queries, nq, k, out, (cudaStream_t)stream);
 }
 
 int sffg_knn(sffg_index *idx, const float *queries, int64_t nq, int k, int32_t *ids_out, float *d2_out) {

@@ -176,6 +176,87 @@ class PeerGather:
         self.own = []
 
 
+class PeerRows:
+    """k-NN row all-gather fused into the search kernels (include/sffg.h, sffg_knn_gather_device).
+
+    Every rank owns two sets of gathered buffers -- ids int32 [world * per][k] and d2 float32 [world * per][k] -- allocated
+    by the engine and exported through CUDA IPC.  ``knn(index, queries_local, k)`` launches the search with ``world``
+    destinations (this rank's row range in every rank's current buffers), then a signal + wait barrier over the flag words:
+    when it has run, every rank holds every rank's rows.  The two buffer sets alternate, so a rank may already write call
+    j + 1 while a slower rank still reads call j; the contract is that the rows of call j are read (on the same stream)
+    before call j + 2 is enqueued.  torch.distributed only ships the IPC handles.
+    """
+
+    NBUF = 2
+
+    def __init__(self, per_rank_rows: int, k: int, group=None):
+        import ctypes as C
+
+        from . import _lib
+        self._C, self._L, self._check = C, _lib.load(), _lib.check
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("PeerRows supports up to 8 ranks (one NVSwitch domain)")
+        self.per, self.k = per_rank_rows, k
+        self.bytes = self.world * self.per * k * 4
+        self.own, handles = [], []
+        for b in range(2 * self.NBUF + 1):              # (ids, d2) x NBUF + one block of flag words
+            p = C.c_void_p()
+            h = (C.c_uint8 * 64)()
+            self._check(self._L.sffg_peer_buffer_create(self.bytes if b < 2 * self.NBUF else 256, C.byref(p), h))
+            self.own.append(p.value)
+            handles.append(bytes(h))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, handles, group=group)
+        self.ptrs, self._opened = [], []
+        for b in range(2 * self.NBUF + 1):
+            row = []
+            for r in range(self.world):
+                if r == self.rank:
+                    row.append(self.own[b])
+                else:
+                    p = C.c_void_p()
+                    hb = (C.c_uint8 * 64).from_buffer_copy(everyone[r][b])
+                    self._check(self._L.sffg_peer_buffer_open(hb, C.byref(p)))
+                    self._opened.append(p.value)
+                    row.append(p.value)
+            self.ptrs.append(row)
+        self._flags = (C.c_void_p * self.world)(*self.ptrs[2 * self.NBUF])
+        self.step = 0
+        dist.barrier(group=group)
+
+    def knn(self, index, queries_local: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """-> (ids [world * per, k], d2 [world * per, k]) views of this rank's gathered buffers of this call; rank r's rows
+        start at r * per.  Enqueued on the current stream (search, then the barrier)."""
+        n = queries_local.shape[0]
+        assert k == self.k and n <= self.per and queries_local.is_cuda and queries_local.is_contiguous()
+        j = self.step
+        self.step += 1
+        b = j % self.NBUF
+        off = self.rank * self.per * k * 4
+        ids_d = (self._C.c_void_p * self.world)(*[self.ptrs[2 * b][r] + off for r in range(self.world)])
+        d2_d = (self._C.c_void_p * self.world)(*[self.ptrs[2 * b + 1][r] + off for r in range(self.world)])
+        st = torch.cuda.current_stream(queries_local.device).cuda_stream
+        self._check(self._L.sffg_knn_gather_device(index._h, queries_local.data_ptr(), n, k, ids_d, d2_d, self.world, st))
+        self._check(self._L.sffg_peer_barrier_device(None, self._flags, self.world, self.rank, j + 1, st))
+        return self._view(self.own[2 * b], torch.int32, queries_local.device), self._view(self.own[2 * b + 1], torch.float32, queries_local.device)
+
+    def _view(self, ptr, dtype, device):
+        typestr = "<i4" if dtype == torch.int32 else "<f4"
+        iface = {"shape": (self.world * self.per, self.k), "typestr": typestr, "data": (ptr, False), "version": 2}
+        holder = type("_Dev", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device=device)
+
+    def close(self) -> None:
+        for p in self._opened:
+            self._L.sffg_peer_buffer_close(p)
+        self._opened = []
+        for p in self.own:
+            self._L.sffg_peer_buffer_destroy(p)
+        self.own = []
+
+
 def gathered_collide(env, pg: "PeerGather", poses_local: torch.Tensor) -> torch.Tensor:
     """one fused step: local slice -> every rank's gathered buffer, then wait for everyone's slice; returns [world, per]"""
     j = pg.collide(env, poses_local)

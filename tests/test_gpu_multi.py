@@ -59,6 +59,25 @@ for n_g in (100003, 64, 1400011):
             assert np.array_equal(full[r, : re_ - rb].cpu().numpy(), want[rb:re_]), ("peer gather mismatch", n_g, rep, r)
     dist.barrier()
     pg.close()
+# k-NN rows gathered by the search kernels' own stores (PeerRows): pruned path (N >= 8192), exhaustive path (small index),
+# sliced + merged small batches, several calls on alternating buffers
+from space_filling_forest_star_b200.sharding import PeerRows
+small = S.Index(nodes[:3000])
+rs = np.random.RandomState(5)
+for index, ref_nodes, nq_total in ((idx, nodes, 9000), (idx, nodes, 40), (small, nodes[:3000], 2500)):
+    qq = np.concatenate([rs.uniform(-50, 50, (nq_total, 3)), rs.uniform(-3.1, 3.1, (nq_total, 3))], 1).astype(np.float32)
+    wi, wd = O.knn_linear(ref_nodes, qq, 16)
+    b, e, per = shard_bounds(nq_total, rank, world)
+    pr = PeerRows(per, 16)
+    for rep in range(3):
+        gi, gd = pr.knn(index, torch.from_numpy(qq[b:e]).cuda().contiguous(), 16)
+        torch.cuda.synchronize()
+        for rr in range(world):
+            rb, re_, _ = shard_bounds(nq_total, rr, world)
+            assert np.array_equal(gi[rr * per: rr * per + re_ - rb].cpu().numpy(), wi[rb:re_]), ("peer rows ids", nq_total, rep, rr)
+            assert np.array_equal(gd[rr * per: rr * per + re_ - rb].cpu().numpy().view(np.uint32), wd[rb:re_].view(np.uint32)), ("peer rows d2", nq_total, rep, rr)
+    dist.barrier()
+    pr.close()
 dist.barrier()
 if rank == 0:
     print("SHARDED_OK")
