@@ -63,6 +63,7 @@ def main():
     ap.add_argument("--impls", default="ref_cpu,batched,ref_gpu")
     ap.add_argument("--timeout", type=float, default=600)
     ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--max-iter", type=int, default=0, help="override MaxIterations of every scenario (0 = keep)")
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "e2e.json"))
     a = ap.parse_args()
     work = Path(tempfile.mkdtemp(prefix="sff_e2e_"))
@@ -70,6 +71,10 @@ def main():
     from space_filling_forest_star_b200 import build as B
     B.build_host()
     results = {}
+    if a.max_iter:
+        for sc in a.scenarios.split(","):
+            cfg = work / f"{sc}.xml"
+            cfg.write_text(re.sub(r'MaxIterations value="\d+"', f'MaxIterations value="{a.max_iter}"', cfg.read_text()))
     for sc in a.scenarios.split(","):
         n_roots = len(re.findall(r"<Point ", (work / f"{sc}.xml").read_text()))
         for impl in a.impls.split(","):
