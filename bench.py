@@ -703,6 +703,27 @@ def extra_metrics(S, env, torch, clocks):
         del s, e, d, free
     except Exception as ex:   # secondary numbers must never break the headline line
         out["edges_error"] = repr(ex)
+    # ---- the headline kernel over a longer stretch: the timed region of `value` is a 0.1 s burst, this one is ~1 s ----------
+    try:
+        P = 1 << 24
+        poses = S.gen_poses_device(SEED, 0, P, RANGE)
+        verdict = torch.empty(P, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            env.collide_device(poses, out=verdict)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(dev.index or 0)
+        sampler.start()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(200):
+            env.collide_device(poses, out=verdict)
+        b.record()
+        torch.cuda.synchronize()
+        out["sustained"] = {"poses_per_s": 200 * P / (a.elapsed_time(b) * 1e-3), "steps": 200, "seconds": a.elapsed_time(b) * 1e-3,
+                            "clocks": sampler.stop()}
+        del poses, verdict
+    except Exception as ex:
+        out["sustained"] = {"error": repr(ex)}
     # ---- exact k-NN at BASELINE.json's configuration: Q = 1e5 queries, N = 1e6 and 1e7 nodes, k = 16 (+ 1, 32) -------------
     try:
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
