@@ -534,10 +534,20 @@ def balanced_e2e(torch, dist, env, dev, rank, world, P, poses, verdict, gbs_per_
     total = world * P
     nbytes = total * 24 + total
     path = f"/dev/shm/sffg_bench_{os.environ.get('MASTER_PORT', '0')}"
+    # tmpfs pages are allocated on first touch and running out of them is a SIGBUS, not an exception: check the room first
+    room = torch.zeros(1, device=dev)
     if rank == 0:
-        with open(path, "wb") as f:
-            f.truncate(nbytes)
-    dist.barrier()
+        try:
+            st = os.statvfs("/dev/shm")
+            if st.f_bavail * st.f_frsize > nbytes + (256 << 20):
+                with open(path, "wb") as f:
+                    f.truncate(nbytes)
+                room += 1
+        except OSError:
+            pass
+    dist.all_reduce(room, op=dist.ReduceOp.MAX)
+    if room.item() < 1:
+        return {"skipped": f"/dev/shm cannot hold {nbytes >> 20} MiB"}
     f = open(path, "r+b")
     mm = mmap.mmap(f.fileno(), nbytes)
     base = ctypes.addressof(ctypes.c_char.from_buffer(mm))
