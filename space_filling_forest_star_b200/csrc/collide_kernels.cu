@@ -54,9 +54,15 @@ struct XTri {        // obstacle triangle in the robot frame (FP32); 13 words = 
   int pad;
 };
 
+#ifndef SFFG_CAND_CAP
+#define SFFG_CAND_CAP 192
+#endif
+constexpr int kCandCap = SFFG_CAND_CAP;    // candidate triangles of one group of edge samples (swept-box traversal)
+
 struct WarpScratch {
   int stack[kStackCap];
   int tri[kTriCap];
+  int cand[kCandCap];
   XTri xt[32];
 };
 
@@ -411,6 +417,119 @@ __device__ __forceinline__ bool slot_overlaps(const EnvDev &E, const PoseU &P, c
   return !(fmaxf(ex, eb) > pad);
 }
 
+// state of the pair stages of one pose: the verdict so far and the pose's double-precision transform (built on first use)
+// (the flags stay separate scalars: the transform arrays are handed to the non-inlined exact stage by address, and a struct
+// holding both would drag the flags into local memory with them -- measured +2.4 % on the pose kernel)
+struct PairCtx {
+  double R2[9], T2[3];
+};
+
+// Triangle stage of one pose over the candidate triangles ws.tri[0, ntri): transform into the robot frame, cull, pair stages
+// P1 (lane-per-pair), P2 (three pairs per cooperative pass) and the FP64 exact stage; stops at the first confirmed contact.
+template <int FMT, bool COUNT>
+__device__ __forceinline__ void triangle_stage(const EnvDev &E, WarpScratch &ws, const RobotTri *srob, const PoseU &P,
+                                               const LanePose<FMT> &lp, int src, int lane, int ntri, bool &hit, bool &have_R2,
+                                               PairCtx &pc, Tally &tally) {
+  const unsigned lt = (1u << lane) - 1u;
+  const int grp10 = lane / 10, k10 = lane - 10 * grp10;
+  const float inv_n_robot = 1.0f / (float)E.n_robot;
+  for (int base = 0; base < ntri && !hit; base += 32) {
+    const int cnt = (ntri - base) < 32 ? (ntri - base) : 32;
+    bool keep = false;
+    XTri x;
+    if (lane < cnt) {
+      const int t = ws.tri[base + lane];
+      const float4 v0 = __ldg(E.tris32 + 3 * (size_t)t), v1 = __ldg(E.tris32 + 3 * (size_t)t + 1),
+                   v2 = __ldg(E.tris32 + 3 * (size_t)t + 2);
+      const float w[9] = {(v0.x - P.Thi[0]) - P.Tlo[0], (v0.y - P.Thi[1]) - P.Tlo[1], (v0.z - P.Thi[2]) - P.Tlo[2],
+                          (v1.x - P.Thi[0]) - P.Tlo[0], (v1.y - P.Thi[1]) - P.Tlo[1], (v1.z - P.Thi[2]) - P.Tlo[2],
+                          (v2.x - P.Thi[0]) - P.Tlo[0], (v2.y - P.Thi[1]) - P.Tlo[1], (v2.z - P.Thi[2]) - P.Tlo[2]};
+      float mabs = 0.f;
+#pragma unroll
+      for (int v = 0; v < 3; ++v)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float val = P.R[c] * w[3 * v] + P.R[3 + c] * w[3 * v + 1] + P.R[6 + c] * w[3 * v + 2];
+          x.v[3 * v + c] = val;
+          mabs = fmaxf(mabs, fabsf(val));
+        }
+      x.err = v0.w;
+      x.mabs = mabs;
+      x.tri = t;
+      x.pad = 0;
+      const float padT = 2.0f * x.err + kEpsSat * fmaxf(mabs, E.rob_radius);
+      keep = true;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float lo = min3f(x.v[c], x.v[3 + c], x.v[6 + c]) - padT, hi = max3f(x.v[c], x.v[3 + c], x.v[6 + c]) + padT;
+        const float rc = c == 0 ? E.rob_c[0] : (c == 1 ? E.rob_c[1] : E.rob_c[2]);
+        const float rh = c == 0 ? E.rob_h[0] : (c == 1 ? E.rob_h[1] : E.rob_h[2]);
+        if (lo > rc + rh || hi < rc - rh) keep = false;
+      }
+    }
+    const unsigned km = __ballot_sync(kFull, keep);
+    const int nx = __popc(km);
+    if (COUNT) { tally.tri_passes += 1; tally.tris += cnt; }
+    if (keep) ws.xt[__popc(km & lt)] = x;
+    __syncwarp();
+    const int npairs = nx * E.n_robot;
+    for (int pb = 0; pb < npairs && !hit; pb += 32) {
+      const int pidx = pb + lane;
+      bool undecided = false;
+      // (triangle, robot triangle) of this lane's pair; the quotient by float reciprocal is exact for pidx < 2^20
+      const int xi_l = (int)(((float)pidx + 0.5f) * inv_n_robot), r_l = pidx - xi_l * E.n_robot;
+      if (pidx < npairs) undecided = !pair_quick_disjoint(ws.xt[xi_l], srob[r_l]);
+      unsigned um = __ballot_sync(kFull, undecided);
+      if (COUNT) {
+        const int np = (npairs - pb) < 32 ? (npairs - pb) : 32;
+        tally.pair += np;
+        tally.exact += __popc(um);   // pairs the lane-per-pair stage P1 left open
+      }
+      while (um && !hit) {
+        const int l0 = __ffs(um) - 1;
+        um &= um - 1;
+        const int l1 = um ? __ffs(um) - 1 : -1;
+        um &= um - 1;   // (0 stays 0)
+        const int l2 = um ? __ffs(um) - 1 : -1;
+        um &= um - 1;
+        const int lmine = grp10 == 0 ? l0 : (grp10 == 1 ? l1 : (grp10 == 2 ? l2 : -1));
+        const int xim = __shfl_sync(kFull, xi_l, lmine & 31), rm = __shfl_sync(kFull, r_l, lmine & 31);
+        bool sep = false;
+        if (lmine >= 0 && k10 < 9) sep = open_pair_axis(ws.xt[xim], srob[rm], k10);
+        const unsigned bs = __ballot_sync(kFull, sep);
+        unsigned open_g = 0;
+        if (!(bs & 0x3ffu)) open_g |= 1u;
+        if (l1 >= 0 && !(bs & (0x3ffu << 10))) open_g |= 2u;
+        if (l2 >= 0 && !(bs & (0x3ffu << 20))) open_g |= 4u;
+        if (open_g == 0) continue;
+        bool con = false;
+        if (lmine >= 0 && k10 < 6 && ((open_g >> grp10) & 1u)) con = open_pair_pierce(ws.xt[xim], srob[rm], k10);
+        if (__any_sync(kFull, con)) {
+          hit = true;
+          break;
+        }
+        while (open_g) {
+          const int g = __ffs(open_g) - 1;
+          open_g &= open_g - 1;
+          const int lg = g == 0 ? l0 : (g == 1 ? l1 : l2);
+          const int xg = __shfl_sync(kFull, xi_l, lg), rg = __shfl_sync(kFull, r_l, lg);
+          if (COUNT) tally.exact_run += 1;
+          if (!have_R2) {
+            lp.exact(src, pc.R2, pc.T2, lane);
+            have_R2 = true;
+          }
+          const int t = ws.xt[xg].tri;
+          if (exact_pair_contact(pc.R2, pc.T2, E.tris64 + 9 * (size_t)t, E.robot64 + 9 * (size_t)rg, lane)) {
+            hit = true;
+            break;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int FMT, bool COUNT>
 __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const CtaShared &cs, const PoseU &P,
                               const LanePose<FMT> &lp, int src, int lane, Tally &tally) {
@@ -425,11 +544,8 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const CtaShared 
   const unsigned lt = (1u << lane) - 1u;
 
   int sp = 0, ntri = 0;
-  const int grp10 = lane / 10, k10 = lane - 10 * grp10;
-  const float inv_n_robot = 1.0f / (float)E.n_robot;
-  bool hit = false;
-  bool have_R2 = false;
-  double R2[9], T2[3];
+  bool hit = false, have_R2 = false;
+  PairCtx pc;
   if (COUNT) tally.past_root += 1;
 
   bool first = true;   // step 0 tests the precomputed <=32-box cut of the top of the hierarchy with all lanes
@@ -492,104 +608,102 @@ __device__ bool warp_pose_hit(const EnvDev &E, WarpScratch &ws, const CtaShared 
       continue;
     }
     // ---------------- triangle stage ----------------
-    for (int base = 0; base < ntri && !hit; base += 32) {
-      const int cnt = (ntri - base) < 32 ? (ntri - base) : 32;
-      bool keep = false;
-      XTri x;
-      if (lane < cnt) {
-        const int t = ws.tri[base + lane];
-        const float4 v0 = __ldg(E.tris32 + 3 * (size_t)t), v1 = __ldg(E.tris32 + 3 * (size_t)t + 1),
-                     v2 = __ldg(E.tris32 + 3 * (size_t)t + 2);
-        const float w[9] = {(v0.x - P.Thi[0]) - P.Tlo[0], (v0.y - P.Thi[1]) - P.Tlo[1], (v0.z - P.Thi[2]) - P.Tlo[2],
-                            (v1.x - P.Thi[0]) - P.Tlo[0], (v1.y - P.Thi[1]) - P.Tlo[1], (v1.z - P.Thi[2]) - P.Tlo[2],
-                            (v2.x - P.Thi[0]) - P.Tlo[0], (v2.y - P.Thi[1]) - P.Tlo[1], (v2.z - P.Thi[2]) - P.Tlo[2]};
-        float mabs = 0.f;
-#pragma unroll
-        for (int v = 0; v < 3; ++v)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float val = P.R[c] * w[3 * v] + P.R[3 + c] * w[3 * v + 1] + P.R[6 + c] * w[3 * v + 2];
-            x.v[3 * v + c] = val;
-            mabs = fmaxf(mabs, fabsf(val));
-          }
-        x.err = v0.w;
-        x.mabs = mabs;
-        x.tri = t;
-        x.pad = 0;
-        const float padT = 2.0f * x.err + kEpsSat * fmaxf(mabs, E.rob_radius);
-        keep = true;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float lo = min3f(x.v[c], x.v[3 + c], x.v[6 + c]) - padT, hi = max3f(x.v[c], x.v[3 + c], x.v[6 + c]) + padT;
-          const float rc = c == 0 ? E.rob_c[0] : (c == 1 ? E.rob_c[1] : E.rob_c[2]);
-          const float rh = c == 0 ? E.rob_h[0] : (c == 1 ? E.rob_h[1] : E.rob_h[2]);
-          if (lo > rc + rh || hi < rc - rh) keep = false;
-        }
-      }
-      const unsigned km = __ballot_sync(kFull, keep);
-      const int nx = __popc(km);
-      if (COUNT) { tally.tri_passes += 1; tally.tris += cnt; }
-      if (keep) ws.xt[__popc(km & lt)] = x;
-      __syncwarp();
-      const int npairs = nx * E.n_robot;
-      for (int pb = 0; pb < npairs && !hit; pb += 32) {
-        const int pidx = pb + lane;
-        bool undecided = false;
-        // (triangle, robot triangle) of this lane's pair; the quotient by float reciprocal is exact for pidx < 2^20
-        const int xi_l = (int)(((float)pidx + 0.5f) * inv_n_robot), r_l = pidx - xi_l * E.n_robot;
-        if (pidx < npairs) undecided = !pair_quick_disjoint(ws.xt[xi_l], srob[r_l]);
-        unsigned um = __ballot_sync(kFull, undecided);
-        if (COUNT) {
-          const int np = (npairs - pb) < 32 ? (npairs - pb) : 32;
-          tally.pair += np;
-          tally.exact += __popc(um);   // pairs the lane-per-pair stage P1 left open
-        }
-        while (um && !hit) {
-          const int l0 = __ffs(um) - 1;
-          um &= um - 1;
-          const int l1 = um ? __ffs(um) - 1 : -1;
-          um &= um - 1;   // (0 stays 0)
-          const int l2 = um ? __ffs(um) - 1 : -1;
-          um &= um - 1;
-          const int lmine = grp10 == 0 ? l0 : (grp10 == 1 ? l1 : (grp10 == 2 ? l2 : -1));
-          const int xim = __shfl_sync(kFull, xi_l, lmine & 31), rm = __shfl_sync(kFull, r_l, lmine & 31);
-          bool sep = false;
-          if (lmine >= 0 && k10 < 9) sep = open_pair_axis(ws.xt[xim], srob[rm], k10);
-          const unsigned bs = __ballot_sync(kFull, sep);
-          unsigned open_g = 0;
-          if (!(bs & 0x3ffu)) open_g |= 1u;
-          if (l1 >= 0 && !(bs & (0x3ffu << 10))) open_g |= 2u;
-          if (l2 >= 0 && !(bs & (0x3ffu << 20))) open_g |= 4u;
-          if (open_g == 0) continue;
-          bool con = false;
-          if (lmine >= 0 && k10 < 6 && ((open_g >> grp10) & 1u)) con = open_pair_pierce(ws.xt[xim], srob[rm], k10);
-          if (__any_sync(kFull, con)) {
-            hit = true;
-            break;
-          }
-          while (open_g) {
-            const int g = __ffs(open_g) - 1;
-            open_g &= open_g - 1;
-            const int lg = g == 0 ? l0 : (g == 1 ? l1 : l2);
-            const int xg = __shfl_sync(kFull, xi_l, lg), rg = __shfl_sync(kFull, r_l, lg);
-            if (COUNT) tally.exact_run += 1;
-            if (!have_R2) {
-              lp.exact(src, R2, T2, lane);
-              have_R2 = true;
-            }
-            const int t = ws.xt[xg].tri;
-            if (exact_pair_contact(R2, T2, E.tris64 + 9 * (size_t)t, E.robot64 + 9 * (size_t)rg, lane)) {
-              hit = true;
-              break;
-            }
-          }
-        }
-      }
-      __syncwarp();
-    }
+    triangle_stage<FMT, COUNT>(E, ws, srob, P, lp, src, lane, ntri, hit, have_R2, pc, tally);
     if (hit) break;
     ntri = 0;
     if (sp == 0) break;
+  }
+  return hit;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Edge samples in reference mode all carry the identity rotation (src/problemStruct.h:157-163), so the robot's box at a
+// sample is the axis-aligned box T + [rob_c - rob_h, rob_c + rob_h] and the boxes of the surviving samples of one
+// 32-sample group lie in one slightly larger axis-aligned box.  ONE traversal with that swept box collects every triangle
+// any of the samples could touch; each sample then runs only the triangle stage over that list.  (The per-sample
+// traversal was 63 % of the edge kernel's instructions.)  The list is a superset of what the per-sample traversal would
+// deliver and every stage after it is unchanged, so the verdicts are the same.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int f2ord(float f) {   // order-preserving float -> int
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// every leaf triangle whose slot box meets [lo, hi] -> ws.cand; returns their number, or -1 when the list would overflow
+template <bool COUNT>
+__device__ int collect_box_candidates(const EnvDev &E, WarpScratch &ws, const CtaShared &cs, const float *lo, const float *hi, int lane,
+                                      Tally &tally) {
+  const unsigned lt = (1u << lane) - 1u;
+  int sp = 0, ncand = 0;
+  bool first = true;
+  while (first || sp > 0) {
+    bool ov = false;
+    int child = kEmptyChild;
+    bool active;
+    float4 a, b;
+    if (first) {
+      active = lane < E.n_top;
+      if (active) {
+        a = cs.top[lane];
+        b = cs.top[kTopSlots + lane];
+      }
+      first = false;
+    } else {
+      const int take = sp > kStackCap - 64 ? 1 : (sp < 4 ? sp : 4);
+      const int grp = lane >> 3;
+      active = grp < take;
+      const int node = active ? ws.stack[sp - 1 - grp] : 0;
+      __syncwarp();
+      sp -= take;
+      if (active) {
+        if (node < cs.n_stage) {
+          const int si = node * kWide + (lane & 7);
+          a = cs.nodes[si];
+          b = cs.nodes[cs.n_stage * kWide + si];
+        } else {
+          const float4 *gn = E.slots + ((size_t)node * kWide + (lane & 7)) * 2;
+          a = __ldg(gn);
+          b = __ldg(gn + 1);
+        }
+      }
+    }
+    if (active) {
+      child = __float_as_int(a.w);
+      // slot box [c - h, c + h] against [lo, hi], directed rounding keeps the test conservative
+      if (child != kEmptyChild)
+        ov = __fadd_ru(a.x, b.x) >= lo[0] && __fsub_rd(a.x, b.x) <= hi[0] && __fadd_ru(a.y, b.y) >= lo[1] && __fsub_rd(a.y, b.y) <= hi[1] &&
+             __fadd_ru(a.z, b.z) >= lo[2] && __fsub_rd(a.z, b.z) <= hi[2];
+    }
+    const unsigned m_int = __ballot_sync(kFull, ov && child >= 0);
+    const unsigned m_leaf = __ballot_sync(kFull, ov && child < 0);
+    if (COUNT) { tally.box += __popc(__ballot_sync(kFull, active && child != kEmptyChild)); tally.steps += 1; }
+    if (ncand + __popc(m_leaf) > kCandCap) return -1;
+    if (ov && child >= 0) {
+      const int pos = sp + __popc(m_int & lt);
+      if (pos < kStackCap) ws.stack[pos] = child;
+    }
+    if (ov && child < 0) ws.cand[ncand + __popc(m_leaf & lt)] = ~child;
+    sp += __popc(m_int);
+    ncand += __popc(m_leaf);
+    if (sp > kStackCap) return -1;   // (the caller falls back to the per-sample traversal, which reports overflows)
+    __syncwarp();
+  }
+  return ncand;
+}
+
+// one sample against the shared candidate list
+template <int FMT, bool COUNT>
+__device__ bool pose_hits_candidates(const EnvDev &E, WarpScratch &ws, const CtaShared &cs, const PoseU &P, const LanePose<FMT> &lp,
+                                     int src, int lane, int ncand, Tally &tally) {
+  bool hit = false, have_R2 = false;
+  PairCtx pc;
+  if (COUNT) tally.past_root += 1;
+  for (int base = 0; base < ncand && !hit; base += 32) {
+    const int cnt = (ncand - base) < 32 ? (ncand - base) : 32;
+    if (lane < cnt) ws.tri[lane] = ws.cand[base + lane];
+    __syncwarp();
+    triangle_stage<FMT, COUNT>(E, ws, cs.rob, P, lp, src, lane, cnt, hit, have_R2, pc, tally);
   }
   return hit;
 }
@@ -662,9 +776,10 @@ __device__ __forceinline__ void flush_tally(const EnvDev &E, const Tally &t, uns
 
 // phase A (lane-per-pose cull + rotation) then phase B over the surviving lanes; returns the mask of colliding lanes
 // (stops at the first hit when `first_only`, which is what an edge needs)
-template <int FMT, bool COUNT>
+template <int FMT, bool COUNT, bool SWEPT_CAPABLE = false>
 __device__ __forceinline__ unsigned check_32_poses(const EnvDev &E, WarpScratch &ws, const CtaShared &cs, bool valid,
-                                                   const LanePose<FMT> &lp, int lane, bool first_only, Tally &tally) {
+                                                   const LanePose<FMT> &lp, int lane, bool first_only, Tally &tally,
+                                                   bool swept = false) {
   float thi[3], tlo[3], R[9];
   lp.split(thi, tlo);
   bool alive = valid && E.n_obst > 0 &&
@@ -674,6 +789,43 @@ __device__ __forceinline__ unsigned check_32_poses(const EnvDev &E, WarpScratch 
   if (alive) lp.rot32(R);
   unsigned todo = __ballot_sync(kFull, alive);
   unsigned hitmask = 0;
+  if (SWEPT_CAPABLE && swept && __popc(todo) >= 2) {
+    // identity rotation on every lane (the caller guarantees it): one traversal with the box that holds the robot's
+    // axis-aligned box at every surviving sample, outward rounded
+    int blo[3], bhi[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float c = __fadd_rd(thi[k], tlo[k]), cu = __fadd_ru(thi[k], tlo[k]);
+      const float pad = kEpsBox * (fabsf(cu) + E.rob_radius);
+      const float l = __fsub_rd(__fadd_rd(c, __fsub_rd(E.rob_c[k], E.rob_h[k])), pad);
+      const float h = __fadd_ru(__fadd_ru(cu, __fadd_ru(E.rob_c[k], E.rob_h[k])), pad);
+      blo[k] = __reduce_min_sync(kFull, alive ? f2ord(l) : 0x7fffffff);
+      bhi[k] = __reduce_max_sync(kFull, alive ? f2ord(h) : (int)0x80000000);
+    }
+    const float lo[3] = {ord2f(blo[0]), ord2f(blo[1]), ord2f(blo[2])}, hi[3] = {ord2f(bhi[0]), ord2f(bhi[1]), ord2f(bhi[2])};
+    const int ncand = collect_box_candidates<COUNT>(E, ws, cs, lo, hi, lane, tally);
+    if (ncand == 0) return 0;
+    if (ncand > 0) {
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        PoseU P;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) P.R[k] = __shfl_sync(kFull, R[k], src);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          P.Thi[k] = __shfl_sync(kFull, thi[k], src);
+          P.Tlo[k] = FMT == kFmtEulerF32 ? 0.f : __shfl_sync(kFull, tlo[k], src);
+        }
+        if (pose_hits_candidates<FMT, COUNT>(E, ws, cs, P, lp, src, lane, ncand, tally)) {
+          hitmask |= 1u << src;
+          if (first_only) break;
+        }
+      }
+      return hitmask;
+    }
+    // (list overflow: fall through to the per-sample traversal)
+  }
   while (todo) {
     const int src = __ffs(todo) - 1;
     todo &= todo - 1;
@@ -791,6 +943,10 @@ __device__ __forceinline__ double wrap_pi(double a) {
 // stop as soon as an earlier hit than anything they could still find is published; finalize_edges_kernel then writes
 // the outputs.  split == 1 writes them directly.
 constexpr int kNoHit = 0x7f7f7f7f;   // what cudaMemsetAsync(..., 0x7f, ...) produces
+#ifndef SFFG_SWEPT_MAX_SPLIT
+#define SFFG_SWEPT_MAX_SPLIT 4
+#endif
+constexpr int kSweptMaxSplit = SFFG_SWEPT_MAX_SPLIT;   // warps per edge up to which a group's samples are close enough for one swept box
 
 template <bool COUNT>
 __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(EnvDev E, const double *starts,
@@ -854,7 +1010,8 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(
         for (int k = 0; k < 3; ++k) lp.a[k] = dadd(s[3 + k], __ddiv_rn(dmul(di, adir[k]), parts));
       }
       if (COUNT) nposes += valid ? 1 : 0;
-      const unsigned hm = check_32_poses<kFmtEulerF64, COUNT>(E, ws, cs, valid, lp, lane, true, tally);
+      const unsigned hm = check_32_poses<kFmtEulerF64, COUNT, true>(E, ws, cs, valid, lp, lane, true, tally,
+                                                                    rot_mode != SFFG_ROT_INTERPOLATE && split <= kSweptMaxSplit);
       if (hm) hit_index = (int)(base + (long long)(__ffs(hm) - 1) * split);
     }
     if (lane == 0) {
