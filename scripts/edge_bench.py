@@ -20,7 +20,7 @@ env = S.Environment(m["building_s10"], m["robot_small_s10"])
 dev = torch.device("cuda", 0)
 out = {}
 for length in (4.0, 12.0):
-    for n in (1 << 20, 1 << 14, 1 << 11):
+    for n in (1 << 20, 1 << 14, 1 << 11, 1 << 9, 1 << 7):
         s = S.gen_poses_device(0x5FF5EED + 1, 0, n, [-45, 45, -45, 45, 0, 125]).double()
         d = torch.randn((n, 3), device=dev, dtype=torch.float64, generator=torch.Generator(device=dev).manual_seed(1))
         e = s.clone()

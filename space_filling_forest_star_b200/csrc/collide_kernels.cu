@@ -937,16 +937,18 @@ __device__ __forceinline__ double wrap_pi(double a) {
   return a;
 }
 
-// `split` (power of two) warps share one edge: warp j of an edge takes the samples with (index - 1) % split == j, so a
-// planner-sized batch still occupies the whole GPU and the serial phase B of one warp covers 1/split of the samples.
+// `split` (power of two) warps share one edge: warp j of an edge takes the j-th contiguous 1/split of the sample indices
+// (neighbouring samples share one swept box), so a planner-sized batch still occupies the whole GPU.
 // With split > 1 the per-edge minimum colliding index is combined with atomicMin in `fh` (pre-set to kNoHit) and warps
 // stop as soon as an earlier hit than anything they could still find is published; finalize_edges_kernel then writes
 // the outputs.  split == 1 writes them directly.
 constexpr int kNoHit = 0x7f7f7f7f;   // what cudaMemsetAsync(..., 0x7f, ...) produces
-#ifndef SFFG_SWEPT_MAX_SPLIT
-#define SFFG_SWEPT_MAX_SPLIT 4
+// work units (edge, range) a planner-sized batch is cut into per resident warp.  Measured with the swept-box traversal
+// (profiles/r02_edges_swept.md): 1 beats 2 / 4 / 8 for the planner's short edges (2 048 edges of length 4: 41.6 us per call
+// against 44.9 / 50.9 / 69.6), long edges lose a little (length 12: 68 against 62 us at 4).
+#ifndef SFFG_EDGE_UNITS_PER_WARP
+#define SFFG_EDGE_UNITS_PER_WARP 1
 #endif
-constexpr int kSweptMaxSplit = SFFG_SWEPT_MAX_SPLIT;   // warps per edge up to which a group's samples are close enough for one swept box
 
 template <bool COUNT>
 __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(EnvDev E, const double *starts,
@@ -995,10 +997,14 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(
       S = (cl > 2.0e9 ? 2000000000LL : (long long)cl) - 1;
     }
     int hit_index = 0;
-    for (long long base = 1 + part; base <= S && hit_index == 0; base += 32LL * split) {
+    // warp `part` of the edge takes a CONTIGUOUS range of the sample indices (neighbouring samples share one swept box)
+    const long long range_len = (S + split - 1) / split;
+    const long long first_idx = 1 + (long long)part * range_len;
+    const long long last_idx = first_idx + range_len - 1 < S ? first_idx + range_len - 1 : S;
+    for (long long base = first_idx; base <= last_idx && hit_index == 0; base += 32) {
       if (split > 1 && *reinterpret_cast<volatile int *>(fh + eidx) < base) break;   // an earlier hit is already known
-      const long long idx = base + (long long)lane * split;
-      const bool valid = idx <= S;
+      const long long idx = base + lane;
+      const bool valid = idx <= last_idx;
       const double di = (double)idx;
       LanePose<kFmtEulerF64> lp;
       lp.clear();
@@ -1011,8 +1017,8 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(
       }
       if (COUNT) nposes += valid ? 1 : 0;
       const unsigned hm = check_32_poses<kFmtEulerF64, COUNT, true>(E, ws, cs, valid, lp, lane, true, tally,
-                                                                    rot_mode != SFFG_ROT_INTERPOLATE && split <= kSweptMaxSplit);
-      if (hm) hit_index = (int)(base + (long long)(__ffs(hm) - 1) * split);
+                                                                    rot_mode != SFFG_ROT_INTERPOLATE);
+      if (hm) hit_index = (int)(base + (long long)(__ffs(hm) - 1));
     }
     if (lane == 0) {
       if (split > 1) {
@@ -1292,7 +1298,7 @@ cudaError_t launch_check_edges(const EnvDev &env_in, const double *d_starts, con
   const size_t smem = collide_smem_bytes(env.n_robot, env.n_stage_max);
   // warps per edge: enough units for ~2 per resident warp, at most 32 (needs the scratch array)
   int split = 1;
-  const long long warps = (long long)cfg.sm_count * 2 * kWarpsPerBlock * 2;
+  const long long warps = (long long)cfg.sm_count * kWarpsPerBlock * SFFG_EDGE_UNITS_PER_WARP;
   if (d_fh_scratch)
     while (split < 32 && m * split < warps) split <<= 1;
   const long long units = m * split;
