@@ -38,7 +38,7 @@ def timeit(fn, reps=3):
 
 rows = []
 cases = [(6, 10_000, 100_000, 16), (6, 100_000, 100_000, 16), (6, 1_000_000, 100_000, 1), (6, 1_000_000, 100_000, 16),
-         (6, 1_000_000, 100_000, 32), (6, 1_000_000, 1, 32), (6, 1_000_000, 64, 32), (6, 10_000_000, 16384, 16),
+         (6, 1_000_000, 100_000, 32), (6, 1_000_000, 100_000, 64), (6, 1_000_000, 100_000, 128), (6, 1_000_000, 1, 32), (6, 1_000_000, 64, 32), (6, 10_000_000, 16384, 16),
          (2, 1_000_000, 100_000, 16)]
 if len(sys.argv) > 1 and sys.argv[1] == "quick":
     cases = [(6, 1_000_000, 32768, 16), (6, 1_000_000, 1, 32), (2, 1_000_000, 32768, 16)]

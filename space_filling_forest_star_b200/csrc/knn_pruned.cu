@@ -180,8 +180,14 @@ __device__ __forceinline__ float box_ub(const float *lo, const float *hi, const 
   return r;
 }
 
+// resident CTAs per SM the pruned kernel is compiled for: 4 (64 registers, 32 warps per SM) measured 65.9M queries/s at
+// N = 1e6, k = 16 against 51.8M at 2 CTAs / 128 registers and 61.9M at 3 / 80 -- the search is latency-bound (shuffle
+// chains of the top-k insertion), more warps hide it better than more registers do
+#ifndef SFFG_KNN_MIN_BLOCKS
+#define SFFG_KNN_MIN_BLOCKS 4
+#endif
 template <int DIM, int QW, int KPL>
-__global__ void __launch_bounds__(kThreads) knn_pruned_kernel(SortedDev sv, const float *__restrict__ queries, long long nq, int k,
+__global__ void __launch_bounds__(kThreads, SFFG_KNN_MIN_BLOCKS) knn_pruned_kernel(SortedDev sv, const float *__restrict__ queries, long long nq, int k,
                                                               int slices, int sb_per_slice, float *out_d, int *out_i,
                                                               int slot_base, int slots_total, const unsigned *__restrict__ perm,
                                                               RowDests rows) {
