@@ -950,8 +950,11 @@ constexpr int kNoHit = 0x7f7f7f7f;   // what cudaMemsetAsync(..., 0x7f, ...) pro
 #define SFFG_EDGE_UNITS_PER_WARP 1
 #endif
 
+#ifndef SFFG_EDGE_MIN_BLOCKS
+#define SFFG_EDGE_MIN_BLOCKS SFFG_MIN_BLOCKS
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) check_edges_kernel(EnvDev E, const double *starts,
+__global__ void __launch_bounds__(kThreads, SFFG_EDGE_MIN_BLOCKS) check_edges_kernel(EnvDev E, const double *starts,
                                                                                 const double *ends, long long m, double sample,
                                                                                 int rot_mode, uint8_t *free_out,
                                                                                 int32_t *first_hit, int split, int *fh) {

@@ -491,8 +491,11 @@ __global__ void __launch_bounds__(kThreads, SFFG_KNN_MIN_BLOCKS) knn_pruned_kern
 
 // radius search over the sorted view: a block whose box lower bound already reaches r2 cannot hold a hit (d2 < r2 is
 // strict and box_lb <= d2).  FILL == false counts, FILL == true writes (d2 bits << 32 | original id) keys.
+#ifndef SFFG_RADIUS_MIN_BLOCKS
+#define SFFG_RADIUS_MIN_BLOCKS 4   // as the k-NN kernel: 6.0 ms per 16 384-query call at N = 1e6 against 6.6 (3) and 7.5 (1)
+#endif
 template <int DIM, int QW, bool FILL>
-__global__ void __launch_bounds__(kThreads) radius_pruned_kernel(SortedDev sv, const float *__restrict__ queries, long long nq,
+__global__ void __launch_bounds__(kThreads, SFFG_RADIUS_MIN_BLOCKS) radius_pruned_kernel(SortedDev sv, const float *__restrict__ queries, long long nq,
                                                                  float r2, int slices, int sb_per_slice, int *counts,
                                                                  const long long *offsets, int *cursor, unsigned long long *keys) {
   constexpr int LIN = DIM == 6 ? 3 : 2;
