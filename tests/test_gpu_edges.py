@@ -44,6 +44,16 @@ def test_edges_seeded_vs_oracle_and_properties(sff, orc, meshes):
     pos = np.zeros((len(hit), 6))
     pos[:, :3] = s[hit, :3] + (first[hit, None] * (e[hit, :3] - s[hit, :3])) / parts[:, None]
     assert env.Collide(pos).all()
+    # opt-in interpolate mode: the rotation varies along the edge (the group's swept box is the cube around the robot's
+    # bounding sphere), start and end orientations unrelated
+    k = 4000
+    e1 = e[:k].copy()
+    e1[:, 3:] = orc.gen_poses(SEED + 6, 0, k, [-45, 45, -45, 45, 0, 125]).astype(np.float64)[:, 3:]
+    free1, first1 = env.isPathFree(s[:k], e1, 0.1, 1, want_first_hit=True)
+    wf1, wh1, _ = orc.edges_free(ob, rb, s[:k], e1, 0.1, 1, models=(orc.ObbModel(ob), orc.ObbModel(rb)))
+    np.testing.assert_array_equal(free1, wf1)
+    np.testing.assert_array_equal(first1, wh1)
+    assert 0.05 < free1.mean() < 0.95
     # a free edge stays free when shortened from the far end at the same sampling phase (prefix property)
     assert env.isPathFree(s[:0], e[:0]).shape == (0,)
 
