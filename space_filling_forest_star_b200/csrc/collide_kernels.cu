@@ -20,7 +20,6 @@
 //            - __ballot/__any early-out on the first confirmed contact (verdict-equivalent to RAPID's ALL_CONTACTS
 //              because the caller only looks at num_contacts != 0)
 // The result equals "OR over all triangle pairs of the double-precision SAT" -- the oracle's ground truth.
-#include <cstddef>
 #include <cstdint>
 #include <mutex>
 
@@ -60,22 +59,12 @@ struct XTri {        // obstacle triangle in the robot frame (FP32); 13 words = 
 #endif
 constexpr int kCandCap = SFFG_CAND_CAP;    // candidate triangles of one group of edge samples (swept-box traversal)
 
-// pose record of the paired flow: what phase A leaves for phase B (R row-major, Thi, Tlo); 20 words per lane keep the
-// lanes' float4 stores on distinct banks
-struct PoseRec {
-  float4 q[5];
-};
-
 struct WarpScratch {
   int stack[kStackCap];
-  int cand[kCandCap];   // (directly behind `stack`: the paired flow cuts the two into one node stack per half-warp)
   int tri[kTriCap];
+  int cand[kCandCap];
   XTri xt[32];
-  PoseRec pr[32];
 };
-static_assert(offsetof(WarpScratch, cand) == offsetof(WarpScratch, stack) + sizeof(int) * kStackCap, "stack and cand must be contiguous");
-constexpr int kHalfCap = (kStackCap + kCandCap) / 2;   // node ids pending for one pose of a pair
-static_assert(kTriCap >= 64, "two triangle lists of 32");
 
 // what a CTA stages once: the robot records, the top cut and the first nodes of the (breadth-first) hierarchy
 struct CtaShared {
@@ -868,291 +857,6 @@ __device__ __forceinline__ unsigned check_32_poses(const EnvDev &E, WarpScratch 
   return hitmask;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Paired flow of the pose kernel: TWO poses in flight per warp, one per half-warp, in lock-step.
-// The per-pose flow above leaves most lanes idle in the stages a single pose cannot fill (2 of 4 node slots per traversal
-// step, 4 of 32 lanes in the triangle transform).  Here each half-warp owns a pose -- its own node stack and triangle
-// list, 2 nodes x 8 slots per step --, both halves run the same stage of the loop below at the same time, and the
-// pose-independent pair stages work on ONE list of transformed triangles tagged with the lane their pose came from, so the
-// pairs of both poses share the lane-per-pair passes and the three-pairs-per-pass cooperative stage.  A pose still retires
-// at its first confirmed contact (its pending pairs are dropped, its half takes the next survivor of phase A); when a
-// single pose is left the idle half joins it (4 nodes per step, 32 triangles per transform pass), i.e. the tail runs
-// exactly like the per-pose flow.  Verdicts are unchanged: every stage is the same test on the same operands, only the
-// order in which pairs are looked at differs, and the verdict is an OR over pairs.
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_pose_rec(PoseRec &r, const float *R, const float *thi, const float *tlo) {
-  r.q[0] = make_float4(R[0], R[1], R[2], R[3]);
-  r.q[1] = make_float4(R[4], R[5], R[6], R[7]);
-  r.q[2] = make_float4(R[8], thi[0], thi[1], thi[2]);
-  r.q[3] = make_float4(tlo[0], tlo[1], tlo[2], 0.f);
-}
-__device__ __forceinline__ void load_pose_rec(const PoseRec &r, PoseU &P) {
-  const float4 a = r.q[0], b = r.q[1], c = r.q[2], d = r.q[3];
-  P.R[0] = a.x; P.R[1] = a.y; P.R[2] = a.z; P.R[3] = a.w;
-  P.R[4] = b.x; P.R[5] = b.y; P.R[6] = b.z; P.R[7] = b.w;
-  P.R[8] = c.x; P.Thi[0] = c.y; P.Thi[1] = c.z; P.Thi[2] = c.w;
-  P.Tlo[0] = d.x; P.Tlo[1] = d.y; P.Tlo[2] = d.z;
-}
-
-// Pair stages over the transformed triangles ws.xt[0, nx) (each tagged in .pad with the lane of its pose): P1 lane-per-pair,
-// P2 three open pairs per cooperative pass, FP64 exact stage.  A confirmed contact sets the pose's bit in `hitmask`
-// (warp-uniform); pairs of a pose whose bit is set are skipped.
-template <int FMT, bool COUNT>
-__device__ __forceinline__ void pair_stages(const EnvDev &E, WarpScratch &ws, const RobotTri *srob, const LanePose<FMT> &lp, int lane,
-                                            int nx, unsigned &hitmask, PairCtx &pc, int &pc_owner, Tally &tally) {
-  const int grp10 = lane / 10, k10 = lane - 10 * grp10;
-  const float inv_n_robot = 1.0f / (float)E.n_robot;
-  const int npairs = nx * E.n_robot;
-  for (int pb = 0; pb < npairs; pb += 32) {
-    const int pidx = pb + lane;
-    // (triangle, robot triangle) of this lane's pair; the quotient by float reciprocal is exact for pidx < 2^20
-    const int xi_l = (int)(((float)pidx + 0.5f) * inv_n_robot), r_l = pidx - xi_l * E.n_robot;
-    int s_l = 0;
-    bool undecided = false;
-    if (pidx < npairs) {
-      s_l = ws.xt[xi_l].pad;
-      if (!((hitmask >> s_l) & 1u)) undecided = !pair_quick_disjoint(ws.xt[xi_l], srob[r_l]);
-    }
-    unsigned um = __ballot_sync(kFull, undecided);
-    if (COUNT) {
-      const int np = (npairs - pb) < 32 ? (npairs - pb) : 32;
-      tally.pair += np;
-      tally.exact += __popc(um);   // pairs the lane-per-pair stage P1 left open
-    }
-    while (um) {
-      const int l0 = __ffs(um) - 1;
-      um &= um - 1;
-      const int l1 = um ? __ffs(um) - 1 : -1;
-      um &= um - 1;   // (0 stays 0)
-      const int l2 = um ? __ffs(um) - 1 : -1;
-      um &= um - 1;
-      const int lmine = grp10 == 0 ? l0 : (grp10 == 1 ? l1 : (grp10 == 2 ? l2 : -1));
-      const int xim = __shfl_sync(kFull, xi_l, lmine & 31), rm = __shfl_sync(kFull, r_l, lmine & 31);
-      bool sep = false;
-      if (lmine >= 0 && k10 < 9) sep = open_pair_axis(ws.xt[xim], srob[rm], k10);
-      const unsigned bs = __ballot_sync(kFull, sep);
-      unsigned open_g = 0;
-      if (!(bs & 0x3ffu)) open_g |= 1u;
-      if (l1 >= 0 && !(bs & (0x3ffu << 10))) open_g |= 2u;
-      if (l2 >= 0 && !(bs & (0x3ffu << 20))) open_g |= 4u;
-      if (open_g == 0) continue;
-      bool con = false;
-      if (lmine >= 0 && k10 < 6 && ((open_g >> grp10) & 1u)) con = open_pair_pierce(ws.xt[xim], srob[rm], k10);
-      const unsigned cb = __ballot_sync(kFull, con);
-      while (open_g) {
-        const int g = __ffs(open_g) - 1;
-        open_g &= open_g - 1;
-        const int lg = g == 0 ? l0 : (g == 1 ? l1 : l2);
-        const int sg = __shfl_sync(kFull, s_l, lg);
-        if ((hitmask >> sg) & 1u) continue;   // its pose was decided by an earlier pair of this pass
-        if (cb & (0x3ffu << (10 * g))) {
-          hitmask |= 1u << sg;
-          continue;
-        }
-        const int xg = __shfl_sync(kFull, xi_l, lg), rg = __shfl_sync(kFull, r_l, lg);
-        if (COUNT) tally.exact_run += 1;
-        if (pc_owner != sg) {
-          lp.exact(sg, pc.R2, pc.T2, lane);
-          pc_owner = sg;
-        }
-        const int t = ws.xt[xg].tri;
-        if (exact_pair_contact(pc.R2, pc.T2, E.tris64 + 9 * (size_t)t, E.robot64 + 9 * (size_t)rg, lane)) hitmask |= 1u << sg;
-      }
-      // the open pairs of a pose that just got its contact need no look any more
-      um &= ~__ballot_sync(kFull, (hitmask >> s_l) & 1u);
-    }
-  }
-}
-
-template <int FMT, bool COUNT>
-__device__ __forceinline__ unsigned check_32_poses_paired(const EnvDev &E, WarpScratch &ws, const CtaShared &cs, bool valid,
-                                                          const LanePose<FMT> &lp, int lane, Tally &tally) {
-  __syncwarp();   // (the previous unit's reads of the scratch are over)
-  unsigned todo;
-  {
-    // phase A, lane-per-pose: root cull, clearance grid; the survivors leave R and T in the warp's pose records
-    float thi[3], tlo[3];
-    lp.split(thi, tlo);
-    bool alive = valid && E.n_obst > 0 &&
-                 sphere_hits_root(E, thi[0], thi[1], thi[2], fabsf(tlo[0]) + fabsf(tlo[1]) + fabsf(tlo[2]));
-    if (alive && E.grid_n[0] > 0) alive = !clearance_says_free(E, thi[0], thi[1], thi[2]);
-    todo = __ballot_sync(kFull, alive);
-    if (COUNT) tally.past_grid += __popc(todo);
-    if (todo == 0) return 0;
-    if (alive) {
-      float R[9];
-      lp.rot32(R);
-      if (FMT == kFmtEulerF32) tlo[0] = tlo[1] = tlo[2] = 0.f;
-      store_pose_rec(ws.pr[lane], R, thi, tlo);
-    }
-  }
-  __syncwarp();
-
-  const RobotTri *srob = cs.rob;
-  const unsigned lt = (1u << lane) - 1u;
-  const int half = lane >> 4;
-  int *const pool = ws.stack;        // stack + cand: one node stack of kHalfCap ids per half
-  unsigned hitmask = 0;              // warp-uniform
-  bool wide = false;                 // warp-uniform: a single pose is left and all 32 lanes serve it
-  unsigned gmask = half ? 0xffff0000u : 0x0000ffffu;   // the lanes of this lane's group
-  int gl = lane & 15;                // index of the lane inside its group
-  int own = half;                    // whose node stack / triangle list the group works on
-  // state of the group's pose (identical in every lane of the group)
-  bool busy = false;
-  int sp = 0, ntri = 0, src = 0;
-  PoseU P;
-  BoxTest bt;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) P.R[k] = 0.f;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { P.Thi[k] = 0.f; P.Tlo[k] = 0.f; bt.o[k] = 0.f; bt.ra[k] = 0.f; }
-  bt.rob_sz = 0.f;
-  PairCtx pc;
-  int pc_owner = -1;
-
-  while (true) {
-    // ---------------- admission: an idle half takes the next survivor; step 0 (the top cut) runs on all 32 lanes ----------------
-    if (!wide) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        bool idle = !__shfl_sync(kFull, (int)busy, 16 * h);
-        while (idle && todo) {
-          const int s = __ffs(todo) - 1;
-          todo &= todo - 1;
-          PoseU Pn;
-          load_pose_rec(ws.pr[s], Pn);
-          const BoxTest bn = make_box_test(E, Pn);
-          bool ov = false;
-          int child = kEmptyChild;
-          if (lane < E.n_top) {
-            const float4 a = cs.top[lane], b = cs.top[kTopSlots + lane];
-            child = __float_as_int(a.w);
-            ov = slot_overlaps(E, Pn, bn, a, b);
-          }
-          const unsigned m_int = __ballot_sync(kFull, ov && child >= 0);
-          const unsigned m_leaf = __ballot_sync(kFull, ov && child < 0);
-          if (COUNT) { tally.past_root += 1; tally.box += E.n_top; tally.steps += 1; }
-          if (!(m_int | m_leaf)) continue;   // nothing near: the pose is free
-          if (ov && child >= 0) pool[h * kHalfCap + __popc(m_int & lt)] = child;
-          if (ov && child < 0) ws.tri[32 * h + __popc(m_leaf & lt)] = ~child;
-          if (half == h) {
-            P = Pn;
-            bt = bn;
-            sp = __popc(m_int);
-            ntri = __popc(m_leaf);
-            src = s;
-            busy = true;
-          }
-          idle = false;
-        }
-      }
-      __syncwarp();
-      const unsigned bm = __ballot_sync(kFull, busy);
-      if (bm == 0) break;
-      if (todo == 0 && (bm == 0x0000ffffu || bm == 0xffff0000u)) {
-        // one pose left: the idle half joins it
-        const int from = (bm & 1u) ? 0 : 16;
-        src = __shfl_sync(kFull, src, from);
-        sp = __shfl_sync(kFull, sp, from);
-        ntri = __shfl_sync(kFull, ntri, from);
-        own = from >> 4;
-        load_pose_rec(ws.pr[src], P);
-        bt = make_box_test(E, P);
-        busy = true;
-        wide = true;
-        gmask = kFull;
-        gl = lane;
-      }
-    } else if (!busy) {
-      break;
-    }
-
-    // ---------------- one traversal step per group: 2 (wide: 4) nodes x 8 slots ----------------
-    {
-      const int maxtake = wide ? 4 : 2;
-      // near the cap fall back to strict depth-first (1 node per step grows the stack by at most 7 per level)
-      const int take = sp > kHalfCap - 64 ? 1 : (sp < maxtake ? sp : maxtake);
-      const bool do_step = busy && sp > 0 && ntri + 8 * take <= 32;
-      if (__any_sync(kFull, do_step)) {
-        const int grp = gl >> 3;
-        const bool active = do_step && grp < take;
-        int *const stk = pool + own * kHalfCap;
-        const int node = active ? stk[sp - 1 - grp] : 0;
-        __syncwarp();
-        if (do_step) sp -= take;
-        bool ov = false;
-        int child = kEmptyChild;
-        if (active) {
-          float4 a, b;
-          if (node < cs.n_stage) {
-            const int si = node * kWide + (lane & 7);
-            a = cs.nodes[si];
-            b = cs.nodes[cs.n_stage * kWide + si];
-          } else {
-            const float4 *gn = E.slots + ((size_t)node * kWide + (lane & 7)) * 2;
-            a = __ldg(gn);
-            b = __ldg(gn + 1);
-          }
-          child = __float_as_int(a.w);
-          if (child != kEmptyChild) ov = slot_overlaps(E, P, bt, a, b);
-        }
-        const unsigned m_int = __ballot_sync(kFull, ov && child >= 0) & gmask;
-        const unsigned m_leaf = __ballot_sync(kFull, ov && child < 0) & gmask;
-        if (COUNT) {
-          tally.box += __popc(__ballot_sync(kFull, active && child != kEmptyChild));
-          tally.steps += __popc(__ballot_sync(kFull, do_step && gl == 0));
-        }
-        if (ov && child >= 0) {
-          const int pos = sp + __popc(m_int & lt);
-          if (pos < kHalfCap) stk[pos] = child;
-        }
-        if (ov && child < 0) ws.tri[32 * own + ntri + __popc(m_leaf & lt)] = ~child;
-        sp += __popc(m_int);
-        ntri += __popc(m_leaf);
-        if (sp > kHalfCap) {     // never silently drop work: flag the launch as failed
-          if (gl == 0) *reinterpret_cast<volatile int *>(E.status) = 1;
-          sp = kHalfCap;
-        }
-        __syncwarp();
-      }
-    }
-
-    // ---------------- triangle stage: transform per group, pair stages on the common list ----------------
-    {
-      const bool want = busy && ntri > 0;
-      if (__any_sync(kFull, want)) {
-        const int gsz = wide ? 32 : 16;
-        const int *const tl = ws.tri + 32 * own;
-        int done = 0;
-        while (true) {
-          const bool go = want && done < ntri && !((hitmask >> src) & 1u);
-          if (!__any_sync(kFull, go)) break;
-          bool keep = false;
-          XTri x;
-          const bool has = go && gl < ntri - done;
-          if (has) keep = transform_triangle(E, P, tl[done + gl], src, x);
-          done += gsz;
-          const unsigned km = __ballot_sync(kFull, keep);
-          const int nx = __popc(km);
-          if (COUNT) { tally.tri_passes += 1; tally.tris += __popc(__ballot_sync(kFull, has)); }
-          if (keep) ws.xt[__popc(km & lt)] = x;
-          __syncwarp();
-          if (nx) pair_stages<FMT, COUNT>(E, ws, srob, lp, lane, nx, hitmask, pc, pc_owner, tally);
-          __syncwarp();
-        }
-        if (want) ntri = 0;
-      }
-    }
-
-    // ---------------- retire ----------------
-    if (busy && (((hitmask >> src) & 1u) || sp == 0)) busy = false;
-  }
-  return hitmask;
-}
-
-#ifndef SFFG_PAIRED
-#define SFFG_PAIRED 0
-#endif
 
 // spins (one thread) until every rank has published an epoch >= `epoch` in the local flag words; bounded by a 10 s timeout
 __device__ __forceinline__ void wait_flags(const FlagSet &f, unsigned epoch, int *status) {
@@ -1199,11 +903,7 @@ __global__ void __launch_bounds__(kThreads, SFFG_MIN_BLOCKS) collide_poses_kerne
     if (mine) lp.load(poses, i);
     else lp.clear();
     if (COUNT) nposes += mine ? 1 : 0;
-#if SFFG_PAIRED
-    const unsigned hitmask = check_32_poses_paired<FMT, COUNT>(E, ws, cs, mine, lp, lane, tally);
-#else
     const unsigned hitmask = check_32_poses<FMT, COUNT>(E, ws, cs, mine, lp, lane, false, tally);
-#endif
     if (outs.n == 1) {
       if (mine) outs.p[0][i] = (uint8_t)((hitmask >> lane) & 1u);
     } else if (chunk == 32 && (long long)c * 32 + 32 <= n) {
