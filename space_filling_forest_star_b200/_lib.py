@@ -81,6 +81,14 @@ SIGNATURES = {
     "sffg_knn_gather_device": (C.c_int, [_p, _p, C.c_int64, C.c_int, _p, _p, C.c_int, _p]),
     "sffg_knn_multi": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, _p, _p]),
     "sffg_radius": (C.c_int, [_p, _p, C.c_int64, C.c_float, _p, _p, _p, C.c_int64, C.POINTER(C.c_int64)]),
+    # asynchronous forms (begin enqueues, the matching end completes)
+    "sffg_radius_begin": (C.c_int, [_p, _p, C.c_int64, C.c_float, _p, _p, _p, C.c_int64, C.POINTER(C.c_int64)]),
+    "sffg_knn_multi_begin": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, _p, _p]),
+    "sffg_index_add_multi_begin": (C.c_int, [_p, _p, C.c_int, _p]),
+    "sffg_index_end": (C.c_int, [_p]),
+    "sffg_check_edges_begin": (C.c_int, [_p, _p, _p, C.c_int64, C.c_double, C.c_int, _p, _p]),
+    "sffg_check_moves_begin": (C.c_int, [_p, _p, _p, C.c_int64, C.c_double, C.c_int, _p]),
+    "sffg_env_end": (C.c_int, [_p]),
 }
 
 _lib = None

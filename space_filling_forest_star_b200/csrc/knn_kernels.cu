@@ -246,9 +246,9 @@ __global__ void __launch_bounds__(kThreads) radius_scan_kernel(IndexDev idx, con
           int at = 0;
           if (lane == 0) at = atomicAdd(cursor + qi, __popc(mask));
           at = __shfl_sync(kFull, at, 0);
-          if (in)
-            keys[offsets[qi] + at + __popc(mask & lt)] =
-                ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)i;
+          const long long o = offsets[qi];   // negative: the device-side scan found the result buffers too small
+          if (in && o >= 0)
+            keys[o + at + __popc(mask & lt)] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)i;
         }
       } else {
         cnt[w] += __popc(mask);
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kThreads) radius_sort_kernel(unsigned long lon
   __shared__ unsigned long long sk[kSortSmem];
   const long long row = blockIdx.x;
   const long long len = counts[row];
-  if (len == 0) return;
+  if (len == 0 || offsets[row] < 0) return;
   unsigned long long *g = keys + offsets[row];
   unsigned long long *a = g;
   const bool in_smem = len <= kSortSmem;
@@ -306,6 +306,35 @@ __global__ void __launch_bounds__(kThreads) radius_sort_kernel(unsigned long lon
     ids[offsets[row] + i] = (int)(unsigned)(key & 0xffffffffull);
     d2[offsets[row] + i] = __uint_as_float((unsigned)(key >> 32));
   }
+}
+
+// Exclusive scan of the per-query counts on the device (one block; planner-sized calls), so that count, fill and sort run
+// back to back without a host round trip.  The total goes to `total_out` (pinned mapped memory the host reads after its one
+// synchronisation); when it exceeds `capacity` every offset is set to -1, which turns the fill and sort kernels into no-ops.
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads) radius_offsets_kernel(const int *__restrict__ counts, long long nq, long long capacity,
+                                                                      long long *offsets, long long *total_out) {
+  __shared__ long long part[kScanThreads];
+  const long long per = (nq + kScanThreads - 1) / kScanThreads;
+  const long long b = (long long)threadIdx.x * per, e = b + per < nq ? b + per : nq;
+  long long s = 0;
+  for (long long i = b; i < e; ++i) s += counts[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int d = 1; d < kScanThreads; d <<= 1) {
+    const long long v = (int)threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  const long long total = part[kScanThreads - 1];
+  const bool fits = total <= capacity;
+  long long run = part[threadIdx.x] - s;
+  for (long long i = b; i < e; ++i) {
+    offsets[i] = fits ? run : -1;
+    run += counts[i];
+  }
+  if (threadIdx.x == 0) *total_out = total;
 }
 
 __global__ void index_append_kernel(float *coords, long long capacity, int dim, long long at, const float *__restrict__ pts,
@@ -447,6 +476,14 @@ cudaError_t launch_radius_sort(unsigned long long *d_keys, const int64_t *d_offs
   if (nq <= 0) return cudaSuccess;
   radius_sort_kernel<<<(unsigned)nq, kThreads, 0, stream>>>(d_keys, reinterpret_cast<const long long *>(d_offsets), d_counts,
                                                             d_ids, d_d2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_radius_offsets(const int32_t *d_counts, int64_t nq, int64_t capacity, int64_t *d_offsets, int64_t *total_out,
+                                  cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  radius_offsets_kernel<<<1, kScanThreads, 0, stream>>>(d_counts, (long long)nq, (long long)capacity,
+                                                        reinterpret_cast<long long *>(d_offsets), reinterpret_cast<long long *>(total_out));
   return cudaGetLastError();
 }
 

@@ -62,6 +62,11 @@ cudaError_t launch_radius_fill(const IndexDev &idx, const float *d_queries, int6
                                int32_t *d_cursor, unsigned long long *d_keys, const KnnPlan &plan, cudaStream_t stream,
                                int64_t first = 0);
 
+// d_offsets = exclusive scan of d_counts (one block, device side), *total_out = sum (device-accessible host word); when the sum
+// exceeds `capacity` all offsets become -1 and the fill / sort launches that follow do nothing
+cudaError_t launch_radius_offsets(const int32_t *d_counts, int64_t nq, int64_t capacity, int64_t *d_offsets, int64_t *total_out,
+                                  cudaStream_t stream);
+
 // sorts every row of d_keys ascending and unpacks it into ids / d2
 cudaError_t launch_radius_sort(unsigned long long *d_keys, const int64_t *d_offsets, const int32_t *d_counts, int64_t nq,
                                int32_t *d_ids, float *d_d2, cudaStream_t stream);

@@ -575,7 +575,8 @@ __global__ void __launch_bounds__(kThreads, SFFG_RADIUS_MIN_BLOCKS) radius_prune
               int at = 0;
               if (lane == 0) at = atomicAdd(cursor + qi, __popc(mask));
               at = __shfl_sync(kFull, at, 0);
-              if (in) keys[offsets[qi] + at + __popc(mask & lt)] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)id;
+              const long long o = offsets[qi];   // negative: the device-side scan found the result buffers too small
+              if (in && o >= 0) keys[o + at + __popc(mask & lt)] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)id;
             }
           } else {
             cnt[w] += __popc(mask);

@@ -112,7 +112,18 @@ struct sffg_env {
   int64_t robot_bytes = 0;
   sffg_env_info_t info{};
   LaunchCfg cfg{};
+  // asynchronous form (sffg_check_edges_begin / sffg_check_moves_begin + sffg_env_end): what the end still has to do
+  struct Pending {
+    int kind = 0;   // 0 none, 1 edges, 2 moves
+    int64_t m = 0;
+    uint8_t *out = nullptr;
+    int32_t *first_out = nullptr;
+  } pend;
 };
+static int env_busy(const sffg_env *env, const char *who) {
+  if (env->pend.kind != 0) return fail(SFFG_ERR_ARG, std::string(who) + ": an asynchronous call on this environment is pending (sffg_env_end first)");
+  return SFFG_OK;
+}
 
 struct sffg_index {
   int dim = 0;
@@ -127,7 +138,26 @@ struct sffg_index {
   DevBuf s_coords, s_ids, s_bb, s_keys, s_vals, s_temp, s_bounds;
   int64_t n_sorted = 0, s_cap = 0, s_nblk_cap = 0;
   bool pruning = true;
+  // asynchronous form (sffg_*_begin / sffg_index_end): what the matching end still has to do.  One pending call per index.
+  struct HostCopy { void *dst; const void *src; size_t bytes; };
+  struct Pending {
+    int kind = 0;   // 0 none, 1 knn_multi, 2 radius, 3 add_multi
+    HostCopy copy[3];
+    int n_copy = 0;
+    // radius
+    int64_t nq = 0, capacity = 0, cap1 = 0;
+    float r2 = 0;
+    int32_t *counts_out = nullptr, *ids_out = nullptr;
+    float *d2_out = nullptr;
+    int64_t *total_out = nullptr;
+    bool small = false, one_sync = false, pruned = false;
+  } pend;
+  cudaEvent_t add_ev = nullptr;   // appends enqueued by sffg_index_add_multi_begin have run
 };
+static int index_busy(const sffg_index *idx, const char *who) {
+  if (idx->pend.kind != 0) return fail(SFFG_ERR_ARG, std::string(who) + ": an asynchronous call on this index is pending (sffg_index_end first)");
+  return SFFG_OK;
+}
 
 extern "C" {
 
@@ -639,6 +669,10 @@ static int env_leave(sffg_env *env, cudaStream_t st) {
 }
 // host-pointer calls run on the environment's own two streams and synchronise before they return
 static int env_enter_host(sffg_env *env) {
+  {
+    const int rc = env_busy(env, "sffg (host-pointer call)");
+    if (rc != SFFG_OK) return rc;
+  }
   if (env->order_pending) {
     SFFG_CUDA(cudaStreamWaitEvent(env->streams[0], env->order_ev, 0));
     SFFG_CUDA(cudaStreamWaitEvent(env->streams[1], env->order_ev, 0));
@@ -857,8 +891,38 @@ int sffg_check_edges_device(sffg_env *env, const double *d_starts, const double 
   return env_leave(env, (cudaStream_t)stream);
 }
 
+static int check_edges_impl(sffg_env *env, const double *starts, const double *ends, int64_t m, double sample_dist, int rot_mode,
+                            uint8_t *free_out, int32_t *first_hit_out, bool async);
 int sffg_check_edges(sffg_env *env, const double *starts, const double *ends, int64_t m, double sample_dist, int rot_mode,
                      uint8_t *free_out, int32_t *first_hit_out) {
+  return check_edges_impl(env, starts, ends, m, sample_dist, rot_mode, free_out, first_hit_out, false);
+}
+int sffg_check_edges_begin(sffg_env *env, const double *starts, const double *ends, int64_t m, double sample_dist, int rot_mode,
+                           uint8_t *free_out, int32_t *first_hit_out) {
+  return check_edges_impl(env, starts, ends, m, sample_dist, rot_mode, free_out, first_hit_out, true);
+}
+
+// completes the asynchronous call pending on this environment (no-op when none is)
+int sffg_env_end(sffg_env *env) {
+  if (!env) return fail(SFFG_ERR_ARG, "sffg_env_end: null environment");
+  if (env->pend.kind == 0) return SFFG_OK;
+  const sffg_env::Pending c = env->pend;
+  env->pend.kind = 0;
+  SFFG_CUDA(cudaStreamSynchronize(env->streams[0]));
+  if (c.kind == 1) {
+    const int32_t *h_first = reinterpret_cast<const int32_t *>(env->h_small + kSmallIn);
+    const uint8_t *h_free = env->h_small + kSmallIn + (size_t)c.m * 4;
+    std::memcpy(c.out, h_free, (size_t)c.m);
+    if (c.first_out) std::memcpy(c.first_out, h_first, (size_t)c.m * 4);
+  } else {
+    const uint8_t *h_free = env->h_small + kSmallIn, *h_hit = h_free + (size_t)c.m;
+    for (int64_t i = 0; i < c.m; ++i) c.out[i] = (uint8_t)(h_free[i] && !h_hit[i]);
+  }
+  return check_status(env);
+}
+
+static int check_edges_impl(sffg_env *env, const double *starts, const double *ends, int64_t m, double sample_dist, int rot_mode,
+                            uint8_t *free_out, int32_t *first_hit_out, bool async) {
   if (!env || m < 0 || (m > 0 && (!starts || !ends || !free_out)) || !(sample_dist > 0) ||
       (rot_mode != SFFG_ROT_REFERENCE && rot_mode != SFFG_ROT_INTERPOLATE))
     return fail(SFFG_ERR_ARG, "sffg_check_edges: bad arguments");
@@ -884,10 +948,11 @@ int sffg_check_edges(sffg_env *env, const double *starts, const double *ends, in
     EnvDev v = env_view(env, &base);
     SFFG_CUDA(launch_check_edges(v, ds, de, m, sample_dist, rot_mode, h_free, h_first, st, env->cfg, env->count, base,
                                  (int *)env->fh.p));
-    SFFG_CUDA(cudaStreamSynchronize(st));
-    std::memcpy(free_out, h_free, (size_t)m);
-    if (first_hit_out) std::memcpy(first_hit_out, h_first, (size_t)m * 4);
-    return check_status(env);
+    env->pend.kind = 1;
+    env->pend.m = m;
+    env->pend.out = free_out;
+    env->pend.first_out = first_hit_out;
+    return async ? SFFG_OK : sffg_env_end(env);
   }
   const int64_t chunk = 1 << 18;
   int s = 0;
@@ -914,8 +979,18 @@ int sffg_check_edges(sffg_env *env, const double *starts, const double *ends, in
   return check_status(env);
 }
 
+static int check_moves_impl(sffg_env *env, const double *starts, const double *ends, int64_t m, double sample_dist, int rot_mode,
+                            uint8_t *ok_out, bool async);
 int sffg_check_moves(sffg_env *env, const double *starts, const double *ends, int64_t m, double sample_dist, int rot_mode,
                      uint8_t *ok_out) {
+  return check_moves_impl(env, starts, ends, m, sample_dist, rot_mode, ok_out, false);
+}
+int sffg_check_moves_begin(sffg_env *env, const double *starts, const double *ends, int64_t m, double sample_dist, int rot_mode,
+                           uint8_t *ok_out) {
+  return check_moves_impl(env, starts, ends, m, sample_dist, rot_mode, ok_out, true);
+}
+static int check_moves_impl(sffg_env *env, const double *starts, const double *ends, int64_t m, double sample_dist, int rot_mode,
+                            uint8_t *ok_out, bool async) {
   if (!env || m < 0 || (m > 0 && (!starts || !ends || !ok_out)) || !(sample_dist > 0) ||
       (rot_mode != SFFG_ROT_REFERENCE && rot_mode != SFFG_ROT_INTERPOLATE))
     return fail(SFFG_ERR_ARG, "sffg_check_moves: bad arguments");
@@ -942,9 +1017,11 @@ int sffg_check_moves(sffg_env *env, const double *starts, const double *ends, in
     EnvDev w = env_view(env, &base);
     SFFG_CUDA(launch_check_edges(w, ds, de, m, sample_dist, rot_mode, h_free, nullptr, st, env->cfg, env->count, base,
                                  (int *)env->fh.p));
-    SFFG_CUDA(cudaStreamSynchronize(st));
-    for (int64_t i = 0; i < m; ++i) ok_out[i] = (uint8_t)(h_free[i] && !h_hit[i]);
-    return check_status(env);
+    env->pend.kind = 2;
+    env->pend.m = m;
+    env->pend.out = ok_out;
+    env->pend.first_out = nullptr;
+    return async ? SFFG_OK : sffg_env_end(env);
   }
   std::vector<uint8_t> hit((size_t)m);
   int rc = sffg_collide_poses_f64(env, ends, m, hit.data());
@@ -974,6 +1051,7 @@ int sffg_index_create(int dim, sffg_index **out) {
   idx->pruning = !(pr && pr[0] == '0');
   cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->ev, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->add_ev, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaHostAlloc((void **)&idx->h_small, kSmallBytes, cudaHostAllocMapped);
   if (e == cudaSuccess) {   // storage exists from the start: the scan kernels may touch the first block of an empty index
     idx->cap = 4096 + 128;
@@ -987,6 +1065,8 @@ int sffg_index_create(int dim, sffg_index **out) {
     cudaFree(idx->d_amax);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     if (idx->ev) cudaEventDestroy(idx->ev);
+  if (idx->add_ev) cudaEventDestroy(idx->add_ev);
+    if (idx->add_ev) cudaEventDestroy(idx->add_ev);
     if (idx->h_small) cudaFreeHost(idx->h_small);
     delete idx;
     return fail(SFFG_ERR_CUDA, cudaGetErrorString(e));
@@ -1005,6 +1085,7 @@ int sffg_index_destroy(sffg_index *idx) {
   for (DevBuf *b : bufs) b->release();
   if (idx->h_small) cudaFreeHost(idx->h_small);
   if (idx->ev) cudaEventDestroy(idx->ev);
+  if (idx->add_ev) cudaEventDestroy(idx->add_ev);
   if (idx->stream) cudaStreamDestroy(idx->stream);
   delete idx;
   return SFFG_OK;
@@ -1042,7 +1123,9 @@ int sffg_index_add_device(sffg_index *idx, const float *d_pts, int64_t n, void *
 int sffg_index_add(sffg_index *idx, const float *pts, int64_t n) {
   if (!idx || n < 0 || (n > 0 && !pts)) return fail(SFFG_ERR_ARG, "sffg_index_add: bad arguments");
   if (n == 0) return SFFG_OK;
-  int rc = idx->stage.reserve((size_t)n * idx->dim * sizeof(float));
+  int rc = index_busy(idx, "sffg_index_add");
+  if (rc != SFFG_OK) return rc;
+  rc = idx->stage.reserve((size_t)n * idx->dim * sizeof(float));
   if (rc != SFFG_OK) return rc;
   SFFG_CUDA(cudaMemcpyAsync(idx->stage.p, pts, (size_t)n * idx->dim * sizeof(float), cudaMemcpyHostToDevice, idx->stream));
   rc = sffg_index_add_device(idx, (const float *)idx->stage.p, n, idx->stream);
@@ -1051,7 +1134,7 @@ int sffg_index_add(sffg_index *idx, const float *pts, int64_t n) {
   return SFFG_OK;
 }
 
-int sffg_index_add_multi(sffg_index *const *idx, const int64_t *n_per, int n_idx, const float *pts) {
+int sffg_index_add_multi_begin(sffg_index *const *idx, const int64_t *n_per, int n_idx, const float *pts) {
   if (!idx || !n_per || n_idx < 1) return fail(SFFG_ERR_ARG, "sffg_index_add_multi: bad arguments");
   int64_t total = 0;
   const int dim = idx[0] ? idx[0]->dim : 0;
@@ -1063,6 +1146,8 @@ int sffg_index_add_multi(sffg_index *const *idx, const int64_t *n_per, int n_idx
   if (!pts) return fail(SFFG_ERR_ARG, "sffg_index_add_multi: null points");
   int rc;
   sffg_index *lead = idx[0];   // one staging buffer, one upload, one synchronisation for all indices
+  for (int i = 0; i < n_idx; ++i)
+    if ((rc = index_busy(idx[i], "sffg_index_add_multi")) != SFFG_OK) return rc;
   cudaStream_t st = lead->stream;
   const size_t bytes = (size_t)total * dim * sizeof(float);
   rc = lead->stage.reserve(bytes);
@@ -1080,8 +1165,19 @@ int sffg_index_add_multi(sffg_index *const *idx, const int64_t *n_per, int n_idx
     if (rc != SFFG_OK) return rc;
     off += n_per[i];
   }
-  SFFG_CUDA(cudaStreamSynchronize(st));
+  // the appends ran on the lead's stream: later work on the other indices' own streams is ordered behind them
+  SFFG_CUDA(cudaEventRecord(lead->add_ev, st));
+  for (int i = 0; i < n_idx; ++i)
+    if (idx[i] != lead && n_per[i] > 0) SFFG_CUDA(cudaStreamWaitEvent(idx[i]->stream, lead->add_ev, 0));
+  lead->pend = sffg_index::Pending{};
+  lead->pend.kind = 3;   // (the staging area of the lead is in use until sffg_index_end)
   return SFFG_OK;
+}
+
+int sffg_index_add_multi(sffg_index *const *idx, const int64_t *n_per, int n_idx, const float *pts) {
+  const int rc = sffg_index_add_multi_begin(idx, n_per, n_idx, pts);
+  if (rc != SFFG_OK) return rc;
+  return idx[0]->pend.kind == 3 ? sffg_index_end(idx[0]) : SFFG_OK;
 }
 
 constexpr int64_t kSortMinNodes = 8192;   // below this the exhaustive scan is already latency-bound
@@ -1195,7 +1291,8 @@ int sffg_knn(sffg_index *idx, const float *queries, int64_t nq, int k, int32_t *
   if (!idx || nq < 0 || k < 1 || k > SFFG_MAX_K || (nq > 0 && (!queries || !ids_out || !d2_out)))
     return fail(SFFG_ERR_ARG, "sffg_knn: bad arguments (1 <= k <= 128)");
   if (nq == 0) return SFFG_OK;
-  int rc;
+  int rc = index_busy(idx, "sffg_knn");
+  if (rc != SFFG_OK) return rc;
   const size_t qbytes = (size_t)nq * idx->dim * 4, obytes = (size_t)nq * k * 4;
   if (qbytes <= (64 << 10) && 2 * obytes <= kSmallBytes - (64 << 10)) {
     // planner-sized call: queries and results live in pinned mapped memory, one synchronisation
@@ -1226,8 +1323,8 @@ int sffg_knn(sffg_index *idx, const float *queries, int64_t nq, int k, int32_t *
   return SFFG_OK;
 }
 
-int sffg_knn_multi(sffg_index *const *idx, const int64_t *nq_per, int n_idx, const float *queries, int k, int32_t *ids_out,
-                   float *d2_out) {
+int sffg_knn_multi_begin(sffg_index *const *idx, const int64_t *nq_per, int n_idx, const float *queries, int k, int32_t *ids_out,
+                         float *d2_out) {
   if (!idx || !nq_per || n_idx < 1 || k < 1 || k > SFFG_MAX_K) return fail(SFFG_ERR_ARG, "sffg_knn_multi: bad arguments");
   int64_t total = 0;
   const int dim = idx[0] ? idx[0]->dim : 0;
@@ -1239,6 +1336,8 @@ int sffg_knn_multi(sffg_index *const *idx, const int64_t *nq_per, int n_idx, con
   if (!queries || !ids_out || !d2_out) return fail(SFFG_ERR_ARG, "sffg_knn_multi: null buffers");
   int rc;
   sffg_index *lead = idx[0];   // its stream and staging carry the whole call
+  for (int i = 0; i < n_idx; ++i)
+    if ((rc = index_busy(idx[i], "sffg_knn_multi")) != SFFG_OK) return rc;
   cudaStream_t st = lead->stream;
   const size_t qbytes = (size_t)total * dim * 4, obytes = (size_t)total * k * 4;
   const bool small = qbytes <= (64 << 10) && 2 * obytes <= kSmallBytes - (64 << 10);
@@ -1268,28 +1367,89 @@ int sffg_knn_multi(sffg_index *const *idx, const int64_t *nq_per, int n_idx, con
     }
     off += nq_per[i];
   }
+  lead->pend = sffg_index::Pending{};
+  lead->pend.kind = 1;
   if (small) {
     unsigned char *ho = lead->h_small + (64 << 10);
     SFFG_CUDA(cudaMemcpyAsync(ho, lead->ids.p, obytes, cudaMemcpyDeviceToHost, st));
     SFFG_CUDA(cudaMemcpyAsync(ho + obytes, lead->d2.p, obytes, cudaMemcpyDeviceToHost, st));
-    SFFG_CUDA(cudaStreamSynchronize(st));
-    std::memcpy(ids_out, ho, obytes);
-    std::memcpy(d2_out, ho + obytes, obytes);
+    lead->pend.copy[0] = {ids_out, ho, obytes};
+    lead->pend.copy[1] = {d2_out, ho + obytes, obytes};
+    lead->pend.n_copy = 2;
   } else {
     SFFG_CUDA(cudaMemcpyAsync(ids_out, lead->ids.p, obytes, cudaMemcpyDeviceToHost, st));
     SFFG_CUDA(cudaMemcpyAsync(d2_out, lead->d2.p, obytes, cudaMemcpyDeviceToHost, st));
+  }
+  return SFFG_OK;
+}
+
+int sffg_knn_multi(sffg_index *const *idx, const int64_t *nq_per, int n_idx, const float *queries, int k, int32_t *ids_out,
+                   float *d2_out) {
+  const int rc = sffg_knn_multi_begin(idx, nq_per, n_idx, queries, k, ids_out, d2_out);
+  if (rc != SFFG_OK) return rc;
+  return idx[0]->pend.kind == 1 ? sffg_index_end(idx[0]) : SFFG_OK;
+}
+
+// second half of a radius call once the counts are on the host: exclusive scan, fill, per-row sort, download
+static int radius_fill_from_host_counts(sffg_index *idx, const sffg_index::Pending &c, int64_t total) {
+  int rc;
+  cudaStream_t st = idx->stream;
+  IndexDev v{idx->d_coords, idx->cap, idx->n, idx->dim, idx->d_amax};
+  const KnnPlan plan = plan_knn(c.nq, idx->n, g_rt.sm_count);
+  const SortedDev sv = sorted_view(idx);
+  const size_t cbytes = (size_t)c.nq * 4;
+  unsigned char *hq = idx->h_small, *hr = idx->h_small + (128 << 10);
+  const size_t hr_bytes = kSmallBytes - (128 << 10);
+  std::vector<int64_t> offs((size_t)c.nq);
+  int64_t run = 0;
+  for (int64_t i = 0; i < c.nq; ++i) {
+    offs[(size_t)i] = run;
+    run += c.counts_out[i];
+  }
+  rc = idx->offsets.reserve((size_t)c.nq * 8);
+  if (rc == SFFG_OK) rc = idx->cursor.reserve(cbytes);
+  if (rc == SFFG_OK) rc = idx->keys.reserve((size_t)total * 8);
+  if (rc == SFFG_OK) rc = idx->ids.reserve((size_t)total * 4);
+  if (rc == SFFG_OK) rc = idx->d2.reserve((size_t)total * 4);
+  if (rc != SFFG_OK) return rc;
+  const bool small_out = c.small && (size_t)c.nq * 8 <= (64 << 10) && (size_t)total * 8 <= hr_bytes;
+  if (small_out) {
+    std::memcpy(hq, offs.data(), (size_t)c.nq * 8);   // the query staging area is free again
+    SFFG_CUDA(cudaMemcpyAsync(idx->offsets.p, hq, (size_t)c.nq * 8, cudaMemcpyHostToDevice, st));
+  } else {
+    SFFG_CUDA(cudaMemcpyAsync(idx->offsets.p, offs.data(), (size_t)c.nq * 8, cudaMemcpyHostToDevice, st));
+  }
+  SFFG_CUDA(cudaMemsetAsync(idx->cursor.p, 0, cbytes, st));
+  if (c.pruned)
+    SFFG_CUDA(launch_radius_fill_pruned(v, sv, (const float *)idx->q.p, c.nq, c.r2, (const int64_t *)idx->offsets.p, (int32_t *)idx->cursor.p,
+                                        (unsigned long long *)idx->keys.p, g_rt.sm_count, st));
+  else
+    SFFG_CUDA(launch_radius_fill(v, (const float *)idx->q.p, c.nq, c.r2, (const int64_t *)idx->offsets.p, (int32_t *)idx->cursor.p,
+                                 (unsigned long long *)idx->keys.p, plan, st));
+  SFFG_CUDA(launch_radius_sort((unsigned long long *)idx->keys.p, (const int64_t *)idx->offsets.p, (const int32_t *)idx->counts.p,
+                               c.nq, (int32_t *)idx->ids.p, (float *)idx->d2.p, st));
+  if (small_out) {
+    SFFG_CUDA(cudaMemcpyAsync(hr, idx->ids.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+    SFFG_CUDA(cudaMemcpyAsync(hr + (size_t)total * 4, idx->d2.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+    SFFG_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(c.ids_out, hr, (size_t)total * 4);
+    std::memcpy(c.d2_out, hr + (size_t)total * 4, (size_t)total * 4);
+  } else {
+    SFFG_CUDA(cudaMemcpyAsync(c.ids_out, idx->ids.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+    SFFG_CUDA(cudaMemcpyAsync(c.d2_out, idx->d2.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
     SFFG_CUDA(cudaStreamSynchronize(st));
   }
   return SFFG_OK;
 }
 
-int sffg_radius(sffg_index *idx, const float *queries, int64_t nq, float r2, int32_t *counts_out, int32_t *ids_out,
-                float *d2_out, int64_t capacity, int64_t *total_out) {
+int sffg_radius_begin(sffg_index *idx, const float *queries, int64_t nq, float r2, int32_t *counts_out, int32_t *ids_out,
+                      float *d2_out, int64_t capacity, int64_t *total_out) {
   if (!idx || nq < 0 || (nq > 0 && (!queries || !counts_out)) || (ids_out && !d2_out))
     return fail(SFFG_ERR_ARG, "sffg_radius: bad arguments");
   if (total_out) *total_out = 0;
   if (nq == 0) return SFFG_OK;
-  int rc;
+  int rc = index_busy(idx, "sffg_radius");
+  if (rc != SFFG_OK) return rc;
   cudaStream_t st = idx->stream;
   IndexDev v{idx->d_coords, idx->cap, idx->n, idx->dim, idx->d_amax};
   KnnPlan plan = plan_knn(nq, idx->n, g_rt.sm_count);
@@ -1315,53 +1475,88 @@ int sffg_radius(sffg_index *idx, const float *queries, int64_t nq, float r2, int
   if (pruned) SFFG_CUDA(launch_radius_count_pruned(v, sv, (const float *)idx->q.p, nq, r2, (int32_t *)idx->counts.p, g_rt.sm_count, st));
   else SFFG_CUDA(launch_radius_count(v, (const float *)idx->q.p, nq, r2, (int32_t *)idx->counts.p, plan, st));
   SFFG_CUDA(cudaMemcpyAsync(small ? (void *)hc : (void *)counts_out, idx->counts.p, cbytes, cudaMemcpyDeviceToHost, st));
-  SFFG_CUDA(cudaStreamSynchronize(st));
-  if (small) std::memcpy(counts_out, hc, cbytes);
-  std::vector<int64_t> offs((size_t)nq);
-  int64_t total = 0;
-  for (int64_t i = 0; i < nq; ++i) {
-    offs[(size_t)i] = total;
-    total += counts_out[i];
-  }
-  if (total_out) *total_out = total;
-  if (!ids_out || total == 0) return SFFG_OK;
-  if (capacity < total)
-    return fail(SFFG_ERR_CAPACITY, "sffg_radius: result buffers hold " + std::to_string(capacity) + " entries, " +
-                                       std::to_string(total) + " needed");
-  rc = idx->offsets.reserve((size_t)nq * 8);
-  if (rc == SFFG_OK) rc = idx->cursor.reserve(cbytes);
-  if (rc == SFFG_OK) rc = idx->keys.reserve((size_t)total * 8);
-  if (rc == SFFG_OK) rc = idx->ids.reserve((size_t)total * 4);
-  if (rc == SFFG_OK) rc = idx->d2.reserve((size_t)total * 4);
-  if (rc != SFFG_OK) return rc;
-  const bool small_out = small && (size_t)nq * 8 <= (64 << 10) && (size_t)total * 8 <= hr_bytes;
-  if (small_out) {
-    std::memcpy(hq, offs.data(), (size_t)nq * 8);   // the query staging area is free again
-    SFFG_CUDA(cudaMemcpyAsync(idx->offsets.p, hq, (size_t)nq * 8, cudaMemcpyHostToDevice, st));
-  } else {
-    SFFG_CUDA(cudaMemcpyAsync(idx->offsets.p, offs.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
-  }
-  SFFG_CUDA(cudaMemsetAsync(idx->cursor.p, 0, cbytes, st));
-  if (pruned)
-    SFFG_CUDA(launch_radius_fill_pruned(v, sv, (const float *)idx->q.p, nq, r2, (const int64_t *)idx->offsets.p, (int32_t *)idx->cursor.p,
-                                        (unsigned long long *)idx->keys.p, g_rt.sm_count, st));
-  else
-    SFFG_CUDA(launch_radius_fill(v, (const float *)idx->q.p, nq, r2, (const int64_t *)idx->offsets.p, (int32_t *)idx->cursor.p,
-                                 (unsigned long long *)idx->keys.p, plan, st));
-  SFFG_CUDA(launch_radius_sort((unsigned long long *)idx->keys.p, (const int64_t *)idx->offsets.p, (const int32_t *)idx->counts.p,
-                               nq, (int32_t *)idx->ids.p, (float *)idx->d2.p, st));
-  if (small_out) {
-    SFFG_CUDA(cudaMemcpyAsync(hr, idx->ids.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-    SFFG_CUDA(cudaMemcpyAsync(hr + (size_t)total * 4, idx->d2.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-    SFFG_CUDA(cudaStreamSynchronize(st));
-    std::memcpy(ids_out, hr, (size_t)total * 4);
-    std::memcpy(d2_out, hr + (size_t)total * 4, (size_t)total * 4);
-  } else {
-    SFFG_CUDA(cudaMemcpyAsync(ids_out, idx->ids.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-    SFFG_CUDA(cudaMemcpyAsync(d2_out, idx->d2.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-    SFFG_CUDA(cudaStreamSynchronize(st));
+  sffg_index::Pending &c = idx->pend;
+  c = sffg_index::Pending{};
+  c.kind = 2;
+  c.nq = nq;
+  c.capacity = capacity;
+  c.r2 = r2;
+  c.counts_out = counts_out;
+  c.ids_out = ids_out;
+  c.d2_out = d2_out;
+  c.total_out = total_out;
+  c.small = small;
+  c.pruned = pruned;
+  if (small) c.copy[c.n_copy++] = {counts_out, hc, cbytes};
+  // Planner-sized call with result buffers: the exclusive scan of the counts runs on the device, so that count, scan, fill
+  // and sort are enqueued back to back and the call costs ONE host synchronisation.  The rows land in pinned mapped
+  // memory ([total][ids][d2] in the result part of the staging area); when they do not fit there, or not into the
+  // caller's capacity, the kernels after the scan do nothing and sffg_index_end takes the two-synchronisation route.
+  c.cap1 = std::min<int64_t>(capacity, (int64_t)((hr_bytes - 8) / 8));
+  c.one_sync = small && ids_out && c.cap1 > 0;
+  if (c.one_sync) {
+    rc = idx->offsets.reserve((size_t)nq * 8);
+    if (rc == SFFG_OK) rc = idx->cursor.reserve(cbytes);
+    if (rc == SFFG_OK) rc = idx->keys.reserve((size_t)c.cap1 * 8);
+    if (rc != SFFG_OK) {
+      c.kind = 0;
+      return rc;
+    }
+    int64_t *h_total = reinterpret_cast<int64_t *>(hr);
+    int32_t *h_ids = reinterpret_cast<int32_t *>(hr + 8);
+    float *h_d2 = reinterpret_cast<float *>(hr + 8 + (size_t)c.cap1 * 4);
+    *h_total = -1;
+    SFFG_CUDA(launch_radius_offsets((const int32_t *)idx->counts.p, nq, c.cap1, (int64_t *)idx->offsets.p, h_total, st));
+    SFFG_CUDA(cudaMemsetAsync(idx->cursor.p, 0, cbytes, st));
+    if (pruned)
+      SFFG_CUDA(launch_radius_fill_pruned(v, sv, (const float *)idx->q.p, nq, r2, (const int64_t *)idx->offsets.p, (int32_t *)idx->cursor.p,
+                                          (unsigned long long *)idx->keys.p, g_rt.sm_count, st));
+    else
+      SFFG_CUDA(launch_radius_fill(v, (const float *)idx->q.p, nq, r2, (const int64_t *)idx->offsets.p, (int32_t *)idx->cursor.p,
+                                   (unsigned long long *)idx->keys.p, plan, st));
+    SFFG_CUDA(launch_radius_sort((unsigned long long *)idx->keys.p, (const int64_t *)idx->offsets.p, (const int32_t *)idx->counts.p, nq,
+                                 h_ids, h_d2, st));
   }
   return SFFG_OK;
+}
+
+// completes the asynchronous call pending on this index (no-op when none is)
+int sffg_index_end(sffg_index *idx) {
+  if (!idx) return fail(SFFG_ERR_ARG, "sffg_index_end: null index");
+  if (idx->pend.kind == 0) return SFFG_OK;
+  const sffg_index::Pending c = idx->pend;
+  idx->pend.kind = 0;
+  SFFG_CUDA(cudaStreamSynchronize(idx->stream));
+  for (int i = 0; i < c.n_copy; ++i) std::memcpy(c.copy[i].dst, c.copy[i].src, c.copy[i].bytes);
+  if (c.kind != 2) return SFFG_OK;
+  int64_t total = 0;
+  if (c.one_sync) {
+    unsigned char *hr = idx->h_small + (128 << 10);
+    total = *reinterpret_cast<const int64_t *>(hr);
+    if (total < 0) return fail(SFFG_ERR_INTERNAL, "sffg_radius: the device-side scan did not report a total");
+    if (c.total_out) *c.total_out = total;
+    if (total == 0) return SFFG_OK;
+    if (total <= c.cap1) {
+      std::memcpy(c.ids_out, hr + 8, (size_t)total * 4);
+      std::memcpy(c.d2_out, hr + 8 + (size_t)c.cap1 * 4, (size_t)total * 4);
+      return SFFG_OK;
+    }
+  } else {
+    for (int64_t i = 0; i < c.nq; ++i) total += c.counts_out[i];
+    if (c.total_out) *c.total_out = total;
+    if (!c.ids_out || total == 0) return SFFG_OK;
+  }
+  if (c.capacity < total)
+    return fail(SFFG_ERR_CAPACITY, "sffg_radius: result buffers hold " + std::to_string(c.capacity) + " entries, " +
+                                       std::to_string(total) + " needed");
+  return radius_fill_from_host_counts(idx, c, total);
+}
+
+int sffg_radius(sffg_index *idx, const float *queries, int64_t nq, float r2, int32_t *counts_out, int32_t *ids_out,
+                float *d2_out, int64_t capacity, int64_t *total_out) {
+  const int rc = sffg_radius_begin(idx, queries, nq, r2, counts_out, ids_out, d2_out, capacity, total_out);
+  if (rc != SFFG_OK) return rc;
+  return idx->pend.kind == 2 ? sffg_index_end(idx) : SFFG_OK;
 }
 
 }  // extern "C"

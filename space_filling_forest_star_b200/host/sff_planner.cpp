@@ -405,7 +405,9 @@ class Planner {
         per.push_back(cnt);
       }
     }
-    check(sffg_index_add_multi(idx.data(), per.data(), (int)idx.size(), rows.data()));
+    // enqueued, not awaited: the appends are ordered before every later search on these indices by the engine, and the
+    // host goes on to pick and sample the next round; the wait (free by then) sits in front of the next radius search
+    check(sffg_index_add_multi_begin(idx.data(), per.data(), (int)idx.size(), rows.data()));
     ++calls_;
     pending_.clear();
   }
@@ -444,6 +446,48 @@ class Planner {
            out[2] >= cfg_.range[4] && out[2] <= cfg_.range[5];
   }
 
+  // one sffg_knn_multi over all trees, in flight between start_knn and finish_knn: queries concatenated in tree order
+  struct KnnAsync {
+    int k = 0;
+    std::vector<int> who;
+    std::vector<float> q;
+    std::vector<int32_t> ids;
+    std::vector<float> d2;
+    bool pending = false;
+  };
+  void start_knn(const std::vector<Cand> &cand, const std::vector<int> &alive, KnnAsync &ka) {
+    const int dim = cfg_.dim, T = (int)tree_idx_.size();
+    ka.k = (int)std::min<double>(2 * M_E * std::log10((double)nodes_.size()), (double)SFFG_MAX_K);   // forest.h:309
+    if (ka.k < 1 || alive.empty()) return;
+    std::vector<int64_t> per(T, 0);
+    for (int t = 0; t < T; ++t)
+      for (int ci : alive)
+        if (nodes_[cand[ci].exp].tree == t) {
+          ka.who.push_back(ci);
+          ++per[t];
+        }
+    ka.q.resize(ka.who.size() * (size_t)dim);
+    for (size_t i = 0; i < ka.who.size(); ++i)
+      for (int c = 0; c < dim; ++c) ka.q[i * dim + c] = (float)cand[ka.who[i]].p[c];
+    ka.ids.resize(ka.who.size() * (size_t)ka.k);
+    ka.d2.resize(ka.ids.size());
+    check(sffg_knn_multi_begin(tree_idx_.data(), per.data(), T, ka.q.data(), ka.k, ka.ids.data(), ka.d2.data()));
+    ka.pending = true;
+    ++calls_;
+    n_queries_ += (long)ka.who.size();
+  }
+  void finish_knn(std::vector<Cand> &cand, KnnAsync &ka) {
+    if (!ka.pending) return;
+    check(sffg_index_end(tree_idx_[0]));
+    ka.pending = false;
+    const int k = ka.k;
+    for (size_t i = 0; i < ka.who.size(); ++i) {
+      Cand &c = cand[ka.who[i]];
+      const int t = nodes_[c.exp].tree;
+      for (int j = 0; j < k && ka.ids[i * k + j] >= 0; ++j) c.knn.push_back(members_[t][ka.ids[i * k + j]]);
+    }
+  }
+
   void run_round(const std::vector<int> &chosen, std::vector<char> &exhausted) {
     const int B = (int)chosen.size(), A = cfg_.threshold_misses, dim = cfg_.dim;
     std::vector<Cand> cand((size_t)B * A);
@@ -479,6 +523,12 @@ class Planner {
       }
     }
     clk_.lap(1);
+    // ---- stage 4 (SFF*), started early: k nearest nodes of the same tree for EVERY valid candidate.  Only the first
+    // surviving attempt of a node will use its row (forest.h:306-351), but which attempt survives is known only after
+    // the crowding rule; the searches do not depend on it, so they are enqueued now (sffg_knn_multi_begin) and run on the
+    // tree indices' streams while the radius search and the crowding edges of this round are answered.
+    KnnAsync ka;
+    if (cfg_.optimize) start_knn(cand, alive, ka);
     // ---- stage 2: radius search over every tree (one global index == union of the per-tree searches).
     // The reference asks for everything within dtree + 2*circum (forest.h:261-267) but its rules only ever fire for
     // neighbours closer than max(parentDistance, dtree) (forest.h:276, :283); with an exact search the smaller radius
@@ -496,6 +546,7 @@ class Planner {
       int64_t total = 0;
       radius_ids_.resize(std::max<size_t>(radius_ids_.size(), alive.size() * 32));
       radius_d2_.resize(radius_ids_.size());
+      check(sffg_index_end(global_idx_));   // the appends of the previous round (enqueued by flush_index_appends)
       int rc = sffg_radius(global_idx_, q.data(), (int64_t)alive.size(), r2, counts.data(), radius_ids_.data(), radius_d2_.data(),
                            (int64_t)radius_ids_.size(), &total);
       ++calls_;
@@ -576,34 +627,7 @@ class Planner {
       }
     EdgeBatch eb2;
     if (cfg_.optimize) {
-      const int k = (int)std::min<double>(2 * M_E * std::log10((double)nodes_.size()), (double)SFFG_MAX_K);   // forest.h:309
-      const int T = (int)tree_idx_.size();
-      if (k >= 1) {
-        // one engine call for all trees: queries concatenated in tree order (sffg_knn_multi)
-        std::vector<int> who;
-        std::vector<int64_t> per(T, 0);
-        for (int t = 0; t < T; ++t)
-          for (int b = 0; b < B; ++b)
-            if (winners[b] >= 0 && nodes_[cand[winners[b]].exp].tree == t) {
-              who.push_back(winners[b]);
-              ++per[t];
-            }
-        if (!who.empty()) {
-          std::vector<float> q(who.size() * (size_t)dim);
-          for (size_t i = 0; i < who.size(); ++i)
-            for (int c = 0; c < dim; ++c) q[i * dim + c] = (float)cand[who[i]].p[c];
-          std::vector<int32_t> ids(who.size() * (size_t)k);
-          std::vector<float> d2(who.size() * (size_t)k);
-          check(sffg_knn_multi(tree_idx_.data(), per.data(), T, q.data(), k, ids.data(), d2.data()));
-          ++calls_;
-          n_queries_ += (long)who.size();
-          for (size_t i = 0; i < who.size(); ++i) {
-            Cand &c = cand[who[i]];
-            const int t = nodes_[c.exp].tree;
-            for (int j = 0; j < k && ids[i * k + j] >= 0; ++j) c.knn.push_back(members_[t][ids[i * k + j]]);
-          }
-        }
-      }
+      finish_knn(cand, ka);
       for (int b = 0; b < B; ++b) {
         if (winners[b] < 0) continue;
         Cand &c = cand[winners[b]];

@@ -172,4 +172,27 @@ SFFG_API int sffg_radius(sffg_index *idx, const float *queries, int64_t nq, floa
   return SFFG_OK;
 }
 
+// asynchronous forms: the double answers at once, the end calls have nothing left to do
+SFFG_API int sffg_radius_begin(sffg_index *idx, const float *queries, int64_t nq, float r2, int32_t *counts_out, int32_t *ids_out,
+                               float *d2_out, int64_t capacity, int64_t *total_out) {
+  return sffg_radius(idx, queries, nq, r2, counts_out, ids_out, d2_out, capacity, total_out);
+}
+SFFG_API int sffg_knn_multi_begin(sffg_index *const *idx, const int64_t *nq_per, int n_idx, const float *queries, int k,
+                                  int32_t *ids_out, float *d2_out) {
+  return sffg_knn_multi(idx, nq_per, n_idx, queries, k, ids_out, d2_out);
+}
+SFFG_API int sffg_index_add_multi_begin(sffg_index *const *idx, const int64_t *n_per, int n_idx, const float *pts) {
+  return sffg_index_add_multi(idx, n_per, n_idx, pts);
+}
+SFFG_API int sffg_index_end(sffg_index *) { return SFFG_OK; }
+SFFG_API int sffg_check_edges_begin(sffg_env *e, const double *starts, const double *ends, int64_t m, double sample_dist, int rot_mode,
+                                    uint8_t *free_out, int32_t *first_hit_out) {
+  return sffg_check_edges(e, starts, ends, m, sample_dist, rot_mode, free_out, first_hit_out);
+}
+SFFG_API int sffg_check_moves_begin(sffg_env *e, const double *starts, const double *ends, int64_t m, double sample_dist, int rot_mode,
+                                    uint8_t *ok_out) {
+  return sffg_check_moves(e, starts, ends, m, sample_dist, rot_mode, ok_out);
+}
+SFFG_API int sffg_env_end(sffg_env *) { return SFFG_OK; }
+
 }  // extern "C"
