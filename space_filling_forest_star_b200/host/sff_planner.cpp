@@ -446,6 +446,7 @@ class Planner {
            out[2] >= cfg_.range[4] && out[2] <= cfg_.range[5];
   }
 
+  static constexpr size_t kEarlyKnnRows = 192;   // rounds with at most this many valid candidates search before the crowding rule
   // one sffg_knn_multi over all trees, in flight between start_knn and finish_knn: queries concatenated in tree order
   struct KnnAsync {
     int k = 0;
@@ -523,12 +524,15 @@ class Planner {
       }
     }
     clk_.lap(1);
-    // ---- stage 4 (SFF*), started early: k nearest nodes of the same tree for EVERY valid candidate.  Only the first
+    // ---- stage 4 (SFF*), started early in small rounds: k nearest nodes of the same tree for EVERY valid candidate.  Only the first
     // surviving attempt of a node will use its row (forest.h:306-351), but which attempt survives is known only after
     // the crowding rule; the searches do not depend on it, so they are enqueued now (sffg_knn_multi_begin) and run on the
     // tree indices' streams while the radius search and the crowding edges of this round are answered.
+    // (Latency-bound rounds only: with many candidates per round the extra rows cost more than the hidden call saves --
+    // measured on the 6-tree scenes --, and the search is started for the winners alone once they are known.)
     KnnAsync ka;
-    if (cfg_.optimize) start_knn(cand, alive, ka);
+    const bool early_knn = cfg_.optimize && alive.size() <= kEarlyKnnRows;
+    if (early_knn) start_knn(cand, alive, ka);
     // ---- stage 2: radius search over every tree (one global index == union of the per-tree searches).
     // The reference asks for everything within dtree + 2*circum (forest.h:261-267) but its rules only ever fire for
     // neighbours closer than max(parentDistance, dtree) (forest.h:276, :283); with an exact search the smaller radius
@@ -627,6 +631,12 @@ class Planner {
       }
     EdgeBatch eb2;
     if (cfg_.optimize) {
+      if (!early_knn) {
+        std::vector<int> won;
+        for (int b = 0; b < B; ++b)
+          if (winners[b] >= 0) won.push_back(winners[b]);
+        start_knn(cand, won, ka);
+      }
       finish_knn(cand, ka);
       for (int b = 0; b < B; ++b) {
         if (winners[b] < 0) continue;
