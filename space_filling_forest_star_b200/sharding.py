@@ -83,6 +83,53 @@ def sharded_knn(index, queries: torch.Tensor, k: int, group=None) -> Tuple[torch
     return ids[:nq], d2[:nq]
 
 
+def sharded_radius(index, queries, radius_sq: float, device="cpu", group=None):
+    """Radius search with the query rows split over the ranks (node set replicated).  Rows have variable length, so the
+    exchange is the counts first, then the packed rows padded to the largest per-rank total (all-gather of the
+    counts -> exclusive scan -> padded all-gather of the rows).  ``queries``: numpy / CPU tensor [nq][dim], identical on
+    every rank; ``device``: where the collective runs ("cuda" for NCCL, "cpu" for gloo).
+    -> (counts int32 [nq], offsets int64 [nq + 1], ids int32 [total], d2 float32 [total]) on every rank, rows in query order,
+    each row sorted by (d2, id) -- exactly what ``Index.radiusSearch`` returns for the whole batch."""
+    import numpy as np
+    q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32))
+    nq = q.shape[0]
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if nq == 0:   # (the same on every rank: nothing to exchange)
+        return (torch.zeros(0, dtype=torch.int32, device=device), torch.zeros(1, dtype=torch.int64, device=device),
+                torch.zeros(0, dtype=torch.int32, device=device), torch.zeros(0, dtype=torch.float32, device=device))
+    b, e, per = shard_bounds(nq, rank, world)
+    if e > b:
+        c_loc, _, i_loc, d_loc = index.radiusSearch(q[b:e], radius_sq)
+    else:
+        c_loc, i_loc, d_loc = np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float32)
+    if world == 1:
+        off = np.zeros(nq + 1, dtype=np.int64)
+        np.cumsum(c_loc, out=off[1:])
+        return (torch.from_numpy(np.ascontiguousarray(c_loc)), torch.from_numpy(off), torch.from_numpy(np.ascontiguousarray(i_loc)),
+                torch.from_numpy(np.ascontiguousarray(d_loc)))
+    counts_pad = torch.zeros(per, dtype=torch.int32, device=device)
+    counts_pad[: e - b] = torch.from_numpy(np.ascontiguousarray(c_loc)).to(device)
+    counts_all = torch.empty(world * per, dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(counts_all, counts_pad, group=group)
+    totals = counts_all.view(world, per).sum(dim=1, dtype=torch.int64)          # rows per rank
+    width = int(totals.max().item())
+    rows = torch.zeros((2, max(width, 1)), dtype=torch.int32, device=device)      # ids and the bit patterns of d2, one exchange
+    if len(i_loc):
+        rows[0, : len(i_loc)] = torch.from_numpy(np.ascontiguousarray(i_loc)).to(device)
+        rows[1, : len(d_loc)] = torch.from_numpy(np.ascontiguousarray(d_loc).view(np.int32)).to(device)
+    rows_all = torch.empty((world * 2, max(width, 1)), dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(rows_all, rows, group=group)
+    rows_all = rows_all.view(world, 2, max(width, 1))
+    tot = [int(t) for t in totals.tolist()]
+    ids = torch.cat([rows_all[r, 0, : tot[r]] for r in range(world)])
+    d2 = torch.cat([rows_all[r, 1, : tot[r]] for r in range(world)]).view(torch.float32)
+    counts = counts_all[:nq]
+    offsets = torch.zeros(nq + 1, dtype=torch.int64, device=device)
+    torch.cumsum(counts.to(torch.int64), 0, out=offsets[1:])
+    return counts, offsets, ids, d2
+
+
 class PeerGather:
     """Verdict all-gather fused into the collision kernel (include/sffg.h "multi-GPU").
 

@@ -39,6 +39,11 @@ idx = S.Index(nodes)
 ids, d2 = sharded_knn(idx, torch.from_numpy(q).cuda(), 16)
 wi, wd = O.knn_linear(nodes, q, 16)
 assert np.array_equal(ids.cpu().numpy(), wi) and np.array_equal(d2.cpu().numpy().view(np.uint32), wd.view(np.uint32)), "sharded knn mismatch"
+from space_filling_forest_star_b200.sharding import sharded_radius
+rc, roff, rids, rd2 = sharded_radius(idx, q, 150.0, device="cuda")
+wc, woff, wri, wrd = O.radius_linear(nodes, q, 150.0)
+assert np.array_equal(rc.cpu().numpy(), wc) and np.array_equal(roff.cpu().numpy(), woff), "sharded radius counts mismatch"
+assert np.array_equal(rids.cpu().numpy(), wri) and np.array_equal(rd2.cpu().numpy().view(np.uint32), wrd.view(np.uint32)), "sharded radius rows mismatch"
 # verdict all-gather fused into the kernel's stores (peer memory over NVLink) == oracle, on every rank, over several steps
 from space_filling_forest_star_b200.sharding import PeerGather, shard_bounds, gathered_collide
 world = dist.get_world_size()

@@ -86,3 +86,39 @@ def test_sharded_knn_in_place_gather_gloo_world2(tmp_path, nq):
     port = 31500 + (os.getpid() + nq) % 2000
     mp.spawn(_knn_worker, args=(2, port, nq, 5, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").read_text() == "True" and (tmp_path / "ok1").read_text() == "True"
+
+
+class _FakeRadiusIndex:
+    """stands in for engine.Index.radiusSearch: row i holds (int(q[i,0]) % 5) entries derived from the query row alone"""
+
+    def radiusSearch(self, queries, radius_sq):
+        import numpy as np
+        cnt = (queries[:, 0].astype(np.int64) % 5).astype(np.int32)
+        off = np.zeros(len(queries) + 1, dtype=np.int64)
+        np.cumsum(cnt, out=off[1:])
+        ids = np.concatenate([np.arange(c, dtype=np.int32) + 10 * int(q0) for c, q0 in zip(cnt, queries[:, 0])] + [np.zeros(0, np.int32)])
+        d2 = ids.astype(np.float32) * np.float32(0.25) + np.float32(radius_sq)
+        return cnt, off, ids, d2
+
+
+def _radius_worker(rank, world, port, nq, tmp):
+    import numpy as np
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from space_filling_forest_star_b200.sharding import sharded_radius
+    q = np.stack([np.arange(nq, dtype=np.float32) * 3 + 1, np.zeros(nq, dtype=np.float32)], 1)
+    counts, offsets, ids, d2 = sharded_radius(_FakeRadiusIndex(), q, 2.0)
+    wc, woff, wi, wd = _FakeRadiusIndex().radiusSearch(q, 2.0)
+    ok = (np.array_equal(counts.numpy(), wc) and np.array_equal(offsets.numpy(), woff) and np.array_equal(ids.numpy(), wi)
+          and np.array_equal(d2.numpy().view(np.uint32), wd.view(np.uint32)))
+    Path(tmp, f"ok{rank}").write_text(str(ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nq", [0, 1, 2, 9, 500])
+def test_sharded_radius_variable_rows_gloo_world2(tmp_path, nq):
+    """counts first, then the packed rows padded to the largest per-rank total; every rank ends with the whole CSR result"""
+    port = 33500 + (os.getpid() + nq) % 2000
+    mp.spawn(_radius_worker, args=(2, port, nq, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").read_text() == "True" and (tmp_path / "ok1").read_text() == "True"
