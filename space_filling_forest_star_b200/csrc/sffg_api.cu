@@ -952,7 +952,8 @@ static int check_edges_impl(sffg_env *env, const double *starts, const double *e
     env->pend.m = m;
     env->pend.out = free_out;
     env->pend.first_out = first_hit_out;
-    return async ? SFFG_OK : sffg_env_end(env);
+    if (async) return env_leave(env, st);   // *_device launches issued before the end call are ordered behind this one
+    return sffg_env_end(env);
   }
   const int64_t chunk = 1 << 18;
   int s = 0;
@@ -1021,7 +1022,8 @@ static int check_moves_impl(sffg_env *env, const double *starts, const double *e
     env->pend.m = m;
     env->pend.out = ok_out;
     env->pend.first_out = nullptr;
-    return async ? SFFG_OK : sffg_env_end(env);
+    if (async) return env_leave(env, st);
+    return sffg_env_end(env);
   }
   std::vector<uint8_t> hit((size_t)m);
   int rc = sffg_collide_poses_f64(env, ends, m, hit.data());
