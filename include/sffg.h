@@ -247,7 +247,7 @@ SFFG_API int sffg_radius(sffg_index *idx, const float *queries, int64_t nq, floa
  * ask one question after the other; the batched hosts ask them per round, and the questions of one round that do not
  * depend on each other (the radius search over all trees, the per-tree k nearest, the edges of the crowding rule,
  * appending the round's new nodes) can be in flight together.  A *_begin call enqueues the whole call -- upload,
- * kernels, download -- and returns; the results are in the caller's buffers (which must stay alive) once the matching
+ * kernels, download -- and returns; the results are in the caller's buffers (which, like the inputs, must stay alive) once the matching
  * end call has returned: sffg_index_end(idx) for sffg_radius_begin, sffg_index_end(idx[0]) for sffg_knn_multi_begin and
  * sffg_index_add_multi_begin, sffg_env_end(env) for sffg_check_edges_begin / sffg_check_moves_begin.  Between begin
  * and end, calls on OTHER objects run concurrently on the GPU (every index and every environment has its own stream);
@@ -256,8 +256,9 @@ SFFG_API int sffg_radius(sffg_index *idx, const float *queries, int64_t nq, floa
  * calls on an index with a pending call share that index's scratch buffers and are the caller's to order.  Appends are ordered before
  * every later search on the indices they went to without any host synchronisation.  Batches too large for the pinned
  * staging area are simply executed by the begin call; the end call is then a no-op.  The blocking calls above are
- * begin + end.  sffg_radius (both forms) costs one host synchronisation for planner-sized batches: the exclusive scan of
- * the per-query counts runs on the device between the count and the fill kernel.                                       */
+ * begin + end.  sffg_radius (both forms) costs one host synchronisation for planner-sized batches: on indices of up to
+ * 32 768 nodes the whole search is one kernel (a block per query), on larger ones the exclusive scan of the per-query
+ * counts runs on the device between the count and the fill kernel.                                                     */
 SFFG_API int sffg_radius_begin(sffg_index *idx, const float *queries, int64_t nq, float r2, int32_t *counts_out,
                                int32_t *ids_out, float *d2_out, int64_t capacity, int64_t *total_out);
 SFFG_API int sffg_knn_multi_begin(sffg_index *const *idx, const int64_t *nq_per, int n_idx, const float *queries, int k,

@@ -308,6 +308,94 @@ __global__ void __launch_bounds__(kThreads) radius_sort_kernel(unsigned long lon
   }
 }
 
+// Planner-sized radius search in ONE kernel (small index, few queries): a block per query scans every node, gathers the
+// hits in shared memory, sorts them by (d2, id) and stores the row at a position it reserves in the packed output with one
+// atomic; the host re-orders the rows by query while it copies them out of the pinned staging area.  counts_out is exact
+// even when a row is too long for the shared buffer or the output is full -- those cases raise `overflow` and the caller
+// repeats the search on the count / scan / fill / sort path.
+constexpr int kFusedRowCap = 2048;
+template <int DIM>
+__global__ void __launch_bounds__(kThreads) radius_fused_kernel(IndexDev idx, const float *__restrict__ queries, float r2, long long out_cap,
+                                                                int *counts_out, long long *rowoff_out, int *ids_out, float *d2_out,
+                                                                unsigned long long *total, int *overflow) {
+  __shared__ unsigned long long sk[kFusedRowCap];
+  __shared__ int s_cnt;
+  __shared__ long long s_off;
+  const long long qi = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_cnt = 0;
+  float q[DIM];
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) q[c] = queries[qi * DIM + c];
+  bool wide = false;
+  if (DIM == 6) wide = wide_needed(q, __uint_as_float(__ldg(idx.amax)));
+  __syncthreads();
+  const unsigned lt = (1u << lane) - 1u;
+  for (long long b = (long long)warp * 32; b < idx.n; b += kThreads) {
+    const long long i = b + lane;
+    const bool valid = i < idx.n;
+    float nd[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) nd[c] = valid ? __ldg(idx.coords + (long long)c * idx.capacity + i) : 0.f;
+    const float d = !valid ? INFINITY : (wide ? metric<DIM, true>(nd, q) : metric<DIM, false>(nd, q));
+    const bool in = d < r2;
+    const unsigned mask = __ballot_sync(kFull, in);
+    if (mask) {
+      int at = 0;
+      if (lane == 0) at = atomicAdd(&s_cnt, __popc(mask));
+      at = __shfl_sync(kFull, at, 0);
+      const int pos = at + __popc(mask & lt);
+      if (in && pos < kFusedRowCap) sk[pos] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)i;
+    }
+  }
+  __syncthreads();
+  const int len = s_cnt;
+  if (len > kFusedRowCap) {
+    if (threadIdx.x == 0) {
+      counts_out[qi] = len;
+      rowoff_out[qi] = -1;
+      *reinterpret_cast<volatile int *>(overflow) = 1;
+    }
+    return;
+  }
+  int pow2 = 1;
+  while (pow2 < len) pow2 <<= 1;
+  for (int k = 2; k <= pow2; k <<= 1) {
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+      const int l = i ^ (k - 1);
+      if (l > i && l < len) cmpswap(sk, i, l);
+    }
+    __syncthreads();
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i && l < len) cmpswap(sk, i, l);
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) s_off = len ? (long long)atomicAdd(total, (unsigned long long)len) : 0;
+  __syncthreads();
+  const long long off = s_off;
+  if (off + len > out_cap) {
+    if (threadIdx.x == 0) {
+      counts_out[qi] = len;
+      rowoff_out[qi] = -1;
+      *reinterpret_cast<volatile int *>(overflow) = 1;
+    }
+    return;
+  }
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const unsigned long long key = sk[i];
+    ids_out[off + i] = (int)(unsigned)(key & 0xffffffffull);
+    d2_out[off + i] = __uint_as_float((unsigned)(key >> 32));
+  }
+  if (threadIdx.x == 0) {
+    counts_out[qi] = len;
+    rowoff_out[qi] = off;
+  }
+}
+
 // Exclusive scan of the per-query counts on the device (one block; planner-sized calls), so that count, fill and sort run
 // back to back without a host round trip.  The total goes to `total_out` (pinned mapped memory the host reads after its one
 // synchronisation); when it exceeds `capacity` every offset is set to -1, which turns the fill and sort kernels into no-ops.
@@ -476,6 +564,19 @@ cudaError_t launch_radius_sort(unsigned long long *d_keys, const int64_t *d_offs
   if (nq <= 0) return cudaSuccess;
   radius_sort_kernel<<<(unsigned)nq, kThreads, 0, stream>>>(d_keys, reinterpret_cast<const long long *>(d_offsets), d_counts,
                                                             d_ids, d_d2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_radius_fused(const IndexDev &idx, const float *queries, int64_t nq, float r2, int64_t out_cap, int32_t *counts_out,
+                                int64_t *rowoff_out, int32_t *ids_out, float *d2_out, unsigned long long *d_total, int *overflow,
+                                cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  if (idx.dim == 6)
+    radius_fused_kernel<6><<<(unsigned)nq, kThreads, 0, stream>>>(idx, queries, r2, (long long)out_cap, counts_out,
+                                                                  reinterpret_cast<long long *>(rowoff_out), ids_out, d2_out, d_total, overflow);
+  else
+    radius_fused_kernel<2><<<(unsigned)nq, kThreads, 0, stream>>>(idx, queries, r2, (long long)out_cap, counts_out,
+                                                                  reinterpret_cast<long long *>(rowoff_out), ids_out, d2_out, d_total, overflow);
   return cudaGetLastError();
 }
 

@@ -62,6 +62,13 @@ cudaError_t launch_radius_fill(const IndexDev &idx, const float *d_queries, int6
                                int32_t *d_cursor, unsigned long long *d_keys, const KnnPlan &plan, cudaStream_t stream,
                                int64_t first = 0);
 
+// planner-sized radius search in one kernel (block per query, exhaustive over a small index): rows sorted by (d2, id), packed in
+// the order the blocks finish (rowoff_out[q] = start of row q, -1 + *overflow = 1 when a row or the output did not fit);
+// counts_out is exact in every case; *d_total must be zero
+cudaError_t launch_radius_fused(const IndexDev &idx, const float *queries, int64_t nq, float r2, int64_t out_cap, int32_t *counts_out,
+                                int64_t *rowoff_out, int32_t *ids_out, float *d2_out, unsigned long long *d_total, int *overflow,
+                                cudaStream_t stream);
+
 // d_offsets = exclusive scan of d_counts (one block, device side), *total_out = sum (device-accessible host word); when the sum
 // exceeds `capacity` all offsets become -1 and the fill / sort launches that follow do nothing
 cudaError_t launch_radius_offsets(const int32_t *d_counts, int64_t nq, int64_t capacity, int64_t *d_offsets, int64_t *total_out,

@@ -150,9 +150,11 @@ struct sffg_index {
     int32_t *counts_out = nullptr, *ids_out = nullptr;
     float *d2_out = nullptr;
     int64_t *total_out = nullptr;
-    bool small = false, one_sync = false, pruned = false;
+    bool small = false, one_sync = false, pruned = false, fused = false;
+    const float *queries = nullptr;
   } pend;
   cudaEvent_t add_ev = nullptr;   // appends enqueued by sffg_index_add_multi_begin have run
+  unsigned long long *d_total = nullptr;   // row allocator of the one-kernel radius search
 };
 static int index_busy(const sffg_index *idx, const char *who) {
   if (idx->pend.kind != 0) return fail(SFFG_ERR_ARG, std::string(who) + ": an asynchronous call on this index is pending (sffg_index_end first)");
@@ -1054,6 +1056,7 @@ int sffg_index_create(int dim, sffg_index **out) {
   cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->ev, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->add_ev, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&idx->d_total, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaHostAlloc((void **)&idx->h_small, kSmallBytes, cudaHostAllocMapped);
   if (e == cudaSuccess) {   // storage exists from the start: the scan kernels may touch the first block of an empty index
     idx->cap = 4096 + 128;
@@ -1068,7 +1071,10 @@ int sffg_index_create(int dim, sffg_index **out) {
     if (idx->stream) cudaStreamDestroy(idx->stream);
     if (idx->ev) cudaEventDestroy(idx->ev);
   if (idx->add_ev) cudaEventDestroy(idx->add_ev);
+  if (idx->d_total) cudaFree(idx->d_total);
     if (idx->add_ev) cudaEventDestroy(idx->add_ev);
+  if (idx->d_total) cudaFree(idx->d_total);
+    if (idx->d_total) cudaFree(idx->d_total);
     if (idx->h_small) cudaFreeHost(idx->h_small);
     delete idx;
     return fail(SFFG_ERR_CUDA, cudaGetErrorString(e));
@@ -1088,6 +1094,7 @@ int sffg_index_destroy(sffg_index *idx) {
   if (idx->h_small) cudaFreeHost(idx->h_small);
   if (idx->ev) cudaEventDestroy(idx->ev);
   if (idx->add_ev) cudaEventDestroy(idx->add_ev);
+  if (idx->d_total) cudaFree(idx->d_total);
   if (idx->stream) cudaStreamDestroy(idx->stream);
   delete idx;
   return SFFG_OK;
@@ -1444,8 +1451,10 @@ static int radius_fill_from_host_counts(sffg_index *idx, const sffg_index::Pendi
   return SFFG_OK;
 }
 
-int sffg_radius_begin(sffg_index *idx, const float *queries, int64_t nq, float r2, int32_t *counts_out, int32_t *ids_out,
-                      float *d2_out, int64_t capacity, int64_t *total_out) {
+constexpr int64_t kFusedRadiusMaxNodes = 32768;   // above this the pruned count / fill kernels win over one exhaustive pass
+
+static int radius_begin_impl(sffg_index *idx, const float *queries, int64_t nq, float r2, int32_t *counts_out, int32_t *ids_out,
+                             float *d2_out, int64_t capacity, int64_t *total_out, bool allow_fused) {
   if (!idx || nq < 0 || (nq > 0 && (!queries || !counts_out)) || (ids_out && !d2_out))
     return fail(SFFG_ERR_ARG, "sffg_radius: bad arguments");
   if (total_out) *total_out = 0;
@@ -1460,6 +1469,38 @@ int sffg_radius_begin(sffg_index *idx, const float *queries, int64_t nq, float r
   const bool small = qbytes <= (64 << 10) && cbytes <= (64 << 10);
   unsigned char *hq = idx->h_small, *hc = idx->h_small + (64 << 10), *hr = idx->h_small + (128 << 10);
   const size_t hr_bytes = kSmallBytes - (128 << 10);
+  if (allow_fused && small && ids_out && capacity > 0 && idx->n <= kFusedRadiusMaxNodes && qbytes <= (64 << 10) - 16 &&
+      (size_t)nq * 8 + 64 <= hr_bytes / 2) {
+    // planner-sized search on a small index: ONE kernel (block per query) that reads the queries from and writes counts,
+    // row offsets and sorted rows to pinned mapped memory -- one stream operation besides zeroing the row allocator, one
+    // host synchronisation.  Staging: [queries | flag] [counts] [row offsets | ids | d2].
+    std::memcpy(hq, queries, qbytes);
+    int *h_flag = reinterpret_cast<int *>(hq + (64 << 10) - 16);
+    *h_flag = 0;
+    int64_t *h_rowoff = reinterpret_cast<int64_t *>(hr);
+    const int64_t cap1 = (int64_t)((hr_bytes - (size_t)nq * 8) / 8);
+    int32_t *h_ids = reinterpret_cast<int32_t *>(hr + (size_t)nq * 8);
+    float *h_d2 = reinterpret_cast<float *>(hr + (size_t)nq * 8 + (size_t)cap1 * 4);
+    SFFG_CUDA(cudaMemsetAsync(idx->d_total, 0, sizeof(unsigned long long), st));
+    SFFG_CUDA(launch_radius_fused(v, reinterpret_cast<const float *>(hq), nq, r2, cap1, reinterpret_cast<int32_t *>(hc), h_rowoff, h_ids,
+                                  h_d2, idx->d_total, h_flag, st));
+    sffg_index::Pending &c = idx->pend;
+    c = sffg_index::Pending{};
+    c.kind = 2;
+    c.fused = true;
+    c.nq = nq;
+    c.capacity = capacity;
+    c.cap1 = cap1;
+    c.r2 = r2;
+    c.queries = queries;
+    c.counts_out = counts_out;
+    c.ids_out = ids_out;
+    c.d2_out = d2_out;
+    c.total_out = total_out;
+    c.small = true;
+    c.copy[c.n_copy++] = {counts_out, hc, cbytes};
+    return SFFG_OK;
+  }
   rc = idx->q.reserve(qbytes);
   if (rc == SFFG_OK) rc = idx->counts.reserve(cbytes);
   if (rc != SFFG_OK) return rc;
@@ -1522,6 +1563,11 @@ int sffg_radius_begin(sffg_index *idx, const float *queries, int64_t nq, float r
   return SFFG_OK;
 }
 
+int sffg_radius_begin(sffg_index *idx, const float *queries, int64_t nq, float r2, int32_t *counts_out, int32_t *ids_out,
+                      float *d2_out, int64_t capacity, int64_t *total_out) {
+  return radius_begin_impl(idx, queries, nq, r2, counts_out, ids_out, d2_out, capacity, total_out, true);
+}
+
 // completes the asynchronous call pending on this index (no-op when none is)
 int sffg_index_end(sffg_index *idx) {
   if (!idx) return fail(SFFG_ERR_ARG, "sffg_index_end: null index");
@@ -1532,6 +1578,33 @@ int sffg_index_end(sffg_index *idx) {
   for (int i = 0; i < c.n_copy; ++i) std::memcpy(c.copy[i].dst, c.copy[i].src, c.copy[i].bytes);
   if (c.kind != 2) return SFFG_OK;
   int64_t total = 0;
+  if (c.fused) {
+    const int flag = *reinterpret_cast<const volatile int *>(idx->h_small + (64 << 10) - 16);
+    for (int64_t i = 0; i < c.nq; ++i) total += c.counts_out[i];
+    if (c.total_out) *c.total_out = total;
+    if (total == 0) return SFFG_OK;
+    if (c.capacity < total)
+      return fail(SFFG_ERR_CAPACITY, "sffg_radius: result buffers hold " + std::to_string(c.capacity) + " entries, " +
+                                         std::to_string(total) + " needed");
+    if (flag) {   // a row longer than the kernel's shared buffer, or rows beyond the staging area: the general path
+      const int rc = radius_begin_impl(idx, c.queries, c.nq, c.r2, c.counts_out, c.ids_out, c.d2_out, c.capacity, c.total_out, false);
+      return rc != SFFG_OK ? rc : sffg_index_end(idx);
+    }
+    const unsigned char *hr = idx->h_small + (128 << 10);
+    const int64_t *h_rowoff = reinterpret_cast<const int64_t *>(hr);
+    const int32_t *h_ids = reinterpret_cast<const int32_t *>(hr + (size_t)c.nq * 8);
+    const float *h_d2 = reinterpret_cast<const float *>(hr + (size_t)c.nq * 8 + (size_t)c.cap1 * 4);
+    int64_t run = 0;
+    for (int64_t i = 0; i < c.nq; ++i) {   // rows were packed in the order the blocks finished: back into query order
+      const int64_t n_i = c.counts_out[i];
+      if (n_i) {
+        std::memcpy(c.ids_out + run, h_ids + h_rowoff[i], (size_t)n_i * 4);
+        std::memcpy(c.d2_out + run, h_d2 + h_rowoff[i], (size_t)n_i * 4);
+      }
+      run += n_i;
+    }
+    return SFFG_OK;
+  }
   if (c.one_sync) {
     unsigned char *hr = idx->h_small + (128 << 10);
     total = *reinterpret_cast<const int64_t *>(hr);

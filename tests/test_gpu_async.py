@@ -144,3 +144,37 @@ def test_appends_without_a_wait_are_seen_by_the_next_search(sff, orc):
     np.testing.assert_array_equal(ids[:, 0], 5000 + np.arange(64))
     glob.close()
     tree.close()
+
+
+def test_one_kernel_radius_on_small_indices(sff, orc):
+    """planner-sized searches on small indices run in one kernel (block per query, rows packed in completion order and put
+    back into query order by the host); rows longer than its shared buffer or a full staging area fall back to the general
+    path -- every case equals the oracle bit for bit, in 6-D (angles out of [-pi, pi) included) and in 2-D"""
+    nodes = _nodes(orc, 6000, SEED + 7)
+    nodes[:, 3:] *= 2.5
+    q = _nodes(orc, 900, SEED + 8)
+    idx = sff.Index(nodes[:4000])
+    idx.addPoints(nodes[4000:])
+    for r2 in (25.0, 400.0, 3000.0, 1.0e9):      # few hits / tens / hundreds (staging area overflows) / every node (row > buffer)
+        for nq in (1, 37, 900):
+            cnt, off, ids, d2 = idx.radiusSearch(q[:nq], r2)
+            wc, woff, wi, wd = orc.radius_linear(nodes, q[:nq], r2)
+            np.testing.assert_array_equal(cnt, wc)
+            np.testing.assert_array_equal(ids, wi)
+            np.testing.assert_array_equal(d2.view(np.uint32), wd.view(np.uint32))
+    assert wc.min() == 6000
+    idx.close()
+    n2 = np.ascontiguousarray(_nodes(orc, 3000, SEED + 9)[:, :2]) * np.float32(10.0)
+    q2 = np.ascontiguousarray(_nodes(orc, 200, SEED + 10)[:, :2]) * np.float32(10.0)
+    idx2 = sff.Index(n2)
+    for r2 in (900.0, 67600.0):                  # the planner's 2-D radius^2 is 67 600
+        cnt, off, ids, d2 = idx2.radiusSearch(q2, r2)
+        wc, woff, wi, wd = orc.radius_linear(n2, q2, r2)
+        np.testing.assert_array_equal(cnt, wc)
+        np.testing.assert_array_equal(ids, wi)
+        np.testing.assert_array_equal(d2.view(np.uint32), wd.view(np.uint32))
+    idx2.close()
+    empty = sff.Index(dim=6)
+    cnt, off, ids, d2 = empty.radiusSearch(q[:5], 10.0)
+    assert cnt.sum() == 0 and len(ids) == 0
+    empty.close()
